@@ -1,0 +1,131 @@
+/* orbit_b200.h -- C ABI of liborbit_b200.so: the sm_100a implementation of the ORBIT few-shot
+ * recogniser's inner episodic loop (reference: microsoft/ORBIT-Dataset @ 97ccae1,
+ * model/few_shot_recognisers.py personalise()/predict()).
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, >0 = cudaError_t, <0 = ORBIT_ERR_* (argument errors).
+ *   - no exceptions, no hidden allocation, no stream synchronisation across the ABI: all device
+ *     memory (parameters, workspace, outputs) is caller-owned; every call takes the cudaStream_t it
+ *     enqueues on (as void*). Pointers are DEVICE pointers unless the name ends in _host.
+ *   - activations are fp32; frames come in as the reference delivers them (fp32, NCHW, contiguous,
+ *     data/datasets.py:384,428-431), features/logits go out as the reference returns them
+ *     (fp32 row-major).
+ *   - thread-safety: functions are re-entrant; an orbit_engine is immutable after create and may be
+ *     shared by threads that use distinct workspaces.
+ */
+#ifndef ORBIT_B200_H
+#define ORBIT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBIT_ABI_VERSION 1
+
+#define ORBIT_OK               0
+#define ORBIT_ERR_ARG         (-1)  /* null pointer / non-positive size / misaligned pointer   */
+#define ORBIT_ERR_UNSUPPORTED (-2)  /* shape or option outside what the kernels implement      */
+#define ORBIT_ERR_WORKSPACE   (-3)  /* caller's workspace is smaller than *_workspace_bytes()   */
+#define ORBIT_ERR_NO_DEVICE   (-4)  /* not running on an sm_100 device                         */
+
+#define ORBIT_METRIC_EUCLIDEAN 0    /* classifier 'proto'        (few_shot_recognisers.py:78-79) */
+#define ORBIT_METRIC_COSINE    1    /* classifier 'proto_cosine' (few_shot_recognisers.py:80-81) */
+
+#define ORBIT_ARCH_EFFICIENTNET_B0 0 /* timm tf_efficientnet_b0 (feature_extractors.py:39-43)   */
+#define ORBIT_ARCH_VIT_S_32        1 /* feature_extractors.py:49-53                             */
+#define ORBIT_ARCH_VIT_B_32        2 /* feature_extractors.py:54-58                             */
+#define ORBIT_ARCH_VIT_B_32_CLIP   3 /* feature_extractors.py:59-64                             */
+#define ORBIT_ARCH_RESNET18        4 /* BASELINE.json extension (not in the reference)          */
+
+#define ORBIT_MAX_CLASSES 64
+
+int         orbit_abi_version(void);
+const char* orbit_error_string(int code);
+/* 0 if the current CUDA device is sm_100 and the library's kernels can run, else ORBIT_ERR_NO_DEVICE */
+int         orbit_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Head: frame pooling + prototype build + all-pairs scoring.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces MeanPooler.forward (model/poolers.py:13-16): out[n,:] = mean_l in[n*L+l,:].  */
+int orbit_pool_clips(const float* frame_feats, int num_clips, int clip_length, int feat_dim,
+                     float* clip_feats, void* stream);
+
+/* Replaces FewShotRecogniser._pool_features + HeadClassifier._build_class_reps +
+ * PrototypicalClassifier.configure (few_shot_recognisers.py:155-166; classifier_heads.py:94-105,
+ * 232-263) in one launch.
+ *   frame_feats [num_clips*clip_length, feat_dim]   support FRAME features (pooling is fused)
+ *   class_index [num_clips] int32 in [0,num_classes): rank of the clip's label among the sorted
+ *               distinct labels (torch.unique order, classifier_heads.py:96,246-248)
+ *   weight [num_classes, feat_dim] <- 2*mu_c ; bias [num_classes] <- -mu_c.mu_c (euclidean only,
+ *               may be NULL for cosine); proto [num_classes, feat_dim] <- mu_c (nullable)
+ *   scratch: >= orbit_proto_configure_scratch_bytes(num_classes, feat_dim) bytes, ZERO-FILLED once by the
+ *               caller before first use (the kernel restores it to zero).                        */
+int64_t orbit_proto_configure_scratch_bytes(int num_classes, int feat_dim);
+int orbit_proto_configure(const float* frame_feats, const int32_t* class_index, int num_clips,
+                          int clip_length, int feat_dim, int num_classes, int metric,
+                          float* weight, float* bias, float* proto, void* scratch, void* stream);
+
+/* Replaces _pool_features + PrototypicalClassifier.predict (classifier_heads.py:202-230), and also
+ * LinearClassifier.predict / VersaClassifier.predict (classifier_heads.py:63-75,137-143) which are
+ * the same s*(qW^T+b) form.
+ *   euclidean: logits = logit_scale * (q W^T + b)          (classifier_heads.py:213)
+ *   cosine   : logits = logit_scale * cos(q, W_c), each norm clamped at 1e-8 (:215-217)
+ *   logits [num_clips, num_classes]; argmax [num_clips] int32 (nullable; first maximal column,
+ *   as torch.argmax)                                                                              */
+int orbit_head_predict(const float* frame_feats, int num_clips, int clip_length, int feat_dim,
+                       const float* weight, const float* bias, int num_classes, int metric,
+                       float logit_scale, float* logits, int32_t* argmax, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backbone engine: the feature extractor forward (reference: timm model called at
+ * few_shot_recognisers.py:114-117,143-146, with FiLM by functional_call parameter substitution).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct orbit_engine orbit_engine;
+
+int  orbit_engine_create(orbit_engine** out, int arch);
+void orbit_engine_destroy(orbit_engine* e);
+int  orbit_engine_feat_dim(const orbit_engine* e);
+
+/* Parameter blob layout. The caller packs the extractor's state_dict (timm key names, e.g.
+ * "blocks.1.0.bn2.weight") into ONE fp32 device array; entry i lives at [offset, offset+numel). */
+int     orbit_engine_num_params(const orbit_engine* e);
+int     orbit_engine_param_info(const orbit_engine* e, int i, char* name, int name_cap,
+                                int64_t* numel, int64_t* offset);
+int64_t orbit_engine_param_floats(const orbit_engine* e);
+
+/* FiLM tensors (reference model/film.py:38-74), in the SORTED-name order the reference's generator
+ * uses (feature_adapters.py:43-44); the film blob is their concatenation.                        */
+int     orbit_engine_num_film(const orbit_engine* e);
+int     orbit_engine_film_info(const orbit_engine* e, int i, char* name, int name_cap,
+                               int64_t* numel, int64_t* offset);
+int64_t orbit_engine_film_floats(const orbit_engine* e);
+
+/* Derived per-task tensors (BatchNorm folded to per-channel scale/shift with the FiLM gamma'/beta'
+ * substituted, re-laid-out depthwise weights, tf32 hi/lo weight splits). `film` may be NULL
+ * (no adaptation). Must be re-run when params or film change.                                    */
+int64_t orbit_engine_derived_floats(const orbit_engine* e);
+int     orbit_engine_prepare(const orbit_engine* e, const float* params, const float* film,
+                             float* derived, void* stream);
+
+/* Options: "chunk_frames" (frames per pass, sized to keep inter-layer tensors in L2),
+ *          "gemm" 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (fp32-accurate), 2 = tcgen05 1xTF32     */
+int orbit_engine_set_option(orbit_engine* e, const char* key, int value);
+int orbit_engine_get_option(const orbit_engine* e, const char* key, int* value);
+
+int64_t orbit_engine_workspace_bytes(const orbit_engine* e, int height, int width);
+
+/* frames [num_frames,3,height,width] fp32 NCHW  ->  feats [num_frames, feat_dim] fp32.          */
+int orbit_engine_forward(const orbit_engine* e, const float* params, const float* derived,
+                         const float* frames, int num_frames, int height, int width,
+                         float* feats, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* number of kernels the last orbit_engine_forward on this engine enqueued (for bench accounting) */
+int64_t orbit_engine_last_launches(const orbit_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBIT_B200_H */

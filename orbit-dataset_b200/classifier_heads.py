@@ -1,0 +1,146 @@
+"""Classifier heads behind the reference's ``configure()/predict()/reset()`` interface.
+
+Mirrors reference ``model/classifier_heads.py`` (class names, attributes ``weight``/``bias`` as
+``nn.Parameter`` while personalised and ``None`` after ``reset()``, error behaviour) and
+``model/poolers.py``; the arithmetic runs in liborbit_b200's fused head kernels.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lib as L
+
+_METRICS = {'euclidean': 0, 'cosine': 1}
+
+
+def _class_index(labels: torch.Tensor):
+    """Rank of each label among the sorted distinct labels (torch.unique order,
+    classifier_heads.py:96,246-248). Done on the host: labels are a few hundred int64s and are
+    needed there anyway to size the [C, D] outputs."""
+    lab = labels.detach().cpu().numpy().astype(np.int64).reshape(-1)
+    classes, inverse = np.unique(lab, return_inverse=True)
+    return classes, inverse.astype(np.int32)
+
+
+class MeanPooler(nn.Module):
+    """poolers.py:7-16."""
+
+    def __init__(self, T, dim=1):
+        super().__init__()
+        self.T = T
+        self.dim = dim
+
+    def forward(self, x):
+        L.require_cuda(x, "features")
+        x = x.contiguous().float()
+        n, d = x.shape[0] // self.T, x.shape[-1]
+        out = torch.empty(n, d, dtype=torch.float32, device=x.device)
+        L.check(L.load().orbit_pool_clips(L.ptr(x), n, self.T, d, L.ptr(out), L.stream_ptr(x.device)), "orbit_pool_clips")
+        L.count_launches(1)
+        return out
+
+
+def _head_predict(features, clip_length, weight, bias, metric, logit_scale, want_argmax=False):
+    L.require_cuda(features, "features")
+    features = features.contiguous().float()
+    n = features.shape[0] // clip_length
+    c, d = weight.shape
+    if features.shape[1] != d:
+        raise ValueError(f"feature dim {features.shape[1]} does not match classifier dim {d}")
+    logits = torch.empty(n, c, dtype=torch.float32, device=features.device)
+    argmax = torch.empty(n, dtype=torch.int32, device=features.device) if want_argmax else None
+    L.check(L.load().orbit_head_predict(L.ptr(features), n, clip_length, d, L.ptr(weight.detach()),
+                                        L.ptr(bias.detach() if bias is not None else None), c, metric,
+                                        float(logit_scale), L.ptr(logits), L.ptr(argmax), L.stream_ptr(features.device)),
+            "orbit_head_predict")
+    L.count_launches(1)
+    return (logits, argmax) if want_argmax else logits
+
+
+class LinearClassifier(nn.Module):
+    """classifier_heads.py:38-79."""
+
+    def __init__(self, feat_dim, logit_scale: float = 1.0):
+        super().__init__()
+        self.feat_dim = feat_dim
+        self.logit_scale = logit_scale
+        self.weight = None
+        self.bias = None
+
+    def init(self, num_classes: int):
+        self.weight = nn.Parameter(torch.zeros(num_classes, self.feat_dim), requires_grad=True)
+        self.bias = nn.Parameter(torch.zeros(num_classes), requires_grad=True)
+
+    def predict(self, features, ops_counter=None, clip_length=1):
+        if self.weight is None:
+            raise AttributeError("Weight and/or bias not set - is model personalised?")
+        return _head_predict(features, clip_length, self.weight, self.bias, 0, self.logit_scale)
+
+    def reset(self):
+        self.weight = None
+        self.bias = None
+
+
+class HeadClassifier(nn.Module):
+    def __init__(self, logit_scale: float = 1.0):
+        super().__init__()
+        self.logit_scale = logit_scale
+
+
+class PrototypicalClassifier(HeadClassifier):
+    """classifier_heads.py:182-263."""
+
+    def __init__(self, logit_scale: float = 1.0, distance_fn: str = 'euclidean'):
+        super().__init__(logit_scale)
+        self.distance_fn = distance_fn
+        self._scratch = None
+        self.reset()
+
+    def reset(self):
+        self.weight = None
+        if self.distance_fn == 'euclidean':
+            self.bias = None
+        self.classes = None
+
+    def configure(self, context_features, context_labels, ops_counter=None, clip_length=1):
+        """``context_features``: clip features [N, D] (reference contract) or, with ``clip_length=L``,
+        the FRAME features [N*L, D] -- pooling is then fused into the same launch."""
+        if self.distance_fn not in _METRICS:
+            raise ValueError(f"Distance function {self.distance_fn} not valid.")
+        L.require_cuda(context_features, "context_features")
+        assert context_features.size(0) == context_labels.size(0) * clip_length, \
+            "context features and labels are different sizes!"
+        lib = L.load()
+        feats = context_features.contiguous().float()
+        dev = feats.device
+        classes, idx = _class_index(context_labels)
+        c, d, n = len(classes), feats.shape[1], len(idx)
+        if c > 64:
+            raise ValueError("orbit_b200 supports at most 64 classes per task")
+        idx_dev = torch.from_numpy(idx).to(dev, non_blocking=True)
+        need = lib.orbit_proto_configure_scratch_bytes(64, d)
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
+            self._scratch = torch.zeros(need, dtype=torch.uint8, device=dev)
+        weight = torch.empty(c, d, dtype=torch.float32, device=dev)
+        euclid = self.distance_fn == 'euclidean'
+        bias = torch.empty(c, dtype=torch.float32, device=dev) if euclid else None
+        L.check(lib.orbit_proto_configure(L.ptr(feats), L.ptr(idx_dev), n, clip_length, d, c, _METRICS[self.distance_fn],
+                                          L.ptr(weight), L.ptr(bias), None, L.ptr(self._scratch), L.stream_ptr(dev)),
+                "orbit_proto_configure")
+        L.count_launches(1)
+        # nn.Parameter wrap as in the reference (classifier_heads.py:261-263): cuts the autograd graph
+        self.weight = nn.Parameter(weight)
+        if euclid:
+            self.bias = nn.Parameter(bias)
+        self.classes = torch.from_numpy(classes)
+
+    def predict(self, features, ops_counter=None, clip_length=1, want_argmax=False):
+        if self.weight is None or (self.distance_fn == 'euclidean' and self.bias is None):
+            raise AttributeError("Weight and/or bias not set - is model personalised?")
+        if self.distance_fn not in _METRICS:
+            raise ValueError(f"Distance function {self.distance_fn} not valid.")
+        bias = self.bias if self.distance_fn == 'euclidean' else None
+        return _head_predict(features, clip_length, self.weight, bias, _METRICS[self.distance_fn], self.logit_scale,
+                             want_argmax)

@@ -1,0 +1,469 @@
+// CUDA-core kernels of the convolutional backbones (EfficientNet-B0 family; fp32, NHWC).
+//
+// Reference op sites (microsoft/ORBIT-Dataset @ 97ccae1): the timm model invoked at
+// model/few_shot_recognisers.py:114-117,143-146 (timm==0.6.12 tf_efficientnet_b0, external), with
+// FiLM = substituted BatchNorm affine parameters (model/film.py:38-74).  Per layer:
+//   conv_stem+bn1+SiLU        -> stem_kernel            (direct conv, NCHW in / NHWC out)
+//   conv_dw+bn(+FiLM)+SiLU    -> dw_kernel              (HBM-bound stencil, fused SE squeeze partials)
+//   SqueezeExcite FCs         -> se_gate_kernel
+//   conv_pw/conv_pwl/conv_head-> pw_ffma_kernel (this file, fp32 FFMA tiles) or the tcgen05 kernel
+//                                in gemm_tcgen05.cu; BN/FiLM scale-shift, SiLU, SE gate and residual fused
+//   global_pool               -> spatial_mean_kernel
+#include "convnet.cuh"
+
+namespace orbit {
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm fold: scale = gamma * rsqrt(var + eps), shift = beta - mean * scale, with FiLM gamma'/beta'
+// substituted where the layer is a FiLM site.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFoldBatch = 32;
+struct FoldTable {
+    FoldEntry e[kFoldBatch];
+};
+
+__global__ void __launch_bounds__(256)
+bn_fold_kernel(FoldTable tab, const float* __restrict__ params, const float* __restrict__ film, float* __restrict__ derived) {
+    const FoldEntry& e = tab.e[blockIdx.y];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < e.channels; c += gridDim.x * blockDim.x) {
+        const float g = (film && e.film_gamma >= 0) ? film[e.film_gamma + c] : params[e.gamma + c];
+        const float b = (film && e.film_beta >= 0) ? film[e.film_beta + c] : params[e.beta + c];
+        const float inv = 1.0f / sqrtf(params[e.var + c] + e.eps);
+        const float sc = g * inv;
+        derived[e.out + c] = sc;
+        derived[e.out + e.channels + c] = b - params[e.mean + c] * sc;
+    }
+}
+
+int launch_bn_fold(const FoldEntry* entries, int n, const float* params, const float* film, float* derived, cudaStream_t st) {
+    for (int s = 0; s < n; s += kFoldBatch) {
+        FoldTable tab;
+        const int m = std::min(kFoldBatch, n - s);
+        int maxc = 1;
+        for (int i = 0; i < m; ++i) { tab.e[i] = entries[s + i]; maxc = std::max(maxc, entries[s + i].channels); }
+        dim3 grid(ceil_div(maxc, 256), m);
+        bn_fold_kernel<<<grid, 256, 0, st>>>(tab, params, film, derived);
+        ORBIT_RETURN_IF_LAUNCH_FAILED();
+    }
+    return ORBIT_OK;
+}
+
+__global__ void dw_relayout_kernel(const float* __restrict__ w, int C, int kk, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C * kk) { const int t = i / C, c = i % C; out[i] = w[c * kk + t]; }
+}
+int launch_dw_relayout(const float* w, int C, int kk, float* out, cudaStream_t st) {
+    dw_relayout_kernel<<<ceil_div(C * kk, 256), 256, 0, st>>>(w, C, kk, out);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_SILU) return siluf_(v);
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: 3x3 stride-2 conv on the fp32 NCHW frames, one output pixel (all COUT channels) per thread.
+// The NCHW->NHWC change of layout is fused here so the frames are read exactly once.
+// ------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(128)
+stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+            const float* __restrict__ shift, float* __restrict__ y, int B, int H, int W, int Ho, int Wo, int pad_t,
+            int pad_l, int act) {
+    __shared__ __align__(16) float s_w[27 * COUT];  // [tap][co]
+    __shared__ __align__(16) float s_sc[COUT], s_sh[COUT];
+    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) { const int tap = i / COUT, co = i % COUT; s_w[i] = w[co * 27 + tap]; }
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) { s_sc[i] = scale[i]; s_sh[i] = shift[i]; }
+    __syncthreads();
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * Ho * Wo) return;
+    const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho), b = (int)(idx / ((int64_t)Wo * Ho));
+    float acc[COUT];
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        const float* xp = x + ((int64_t)b * 3 + ci) * H * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * 2 - pad_t + ky;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * 2 - pad_l + kx;
+                if (ix < 0 || ix >= W) continue;
+                const float v = __ldg(xp + (int64_t)iy * W + ix);
+                const float4* wp = reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * COUT);
+#pragma unroll
+                for (int q = 0; q < COUT / 4; ++q) {
+                    const float4 w4 = wp[q];
+                    acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+                }
+            }
+        }
+    }
+    float4* yp = reinterpret_cast<float4*>(y + idx * COUT);
+#pragma unroll
+    for (int q = 0; q < COUT / 4; ++q) {
+        float4 o;
+        o.x = apply_act(fmaf(acc[4 * q + 0], s_sc[4 * q + 0], s_sh[4 * q + 0]), act);
+        o.y = apply_act(fmaf(acc[4 * q + 1], s_sc[4 * q + 1], s_sh[4 * q + 1]), act);
+        o.z = apply_act(fmaf(acc[4 * q + 2], s_sc[4 * q + 2], s_sh[4 * q + 2]), act);
+        o.w = apply_act(fmaf(acc[4 * q + 3], s_sc[4 * q + 3], s_sh[4 * q + 3]), act);
+        yp[q] = o;
+    }
+}
+
+int launch_stem(const float* x, const float* w, const float* scale, const float* shift, float* y, int B, int H, int W,
+                int Ho, int Wo, int pad_t, int pad_l, int cout, int act, cudaStream_t st) {
+    if (cout != 32) return ORBIT_ERR_UNSUPPORTED;
+    const int64_t total = (int64_t)B * Ho * Wo;
+    stem_kernel<32><<<(unsigned)ceil_div64(total, 128), 128, 0, st>>>(x, w, scale, shift, y, B, H, W, Ho, Wo, pad_t, pad_l, act);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise KxK conv + folded BN/FiLM + activation, NHWC. A thread owns 4 channels (one 128-bit
+// lane) and a strip of TW output pixels along x; neighbouring taps are reused from registers.
+// grid (tiles, channel chunks, frames); block = LX lanes x LY strips.
+// Epilogue: the activated outputs are summed per (frame, tile, channel) for the SE squeeze with a
+// fixed-order shared-memory reduction (deterministic; no atomics).
+// ------------------------------------------------------------------------------------------------
+constexpr int kDwTW = 4;
+
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+dw_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
+          const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C,
+          int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile) {
+    extern __shared__ __align__(16) float4 s_dw[];  // weights [K*K][LX] then reduction [LY][LX]
+    float4* s_w = s_dw;
+    float4* s_red = s_dw + K * K * LX;
+    const int tile = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z, tiles = gridDim.x;
+    const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
+    const int C4 = C >> 2;
+    const int c4 = chunk * LX + lx;
+    const bool live = c4 < C4;
+    for (int i = threadIdx.x; i < K * K * LX; i += blockDim.x) {
+        const int t = i / LX, cc = chunk * LX + (i % LX);
+        s_w[i] = cc < C4 ? ldg4(wt + (int64_t)t * C + cc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc, sum = sc;
+    if (live) { sc = ldg4(scale + c4 * 4); sh = ldg4(shift + c4 * 4); }
+    const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
+    const int strips_per_row = ceil_div(Wo, kDwTW);
+    const int nstrips = (row1 - row0) * strips_per_row;
+    constexpr int SPAN = (kDwTW - 1) * S + K;
+    if (live) {
+        const float* xb = x + (int64_t)b * H * W * C + c4 * 4;
+        float* yb = y + (int64_t)b * Ho * Wo * C + c4 * 4;
+        for (int s = ly; s < nstrips; s += LY) {
+            const int oy = row0 + s / strips_per_row, ox0 = (s % strips_per_row) * kDwTW;
+            float4 o[kDwTW];
+#pragma unroll
+            for (int t = 0; t < kDwTW; ++t) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const int iy = oy * S - pad_t + ky;
+                if (iy < 0 || iy >= H) continue;
+                const float* rowp = xb + (int64_t)iy * W * C;
+                const int ixb = ox0 * S - pad_l;
+#pragma unroll
+                for (int j = 0; j < SPAN; ++j) {
+                    const int ix = ixb + j;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ix >= 0 && ix < W) v = ldg4(rowp + (int64_t)ix * C);
+#pragma unroll
+                    for (int t = 0; t < kDwTW; ++t) {
+                        const int kx = j - t * S;
+                        if (kx >= 0 && kx < K) fma4(o[t], v, s_w[(ky * K + kx) * LX + lx]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kDwTW; ++t) {
+                if (ox0 + t < Wo) {
+                    float4 r;
+                    r.x = apply_act(fmaf(o[t].x, sc.x, sh.x), act); r.y = apply_act(fmaf(o[t].y, sc.y, sh.y), act);
+                    r.z = apply_act(fmaf(o[t].z, sc.z, sh.z), act); r.w = apply_act(fmaf(o[t].w, sc.w, sh.w), act);
+                    *reinterpret_cast<float4*>(yb + ((int64_t)oy * Wo + ox0 + t) * C) = r;
+                    add4(sum, r);
+                }
+            }
+        }
+    }
+    if (partial) {
+        s_red[ly * LX + lx] = sum;
+        __syncthreads();
+        if (ly == 0 && live) {
+            float4 t = s_red[lx];
+            for (int r = 1; r < LY; ++r) add4(t, s_red[r * LX + lx]);
+            *reinterpret_cast<float4*>(partial + ((int64_t)b * tiles + tile) * C + c4 * 4) = t;
+        }
+    }
+}
+
+int dw_num_tiles(int Ho) { return std::min(Ho, 8); }
+
+int launch_depthwise(const float* x, const float* wt, const float* scale, const float* shift, float* y, float* partial,
+                     int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, int act,
+                     cudaStream_t st) {
+    if (C % 4) return ORBIT_ERR_UNSUPPORTED;
+    const int C4 = C / 4;
+    const int nchunks = ceil_div(C4, 32);
+    const int LX = ceil_div(C4, nchunks);
+    const int LY = std::max(1, 256 / LX);
+    const int tiles = dw_num_tiles(Ho);
+    const int rows_per_tile = ceil_div(Ho, tiles);
+    dim3 grid(tiles, nchunks, B), block(LX * LY);
+    const size_t smem = sizeof(float4) * ((size_t)k * k * LX + (size_t)LY * LX);
+#define ORBIT_DW_CASE(KK, SS)                                                                                         \
+    if (k == KK && stride == SS) {                                                                                    \
+        dw_kernel<KK, SS><<<grid, block, smem, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t, pad_l,  \
+                                                    act, LX, LY, rows_per_tile);                                      \
+        ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                              \
+        return ORBIT_OK;                                                                                              \
+    }
+    ORBIT_DW_CASE(3, 1) ORBIT_DW_CASE(3, 2) ORBIT_DW_CASE(5, 1) ORBIT_DW_CASE(5, 2)
+#undef ORBIT_DW_CASE
+    return ORBIT_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Squeeze-excite gate, one block per frame.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const float* __restrict__ w1,
+               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+               float* __restrict__ gate, int C, int R) {
+    extern __shared__ float s_se[];  // mean[C], hidden[R]
+    float* s_mean = s_se;
+    float* s_hid = s_se + C;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const float* pb = partial + (int64_t)b * tiles * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int t = 0; t < tiles; ++t) s += pb[(int64_t)t * C + c];
+        s_mean[c] = s * inv_hw;
+    }
+    __syncthreads();
+    for (int r = warp; r < R; r += n_warps) {
+        float s = 0.f;
+        const float* wr = w1 + (int64_t)r * C;
+        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + c), s_mean[c], s);
+        s = warp_sum(s);
+        if (lane == 0) s_hid[r] = siluf_(s + __ldg(b1 + r));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = __ldg(b2 + c);
+        const float* wr = w2 + (int64_t)c * R;
+        for (int r = 0; r < R; ++r) s = fmaf(__ldg(wr + r), s_hid[r], s);
+        gate[(int64_t)b * C + c] = sigmoidf_(s);
+    }
+}
+
+int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2,
+                   const float* b2, float* gate, int B, int C, int R, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (size_t)(C + R);
+    se_gate_kernel<<<B, 256, smem, st>>>(partial, tiles, 1.0f / (float)hw, w1, b1, w2, b2, gate, C, R);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pointwise conv as an fp32 FFMA GEMM: out[M,N] = epi(A[M,K] . W[N,K]^T). 128 x BN x 16 tiles, 256 threads,
+// 8 x (BN/16) register micro-tiles, register-prefetch double buffering. The A loader applies the
+// SE gate (per frame, per input channel) so the gated tensor is never materialised.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(256)
+pw_ffma_kernel(const float* __restrict__ A, const float* __restrict__ Wt, const float* __restrict__ scale,
+               const float* __restrict__ shift, const float* __restrict__ gate, const float* __restrict__ residual,
+               float* __restrict__ out, int M, int N, int K, int rows_per_frame, int act) {
+    constexpr int BM = 128, BK = 16, TN = BN / 16, LDA = BM + 4, LDB = BN + 4;
+    constexpr int B_LOADS = (BN * 4 + 255) / 256;  // float4 loads per thread for the W tile
+    __shared__ __align__(16) float As[2][BK][LDA];
+    __shared__ __align__(16) float Bs[2][BK][LDB];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t block_m = (int64_t)blockIdx.x * BM;
+    const int block_n = blockIdx.y * BN;
+
+    const int a_q = tid & 3;
+    int a_row[2];
+    const float* a_ptr[2];
+    const float* g_ptr[2];
+    bool a_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        a_row[i] = (tid >> 2) + i * 64;
+        const int64_t gm = block_m + a_row[i];
+        a_ok[i] = gm < M;
+        a_ptr[i] = A + (a_ok[i] ? gm : 0) * K + a_q * 4;
+        g_ptr[i] = gate ? gate + ((a_ok[i] ? gm : 0) / rows_per_frame) * K + a_q * 4 : nullptr;
+    }
+    int b_row[B_LOADS];
+    const float* b_ptr[B_LOADS];
+    bool b_ok[B_LOADS];
+#pragma unroll
+    for (int i = 0; i < B_LOADS; ++i) {
+        const int e = tid + i * 256;
+        b_row[i] = e >> 2;
+        const int gn = block_n + b_row[i];
+        b_ok[i] = (e < BN * 4) && gn < N;
+        b_ptr[i] = Wt + (int64_t)(b_ok[i] ? gn : 0) * K + a_q * 4;
+    }
+
+    float4 ra[2], rb[B_LOADS];
+    auto load_tiles = [&](int k0) {
+        const bool kin = k0 + a_q * 4 < K;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a_ok[i] && kin) {
+                ra[i] = ldg4(a_ptr[i] + k0);
+                if (gate) { const float4 g = ldg4(g_ptr[i] + k0); ra[i].x *= g.x; ra[i].y *= g.y; ra[i].z *= g.z; ra[i].w *= g.w; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < B_LOADS; ++i) {
+            rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b_ok[i] && kin) rb[i] = ldg4(b_ptr[i] + k0);
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            As[buf][a_q * 4 + 0][a_row[i]] = ra[i].x; As[buf][a_q * 4 + 1][a_row[i]] = ra[i].y;
+            As[buf][a_q * 4 + 2][a_row[i]] = ra[i].z; As[buf][a_q * 4 + 3][a_row[i]] = ra[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < B_LOADS; ++i) {
+            if (tid + i * 256 < BN * 4) {
+                Bs[buf][a_q * 4 + 0][b_row[i]] = rb[i].x; Bs[buf][a_q * 4 + 1][b_row[i]] = rb[i].y;
+                Bs[buf][a_q * 4 + 2][b_row[i]] = rb[i].z; Bs[buf][a_q * 4 + 3][b_row[i]] = rb[i].w;
+            }
+        }
+    };
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int n_k = ceil_div(K, BK);
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < n_k; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < n_k) load_tiles((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[8], bb[TN];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            if constexpr (TN == 8) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+                bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+            } else if constexpr (TN == 4) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+                bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+            } else if constexpr (TN == 2) {
+                const float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 2]);
+                bb[0] = b0.x; bb[1] = b0.y;
+            } else {
+                bb[0] = Bs[buf][k][tx];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        if (kt + 1 < n_k) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // epilogue: folded BN/FiLM scale-shift, activation, residual
+    constexpr int NG = TN == 8 ? 2 : 1;       // column groups per thread
+    constexpr int GW = TN == 8 ? 4 : TN;      // group width
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const int col0 = block_n + (TN == 8 ? g * 64 + tx * 4 : tx * TN);
+        if (col0 >= N) continue;
+        float sc[GW], sh[GW];
+#pragma unroll
+        for (int j = 0; j < GW; ++j) { sc[j] = __ldg(scale + col0 + j); sh[j] = __ldg(shift + col0 + j); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t row = block_m + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+            if (row >= M) continue;
+            float v[GW];
+#pragma unroll
+            for (int j = 0; j < GW; ++j) v[j] = apply_act(fmaf(acc[i][g * 4 + j], sc[j], sh[j]), act);
+            float* op = out + row * N + col0;
+            if (residual) {
+                const float* rp = residual + row * N + col0;
+#pragma unroll
+                for (int j = 0; j < GW; ++j) v[j] += __ldg(rp + j);
+            }
+            if constexpr (GW == 4) *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+            else if constexpr (GW == 2) *reinterpret_cast<float2*>(op) = make_float2(v[0], v[1]);
+            else op[0] = v[0];
+        }
+    }
+}
+
+int launch_pointwise_ffma(const float* A, const float* Wt, const float* scale, const float* shift, const float* gate,
+                          const float* residual, float* out, int M, int N, int K, int rows_per_frame, int act,
+                          cudaStream_t st) {
+    if (K % 4 || N % 4) return ORBIT_ERR_UNSUPPORTED;
+    int BN;
+    if (N <= 16) BN = 16;
+    else if (N <= 32) BN = 32;
+    else BN = (ceil_div(N, 64) * 64 < ceil_div(N, 128) * 128) ? 64 : 128;
+    dim3 grid((unsigned)ceil_div(M, 128), ceil_div(N, BN));
+#define ORBIT_PW_CASE(BNN)                                                                                             \
+    if (BN == BNN) pw_ffma_kernel<BNN><<<grid, 256, 0, st>>>(A, Wt, scale, shift, gate, residual, out, M, N, K,        \
+                                                            rows_per_frame, act);
+    ORBIT_PW_CASE(16) ORBIT_PW_CASE(32) ORBIT_PW_CASE(64) ORBIT_PW_CASE(128)
+#undef ORBIT_PW_CASE
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Global average pool over the spatial positions: x [B,HW,C] -> y [B,C]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spatial_mean_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+    const int C4 = C >> 2;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * C4) return;
+    const int b = (int)(i / C4), q = (int)(i % C4);
+    const float* p = x + (int64_t)b * HW * C + q * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < HW; ++r) add4(s, ldg4_stream(p + (int64_t)r * C));
+    const float d = (float)HW;
+    *reinterpret_cast<float4*>(y + (int64_t)b * C + q * 4) = make_float4(s.x / d, s.y / d, s.z / d, s.w / d);
+}
+
+int launch_spatial_mean(const float* x, float* y, int B, int HW, int C, cudaStream_t st) {
+    if (C % 4) return ORBIT_ERR_UNSUPPORTED;
+    spatial_mean_kernel<<<(unsigned)ceil_div64((int64_t)B * (C / 4), 256), 256, 0, st>>>(x, y, B, HW, C);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+}  // namespace orbit

@@ -1,0 +1,47 @@
+// Launchers of the convolutional-backbone kernels (NHWC fp32 activations). Internal to the library.
+#pragma once
+#include "common.cuh"
+
+namespace orbit {
+
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2 };
+
+// One BatchNorm (or FiLM-modulated BatchNorm) to fold into per-channel scale/shift.
+struct FoldEntry {
+    int64_t gamma, beta, mean, var;  // offsets into the params blob
+    int64_t film_gamma, film_beta;   // offsets into the film blob, or -1
+    int64_t out;                     // offset into derived: scale[C] then shift[C]
+    int channels;
+    float eps;
+};
+
+int launch_bn_fold(const FoldEntry* entries_host, int n, const float* params, const float* film, float* derived,
+                   cudaStream_t st);
+
+// depthwise weights [C,1,k,k] -> [k*k][C]
+int launch_dw_relayout(const float* w, int C, int kk, float* out, cudaStream_t st);
+
+// stem: x [B,3,H,W] NCHW -> y [B,Ho,Wo,32] NHWC, 3x3 stride 2, pad (top,left), scale/shift + act
+int launch_stem(const float* x, const float* w, const float* scale, const float* shift, float* y, int B, int H, int W,
+                int Ho, int Wo, int pad_t, int pad_l, int cout, int act, cudaStream_t st);
+
+// depthwise kxk: x [B,H,W,C] -> y [B,Ho,Wo,C]; wt is [k*k][C]; also writes per-(frame,tile,channel) sums
+// of the activated output into partial [B][tiles][C] (deterministic SE squeeze); returns tiles via *tiles_out
+int dw_num_tiles(int Ho);
+int launch_depthwise(const float* x, const float* wt, const float* scale, const float* shift, float* y, float* partial,
+                     int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, int act,
+                     cudaStream_t st);
+
+// squeeze-excite gate: partial [B][tiles][C] -> gate [B][C] = sigmoid(W2 silu(W1 mean + b1) + b2)
+int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2,
+                   const float* b2, float* gate, int B, int C, int R, cudaStream_t st);
+
+// pointwise conv as GEMM: out[M,N] = act((A[M,K] (*gate[m/rows_per_frame, k])) W[N,K]^T * scale[n] + shift[n]) (+res)
+int launch_pointwise_ffma(const float* A, const float* Wt, const float* scale, const float* shift, const float* gate,
+                          const float* residual, float* out, int M, int N, int K, int rows_per_frame, int act,
+                          cudaStream_t st);
+
+// spatial mean: x [B,HW,C] -> y [B,C]
+int launch_spatial_mean(const float* x, float* y, int B, int HW, int C, cudaStream_t st);
+
+}  // namespace orbit

@@ -1,0 +1,360 @@
+// Backbone engine: builds a layer plan per architecture and runs it natively (C++), so one
+// orbit_engine_forward call enqueues the whole feature-extractor pass on the caller's stream.
+//
+// Reference: the timm model created in model/feature_extractors.py:37-79 and invoked at
+// model/few_shot_recognisers.py:114-117,143-146; FiLM sites per model/film.py:38-74.
+#include <atomic>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "convnet.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace orbit {
+
+struct ParamInfo {
+    std::string name;
+    int64_t numel, offset;
+};
+
+enum OpKind { OP_STEM, OP_DW, OP_SE, OP_PW, OP_SPATIAL_MEAN };
+enum Buf { BUF_X0 = 0, BUF_X1, BUF_E, BUF_D, BUF_H, BUF_PARTIAL, BUF_GATE, BUF_COUNT, BUF_INPUT = 100, BUF_OUTPUT = 101, BUF_NONE = -1 };
+
+struct Op {
+    OpKind kind;
+    int in = BUF_NONE, out = BUF_NONE, res = BUF_NONE;
+    int cin = 0, cout = 0, k = 1, stride = 1, act = ACT_NONE;
+    bool gated = false;         // PW: multiply A by the SE gate
+    int64_t w = -1, b = -1;     // param offsets (conv weight / bias)
+    int64_t w2 = -1, b2 = -1;   // SE expand
+    int64_t fold = -1;          // derived offset of scale[C], shift[C]
+    int64_t dw_wt = -1;         // derived offset of re-laid-out depthwise weights
+    int64_t w_split = -1;       // derived offset of tf32 hi/lo split weights (PW, tcgen05 path)
+    int se_reduce = 0;
+};
+
+}  // namespace orbit
+
+using namespace orbit;
+
+struct orbit_engine {
+    int arch = 0, feat_dim = 0;
+    std::vector<ParamInfo> params, film;
+    int64_t param_floats = 0, film_floats = 0, derived_floats = 0;
+    std::vector<FoldEntry> folds;
+    std::vector<Op> ops;
+    int chunk_frames = 16;
+    int gemm_mode = 0;
+    mutable std::atomic<int64_t> last_launches{0};
+
+    int64_t add_param(const std::string& name, int64_t numel) {
+        params.push_back({name, numel, param_floats});
+        param_floats += numel;
+        return params.back().offset;
+    }
+    int64_t add_derived(int64_t numel) {
+        const int64_t o = derived_floats;
+        derived_floats += (numel + 3) / 4 * 4;  // keep 16-byte alignment
+        return o;
+    }
+    // BatchNorm: registers weight/bias/running_mean/running_var and a fold entry; returns derived offset
+    int64_t add_bn(const std::string& name, int c, float eps, bool film_site) {
+        FoldEntry f;
+        f.gamma = add_param(name + ".weight", c);
+        f.beta = add_param(name + ".bias", c);
+        f.mean = add_param(name + ".running_mean", c);
+        f.var = add_param(name + ".running_var", c);
+        f.film_gamma = f.film_beta = -1;
+        f.channels = c;
+        f.eps = eps;
+        f.out = add_derived(2 * (int64_t)c);
+        if (film_site) {
+            film.push_back({name + ".weight", c, (int64_t)folds.size()});  // offset filled after sorting
+            film.push_back({name + ".bias", c, (int64_t)folds.size()});
+        }
+        folds.push_back(f);
+        return f.out;
+    }
+    void finalize_film() {
+        // generator order = sorted names (feature_adapters.py:43-44); remember which fold entry each feeds
+        std::sort(film.begin(), film.end(), [](const ParamInfo& a, const ParamInfo& b) { return a.name < b.name; });
+        int64_t off = 0;
+        for (auto& f : film) {
+            const int64_t fold_idx = f.offset;
+            f.offset = off;
+            const bool is_weight = f.name.size() > 7 && f.name.compare(f.name.size() - 7, 7, ".weight") == 0;
+            if (is_weight) folds[fold_idx].film_gamma = off; else folds[fold_idx].film_beta = off;
+            off += f.numel;
+        }
+        film_floats = off;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// EfficientNet-B0 plan (timm tf_efficientnet_b0: TF SAME padding, BN eps 1e-3, SiLU, SE reduce = cin/4)
+// ------------------------------------------------------------------------------------------------
+static void build_efficientnet_b0(orbit_engine* e) {
+    const float eps = 1e-3f;
+    struct Stage { int repeats, k, stride, cout, expand; };
+    const Stage stages[7] = {{1, 3, 1, 16, 1}, {2, 3, 2, 24, 6}, {2, 5, 2, 40, 6}, {3, 3, 2, 80, 6},
+                             {3, 5, 1, 112, 6}, {4, 5, 2, 192, 6}, {1, 3, 1, 320, 6}};
+    e->feat_dim = 1280;
+    {
+        Op op; op.kind = OP_STEM; op.in = BUF_INPUT; op.out = BUF_X0; op.cin = 3; op.cout = 32; op.k = 3; op.stride = 2; op.act = ACT_SILU;
+        op.w = e->add_param("conv_stem.weight", 32 * 27);
+        op.fold = e->add_bn("bn1", 32, eps, true);
+        e->ops.push_back(op);
+    }
+    int cin = 32, cur = BUF_X0;
+    for (int s = 0; s < 7; ++s) {
+        for (int j = 0; j < stages[s].repeats; ++j) {
+            const std::string p = "blocks." + std::to_string(s) + "." + std::to_string(j) + ".";
+            const int stride = j == 0 ? stages[s].stride : 1, k = stages[s].k, cout = stages[s].cout;
+            const int mid = cin * stages[s].expand;
+            const bool ds = stages[s].expand == 1;
+            int dw_in = cur;
+            if (!ds) {  // expand 1x1 + bn1 + SiLU
+                Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_E; op.cin = cin; op.cout = mid; op.act = ACT_SILU;
+                op.w = e->add_param(p + "conv_pw.weight", (int64_t)mid * cin);
+                op.fold = e->add_bn(p + "bn1", mid, eps, false);
+                op.w_split = e->add_derived(2 * (int64_t)mid * cin);
+                e->ops.push_back(op);
+                dw_in = BUF_E;
+            }
+            {   // depthwise + bn + SiLU (the FiLM site of InvertedResidual: bn2)
+                Op op; op.kind = OP_DW; op.in = dw_in; op.out = BUF_D; op.cin = op.cout = mid; op.k = k; op.stride = stride; op.act = ACT_SILU;
+                op.w = e->add_param(p + "conv_dw.weight", (int64_t)mid * k * k);
+                op.fold = e->add_bn(p + (ds ? "bn1" : "bn2"), mid, eps, !ds);
+                op.dw_wt = e->add_derived((int64_t)mid * k * k);
+                e->ops.push_back(op);
+            }
+            {   // squeeze-excite gate
+                Op op; op.kind = OP_SE; op.in = BUF_PARTIAL; op.out = BUF_GATE; op.cin = op.cout = mid;
+                op.se_reduce = std::max(1, cin / 4);
+                op.w = e->add_param(p + "se.conv_reduce.weight", (int64_t)op.se_reduce * mid);
+                op.b = e->add_param(p + "se.conv_reduce.bias", op.se_reduce);
+                op.w2 = e->add_param(p + "se.conv_expand.weight", (int64_t)mid * op.se_reduce);
+                op.b2 = e->add_param(p + "se.conv_expand.bias", mid);
+                e->ops.push_back(op);
+            }
+            {   // project 1x1 (gated input) + bn (+ residual)
+                Op op; op.kind = OP_PW; op.in = BUF_D; op.cin = mid; op.cout = cout; op.act = ACT_NONE; op.gated = true;
+                op.out = cur == BUF_X0 ? BUF_X1 : BUF_X0;
+                if (stride == 1 && cin == cout) op.res = cur;
+                op.w = e->add_param(p + (ds ? "conv_pw.weight" : "conv_pwl.weight"), (int64_t)cout * mid);
+                op.fold = e->add_bn(p + (ds ? "bn2" : "bn3"), cout, eps, false);
+                op.w_split = e->add_derived(2 * (int64_t)cout * mid);
+                e->ops.push_back(op);
+                cur = op.out;
+            }
+            cin = cout;
+        }
+    }
+    {   // conv_head + bn2 (FiLM, root) + SiLU, then global average pool
+        Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_H; op.cin = cin; op.cout = 1280; op.act = ACT_SILU;
+        op.w = e->add_param("conv_head.weight", (int64_t)1280 * cin);
+        op.fold = e->add_bn("bn2", 1280, eps, true);
+        op.w_split = e->add_derived(2 * (int64_t)1280 * cin);
+        e->ops.push_back(op);
+        Op pool; pool.kind = OP_SPATIAL_MEAN; pool.in = BUF_H; pool.out = BUF_OUTPUT; pool.cin = pool.cout = 1280;
+        e->ops.push_back(pool);
+    }
+    e->finalize_film();
+}
+
+// TF "SAME" geometry: out = ceil(in/s), pad_before = total/2 (stride 1 => symmetric (k-1)/2)
+static void same_geometry(int in, int k, int s, int* out, int* pad_before) {
+    *out = (in + s - 1) / s;
+    const int total = std::max((*out - 1) * s + k - in, 0);
+    *pad_before = total / 2;
+}
+
+struct BufSizes {
+    int64_t per_frame[BUF_COUNT];
+};
+
+// dry-run of the plan for an HxW frame: maximum floats per frame each workspace buffer must hold
+static int plan_buffers(const orbit_engine* e, int H, int W, BufSizes* bs) {
+    for (int i = 0; i < BUF_COUNT; ++i) bs->per_frame[i] = 0;
+    int h = H, w = W;
+    auto need = [&](int buf, int64_t n) { if (buf >= 0 && buf < BUF_COUNT) bs->per_frame[buf] = std::max(bs->per_frame[buf], n); };
+    for (const Op& op : e->ops) {
+        switch (op.kind) {
+            case OP_STEM:
+            case OP_DW: {
+                int ho, wo, p;
+                same_geometry(h, op.k, op.stride, &ho, &p);
+                same_geometry(w, op.k, op.stride, &wo, &p);
+                h = ho; w = wo;
+                if (h < 1 || w < 1) return ORBIT_ERR_UNSUPPORTED;
+                need(op.out, (int64_t)h * w * op.cout);
+                if (op.kind == OP_DW) need(BUF_PARTIAL, (int64_t)dw_num_tiles(h) * op.cout);
+                break;
+            }
+            case OP_SE: need(BUF_GATE, op.cout); break;
+            case OP_PW: need(op.out, (int64_t)h * w * op.cout); break;
+            case OP_SPATIAL_MEAN: break;
+        }
+    }
+    return ORBIT_OK;
+}
+
+extern "C" int orbit_engine_create(orbit_engine** out, int arch) {
+    if (!out) return ORBIT_ERR_ARG;
+    orbit_engine* e = new orbit_engine();
+    e->arch = arch;
+    switch (arch) {
+        case ORBIT_ARCH_EFFICIENTNET_B0: build_efficientnet_b0(e); break;
+        default: delete e; return ORBIT_ERR_UNSUPPORTED;
+    }
+    *out = e;
+    return ORBIT_OK;
+}
+
+extern "C" void orbit_engine_destroy(orbit_engine* e) { delete e; }
+extern "C" int orbit_engine_feat_dim(const orbit_engine* e) { return e ? e->feat_dim : ORBIT_ERR_ARG; }
+extern "C" int orbit_engine_num_params(const orbit_engine* e) { return e ? (int)e->params.size() : ORBIT_ERR_ARG; }
+extern "C" int64_t orbit_engine_param_floats(const orbit_engine* e) { return e ? e->param_floats : ORBIT_ERR_ARG; }
+extern "C" int orbit_engine_num_film(const orbit_engine* e) { return e ? (int)e->film.size() : ORBIT_ERR_ARG; }
+extern "C" int64_t orbit_engine_film_floats(const orbit_engine* e) { return e ? e->film_floats : ORBIT_ERR_ARG; }
+extern "C" int64_t orbit_engine_derived_floats(const orbit_engine* e) { return e ? e->derived_floats : ORBIT_ERR_ARG; }
+extern "C" int64_t orbit_engine_last_launches(const orbit_engine* e) { return e ? e->last_launches.load() : ORBIT_ERR_ARG; }
+
+static int info(const std::vector<ParamInfo>& v, int i, char* name, int cap, int64_t* numel, int64_t* offset) {
+    if (i < 0 || i >= (int)v.size()) return ORBIT_ERR_ARG;
+    if (name && cap > 0) { std::strncpy(name, v[i].name.c_str(), cap - 1); name[cap - 1] = 0; }
+    if (numel) *numel = v[i].numel;
+    if (offset) *offset = v[i].offset;
+    return ORBIT_OK;
+}
+extern "C" int orbit_engine_param_info(const orbit_engine* e, int i, char* name, int cap, int64_t* numel, int64_t* offset) {
+    return e ? info(e->params, i, name, cap, numel, offset) : ORBIT_ERR_ARG;
+}
+extern "C" int orbit_engine_film_info(const orbit_engine* e, int i, char* name, int cap, int64_t* numel, int64_t* offset) {
+    return e ? info(e->film, i, name, cap, numel, offset) : ORBIT_ERR_ARG;
+}
+
+extern "C" int orbit_engine_set_option(orbit_engine* e, const char* key, int value) {
+    if (!e || !key) return ORBIT_ERR_ARG;
+    if (!std::strcmp(key, "chunk_frames")) { if (value < 1 || value > 4096) return ORBIT_ERR_ARG; e->chunk_frames = value; return ORBIT_OK; }
+    if (!std::strcmp(key, "gemm")) { if (value < 0 || value > 2) return ORBIT_ERR_ARG; e->gemm_mode = value; return ORBIT_OK; }
+    return ORBIT_ERR_UNSUPPORTED;
+}
+extern "C" int orbit_engine_get_option(const orbit_engine* e, const char* key, int* value) {
+    if (!e || !key || !value) return ORBIT_ERR_ARG;
+    if (!std::strcmp(key, "chunk_frames")) { *value = e->chunk_frames; return ORBIT_OK; }
+    if (!std::strcmp(key, "gemm")) { *value = e->gemm_mode; return ORBIT_OK; }
+    return ORBIT_ERR_UNSUPPORTED;
+}
+
+extern "C" int orbit_engine_prepare(const orbit_engine* e, const float* params, const float* film, float* derived, void* stream) {
+    if (!e || !params || !derived) return ORBIT_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_bn_fold(e->folds.data(), (int)e->folds.size(), params, film, derived, st);
+    if (rc) return rc;
+    for (const Op& op : e->ops) {
+        if (op.kind == OP_DW) {
+            rc = launch_dw_relayout(params + op.w, op.cin, op.k * op.k, derived + op.dw_wt, st);
+            if (rc) return rc;
+        } else if (op.kind == OP_PW && op.w_split >= 0) {
+            rc = launch_tf32_split(params + op.w, (int64_t)op.cout * op.cin, derived + op.w_split, st);
+            if (rc) return rc;
+        }
+    }
+    return ORBIT_OK;
+}
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int64_t orbit_engine_workspace_bytes(const orbit_engine* e, int height, int width) {
+    if (!e || height <= 0 || width <= 0) return ORBIT_ERR_ARG;
+    BufSizes bs;
+    if (plan_buffers(e, height, width, &bs)) return ORBIT_ERR_UNSUPPORTED;
+    int64_t total = 0;
+    for (int i = 0; i < BUF_COUNT; ++i) total += align_up(bs.per_frame[i] * e->chunk_frames * (int64_t)sizeof(float), 1024);
+    return total + 1024;
+}
+
+extern "C" int orbit_engine_forward(const orbit_engine* e, const float* params, const float* derived, const float* frames,
+                                    int num_frames, int height, int width, float* feats, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+    if (!e || !params || !derived || !frames || !feats || !workspace) return ORBIT_ERR_ARG;
+    if (num_frames < 0 || height <= 0 || width <= 0) return ORBIT_ERR_ARG;
+    if (!aligned16(frames) || !aligned16(feats) || !aligned16(params) || !aligned16(derived)) return ORBIT_ERR_UNSUPPORTED;
+    BufSizes bs;
+    int rc = plan_buffers(e, height, width, &bs);
+    if (rc) return rc;
+    if (workspace_bytes < orbit_engine_workspace_bytes(e, height, width)) return ORBIT_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    float* buf[BUF_COUNT];
+    {
+        char* p = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 1024));
+        for (int i = 0; i < BUF_COUNT; ++i) {
+            buf[i] = reinterpret_cast<float*>(p);
+            p += align_up(bs.per_frame[i] * e->chunk_frames * (int64_t)sizeof(float), 1024);
+        }
+    }
+    int64_t launches = 0;
+    for (int f0 = 0; f0 < num_frames; f0 += e->chunk_frames) {
+        const int B = std::min(e->chunk_frames, num_frames - f0);
+        const float* in_frames = frames + (int64_t)f0 * 3 * height * width;
+        float* out_feats = feats + (int64_t)f0 * e->feat_dim;
+        auto ptr = [&](int b) -> float* {
+            if (b == BUF_INPUT) return const_cast<float*>(in_frames);
+            if (b == BUF_OUTPUT) return out_feats;
+            return b >= 0 ? buf[b] : nullptr;
+        };
+        int h = height, w = width, se_tiles = 0, se_hw = 0;
+        for (const Op& op : e->ops) {
+            switch (op.kind) {
+                case OP_STEM: {
+                    int ho, wo, pt, pl;
+                    same_geometry(h, op.k, op.stride, &ho, &pt);
+                    same_geometry(w, op.k, op.stride, &wo, &pl);
+                    rc = launch_stem(ptr(op.in), params + op.w, derived + op.fold, derived + op.fold + op.cout, ptr(op.out), B,
+                                     h, w, ho, wo, pt, pl, op.cout, op.act, st);
+                    h = ho; w = wo;
+                    break;
+                }
+                case OP_DW: {
+                    int ho, wo, pt, pl;
+                    same_geometry(h, op.k, op.stride, &ho, &pt);
+                    same_geometry(w, op.k, op.stride, &wo, &pl);
+                    rc = launch_depthwise(ptr(op.in), derived + op.dw_wt, derived + op.fold, derived + op.fold + op.cout,
+                                          ptr(op.out), buf[BUF_PARTIAL], B, h, w, op.cin, ho, wo, op.k, op.stride, pt, pl,
+                                          op.act, st);
+                    h = ho; w = wo;
+                    se_tiles = dw_num_tiles(h); se_hw = h * w;
+                    break;
+                }
+                case OP_SE:
+                    rc = launch_se_gate(buf[BUF_PARTIAL], se_tiles, se_hw, params + op.w, params + op.b, params + op.w2,
+                                        params + op.b2, buf[BUF_GATE], B, op.cin, op.se_reduce, st);
+                    break;
+                case OP_PW: {
+                    const int M = B * h * w;
+                    const float* gate = op.gated ? buf[BUF_GATE] : nullptr;
+                    if (e->gemm_mode == 0) {
+                        rc = launch_pointwise_ffma(ptr(op.in), params + op.w, derived + op.fold, derived + op.fold + op.cout,
+                                                   gate, ptr(op.res), ptr(op.out), M, op.cout, op.cin, h * w, op.act, st);
+                    } else {
+                        rc = launch_pointwise_tcgen05(ptr(op.in), derived + op.w_split, derived + op.fold,
+                                                      derived + op.fold + op.cout, gate, ptr(op.res), ptr(op.out), M, op.cout,
+                                                      op.cin, h * w, op.act, e->gemm_mode == 1 ? 3 : 1, st);
+                    }
+                    break;
+                }
+                case OP_SPATIAL_MEAN:
+                    rc = launch_spatial_mean(ptr(op.in), ptr(op.out), B, h * w, op.cin, st);
+                    break;
+            }
+            if (rc) return rc;
+            ++launches;
+        }
+    }
+    e->last_launches.store(launches);
+    return ORBIT_OK;
+}

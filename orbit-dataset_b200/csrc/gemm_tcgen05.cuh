@@ -1,0 +1,17 @@
+// tcgen05 (5th-gen tensor core) pointwise-conv GEMM: TMA-fed, TMEM accumulators, 3xTF32 split for
+// fp32-grade accuracy, with the BN/FiLM scale-shift + activation + residual epilogue. Internal.
+#pragma once
+#include "common.cuh"
+
+namespace orbit {
+
+// w [n] fp32 -> out [2][n]: hi = w with the low 13 mantissa bits cleared (exactly tf32), lo = tf32(w - hi)
+int launch_tf32_split(const float* w, int64_t n, float* out, cudaStream_t st);
+
+// out[M,N] = act((A[M,K] (*gate)) W[N,K]^T * scale + shift) (+ residual); w_split = [hi | lo] from launch_tf32_split.
+// passes = 3 (hi*hi + hi*lo + lo*hi, fp32-grade) or 1 (plain tf32).
+int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* scale, const float* shift,
+                             const float* gate, const float* residual, float* out, int M, int N, int K,
+                             int rows_per_frame, int act, int passes, cudaStream_t st);
+
+}  // namespace orbit

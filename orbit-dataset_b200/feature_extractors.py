@@ -1,0 +1,264 @@
+"""Feature extractors behind the reference's ``create_feature_extractor`` interface.
+
+Mirrors reference ``model/feature_extractors.py:37-87`` and ``model/film.py:68-94``: same extractor
+strings, same (extractor, film_parameter_names) return value, same ``output_size`` attribute, the
+same timm state-dict key names.  The module only HOLDS the parameters (as views into one flat fp32
+blob that the CUDA engine reads directly); the forward pass is liborbit_b200's native layer plan.
+"""
+import ctypes as C
+import os
+
+import torch
+import torch.nn as nn
+
+from . import lib as L
+
+ARCH_IDS = {
+    'efficientnet_b0': 0,
+    'vit_s_32': 1,
+    'vit_b_32': 2,
+    'vit_b_32_clip': 3,
+    'resnet18': 4,  # BASELINE.json extension; not in the reference at this commit
+}
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce timm's dotted parameter paths."""
+
+
+def _engine_table(engine, count_fn, info_fn):
+    lib = L.load()
+    out = []
+    name = C.create_string_buffer(256)
+    numel, offset = C.c_int64(), C.c_int64()
+    for i in range(count_fn(engine)):
+        L.check(info_fn(engine, i, name, 256, C.byref(numel), C.byref(offset)), "param_info")
+        out.append((name.value.decode(), numel.value, offset.value))
+    return out
+
+
+_SHAPES_4D = ('conv_stem.weight', 'conv_dw.weight', 'conv_pw.weight', 'conv_pwl.weight', 'conv_head.weight',
+              'se.conv_reduce.weight', 'se.conv_expand.weight')
+
+
+class FeatureExtractor(nn.Module):
+    """Parameter holder + native forward. ``forward(frames[B,3,H,W]) -> [B, output_size]``."""
+
+    def __init__(self, name: str, seed: int = 0):
+        super().__init__()
+        if name not in ARCH_IDS:
+            raise ValueError(f"Invalid feature_extractor_name: {name}")
+        lib = L.load()
+        self.extractor_name = name
+        handle = C.c_void_p()
+        rc = lib.orbit_engine_create(C.byref(handle), ARCH_IDS[name])
+        if rc == -2:
+            raise NotImplementedError(f"feature extractor '{name}' is not implemented by liborbit_b200 yet")
+        L.check(rc, "orbit_engine_create")
+        self._engine = handle
+        self.output_size = lib.orbit_engine_feat_dim(handle)
+        self._table = _engine_table(handle, lib.orbit_engine_num_params, lib.orbit_engine_param_info)
+        self._film_table = _engine_table(handle, lib.orbit_engine_num_film, lib.orbit_engine_film_info)
+        self._n_floats = lib.orbit_engine_param_floats(handle)
+        self._blob = torch.zeros(self._n_floats, dtype=torch.float32)
+        self._shapes = {}
+        self._derived = None
+        self._workspace = None
+        self._prepared_key = None
+        self._build_tree()
+        self.reset_parameters(seed)
+
+    # ---- parameter tree ------------------------------------------------------------------------
+    def _shape_of(self, name, numel):
+        leaf = name.rsplit('.', 1)[-1]
+        if any(name.endswith(s) for s in _SHAPES_4D):
+            return None  # resolved from neighbours below
+        return (numel,)
+
+    def _build_tree(self):
+        # 4-D conv shapes are recovered from the channel counts of the adjacent norm / bias entries.
+        sizes = {n: k for n, k, _ in self._table}
+        for name, numel, offset in self._table:
+            shape = (numel,)
+            if name == 'conv_stem.weight':
+                shape = (numel // 27, 3, 3, 3)
+            elif name.endswith('conv_dw.weight'):
+                pre = name[:-len('conv_dw.weight')]
+                c = sizes[pre + ('bn2.weight' if pre + 'bn3.weight' in sizes else 'bn1.weight')]
+                k = int(round((numel // c) ** 0.5))
+                shape = (c, 1, k, k)
+            elif name.endswith('se.conv_reduce.weight'):
+                r = sizes[name[:-len('weight')] + 'bias']
+                shape = (r, numel // r, 1, 1)
+            elif name.endswith('se.conv_expand.weight'):
+                c = sizes[name[:-len('weight')] + 'bias']
+                shape = (c, numel // c, 1, 1)
+            elif name.endswith(('conv_pw.weight', 'conv_pwl.weight', 'conv_head.weight')):
+                pre = name.rsplit('conv_', 1)[0]
+                kind = name.rsplit('.', 2)[-2]
+                if kind == 'conv_head':
+                    cout = sizes['bn2.weight']
+                elif kind == 'conv_pwl':
+                    cout = sizes[pre + 'bn3.weight']
+                else:  # conv_pw: expand (-> bn1) in InvertedResidual, project (-> bn2) in DepthwiseSeparable
+                    cout = sizes[pre + ('bn1.weight' if pre + 'conv_pwl.weight' in sizes else 'bn2.weight')]
+                shape = (cout, numel // cout, 1, 1)
+            self._shapes[name] = shape
+            parent = self
+            parts = name.split('.')
+            for p in parts[:-1]:
+                if not hasattr(parent, p):
+                    parent.add_module(p, _Node())
+                parent = getattr(parent, p)
+            view = self._blob[offset:offset + numel].view(shape)
+            if parts[-1] in ('running_mean', 'running_var'):
+                parent.register_buffer(parts[-1], view)
+                if parts[-1] == 'running_var':
+                    parent.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+            else:
+                parent.register_parameter(parts[-1], nn.Parameter(view, requires_grad=True))
+
+    def _rebind(self):
+        params, bufs = dict(self.named_parameters()), dict(self.named_buffers())
+        for name, numel, offset in self._table:
+            view = self._blob[offset:offset + numel].view(self._shapes[name])
+            (params[name] if name in params else bufs[name]).data = view
+
+    def _apply(self, fn, recurse=True):
+        new_blob = fn(self._blob)
+        if new_blob.dtype != torch.float32:
+            raise TypeError("orbit_b200 feature extractors are fp32 only")
+        for mod in self.modules():  # non-blob buffers (num_batches_tracked)
+            if mod is not self and 'num_batches_tracked' in mod._buffers:
+                mod._buffers['num_batches_tracked'] = fn(mod._buffers['num_batches_tracked'])
+        self._blob = new_blob
+        self._rebind()
+        self._derived = self._workspace = self._prepared_key = None
+        return self
+
+    @torch.no_grad()
+    def reset_parameters(self, seed=0):
+        """Seeded stand-in for the reference's ``pretrained=True`` download (there is no network):
+        fan-out-scaled conv weights, identity norms. Real use loads a checkpoint with load_state_dict."""
+        g = torch.Generator().manual_seed(seed)
+        for name, numel, offset in self._table:
+            dst = self._blob[offset:offset + numel]
+            leaf = name.rsplit('.', 1)[-1]
+            shape = self._shapes[name]
+            if leaf == 'running_var' or (leaf == 'weight' and len(shape) == 1):
+                dst.fill_(1.0)
+            elif leaf in ('running_mean', 'bias'):
+                dst.zero_()
+            else:
+                fan_out = shape[0] * (shape[2] * shape[3] if len(shape) == 4 else 1)
+                if len(shape) == 4 and shape[1] == 1:
+                    fan_out = shape[2] * shape[3]
+                dst.copy_(torch.randn(numel, generator=g) * (2.0 / fan_out) ** 0.5)
+
+    # ---- FiLM ----------------------------------------------------------------------------------
+    def film_parameter_names(self):
+        """Names in module-registration order, as get_film_parameter_names walks named_modules()
+        (film.py:68-74); weight before bias per layer."""
+        tagged = {n for n, _, _ in self._film_table}
+        return [n for n, _, _ in self._table if n in tagged]
+
+    def film_layout(self):
+        """[(name, numel, offset)] of the film blob, in the generator's sorted order."""
+        return list(self._film_table)
+
+    # ---- native forward ------------------------------------------------------------------------
+    def set_option(self, key: str, value: int):
+        L.check(L.load().orbit_engine_set_option(self._engine, key.encode(), int(value)), f"set_option({key})")
+        self._workspace = None
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int()
+        L.check(L.load().orbit_engine_get_option(self._engine, key.encode(), C.byref(v)), f"get_option({key})")
+        return v.value
+
+    def prepare(self, film_blob=None):
+        """Folds norms (+ FiLM gamma'/beta'), re-lays-out weights. Cheap; re-run when params/film change."""
+        lib = L.load()
+        L.require_cuda(self._blob, "feature extractor parameters")
+        if self._derived is None:
+            self._derived = torch.empty(lib.orbit_engine_derived_floats(self._engine), dtype=torch.float32,
+                                        device=self._blob.device)
+        key = (self._blob._version, None if film_blob is None else (film_blob.data_ptr(), film_blob._version))
+        if key == self._prepared_key:
+            return
+        if film_blob is not None:
+            L.require_cuda(film_blob, "film parameters")
+            assert film_blob.dtype == torch.float32 and film_blob.numel() == lib.orbit_engine_film_floats(self._engine)
+        L.check(lib.orbit_engine_prepare(self._engine, L.ptr(self._blob), L.ptr(film_blob), L.ptr(self._derived),
+                                         L.stream_ptr(self._blob.device)), "orbit_engine_prepare")
+        L.count_launches(2 + len(self._table) // 4)
+        self._prepared_key = key
+
+    def forward(self, frames: torch.Tensor, film_blob=None) -> torch.Tensor:
+        lib = L.load()
+        L.require_cuda(frames, "frames")
+        if frames.dim() != 4 or frames.shape[1] != 3:
+            raise ValueError(f"frames must be [B,3,H,W], got {tuple(frames.shape)}")
+        frames = frames.contiguous().float()
+        self.prepare(film_blob)
+        n, _, h, w = frames.shape
+        ws_bytes = lib.orbit_engine_workspace_bytes(self._engine, h, w)
+        if ws_bytes < 0:
+            L.check(int(ws_bytes), "orbit_engine_workspace_bytes")
+        if self._workspace is None or self._workspace.numel() < ws_bytes:
+            self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
+        feats = torch.empty(n, self.output_size, dtype=torch.float32, device=frames.device)
+        L.check(lib.orbit_engine_forward(self._engine, L.ptr(self._blob), L.ptr(self._derived), L.ptr(frames), n, h, w,
+                                         L.ptr(feats), L.ptr(self._workspace), self._workspace.numel(),
+                                         L.stream_ptr(frames.device)), "orbit_engine_forward")
+        L.count_launches(lib.orbit_engine_last_launches(self._engine))
+        return feats
+
+    def __del__(self):
+        try:
+            if getattr(self, '_engine', None):
+                L.load().orbit_engine_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
+
+
+def freeze_extractor(feature_extractor):
+    """feature_extractors.py:81-87."""
+    for param in feature_extractor.parameters():
+        param.requires_grad = False
+
+
+def create_feature_extractor(feature_extractor_name: str, pretrained: bool, with_film: bool = False,
+                             learn_extractor: bool = True):
+    """Same contract as reference feature_extractors.py:37-79. ``pretrained=True`` cannot download
+    (no network): weights come from $ORBIT_B200_PRETRAINED/<name>.pth when that file exists, else a
+    seeded initialisation; callers normally ``load_state_dict`` a checkpoint afterwards."""
+    feature_extractor = FeatureExtractor(feature_extractor_name)
+    root = os.environ.get('ORBIT_B200_PRETRAINED')
+    if pretrained and root and os.path.exists(os.path.join(root, feature_extractor_name + '.pth')):
+        feature_extractor.load_state_dict(torch.load(os.path.join(root, feature_extractor_name + '.pth')))
+    if not learn_extractor:
+        freeze_extractor(feature_extractor)
+    film_param_names = feature_extractor.film_parameter_names() if with_film else None
+    return feature_extractor, film_param_names
+
+
+# ---- reference model/film.py helpers, same names/semantics -----------------------------------------
+def unfreeze_film(film_parameter_names, feature_extractor):
+    for name, param in feature_extractor.named_parameters():
+        if name in film_parameter_names:
+            param.requires_grad = True
+
+
+def get_film_parameters(film_parameter_names, feature_extractor):
+    film_params = {}
+    if film_parameter_names is not None:
+        for name, param in feature_extractor.named_parameters():
+            if name in film_parameter_names:
+                film_params[name] = param.detach().clone()
+    return film_params
+
+
+def get_film_parameter_sizes(film_parameter_names, feature_extractor):
+    return {name: len(param) for name, param in feature_extractor.named_parameters() if name in film_parameter_names}

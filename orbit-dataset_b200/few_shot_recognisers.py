@@ -1,0 +1,320 @@
+"""Few-shot recognisers with the reference's Python API, running on liborbit_b200 (sm_100a).
+
+Drop-in mirror of reference ``model/few_shot_recognisers.py`` (same class names, constructor
+signatures, methods and attributes):
+  FewShotRecogniser            :46-183
+  MultiStepFewShotRecogniser   :185-269
+  SingleStepFewShotRecogniser  :271-473
+The control flow (batching by ``batch_size`` clips, FiLM generation, pooling, head configure /
+predict, per-task state and reset) follows the reference; every tensor operation on the path is a
+hand-written CUDA kernel reached through the C ABI.  There is no CPU fallback: tensors that are not
+on an sm_100 device raise ``OrbitError``.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from .classifier_heads import LinearClassifier, MeanPooler, PrototypicalClassifier
+from .data_utils import get_batch_indices
+from .feature_extractors import (create_feature_extractor, get_film_parameter_sizes, get_film_parameters,
+                                 unfreeze_film)
+
+
+class _HostStager:
+    """Moves CPU-resident clips to the device in slices on a side stream so the copy of slice i+1
+    overlaps the backbone pass of slice i (reference: ``clips.to(self.device, non_blocking=True)``
+    from pageable memory, few_shot_recognisers.py:112,142)."""
+
+    def __init__(self, device, slice_frames):
+        self.device = device
+        self.slice_frames = slice_frames
+        self.copy_stream = torch.cuda.Stream(device)
+        self.dev = [None, None]
+        self.pinned = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.used = [False, False]
+        self.bytes_copied = 0
+
+    def _buffers(self, i, shape):
+        n = int(np.prod(shape))
+        if self.dev[i] is None or self.dev[i].numel() < n:
+            self.dev[i] = torch.empty(n, dtype=torch.float32, device=self.device)
+        return self.dev[i][:n].view(shape)
+
+    def stream(self, frames_cpu):
+        """Yields device views of consecutive slices of ``frames_cpu`` [F,3,H,W]; each view is valid
+        until the next iteration's forward has been enqueued."""
+        compute = torch.cuda.current_stream(self.device)
+        total = frames_cpu.shape[0]
+        starts = list(range(0, total, self.slice_frames))
+        pinned_src = frames_cpu.is_pinned()
+
+        def issue(j):
+            i = j % 2
+            src = frames_cpu[starts[j]:starts[j] + self.slice_frames]
+            dst = self._buffers(i, src.shape)
+            if not pinned_src:
+                n = src.numel()
+                if self.pinned[i] is None or self.pinned[i].numel() < n:
+                    self.pinned[i] = torch.empty(n, dtype=torch.float32).pin_memory()
+                if self.used[i]:
+                    self.h2d_done[i].synchronize()  # staging buffer still in flight
+                stage = self.pinned[i][:n].view(src.shape)
+                stage.copy_(src)
+                src = stage
+            if self.used[i]:
+                self.copy_stream.wait_event(self.consumed[i])  # device buffer free again
+            with torch.cuda.stream(self.copy_stream):
+                dst.copy_(src, non_blocking=True)
+                self.h2d_done[i].record(self.copy_stream)
+                self.ready[i].record(self.copy_stream)
+            self.used[i] = True
+            self.bytes_copied += src.numel() * 4
+            return dst
+
+        pending = issue(0) if starts else None
+        for j in range(len(starts)):
+            cur, i = pending, j % 2
+            if j + 1 < len(starts):
+                pending = issue(j + 1)
+            compute.wait_event(self.ready[i])
+            yield cur
+            self.consumed[i].record(compute)
+
+
+class FewShotRecogniser(nn.Module):
+    """Generic few-shot classification model (few_shot_recognisers.py:46-183)."""
+
+    def __init__(self, feature_extractor_name: str, adapt_features: bool, classifier: str, clip_length: int,
+                 batch_size: int, learn_extractor: bool, logit_scale: float = 1.0):
+        super().__init__()
+        self.adapt_features = adapt_features
+        self.learn_extractor = learn_extractor
+        self.clip_length = clip_length
+        self.batch_size = batch_size
+        self.logit_scale = logit_scale
+
+        self.feature_extractor, self.film_parameter_names = create_feature_extractor(
+            feature_extractor_name=feature_extractor_name, pretrained=True, with_film=self.adapt_features,
+            learn_extractor=self.learn_extractor)
+
+        self.classifier_name = classifier
+        if classifier == 'linear':
+            self.classifier = LinearClassifier(self.feature_extractor.output_size, self.logit_scale)
+        elif classifier == 'versa':
+            from .classifier_heads_ext import VersaClassifier
+            self.classifier = VersaClassifier(self.feature_extractor.output_size, self.logit_scale)
+        elif classifier == 'proto':
+            self.classifier = PrototypicalClassifier(self.logit_scale)
+        elif classifier == 'proto_cosine':
+            self.classifier = PrototypicalClassifier(self.logit_scale, distance_fn='cosine')
+        elif classifier == 'mahalanobis':
+            from .classifier_heads_ext import MahalanobisClassifier
+            self.classifier = MahalanobisClassifier(self.logit_scale)
+        else:
+            raise ValueError(f"Classifier {classifier} not valid.")
+
+        self.frame_pooler = MeanPooler(T=self.clip_length)
+        self.device = torch.device('cpu')
+        self._stager = None
+        self.stage_slice_frames = 64  # frames per overlapped H2D slice for CPU-resident clips
+
+    def _set_device(self, device):
+        self.device = torch.device(device)
+
+    def _send_to_device(self):
+        self.to(self.device)
+
+    # ---- features --------------------------------------------------------------------------------
+    def _require_device(self):
+        if self.device.type != 'cuda':
+            raise L.OrbitError("orbit_b200 runs only on a CUDA (sm_100) device; call _set_device('cuda:N') and "
+                               "_send_to_device() first (there is no CPU fallback)")
+
+    def _film_blob(self, film_dict):
+        return None  # overridden by SingleStepFewShotRecogniser
+
+    def _run_extractor(self, frames, film_dict):
+        """frames [F,3,H,W] on CPU or device -> [F, D] on device."""
+        blob = self._film_blob(film_dict) if film_dict else None
+        if frames.is_cuda:
+            return self.feature_extractor(frames, blob)
+        if self._stager is None or self._stager.device != self.device or \
+                self._stager.slice_frames != self.stage_slice_frames:
+            self._stager = _HostStager(self.device, self.stage_slice_frames)
+        outs = [self.feature_extractor(dev_frames, blob) for dev_frames in self._stager.stream(frames.float())]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def _get_features(self, clips, film_dict={}, ops_counter=None):
+        """few_shot_recognisers.py:99-122."""
+        self._require_device()
+        if len(clips.shape) == 5:
+            clips = clips.reshape(clips.shape[0] * clips.shape[1], *clips.shape[2:])
+        return self._run_extractor(clips, film_dict)
+
+    def _get_features_in_batches(self, clips, film_dict={}, ops_counter=None):
+        """few_shot_recognisers.py:124-153: chunks of ``batch_size`` CLIPS, flattened to frames."""
+        self._require_device()
+        features = []
+        num_clips = len(clips)
+        num_batches = int(np.ceil(float(num_clips) / float(self.batch_size)))
+        for batch in range(num_batches):
+            batch_start_index, batch_end_index = get_batch_indices(batch, num_clips, self.batch_size)
+            batch_clips = clips[batch_start_index:batch_end_index]
+            if len(batch_clips.shape) == 5:
+                batch_clips = batch_clips.flatten(end_dim=1)
+            features.append(self._run_extractor(batch_clips, film_dict))
+        if not features:
+            return torch.empty(0, self.feature_extractor.output_size, device=self.device)
+        return features[0] if len(features) == 1 else torch.cat(features, dim=0)
+
+    def _pool_features(self, features, ops_counter=None):
+        """few_shot_recognisers.py:155-166."""
+        return self.frame_pooler(features)
+
+    def set_test_mode(self, test_mode):
+        self.test_mode = test_mode
+
+    def _set_batch_norm_state(self):
+        """few_shot_recognisers.py:176-183. The native extractor always normalises with the running
+        statistics (eval mode); meta-training an unfrozen extractor with batch statistics is not
+        implemented and is refused rather than silently approximated."""
+        self.eval()
+        if self.learn_extractor and not self.test_mode:
+            raise NotImplementedError("training the extractor (train-mode BatchNorm + backward) is outside the "
+                                      "B200 hot path implemented so far")
+
+
+class SingleStepFewShotRecogniser(FewShotRecogniser):
+    """ProtoNets / CNAPs / SimpleCNAPs: personalised in one forward pass (few_shot_recognisers.py:271-473)."""
+
+    def __init__(self, feature_extractor_name: str, adapt_features: bool, classifier: str, clip_length: int,
+                 batch_size: int, learn_extractor: bool, num_lite_samples: int, logit_scale: float = 1.0):
+        super().__init__(feature_extractor_name, adapt_features, classifier, clip_length, batch_size, learn_extractor,
+                         logit_scale)
+        self.num_lite_samples = num_lite_samples
+        if self.adapt_features:
+            from .feature_adapters import FilmParameterGenerator, SetEncoder
+            self.set_encoder = SetEncoder()
+            self.film_parameter_sizes = get_film_parameter_sizes(self.film_parameter_names, self.feature_extractor)
+            initial_film_parameters = get_film_parameters(self.film_parameter_names, self.feature_extractor)
+            self.film_generator = FilmParameterGenerator(self.film_parameter_sizes, initial_film_parameters,
+                                                         pooled_size=self.set_encoder.output_size,
+                                                         hidden_size=self.set_encoder.output_size)
+        else:
+            from .feature_adapters import NullGenerator, NullSetEncoder
+            self.set_encoder = NullSetEncoder()
+            self.film_generator = NullGenerator()
+        self.film_dict = None
+        self.test_mode = False
+
+    def _reset(self):
+        self.film_dict = None
+        self.classifier.reset()
+
+    def _clear_caches(self):
+        self.reps_cache = None
+        self.features_cache = None
+
+    def _film_blob(self, film_dict):
+        return self.film_generator.as_blob(film_dict)
+
+    def personalise(self, context_clips, context_labels, ops_counter=None):
+        """few_shot_recognisers.py:313-326."""
+        self._set_batch_norm_state()
+        task_embedding = self._get_task_embedding_in_batches(context_clips, ops_counter)
+        self.film_dict = self._generate_film_params(task_embedding, ops_counter)
+        context_features = self._get_features_in_batches(context_clips, self.film_dict, ops_counter)
+        # pooling (poolers.py:13-16) is fused into the head's configure kernel
+        self.classifier.configure(context_features, context_labels, ops_counter, clip_length=self.clip_length)
+
+    def personalise_with_lite(self, context_clips, context_labels):
+        """LITE (few_shot_recognisers.py:328-343) back-propagates through the extractor; the backward
+        kernels are not part of the B200 hot path yet."""
+        raise NotImplementedError("LITE training needs backbone backward kernels (SURVEY.md 8f-3)")
+
+    def _get_task_embedding_in_batches(self, context_clips, ops_counter=None, aggregation='mean'):
+        """few_shot_recognisers.py:361-386."""
+        from .feature_adapters import NullSetEncoder
+        if isinstance(self.set_encoder, NullSetEncoder):
+            return None
+        self._require_device()
+        reps = []
+        num_clips = len(context_clips)
+        num_batches = int(np.ceil(float(num_clips) / float(self.batch_size)))
+        for batch in range(num_batches):
+            batch_start_index, batch_end_index = get_batch_indices(batch, num_clips, self.batch_size)
+            batch_clips = context_clips[batch_start_index:batch_end_index].to(self.device, non_blocking=True)
+            reps.append(self.set_encoder(batch_clips))
+        return self.set_encoder.aggregate(reps, aggregation=aggregation)
+
+    def _generate_film_params(self, task_embedding, ops_counter=None):
+        """few_shot_recognisers.py:439-451."""
+        return self.film_generator(task_embedding)
+
+    def predict(self, target_clips, want_argmax=False):
+        """few_shot_recognisers.py:453-462 (+ optional fused arg-max output)."""
+        self._set_batch_norm_state()
+        target_features = self._get_features_in_batches(target_clips, self.film_dict)
+        return self.classifier.predict(target_features, clip_length=self.clip_length, **(
+            {'want_argmax': True} if want_argmax else {}))
+
+    def predict_a_batch(self, target_clips):
+        """few_shot_recognisers.py:464-473."""
+        self._set_batch_norm_state()
+        target_features = self._get_features(target_clips, self.film_dict)
+        return self.classifier.predict(target_features, clip_length=self.clip_length)
+
+
+class MultiStepFewShotRecogniser(FewShotRecogniser):
+    """FineTuner: personalised with gradient steps on a new linear head (few_shot_recognisers.py:185-269)."""
+
+    def __init__(self, feature_extractor_name: str, adapt_features: bool, classifier: str, clip_length: int,
+                 batch_size: int, learn_extractor: bool, logit_scale: float = 1.0):
+        super().__init__(feature_extractor_name, adapt_features, classifier, clip_length, batch_size, learn_extractor,
+                         logit_scale)
+        if self.adapt_features:
+            self.film_parameter_sizes = get_film_parameter_sizes(self.film_parameter_names, self.feature_extractor)
+            unfreeze_film(self.film_parameter_names, self.feature_extractor)
+        self.test_mode = True
+
+    def _reset(self):
+        self.classifier.reset()
+
+    def init_classifier(self, num_classes: int):
+        self.classifier.init(num_classes)
+        self.classifier.to(self.device)
+
+    def personalise(self, context_clips, context_labels, learning_args, ops_counter=None):
+        """few_shot_recognisers.py:207-246 for the default FineTuner (frozen extractor, new linear head).
+        The extractor is frozen and in eval mode, so the support features are loop-invariant: they are
+        computed ONCE, then the num_grad_steps x batches loop (CE mean * batch_len/N, one optimiser step
+        per grad step) runs on the device in a single kernel."""
+        from .finetune import finetune_linear_head
+        self._set_batch_norm_state()
+        num_grad_steps = learning_args.pop('num_grad_steps')
+        learning_rate = learning_args.pop('learning_rate')
+        optimizer = learning_args.pop('optimizer')
+        learning_args.pop('loss_fn')
+        learning_args.pop('extractor_lr_scale')
+        if self.adapt_features or self.learn_extractor:
+            raise NotImplementedError("fine-tuning FiLM layers / the extractor needs backbone backward kernels "
+                                      "(SURVEY.md 8f-3)")
+        num_classes = len(torch.unique(context_labels))
+        self.init_classifier(num_classes)
+        features = self._get_features_in_batches(context_clips, ops_counter=ops_counter)
+        features = self._pool_features(features)
+        finetune_linear_head(self.classifier, features, context_labels, self.batch_size, num_grad_steps,
+                             learning_rate, optimizer, learning_args, self.logit_scale)
+
+    def predict(self, clips, ops_counter=None):
+        """few_shot_recognisers.py:248-258."""
+        self._set_batch_norm_state()
+        features = self._get_features_in_batches(clips, ops_counter=ops_counter)
+        return self.classifier.predict(features, clip_length=self.clip_length)
+
+    def personalise_with_lite(self, context_clips, context_labels):
+        NotImplementedError

@@ -1,0 +1,91 @@
+"""ctypes binding of liborbit_b200.so (the C ABI declared in include/orbit_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised."""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liborbit_b200.so")
+
+_i, _i64, _f, _p = C.c_int, C.c_int64, C.c_float, C.c_void_p
+_SIGNATURES = {
+    "orbit_abi_version": (_i, []),
+    "orbit_error_string": (C.c_char_p, [_i]),
+    "orbit_device_check": (_i, []),
+    "orbit_pool_clips": (_i, [_p, _i, _i, _i, _p, _p]),
+    "orbit_proto_configure_scratch_bytes": (_i64, [_i, _i]),
+    "orbit_proto_configure": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "orbit_head_predict": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _f, _p, _p, _p]),
+    "orbit_engine_create": (_i, [C.POINTER(_p), _i]),
+    "orbit_engine_destroy": (None, [_p]),
+    "orbit_engine_feat_dim": (_i, [_p]),
+    "orbit_engine_num_params": (_i, [_p]),
+    "orbit_engine_param_info": (_i, [_p, _i, C.c_char_p, _i, C.POINTER(_i64), C.POINTER(_i64)]),
+    "orbit_engine_param_floats": (_i64, [_p]),
+    "orbit_engine_num_film": (_i, [_p]),
+    "orbit_engine_film_info": (_i, [_p, _i, C.c_char_p, _i, C.POINTER(_i64), C.POINTER(_i64)]),
+    "orbit_engine_film_floats": (_i64, [_p]),
+    "orbit_engine_derived_floats": (_i64, [_p]),
+    "orbit_engine_prepare": (_i, [_p, _p, _p, _p, _p]),
+    "orbit_engine_set_option": (_i, [_p, C.c_char_p, _i]),
+    "orbit_engine_get_option": (_i, [_p, C.c_char_p, C.POINTER(_i)]),
+    "orbit_engine_workspace_bytes": (_i64, [_p, _i, _i]),
+    "orbit_engine_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p]),
+    "orbit_engine_last_launches": (_i64, [_p]),
+}
+
+_lib = None
+
+
+class OrbitError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once). Raises loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OrbitError(f"{LIB_PATH} not found: build it with `python __graft_entry__.py build` "
+                             "(orbit_b200 has no CPU/PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if lib.orbit_abi_version() != 1:
+            raise OrbitError("liborbit_b200.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().orbit_error_string(int(rc)).decode()
+        raise OrbitError(f"{what} failed with code {rc}: {msg}")
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise OrbitError(f"{name} must be a CUDA tensor: orbit_b200 runs only on an sm_100 GPU (no CPU fallback)")
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+_launches = 0  # kernels enqueued through this binding (bench.py reports it as gpu_launches)
+
+
+def count_launches(n):
+    global _launches
+    _launches += int(n)
+
+
+def launches():
+    return _launches

@@ -1,0 +1,68 @@
+"""GPU parity of the native EfficientNet-B0 forward (through the C ABI) against the oracle
+restatement of timm tf_efficientnet_b0 (oracle/backbones.py), same seeded weights."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _product(oracle, cuda_device, clip_length=2):
+    import orbit_b200
+    m = orbit_b200.SingleStepFewShotRecogniser('efficientnet_b0', False, 'proto', clip_length, 256, False, 16)
+    m.load_state_dict(oracle.state_dict(), strict=True)
+    m._set_device(cuda_device)
+    m._send_to_device()
+    m.set_test_mode(True)
+    return m
+
+
+@pytest.mark.parametrize("size,n", [(224, 5), (84, 7), (64, 3), (96, 33)])
+@pytest.mark.parametrize("gemm", [0])
+def test_efficientnet_features_match_oracle(cuda_device, oracle_effnet, size, n, gemm):
+    m = _product(oracle_effnet, cuda_device)
+    m.feature_extractor.set_option('gemm', gemm)
+    m.feature_extractor.set_option('chunk_frames', 4)   # exercises the multi-chunk path (n > chunk)
+    x = torch.randn(n, 3, size, size, generator=torch.Generator().manual_seed(size + n))
+    with torch.no_grad():
+        ref = oracle_effnet.extractor(x)
+    out = m.feature_extractor(x.to(cuda_device)).cpu()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"size={size} n={n} max|err|={err:.3e} max|ref|={scale:.3f}")
+    assert out.shape == ref.shape
+    assert err <= 2e-5 * max(1.0, scale)
+
+
+def test_chunking_is_invisible(cuda_device, oracle_effnet):
+    """Results must not depend on chunk_frames (eval-mode BN: frames are independent)."""
+    m = _product(oracle_effnet, cuda_device)
+    x = torch.randn(9, 3, 96, 96, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    m.feature_extractor.set_option('chunk_frames', 16)
+    a = m.feature_extractor(x)
+    m.feature_extractor.set_option('chunk_frames', 2)
+    b = m.feature_extractor(x)
+    assert torch.equal(a, b)
+
+
+def test_episode_logits_and_argmax(cuda_device, oracle_effnet):
+    """personalise()+predict() on a synthetic episode: logits within 1e-3 (north-star tolerance, fp32)
+    of the oracle and identical class indices; CPU-resident clips exercise the staged H2D path."""
+    from orbit_b200.synthetic import EpisodeSpec, make_episode
+    spec = EpisodeSpec(way=5, support_clips_per_class=3, query_clips_per_class=4, clip_length=2, frame_size=96)
+    ctx, ctx_y, tgt, tgt_y = make_episode(spec, index=3)
+    oracle_effnet.reset()
+    oracle_effnet.personalise(ctx, ctx_y)
+    ref = oracle_effnet.predict(tgt)
+
+    m = _product(oracle_effnet, cuda_device)
+    m.stage_slice_frames = 8
+    for clips_dev in (False, True):
+        c, t = (ctx.to(cuda_device), tgt.to(cuda_device)) if clips_dev else (ctx, tgt)
+        m.personalise(c, ctx_y.to(cuda_device))
+        logits, am = m.predict(t, want_argmax=True)
+        err = (logits.cpu() - ref).abs().max().item()
+        print(f"device_clips={clips_dev} max|dlogit|={err:.3e} max|logit|={ref.abs().max().item():.2f}")
+        assert err <= 1e-3
+        assert torch.equal(am.cpu().long(), ref.argmax(dim=1))
+        m._reset()
+        assert m.classifier.weight is None
