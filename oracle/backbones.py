@@ -259,19 +259,35 @@ def build(name: str) -> nn.Module:
 
 
 @torch.no_grad()
-def seeded_init(model: nn.Module, seed: int = 1991, calib_frames: int = 32, size: int = 224):
-    """Synthetic 'pretrained' weights: seeded timm-style init, mildly random
-    norm affine params, then ONE train-mode calibration pass (momentum 1 => running stats ==
-    batch stats) so eval-mode activations stay O(1). Returns the model in eval mode."""
+def seeded_init(model: nn.Module, seed: int = 1991, calib_input: torch.Tensor = None):
+    """Synthetic 'pretrained' weights (there is no network for real checkpoints).
+
+    A Gaussian-initialised deep net sits at the edge of chaos: per-frame deviations are amplified
+    layer after layer, a few frames end up with |feature| ~ 10 and |logit| ~ 1e4 (where an absolute
+    1e-3 logit tolerance is below fp32 resolution), and the slightest damping collapses all frames
+    onto one point instead. So the weights are drawn for *dynamical isometry*: (semi-)orthogonal
+    dense / pointwise / full convolutions, depthwise kernels = centre tap + small noise, mildly
+    random norm affine parameters; then ONE train-mode calibration pass over ``calib_input``
+    [n,3,H,W] (momentum 1 => running stats == batch stats). Features stay O(1) for every frame,
+    logits O(100), top-2 gaps >> 1e-3. Returns the model in eval mode with frozen parameters."""
     g = torch.Generator().manual_seed(seed)
-    for mod in model.modules():
+    for name, mod in model.named_modules():
         if isinstance(mod, nn.Conv2d):
-            fan_out = mod.kernel_size[0] * mod.kernel_size[1] * mod.out_channels // mod.groups
-            mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * math.sqrt(2.0 / fan_out))
+            w = mod.weight
+            if mod.groups > 1 and w.shape[1] == 1:                 # depthwise
+                k = w.shape[-1]
+                w.copy_(torch.randn(w.shape, generator=g) * (0.2 / k))
+                w[:, 0, k // 2, k // 2] += 1.0
+            elif '.se.' in name:                                   # squeeze-excite FCs: gates around 0.5
+                w.copy_(torch.randn(w.shape, generator=g) * (0.5 * w.shape[1] ** -0.5))
+            else:
+                flat = torch.empty(w.shape[0], w[0].numel())
+                nn.init.orthogonal_(flat, generator=g)
+                w.copy_(flat.view_as(w))
             if mod.bias is not None:
                 mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.05)
         elif isinstance(mod, nn.Linear):
-            mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * (mod.in_features ** -0.5))
+            nn.init.orthogonal_(mod.weight, generator=g)
             mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.02)
         elif isinstance(mod, (nn.BatchNorm2d, nn.LayerNorm)):
             mod.weight.copy_(1.0 + 0.1 * torch.randn(mod.weight.shape, generator=g))
@@ -279,12 +295,13 @@ def seeded_init(model: nn.Module, seed: int = 1991, calib_frames: int = 32, size
     if isinstance(model, VisionTransformer):
         model.cls_token.copy_(0.02 * torch.randn(model.cls_token.shape, generator=g))
         model.pos_embed.copy_(0.02 * torch.randn(model.pos_embed.shape, generator=g))
+        model.norm.weight.mul_(0.3)   # token features O(0.3) -> logits O(100) instead of O(1000)
     bns = [m for m in model.modules() if isinstance(m, nn.BatchNorm2d)]
-    if bns:
+    if bns and calib_input is not None:
         for m in bns:
             m.momentum = 1.0
         model.train()
-        model(torch.randn(calib_frames, 3, size, size, generator=g))
+        model(calib_input)
         for m in bns:
             m.momentum = 0.1
     model.eval()

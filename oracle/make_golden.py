@@ -1,0 +1,190 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference code (TEST INFRASTRUCTURE).
+
+Run in the build container, where /root/reference exists:   python oracle/make_golden.py
+The GPU box has no /root/reference, so the vectors are committed as small fixtures and the tests
+compare the oracle restatement (and, on the GPU, the CUDA path) against them.
+
+What comes from the reference itself (imported from /root/reference, not copied):
+  * model/poolers.MeanPooler, model/classifier_heads.{Prototypical,Linear,Versa,Mahalanobis}Classifier
+  * model/set_encoders.SetEncoder, model/feature_adapters.FilmParameterGenerator
+  * data/utils.attach_frame_history
+  * model/few_shot_recognisers.{SingleStep,MultiStep}FewShotRecogniser end to end, on top of
+    oracle/timm_shim (timm itself is not installable here; the backbone arithmetic is the restatement)
+Inputs are regenerated from seeds by the tests (torch CPU RNG is deterministic for a fixed torch
+version); every fixture stores an input checksum so that an RNG drift is detected, not mis-reported.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get('ORBIT_REFERENCE', '/root/reference')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'timm_shim'))
+sys.path.insert(0, REF)
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def checksum(*tensors):
+    return float(sum(t.double().abs().sum().item() for t in tensors))
+
+
+def head_case(seed, ns, nq, L, D, C, offset=0, stride=1):
+    g = torch.Generator().manual_seed(seed)
+    sf = torch.randn(ns * L, D, generator=g) * 0.7 + 0.3
+    qf = torch.randn(nq * L, D, generator=g) * 0.7 + 0.3
+    labels = ((torch.arange(ns) % C) * stride + offset)[torch.randperm(ns, generator=g)]
+    return sf, qf, labels
+
+
+def golden_parts():
+    from model.poolers import MeanPooler
+    from model.classifier_heads import (PrototypicalClassifier, VersaClassifier, MahalanobisClassifier,
+                                        LinearClassifier)
+    from model.set_encoders import SetEncoder
+    from model.feature_adapters import FilmParameterGenerator
+    from data.utils import attach_frame_history
+    from oracle import parts
+    out = {}
+    # prototypical head, euclidean + cosine, incl. non-contiguous labels
+    for i, (ns, nq, L, D, C, off, st) in enumerate([(200, 80, 8, 1280, 5, 0, 1), (25, 75, 1, 512, 5, 0, 1),
+                                                     (150, 60, 1, 768, 15, 0, 1), (30, 12, 2, 256, 5, 100, 7)]):
+        sf, qf, labels = head_case(100 + i, ns, nq, L, D, C, off, st)
+        pool = MeanPooler(T=L)
+        for metric, name in (('euclidean', 'proto'), ('cosine', 'proto_cosine')):
+            head = PrototypicalClassifier(1.7, metric)
+            head.configure(pool(sf), labels)
+            out[f'{name}{i}_args'] = np.array([100 + i, ns, nq, L, D, C, off, st])
+            out[f'{name}{i}_weight'] = head.weight.detach().numpy()
+            if metric == 'euclidean':
+                out[f'{name}{i}_bias'] = head.bias.detach().numpy()
+            out[f'{name}{i}_logits'] = head.predict(pool(qf)).detach().numpy()
+            out[f'{name}{i}_checksum'] = np.array(checksum(sf, qf, labels))
+    # versa head with oracle-initialised hyper-net params
+    sf, qf, labels = head_case(200, 40, 16, 1, 128, 5)
+    vp = parts.init_versa_params(128, seed=7)
+    versa = VersaClassifier(128, 0.5)
+    versa.load_state_dict(vp, strict=True)
+    with torch.no_grad():
+        versa.configure(sf, labels)
+        out['versa_weight'] = versa.weight.detach().numpy()
+        out['versa_bias'] = versa.bias.detach().numpy()
+        out['versa_logits'] = versa.predict(qf).detach().numpy()
+    out['versa_checksum'] = np.array(checksum(sf, qf, labels))
+    # mahalanobis head (small D)
+    sf, qf, labels = head_case(201, 40, 16, 1, 32, 4)
+    maha = MahalanobisClassifier(2.0)
+    maha.configure(sf, labels)
+    out['maha_logits'] = maha.predict(qf).detach().numpy()
+    out['maha_means'] = maha.means.detach().numpy()
+    out['maha_checksum'] = np.array(checksum(sf, qf, labels))
+    # linear head
+    lin = LinearClassifier(64, 3.0)
+    lin.init(6)
+    g = torch.Generator().manual_seed(202)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(6, 64, generator=g)); lin.bias.copy_(torch.randn(6, generator=g))
+    x = torch.randn(10, 64, generator=g)
+    out['linear_logits'] = lin.predict(x).detach().numpy()
+    # set encoder at 84 and 224
+    sp = parts.init_set_encoder_params(seed=11)
+    enc = SetEncoder().eval()
+    enc.load_state_dict(sp, strict=True)
+    g = torch.Generator().manual_seed(203)
+    for size in (84, 224):
+        clips = torch.randn(3, 2, 3, size, size, generator=g)
+        with torch.no_grad():
+            reps = enc(clips)
+            out[f'setenc{size}_reps'] = reps.numpy()
+            out[f'setenc{size}_agg'] = enc.aggregate([reps[:2], reps[2:]]).numpy()
+        out[f'setenc{size}_checksum'] = np.array(checksum(clips))
+    # FiLM generator
+    names = ['blocks.1.0.bn2.bias', 'blocks.1.0.bn2.weight', 'bn1.bias', 'bn1.weight']
+    sizes = {'blocks.1.0.bn2.bias': 96, 'blocks.1.0.bn2.weight': 96, 'bn1.bias': 32, 'bn1.weight': 32}
+    g = torch.Generator().manual_seed(204)
+    initial = {n: torch.randn(sizes[n], generator=g) for n in names}
+    gp = parts.init_film_generator_params([sizes[n] for n in sorted(names)], seed=13)
+    gen = FilmParameterGenerator(sizes, {k: v.clone() for k, v in initial.items()}, 64, 64)
+    gen.load_state_dict(gp, strict=True)
+    z = torch.randn(1, 64, generator=g)
+    with torch.no_grad():
+        fd = gen(z)
+    for n in names:
+        out['film_' + n] = fd[n].numpy()
+    out['film_l2'] = np.array(float(gen.regularization_term()))
+    out['film_checksum'] = np.array(checksum(z, *initial.values()))
+    # attach_frame_history
+    fr = torch.arange(7 * 2, dtype=torch.float32).reshape(7, 2, 1, 1)
+    for L in (1, 3, 8):
+        out[f'history{L}'] = attach_frame_history(fr, L).numpy()
+    np.savez_compressed(os.path.join(OUT, 'parts.npz'), **out)
+    print('parts.npz', len(out), 'arrays')
+
+
+def golden_recogniser():
+    """The whole reference recogniser on the timm shim, weights = oracle state_dict (strict load)."""
+    import timm.models.efficientnet as shim_cfg
+    from model.few_shot_recognisers import SingleStepFewShotRecogniser, MultiStepFewShotRecogniser
+    from utils.optim import cross_entropy
+    from oracle.recogniser import OracleRecogniser
+    from orbit_b200.synthetic import EpisodeSpec, make_episode, calibration_frames
+    out = {}
+    cases = [
+        ('proto_b0', 'efficientnet_b0', False, 'proto', EpisodeSpec(5, 3, 4, 2, 96)),
+        ('cosine_b0', 'efficientnet_b0', False, 'proto_cosine', EpisodeSpec(4, 2, 3, 1, 64)),
+        ('cnaps_b0', 'efficientnet_b0', True, 'versa', EpisodeSpec(5, 2, 3, 2, 96)),
+        ('protofilm_b0', 'efficientnet_b0', True, 'proto', EpisodeSpec(3, 2, 2, 1, 84)),
+        ('simplecnaps_b0', 'efficientnet_b0', True, 'mahalanobis', EpisodeSpec(3, 3, 2, 1, 64)),
+        ('proto_vit', 'vit_b_32', False, 'proto', EpisodeSpec(3, 2, 2, 1, 224)),
+    ]
+    for tag, extractor, adapt, head, spec in cases:
+        calib = calibration_frames(spec.frame_size)
+        shim_cfg._SEED_ARGS = (1991, calib)
+        oracle = OracleRecogniser(extractor, adapt, head, spec.clip_length, 4, 1.0, 1991, calib)
+        ref = SingleStepFewShotRecogniser(extractor, adapt, head, spec.clip_length, 4, False, 16, 1.0)
+        ref.load_state_dict(oracle.state_dict(), strict=True)
+        ref._set_device(torch.device('cpu'))
+        ref.set_test_mode(True)
+        ctx, ctx_y, tgt, tgt_y = make_episode(spec, index=1)
+        with torch.no_grad():
+            ref.personalise(ctx, ctx_y)
+            logits = ref.predict(tgt)
+        out[tag + '_logits'] = logits.numpy()
+        out[tag + '_spec'] = np.array([spec.way, spec.support_clips_per_class, spec.query_clips_per_class,
+                                       spec.clip_length, spec.frame_size])
+        out[tag + '_checksum'] = np.array(checksum(ctx, tgt, ctx_y))
+        if adapt:
+            out[tag + '_film_bn1_weight'] = ref.film_dict['bn1.weight'].numpy()
+        top = logits.topk(2, dim=1).values
+        print(tag, tuple(logits.shape), 'max|logit| %.2f' % float(logits.abs().max()),
+              'min top-2 gap %.4f' % float((top[:, 0] - top[:, 1]).min()),
+              'acc %.2f' % float((logits.argmax(1) == tgt_y).float().mean()))
+    # FineTuner (multi-step) on efficientnet_b0 + linear head, 5 Adam steps
+    spec = EpisodeSpec(4, 3, 2, 1, 64)
+    shim_cfg._SEED_ARGS = (1991, calibration_frames(64))
+    oracle = OracleRecogniser('efficientnet_b0', False, 'linear', 1, 5, 1.0, 1991, calibration_frames(64))
+    ref = MultiStepFewShotRecogniser('efficientnet_b0', False, 'linear', 1, 5, False, 1.0)
+    ref.load_state_dict(oracle.state_dict(), strict=True)
+    ref._set_device(torch.device('cpu'))
+    ref.set_test_mode(True)
+    ctx, ctx_y, tgt, _ = make_episode(spec, index=2)
+    args = {'num_grad_steps': 5, 'learning_rate': 0.1, 'optimizer': 'adam', 'loss_fn': cross_entropy,
+            'extractor_lr_scale': 0.1, 'epsilon': 1e-8, 'weight_decay': 0.0, 'betas': (0.9, 0.999), 'momentum': 0.0}
+    ref.personalise(ctx, ctx_y, dict(args))
+    with torch.no_grad():
+        out['finetune_logits'] = ref.predict(tgt).numpy()
+    out['finetune_weight'] = ref.classifier.weight.detach().numpy()
+    out['finetune_bias'] = ref.classifier.bias.detach().numpy()
+    out['finetune_checksum'] = np.array(checksum(ctx, tgt, ctx_y))
+    np.savez_compressed(os.path.join(OUT, 'recogniser.npz'), **out)
+    print('recogniser.npz', len(out), 'arrays')
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    golden_parts()
+    golden_recogniser()

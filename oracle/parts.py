@@ -124,11 +124,12 @@ def set_encoder_forward(x, p, eps=1e-5):
     return x.mean((2, 3))
 
 
-def init_set_encoder_params(seed=11, size=224, calib_frames=16):
-    """Seeded weights + BN stats calibrated on synthetic frames (activations O(1))."""
+def init_set_encoder_params(seed=11, calib_input=None):
+    """Seeded weights + BN stats calibrated on ``calib_input`` [n,3,H,W] (activations O(1))."""
     g = torch.Generator().manual_seed(seed)
     p = {}
-    x = torch.randn(calib_frames, 3, size, size, generator=g)
+    x = calib_input if calib_input is not None else torch.randn(16, 3, 84, 84, generator=g)
+    x = x[:16]
     cin = 3
     for i in range(1, 6):
         pre = f'encoder.layer{i}.'

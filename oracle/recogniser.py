@@ -22,7 +22,7 @@ class OracleRecogniser:
     (few_shot_recognisers.py:72-84)."""
 
     def __init__(self, feature_extractor_name, adapt_features, classifier, clip_length, batch_size,
-                 logit_scale=1.0, seed=1991, frame_size=224, calib_frames=32):
+                 logit_scale=1.0, seed=1991, calib_input=None):
         if classifier not in ('linear', 'versa', 'proto', 'proto_cosine', 'mahalanobis'):
             raise ValueError(f"Classifier {classifier} not valid.")
         self.name = feature_extractor_name
@@ -31,8 +31,7 @@ class OracleRecogniser:
         self.clip_length = clip_length
         self.batch_size = batch_size
         self.logit_scale = logit_scale
-        self.extractor = backbones.seeded_init(backbones.build(feature_extractor_name), seed,
-                                               calib_frames, frame_size)
+        self.extractor = backbones.seeded_init(backbones.build(feature_extractor_name), seed, calib_input)
         self.feat_dim = self.extractor.output_size
         self.film_names = None
         if adapt_features:
@@ -40,7 +39,7 @@ class OracleRecogniser:
             self.film_names = sorted(names)
             ext = dict(self.extractor.named_parameters())
             self.film_initial = {n: ext[n].detach().clone() for n in names}
-            self.set_encoder_params = parts.init_set_encoder_params(seed + 1, frame_size)
+            self.set_encoder_params = parts.init_set_encoder_params(seed + 1, calib_input)
             self.film_gen_params = parts.init_film_generator_params(
                 [self.film_initial[n].numel() for n in self.film_names], seed + 2)
         if classifier == 'versa':

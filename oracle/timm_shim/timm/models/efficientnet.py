@@ -11,4 +11,4 @@ def tf_efficientnetv2_s_in21k(*a, **kw):
     raise NotImplementedError("efficientnet_v2_s is not restated by the shim")
 
 
-_SEED_ARGS = (1991, 32, 224)  # (seed, calib_frames, size): set by make_golden before construction
+_SEED_ARGS = (1991, None)  # (seed, calib_input): set by make_golden before construction

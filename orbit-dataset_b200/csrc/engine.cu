@@ -51,7 +51,7 @@ struct orbit_engine {
 
     int64_t add_param(const std::string& name, int64_t numel) {
         params.push_back({name, numel, param_floats});
-        param_floats += numel;
+        param_floats += (numel + 3) / 4 * 4;  // every tensor starts 16-byte aligned (128-bit loads)
         return params.back().offset;
     }
     int64_t add_derived(int64_t numel) {

@@ -1,8 +1,16 @@
-"""Synthetic episodes of the BASELINE.json shapes: seeded fp32 NCHW frames that look like
-normalised pixels (reference data/datasets.py:428-431) and class-balanced labels. Shared by tests and bench."""
+"""Synthetic ORBIT-like data of the BASELINE.json shapes. Shared by tests and bench.
+
+Frames are seeded fp32 NCHW tensors that look like normalised pixels (reference
+data/datasets.py:428-431): unit Gaussian noise plus the fixed low-frequency "appearance" of one of
+16 synthetic object classes, so that prototypes separate and arg-max parity is meaningful.
+Labels are class-balanced and permuted (seed = 1991 + episode index; reference default seed
+utils/args.py:99)."""
 from dataclasses import dataclass
 
 import torch
+
+NUM_OBJECTS = 16
+_BANK_SEED = 1991
 
 
 @dataclass
@@ -14,14 +22,36 @@ class EpisodeSpec:
     frame_size: int = 224
 
 
-S2 = EpisodeSpec()                                     # ProtoNet + efficientnet_b0, 224, 5-way 5-shot 8 clips x 8 frames
-S1 = EpisodeSpec(5, 5, 15, 1, 84)                      # config 1 shape (84x84, 1-clip)
-TINY = EpisodeSpec(5, 2, 2, 2, 64)                     # unit tests
+S2 = EpisodeSpec()                      # ProtoNet + efficientnet_b0, 224, 5-way 5-shot, 8 clips x 8 frames
+S1 = EpisodeSpec(5, 5, 15, 1, 84)       # config 1 shape (84x84, 1-clip)
+
+
+def object_bank(size: int):
+    """Appearance [NUM_OBJECTS,3,size,size] of the synthetic objects: colour offset + smooth pattern."""
+    g = torch.Generator().manual_seed(_BANK_SEED)
+    colour = torch.randn(NUM_OBJECTS, 3, 1, 1, generator=g) * 0.5
+    ramp = torch.linspace(-1, 1, size)
+    fx = torch.rand(NUM_OBJECTS, generator=g) * 4 + 1
+    fy = torch.rand(NUM_OBJECTS, generator=g) * 4 + 1
+    pat = torch.stack([torch.sin(fx[c] * ramp)[None, :] * torch.cos(fy[c] * ramp)[:, None] for c in range(NUM_OBJECTS)])
+    return colour + 1.0 * pat[:, None]
+
+
+def calibration_frames(size: int, per_object: int = None, seed: int = 7):
+    """Frames of the episode distribution (every object equally often) used to calibrate the synthetic
+    weights' BatchNorm statistics."""
+    if per_object is None:
+        fs = -(-size // 32)
+        per_object = max(2, -(-64 // (fs * fs)))
+    g = torch.Generator().manual_seed(seed)
+    n = per_object * NUM_OBJECTS
+    x = torch.randn(n, 3, size, size, generator=g)
+    return x + object_bank(size)[torch.arange(n) % NUM_OBJECTS]
 
 
 def make_episode(spec: EpisodeSpec, index: int = 0, seed: int = 1991, pin: bool = False):
     """Returns (context_clips [Ns,L,3,H,W], context_labels [Ns] int64, target_clips [Nq,L,3,H,W],
-    target_labels [Nq]). Seed = 1991 + episode index (reference default seed, utils/args.py:99)."""
+    target_labels [Nq])."""
     g = torch.Generator().manual_seed(seed + index)
     ns, nq = spec.way * spec.support_clips_per_class, spec.way * spec.query_clips_per_class
     shape = (spec.clip_length, 3, spec.frame_size, spec.frame_size)
@@ -29,16 +59,12 @@ def make_episode(spec: EpisodeSpec, index: int = 0, seed: int = 1991, pin: bool 
     tgt = torch.empty((nq,) + shape, dtype=torch.float32, pin_memory=pin)
     ctx.normal_(generator=g)
     tgt.normal_(generator=g)
+    objects = torch.randperm(NUM_OBJECTS, generator=g)[:spec.way]      # which objects this task is about
     ctx_labels = torch.arange(spec.way).repeat_interleave(spec.support_clips_per_class)
     tgt_labels = torch.arange(spec.way).repeat_interleave(spec.query_clips_per_class)
     ctx_labels = ctx_labels[torch.randperm(ns, generator=g)]
     tgt_labels = tgt_labels[torch.randperm(nq, generator=g)]
-    # give every class a distinct low-frequency signature so that prototypes separate (random-init nets
-    # otherwise map i.i.d. noise frames to nearly identical features and arg-max ties are meaningless)
-    sig = torch.randn(spec.way, 3, 1, 1, generator=g) * 0.75
-    ramp = torch.linspace(-1, 1, spec.frame_size)
-    pat = torch.stack([torch.sin((c + 1) * 1.7 * ramp)[None, :] * torch.cos((c + 1) * 1.1 * ramp)[:, None]
-                       for c in range(spec.way)])[:, None]          # [way,1,H,W]
-    ctx += (sig[ctx_labels] + pat[ctx_labels])[:, None]
-    tgt += (sig[tgt_labels] + pat[tgt_labels])[:, None]
+    bank = object_bank(spec.frame_size)[objects]
+    ctx += bank[ctx_labels][:, None]
+    tgt += bank[tgt_labels][:, None]
     return ctx, ctx_labels, tgt, tgt_labels

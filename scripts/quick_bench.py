@@ -12,7 +12,7 @@ m._set_device(dev); m._send_to_device(); m.set_test_mode(True)
 fe = m.feature_extractor
 fe.set_option('gemm', gemm)
 x = torch.randn(frames, 3, 224, 224, device=dev)
-for chunk in [int(c) for c in (sys.argv[3].split(',') if len(sys.argv) > 3 else "4,8,16,32,64,128")]:
+for chunk in [int(c) for c in (sys.argv[3] if len(sys.argv) > 3 else "4,8,16,32,64,128").split(',')]:
     fe.set_option('chunk_frames', chunk)
     for _ in range(2):
         fe(x)

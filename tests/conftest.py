@@ -24,4 +24,6 @@ def cuda_device():
 def oracle_effnet():
     """Seeded + calibrated oracle recogniser (efficientnet_b0, proto) shared by the GPU parity tests."""
     from oracle.recogniser import OracleRecogniser
-    return OracleRecogniser('efficientnet_b0', False, 'proto', clip_length=2, batch_size=256, calib_frames=16)
+    from orbit_b200.synthetic import calibration_frames
+    return OracleRecogniser('efficientnet_b0', False, 'proto', clip_length=2, batch_size=256,
+                            calib_input=calibration_frames(96))
