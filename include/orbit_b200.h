@@ -111,7 +111,8 @@ int     orbit_engine_prepare(const orbit_engine* e, const float* params, const f
                              float* derived, void* stream);
 
 /* Options: "chunk_frames" (frames per pass, sized to keep inter-layer tensors in L2),
- *          "gemm" 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (fp32-accurate), 2 = tcgen05 1xTF32     */
+ *          "gemm" 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (fp32-accurate), 2 = tcgen05 1xTF32,
+ *          "profile" 0/1 = CUDA-event timing of every launch (see orbit_engine_profile_read)      */
 int orbit_engine_set_option(orbit_engine* e, const char* key, int value);
 int orbit_engine_get_option(const orbit_engine* e, const char* key, int* value);
 
@@ -121,6 +122,23 @@ int64_t orbit_engine_workspace_bytes(const orbit_engine* e, int height, int widt
 int orbit_engine_forward(const orbit_engine* e, const float* params, const float* derived,
                          const float* frames, int num_frames, int height, int width,
                          float* feats, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Batch-statistics pass (the train-mode BatchNorm of few_shot_recognisers.py:181-183, used here to
+ * calibrate synthetic checkpoints): one forward over `frames` (num_frames <= chunk_frames) in which every
+ * BatchNorm normalises with the statistics of this batch; the batch mean / unbiased variance are WRITTEN
+ * into the running_mean / running_var entries of `params`, and `derived` is refolded accordingly.       */
+int orbit_engine_calibrate(const orbit_engine* e, float* params, float* derived, const float* frames,
+                           int num_frames, int height, int width, float* feats, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+
+/* Per-kernel-family timing. With option "profile"=1 every launch of orbit_engine_forward is bracketed by
+ * CUDA events on the caller's stream (the only place the library creates CUDA objects). profile_read blocks
+ * until those launches finished and returns, per family, the summed device time [ms], launch count and the
+ * ALGORITHMIC bytes / flops (each input and output tensor counted once) since the previous read.
+ * Families: 0 stem conv, 1 depthwise conv, 2 squeeze-excite gate, 3 pointwise-conv GEMM, 4 spatial mean,
+ * 5 calibration statistics.                                                                           */
+#define ORBIT_PROFILE_FAMILIES 6
+int orbit_engine_profile_read(const orbit_engine* e, double* ms, int64_t* launches, double* bytes, double* flops);
 
 /* number of kernels the last orbit_engine_forward on this engine enqueued (for bench accounting) */
 int64_t orbit_engine_last_launches(const orbit_engine* e);

@@ -48,6 +48,53 @@ int launch_bn_fold(const FoldEntry* entries, int n, const float* params, const f
     return ORBIT_OK;
 }
 
+__global__ void fill_identity_kernel(float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out[i] = 1.0f; out[n + i] = 0.0f; }
+}
+int launch_fill_identity(float* out, int n, cudaStream_t st) {
+    fill_identity_kernel<<<ceil_div(n, 256), 256, 0, st>>>(out, n);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+// One block per 32 channels; 8 row lanes x 32 channels; two passes (mean, then centred second moment).
+__global__ void __launch_bounds__(256)
+channel_stats_kernel(const float* __restrict__ x, int64_t M, int C, float* __restrict__ mean, float* __restrict__ var) {
+    __shared__ double s_acc[8][33];
+    __shared__ double s_mean[32];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const bool live = c < C;
+    double acc = 0.0;
+    if (live) for (int64_t r = rl; r < M; r += 8) acc += (double)x[r * C + c];
+    s_acc[rl][cl] = acc;
+    __syncthreads();
+    if (rl == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += s_acc[i][cl];
+        s_mean[cl] = t / (double)M;
+    }
+    __syncthreads();
+    const double mu = s_mean[cl];
+    acc = 0.0;
+    if (live) for (int64_t r = rl; r < M; r += 8) { const double d = (double)x[r * C + c] - mu; acc += d * d; }
+    __syncthreads();
+    s_acc[rl][cl] = acc;
+    __syncthreads();
+    if (rl == 0 && live) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += s_acc[i][cl];
+        mean[c] = (float)mu;
+        var[c] = (float)(t / (double)(M > 1 ? M - 1 : 1));
+    }
+}
+int launch_channel_stats(const float* x, int64_t M, int C, float* mean, float* var, cudaStream_t st) {
+    channel_stats_kernel<<<ceil_div(C, 32), 256, 0, st>>>(x, M, C, mean, var);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
 __global__ void dw_relayout_kernel(const float* __restrict__ w, int C, int kk, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < C * kk) { const int t = i / C, c = i % C; out[i] = w[c * kk + t]; }

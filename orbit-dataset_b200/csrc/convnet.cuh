@@ -18,6 +18,12 @@ struct FoldEntry {
 int launch_bn_fold(const FoldEntry* entries_host, int n, const float* params, const float* film, float* derived,
                    cudaStream_t st);
 
+// out = [ones(n) | zeros(n)]
+int launch_fill_identity(float* out, int n, cudaStream_t st);
+
+// per-channel batch statistics of x [M,C]: mean and UNBIASED variance (double accumulation, deterministic)
+int launch_channel_stats(const float* x, int64_t M, int C, float* mean, float* var, cudaStream_t st);
+
 // depthwise weights [C,1,k,k] -> [k*k][C]
 int launch_dw_relayout(const float* w, int C, int kk, float* out, cudaStream_t st);
 

@@ -30,6 +30,7 @@ struct Op {
     int64_t w = -1, b = -1;     // param offsets (conv weight / bias)
     int64_t w2 = -1, b2 = -1;   // SE expand
     int64_t fold = -1;          // derived offset of scale[C], shift[C]
+    int fold_idx = -1;          // index into orbit_engine::folds
     int64_t dw_wt = -1;         // derived offset of re-laid-out depthwise weights
     int64_t w_split = -1;       // derived offset of tf32 hi/lo split weights (PW, tcgen05 path)
     int se_reduce = 0;
@@ -43,11 +44,20 @@ struct orbit_engine {
     int arch = 0, feat_dim = 0;
     std::vector<ParamInfo> params, film;
     int64_t param_floats = 0, film_floats = 0, derived_floats = 0;
+    int64_t ident = -1;  // derived offset of [ones(max_c) | zeros(max_c)] (identity scale/shift for calibration)
+    int max_c = 0;
     std::vector<FoldEntry> folds;
     std::vector<Op> ops;
     int chunk_frames = 16;
     int gemm_mode = 0;
     mutable std::atomic<int64_t> last_launches{0};
+    // optional per-launch CUDA-event timing (option "profile"): one event before every launch + one at the end
+    int profile = 0;
+    struct ProfRec { int family; double bytes, flops; };
+    mutable std::vector<cudaEvent_t> prof_events;
+    mutable std::vector<ProfRec> prof_recs;
+    mutable size_t prof_used = 0;
+    mutable std::vector<size_t> prof_ends;   // index of the closing event of each forward call
 
     int64_t add_param(const std::string& name, int64_t numel) {
         params.push_back({name, numel, param_floats});
@@ -60,8 +70,10 @@ struct orbit_engine {
         return o;
     }
     // BatchNorm: registers weight/bias/running_mean/running_var and a fold entry; returns derived offset
-    int64_t add_bn(const std::string& name, int c, float eps, bool film_site) {
+    int64_t add_bn(const std::string& name, int c, float eps, bool film_site, Op* op = nullptr) {
         FoldEntry f;
+        if (op) op->fold_idx = (int)folds.size();
+        max_c = std::max(max_c, c);
         f.gamma = add_param(name + ".weight", c);
         f.beta = add_param(name + ".bias", c);
         f.mean = add_param(name + ".running_mean", c);
@@ -104,7 +116,7 @@ static void build_efficientnet_b0(orbit_engine* e) {
     {
         Op op; op.kind = OP_STEM; op.in = BUF_INPUT; op.out = BUF_X0; op.cin = 3; op.cout = 32; op.k = 3; op.stride = 2; op.act = ACT_SILU;
         op.w = e->add_param("conv_stem.weight", 32 * 27);
-        op.fold = e->add_bn("bn1", 32, eps, true);
+        op.fold = e->add_bn("bn1", 32, eps, true, &op);
         e->ops.push_back(op);
     }
     int cin = 32, cur = BUF_X0;
@@ -118,7 +130,7 @@ static void build_efficientnet_b0(orbit_engine* e) {
             if (!ds) {  // expand 1x1 + bn1 + SiLU
                 Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_E; op.cin = cin; op.cout = mid; op.act = ACT_SILU;
                 op.w = e->add_param(p + "conv_pw.weight", (int64_t)mid * cin);
-                op.fold = e->add_bn(p + "bn1", mid, eps, false);
+                op.fold = e->add_bn(p + "bn1", mid, eps, false, &op);
                 op.w_split = e->add_derived(2 * (int64_t)mid * cin);
                 e->ops.push_back(op);
                 dw_in = BUF_E;
@@ -126,7 +138,7 @@ static void build_efficientnet_b0(orbit_engine* e) {
             {   // depthwise + bn + SiLU (the FiLM site of InvertedResidual: bn2)
                 Op op; op.kind = OP_DW; op.in = dw_in; op.out = BUF_D; op.cin = op.cout = mid; op.k = k; op.stride = stride; op.act = ACT_SILU;
                 op.w = e->add_param(p + "conv_dw.weight", (int64_t)mid * k * k);
-                op.fold = e->add_bn(p + (ds ? "bn1" : "bn2"), mid, eps, !ds);
+                op.fold = e->add_bn(p + (ds ? "bn1" : "bn2"), mid, eps, !ds, &op);
                 op.dw_wt = e->add_derived((int64_t)mid * k * k);
                 e->ops.push_back(op);
             }
@@ -144,7 +156,7 @@ static void build_efficientnet_b0(orbit_engine* e) {
                 op.out = cur == BUF_X0 ? BUF_X1 : BUF_X0;
                 if (stride == 1 && cin == cout) op.res = cur;
                 op.w = e->add_param(p + (ds ? "conv_pw.weight" : "conv_pwl.weight"), (int64_t)cout * mid);
-                op.fold = e->add_bn(p + (ds ? "bn2" : "bn3"), cout, eps, false);
+                op.fold = e->add_bn(p + (ds ? "bn2" : "bn3"), cout, eps, false, &op);
                 op.w_split = e->add_derived(2 * (int64_t)cout * mid);
                 e->ops.push_back(op);
                 cur = op.out;
@@ -155,13 +167,14 @@ static void build_efficientnet_b0(orbit_engine* e) {
     {   // conv_head + bn2 (FiLM, root) + SiLU, then global average pool
         Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_H; op.cin = cin; op.cout = 1280; op.act = ACT_SILU;
         op.w = e->add_param("conv_head.weight", (int64_t)1280 * cin);
-        op.fold = e->add_bn("bn2", 1280, eps, true);
+        op.fold = e->add_bn("bn2", 1280, eps, true, &op);
         op.w_split = e->add_derived(2 * (int64_t)1280 * cin);
         e->ops.push_back(op);
         Op pool; pool.kind = OP_SPATIAL_MEAN; pool.in = BUF_H; pool.out = BUF_OUTPUT; pool.cin = pool.cout = 1280;
         e->ops.push_back(pool);
     }
     e->finalize_film();
+    e->ident = e->add_derived(2 * (int64_t)e->max_c);
 }
 
 // TF "SAME" geometry: out = ceil(in/s), pad_before = total/2 (stride 1 => symmetric (k-1)/2)
@@ -213,7 +226,11 @@ extern "C" int orbit_engine_create(orbit_engine** out, int arch) {
     return ORBIT_OK;
 }
 
-extern "C" void orbit_engine_destroy(orbit_engine* e) { delete e; }
+extern "C" void orbit_engine_destroy(orbit_engine* e) {
+    if (!e) return;
+    for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+    delete e;
+}
 extern "C" int orbit_engine_feat_dim(const orbit_engine* e) { return e ? e->feat_dim : ORBIT_ERR_ARG; }
 extern "C" int orbit_engine_num_params(const orbit_engine* e) { return e ? (int)e->params.size() : ORBIT_ERR_ARG; }
 extern "C" int64_t orbit_engine_param_floats(const orbit_engine* e) { return e ? e->param_floats : ORBIT_ERR_ARG; }
@@ -240,12 +257,14 @@ extern "C" int orbit_engine_set_option(orbit_engine* e, const char* key, int val
     if (!e || !key) return ORBIT_ERR_ARG;
     if (!std::strcmp(key, "chunk_frames")) { if (value < 1 || value > 4096) return ORBIT_ERR_ARG; e->chunk_frames = value; return ORBIT_OK; }
     if (!std::strcmp(key, "gemm")) { if (value < 0 || value > 2) return ORBIT_ERR_ARG; e->gemm_mode = value; return ORBIT_OK; }
+    if (!std::strcmp(key, "profile")) { e->profile = value != 0; return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 extern "C" int orbit_engine_get_option(const orbit_engine* e, const char* key, int* value) {
     if (!e || !key || !value) return ORBIT_ERR_ARG;
     if (!std::strcmp(key, "chunk_frames")) { *value = e->chunk_frames; return ORBIT_OK; }
     if (!std::strcmp(key, "gemm")) { *value = e->gemm_mode; return ORBIT_OK; }
+    if (!std::strcmp(key, "profile")) { *value = e->profile; return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 
@@ -254,6 +273,10 @@ extern "C" int orbit_engine_prepare(const orbit_engine* e, const float* params, 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_bn_fold(e->folds.data(), (int)e->folds.size(), params, film, derived, st);
     if (rc) return rc;
+    if (e->ident >= 0) {
+        rc = launch_fill_identity(derived + e->ident, e->max_c, st);
+        if (rc) return rc;
+    }
     for (const Op& op : e->ops) {
         if (op.kind == OP_DW) {
             rc = launch_dw_relayout(params + op.w, op.cin, op.k * op.k, derived + op.dw_wt, st);
@@ -277,17 +300,48 @@ extern "C" int64_t orbit_engine_workspace_bytes(const orbit_engine* e, int heigh
     return total + 1024;
 }
 
-extern "C" int orbit_engine_forward(const orbit_engine* e, const float* params, const float* derived, const float* frames,
-                                    int num_frames, int height, int width, float* feats, void* workspace,
-                                    int64_t workspace_bytes, void* stream) {
-    if (!e || !params || !derived || !frames || !feats || !workspace) return ORBIT_ERR_ARG;
-    if (num_frames < 0 || height <= 0 || width <= 0) return ORBIT_ERR_ARG;
-    if (!aligned16(frames) || !aligned16(feats) || !aligned16(params) || !aligned16(derived)) return ORBIT_ERR_UNSUPPORTED;
+static int prof_mark(const orbit_engine* e, cudaStream_t st) {
+    if (e->prof_used == e->prof_events.size()) {
+        cudaEvent_t ev;
+        ORBIT_CUDA(cudaEventCreate(&ev));
+        e->prof_events.push_back(ev);
+    }
+    ORBIT_CUDA(cudaEventRecord(e->prof_events[e->prof_used++], st));
+    return ORBIT_OK;
+}
+
+// Sums the event-timed launches recorded since the last read, per kernel family (OpKind; 5 = calibration
+// statistics). Blocks until the recorded work has finished. Arrays have ORBIT_PROFILE_FAMILIES entries.
+extern "C" int orbit_engine_profile_read(const orbit_engine* e, double* ms, int64_t* launches, double* bytes, double* flops) {
+    if (!e || !ms || !launches || !bytes || !flops) return ORBIT_ERR_ARG;
+    for (int i = 0; i < ORBIT_PROFILE_FAMILIES; ++i) { ms[i] = 0; launches[i] = 0; bytes[i] = 0; flops[i] = 0; }
+    if (e->prof_used == 0) return ORBIT_OK;
+    ORBIT_CUDA(cudaEventSynchronize(e->prof_events[e->prof_used - 1]));
+    // events: [k0 k1 ... kn-1 END] per forward call; records are in the same order without the END entries
+    size_t ev = 0, end_i = 0;
+    for (size_t r = 0; r < e->prof_recs.size(); ++r) {
+        while (end_i < e->prof_ends.size() && ev == e->prof_ends[end_i]) { ++ev; ++end_i; }
+        float t = 0.f;
+        ORBIT_CUDA(cudaEventElapsedTime(&t, e->prof_events[ev], e->prof_events[ev + 1]));
+        const auto& rec = e->prof_recs[r];
+        ms[rec.family] += t; launches[rec.family] += 1; bytes[rec.family] += rec.bytes; flops[rec.family] += rec.flops;
+        ++ev;
+    }
+    e->prof_recs.clear(); e->prof_ends.clear(); e->prof_used = 0;
+    return ORBIT_OK;
+}
+
+// Runs the layer plan. With `calib` (mutable params blob) each normalised layer is run twice: once raw
+// (identity scale/shift, no activation) to measure the per-channel batch statistics, which are written
+// into running_mean/running_var (unbiased variance, as torch momentum=1 would) and folded, then normally.
+static int run_plan(const orbit_engine* e, const float* params, float* calib, float* derived, const float* frames,
+                    int num_frames, int height, int width, float* feats, void* workspace, int64_t workspace_bytes,
+                    cudaStream_t st) {
     BufSizes bs;
     int rc = plan_buffers(e, height, width, &bs);
     if (rc) return rc;
     if (workspace_bytes < orbit_engine_workspace_bytes(e, height, width)) return ORBIT_ERR_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
+    if (calib && num_frames > e->chunk_frames) return ORBIT_ERR_UNSUPPORTED;  // statistics need ONE chunk
 
     float* buf[BUF_COUNT];
     {
@@ -309,52 +363,111 @@ extern "C" int orbit_engine_forward(const orbit_engine* e, const float* params, 
         };
         int h = height, w = width, se_tiles = 0, se_hw = 0;
         for (const Op& op : e->ops) {
-            switch (op.kind) {
-                case OP_STEM: {
-                    int ho, wo, pt, pl;
-                    same_geometry(h, op.k, op.stride, &ho, &pt);
-                    same_geometry(w, op.k, op.stride, &wo, &pl);
-                    rc = launch_stem(ptr(op.in), params + op.w, derived + op.fold, derived + op.fold + op.cout, ptr(op.out), B,
-                                     h, w, ho, wo, pt, pl, op.cout, op.act, st);
-                    h = ho; w = wo;
-                    break;
-                }
-                case OP_DW: {
-                    int ho, wo, pt, pl;
-                    same_geometry(h, op.k, op.stride, &ho, &pt);
-                    same_geometry(w, op.k, op.stride, &wo, &pl);
-                    rc = launch_depthwise(ptr(op.in), derived + op.dw_wt, derived + op.fold, derived + op.fold + op.cout,
-                                          ptr(op.out), buf[BUF_PARTIAL], B, h, w, op.cin, ho, wo, op.k, op.stride, pt, pl,
-                                          op.act, st);
-                    h = ho; w = wo;
-                    se_tiles = dw_num_tiles(h); se_hw = h * w;
-                    break;
-                }
-                case OP_SE:
-                    rc = launch_se_gate(buf[BUF_PARTIAL], se_tiles, se_hw, params + op.w, params + op.b, params + op.w2,
-                                        params + op.b2, buf[BUF_GATE], B, op.cin, op.se_reduce, st);
-                    break;
-                case OP_PW: {
-                    const int M = B * h * w;
-                    const float* gate = op.gated ? buf[BUF_GATE] : nullptr;
-                    if (e->gemm_mode == 0) {
-                        rc = launch_pointwise_ffma(ptr(op.in), params + op.w, derived + op.fold, derived + op.fold + op.cout,
-                                                   gate, ptr(op.res), ptr(op.out), M, op.cout, op.cin, h * w, op.act, st);
-                    } else {
-                        rc = launch_pointwise_tcgen05(ptr(op.in), derived + op.w_split, derived + op.fold,
-                                                      derived + op.fold + op.cout, gate, ptr(op.res), ptr(op.out), M, op.cout,
-                                                      op.cin, h * w, op.act, e->gemm_mode == 1 ? 3 : 1, st);
+            const int passes = (calib && op.fold_idx >= 0) ? 2 : 1;
+            int ho = h, wo = w;
+            for (int pass = 0; pass < passes; ++pass) {
+                const bool raw = passes == 2 && pass == 0;
+                const float* scale = raw ? derived + e->ident : derived + op.fold;
+                const float* shift = raw ? derived + e->ident + e->max_c : derived + op.fold + op.cout;
+                const int act = raw ? ACT_NONE : op.act;
+                double p_bytes = 0, p_flops = 0;
+                if (e->profile) { rc = prof_mark(e, st); if (rc) return rc; }
+                switch (op.kind) {
+                    case OP_STEM: {
+                        int pt, pl;
+                        same_geometry(h, op.k, op.stride, &ho, &pt);
+                        same_geometry(w, op.k, op.stride, &wo, &pl);
+                        rc = launch_stem(ptr(op.in), params + op.w, scale, shift, ptr(op.out), B, h, w, ho, wo, pt, pl,
+                                         op.cout, act, st);
+                        p_bytes = 4.0 * B * (3.0 * h * w + (double)ho * wo * op.cout);
+                        p_flops = 2.0 * 27 * op.cout * (double)B * ho * wo;
+                        break;
                     }
-                    break;
+                    case OP_DW: {
+                        int pt, pl;
+                        same_geometry(h, op.k, op.stride, &ho, &pt);
+                        same_geometry(w, op.k, op.stride, &wo, &pl);
+                        rc = launch_depthwise(ptr(op.in), derived + op.dw_wt, scale, shift, ptr(op.out),
+                                              raw ? nullptr : buf[BUF_PARTIAL], B, h, w, op.cin, ho, wo, op.k, op.stride, pt,
+                                              pl, act, st);
+                        se_tiles = dw_num_tiles(ho); se_hw = ho * wo;
+                        p_bytes = 4.0 * B * op.cin * ((double)h * w + (double)ho * wo + se_tiles);
+                        p_flops = 2.0 * op.k * op.k * op.cin * (double)B * ho * wo;
+                        break;
+                    }
+                    case OP_SE:
+                        rc = launch_se_gate(buf[BUF_PARTIAL], se_tiles, se_hw, params + op.w, params + op.b, params + op.w2,
+                                            params + op.b2, buf[BUF_GATE], B, op.cin, op.se_reduce, st);
+                        p_bytes = 4.0 * (B * op.cin * (se_tiles + 1.0) + 2.0 * op.cin * op.se_reduce);
+                        p_flops = 4.0 * B * op.cin * op.se_reduce;
+                        break;
+                    case OP_PW: {
+                        const int M = B * h * w;
+                        const float* gate = op.gated ? buf[BUF_GATE] : nullptr;
+                        const float* res = raw ? nullptr : ptr(op.res);
+                        if (e->gemm_mode == 0 || raw) {
+                            rc = launch_pointwise_ffma(ptr(op.in), params + op.w, scale, shift, gate, res, ptr(op.out), M,
+                                                       op.cout, op.cin, h * w, act, st);
+                        } else {
+                            rc = launch_pointwise_tcgen05(ptr(op.in), derived + op.w_split, scale, shift, gate, res,
+                                                          ptr(op.out), M, op.cout, op.cin, h * w, act,
+                                                          e->gemm_mode == 1 ? 3 : 1, st);
+                        }
+                        p_bytes = 4.0 * ((double)M * op.cin + (double)M * op.cout * (res ? 2 : 1) + (double)op.cin * op.cout +
+                                         (gate ? (double)B * op.cin : 0.0));
+                        p_flops = 2.0 * M * (double)op.cin * op.cout;
+                        break;
+                    }
+                    case OP_SPATIAL_MEAN:
+                        rc = launch_spatial_mean(ptr(op.in), ptr(op.out), B, h * w, op.cin, st);
+                        p_bytes = 4.0 * B * op.cin * (h * w + 1.0);
+                        p_flops = (double)B * op.cin * h * w;
+                        break;
                 }
-                case OP_SPATIAL_MEAN:
-                    rc = launch_spatial_mean(ptr(op.in), ptr(op.out), B, h * w, op.cin, st);
-                    break;
+                if (rc) return rc;
+                ++launches;
+                if (e->profile) e->prof_recs.push_back({(int)op.kind, p_bytes, p_flops});
+                if (raw) {
+                    const FoldEntry& fe = e->folds[op.fold_idx];
+                    if (e->profile) { rc = prof_mark(e, st); if (rc) return rc; e->prof_recs.push_back({5, 0.0, 0.0}); }
+                    rc = launch_channel_stats(ptr(op.out), (int64_t)B * ho * wo, op.cout, calib + fe.mean, calib + fe.var, st);
+                    if (rc) return rc;
+                    rc = launch_bn_fold(&fe, 1, calib, nullptr, derived, st);
+                    if (rc) return rc;
+                    launches += 2;
+                }
             }
-            if (rc) return rc;
-            ++launches;
+            h = ho; w = wo;
         }
     }
+    if (e->profile) { rc = prof_mark(e, st); if (rc) return rc; e->prof_ends.push_back(e->prof_used - 1); }
     e->last_launches.store(launches);
     return ORBIT_OK;
+}
+
+static int check_forward_args(const orbit_engine* e, const float* params, const float* derived, const float* frames,
+                              int num_frames, int height, int width, const float* feats, const void* workspace) {
+    if (!e || !params || !derived || !frames || !feats || !workspace) return ORBIT_ERR_ARG;
+    if (num_frames < 0 || height <= 0 || width <= 0) return ORBIT_ERR_ARG;
+    if (!aligned16(frames) || !aligned16(feats) || !aligned16(params) || !aligned16(derived)) return ORBIT_ERR_UNSUPPORTED;
+    return ORBIT_OK;
+}
+
+extern "C" int orbit_engine_forward(const orbit_engine* e, const float* params, const float* derived, const float* frames,
+                                    int num_frames, int height, int width, float* feats, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+    const int rc = check_forward_args(e, params, derived, frames, num_frames, height, width, feats, workspace);
+    if (rc) return rc;
+    return run_plan(e, params, nullptr, const_cast<float*>(derived), frames, num_frames, height, width, feats, workspace,
+                    workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int orbit_engine_calibrate(const orbit_engine* e, float* params, float* derived, const float* frames,
+                                      int num_frames, int height, int width, float* feats, void* workspace,
+                                      int64_t workspace_bytes, void* stream) {
+    const int rc = check_forward_args(e, params, derived, frames, num_frames, height, width, feats, workspace);
+    if (rc) return rc;
+    if (num_frames < 2) return ORBIT_ERR_ARG;
+    return run_plan(e, params, params, derived, frames, num_frames, height, width, feats, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }

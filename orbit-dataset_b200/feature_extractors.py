@@ -69,12 +69,6 @@ class FeatureExtractor(nn.Module):
         self.reset_parameters(seed)
 
     # ---- parameter tree ------------------------------------------------------------------------
-    def _shape_of(self, name, numel):
-        leaf = name.rsplit('.', 1)[-1]
-        if any(name.endswith(s) for s in _SHAPES_4D):
-            return None  # resolved from neighbours below
-        return (numel,)
-
     def _build_tree(self):
         # 4-D conv shapes are recovered from the channel counts of the adjacent norm / bias entries.
         sizes = {n: k for n, k, _ in self._table}
@@ -138,22 +132,65 @@ class FeatureExtractor(nn.Module):
 
     @torch.no_grad()
     def reset_parameters(self, seed=0):
-        """Seeded stand-in for the reference's ``pretrained=True`` download (there is no network):
-        fan-out-scaled conv weights, identity norms. Real use loads a checkpoint with load_state_dict."""
+        """Seeded stand-in for the reference's ``pretrained=True`` download (there is no network).
+        Drawn for dynamical isometry so that a random deep net neither explodes nor collapses:
+        (semi-)orthogonal pointwise / dense / stem weights, depthwise = centre tap + small noise,
+        small squeeze-excite FCs, near-identity norms. Follow with ``calibrate_batchnorm`` (or load a
+        real checkpoint with ``load_state_dict``)."""
         g = torch.Generator().manual_seed(seed)
         for name, numel, offset in self._table:
             dst = self._blob[offset:offset + numel]
             leaf = name.rsplit('.', 1)[-1]
             shape = self._shapes[name]
-            if leaf == 'running_var' or (leaf == 'weight' and len(shape) == 1):
+            if leaf == 'running_var':
                 dst.fill_(1.0)
-            elif leaf in ('running_mean', 'bias'):
+            elif leaf == 'running_mean':
                 dst.zero_()
+            elif leaf == 'weight' and len(shape) == 1:
+                dst.copy_(1.0 + 0.1 * torch.randn(numel, generator=g))
+            elif leaf == 'bias':
+                dst.copy_((0.1 if name.rsplit('.', 2)[-2].startswith(('bn', 'norm')) else 0.05) *
+                          torch.randn(numel, generator=g))
+            elif len(shape) == 4 and shape[1] == 1:            # depthwise
+                k = shape[2]
+                w = torch.randn(shape, generator=g) * (0.2 / k)
+                w[:, 0, k // 2, k // 2] += 1.0
+                dst.copy_(w.flatten())
+            elif '.se.' in name:
+                dst.copy_(torch.randn(numel, generator=g) * (0.5 * shape[1] ** -0.5))
             else:
-                fan_out = shape[0] * (shape[2] * shape[3] if len(shape) == 4 else 1)
-                if len(shape) == 4 and shape[1] == 1:
-                    fan_out = shape[2] * shape[3]
-                dst.copy_(torch.randn(numel, generator=g) * (2.0 / fan_out) ** 0.5)
+                flat = torch.empty(shape[0], numel // shape[0])
+                nn.init.orthogonal_(flat, generator=g)
+                dst.copy_(flat.flatten())
+
+    @torch.no_grad()
+    def calibrate_batchnorm(self, frames: torch.Tensor) -> torch.Tensor:
+        """Sets every BatchNorm's running statistics to the batch statistics of ``frames`` [B,3,H,W]
+        (one native pass in which each layer normalises with this batch, i.e. train-mode BatchNorm with
+        momentum 1). Returns the features of that pass."""
+        lib = L.load()
+        L.require_cuda(frames, "frames")
+        frames = frames.contiguous().float()
+        n, _, h, w = frames.shape
+        old_chunk = self.get_option('chunk_frames')
+        self.set_option('chunk_frames', max(n, 2))
+        try:
+            self._prepared_key = None
+            self.prepare(None)
+            ws_bytes = lib.orbit_engine_workspace_bytes(self._engine, h, w)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
+            feats = torch.empty(n, self.output_size, dtype=torch.float32, device=frames.device)
+            L.check(lib.orbit_engine_calibrate(self._engine, L.ptr(self._blob), L.ptr(self._derived), L.ptr(frames), n, h, w,
+                                               L.ptr(feats), L.ptr(ws), ws.numel(), L.stream_ptr(frames.device)),
+                    "orbit_engine_calibrate")
+            L.count_launches(lib.orbit_engine_last_launches(self._engine))
+            for mod in self.modules():
+                if 'num_batches_tracked' in mod._buffers:
+                    mod._buffers['num_batches_tracked'].fill_(1)
+        finally:
+            self.set_option('chunk_frames', old_chunk)
+            self._prepared_key = None
+        return feats
 
     # ---- FiLM ----------------------------------------------------------------------------------
     def film_parameter_names(self):
@@ -175,6 +212,17 @@ class FeatureExtractor(nn.Module):
         v = C.c_int()
         L.check(L.load().orbit_engine_get_option(self._engine, key.encode(), C.byref(v)), f"get_option({key})")
         return v.value
+
+    PROFILE_FAMILIES = ('stem_conv', 'depthwise_conv', 'se_gate', 'pointwise_gemm', 'spatial_mean', 'calibration')
+
+    def profile_read(self):
+        """{family: dict(ms, launches, bytes, flops)} of the launches timed since the last read
+        (needs set_option('profile', 1)); blocks until they have finished."""
+        n = len(self.PROFILE_FAMILIES)
+        ms, la, by, fl = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_double * n)(), (C.c_double * n)()
+        L.check(L.load().orbit_engine_profile_read(self._engine, ms, la, by, fl), "orbit_engine_profile_read")
+        return {name: dict(ms=ms[i], launches=la[i], bytes=by[i], flops=fl[i])
+                for i, name in enumerate(self.PROFILE_FAMILIES)}
 
     def prepare(self, film_blob=None):
         """Folds norms (+ FiLM gamma'/beta'), re-lays-out weights. Cheap; re-run when params/film change."""

@@ -68,3 +68,16 @@ def make_episode(spec: EpisodeSpec, index: int = 0, seed: int = 1991, pin: bool 
     ctx += bank[ctx_labels][:, None]
     tgt += bank[tgt_labels][:, None]
     return ctx, ctx_labels, tgt, tgt_labels
+
+
+def load_synthetic_checkpoint(model, frame_size: int = 224, seed: int = 1991):
+    """Gives a recogniser that is already on its CUDA device a synthetic 'pretrained' extractor: seeded
+    isometric weights (FeatureExtractor.reset_parameters) + BatchNorm statistics calibrated on device over
+    ``calibration_frames(frame_size)``. Deterministic, so every rank of a multi-GPU run gets the same weights."""
+    fe = model.feature_extractor
+    fe.reset_parameters(seed)          # CPU RNG, written into the (device-resident) parameter blob
+    fe.calibrate_batchnorm(calibration_frames(frame_size).to(fe._blob.device))
+    if getattr(model, 'adapt_features', False) and hasattr(model, 'film_generator'):
+        from .feature_extractors import get_film_parameters
+        model.film_generator.initial_film_parameters = get_film_parameters(model.film_parameter_names, fe)
+    return model

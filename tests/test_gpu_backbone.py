@@ -66,3 +66,38 @@ def test_episode_logits_and_argmax(cuda_device, oracle_effnet):
         assert torch.equal(am.cpu().long(), ref.argmax(dim=1))
         m._reset()
         assert m.classifier.weight is None
+
+
+def test_device_calibration_matches_oracle(cuda_device):
+    """orbit_engine_calibrate == one train-mode pass of the oracle with momentum 1 (batch statistics written
+    to running_mean/var); afterwards both sides hold the same checkpoint and give the same features."""
+    import orbit_b200
+    from oracle import backbones
+    from orbit_b200.synthetic import calibration_frames, load_synthetic_checkpoint
+    m = orbit_b200.SingleStepFewShotRecogniser('efficientnet_b0', False, 'proto', 1, 256, False, 16)
+    m._set_device(cuda_device)
+    m._send_to_device()
+    load_synthetic_checkpoint(m, 96, seed=5)
+    sd = {k[len('feature_extractor.'):]: v.cpu() for k, v in m.state_dict().items() if k.startswith('feature_extractor.')}
+    ref = backbones.build('efficientnet_b0')
+    # same weights, but let the ORACLE compute the batch statistics itself
+    ref.load_state_dict(sd, strict=True)
+    bns = [b for b in ref.modules() if isinstance(b, torch.nn.BatchNorm2d)]
+    for b in bns:
+        b.reset_running_stats()
+        b.momentum = 1.0
+    ref.train()
+    with torch.no_grad():
+        ref(calibration_frames(96))
+    ref.eval()
+    for (k, b) in [(k, b) for k, b in ref.named_modules() if isinstance(b, torch.nn.BatchNorm2d)]:
+        assert (b.running_mean - sd[k + '.running_mean']).abs().max() <= 1e-4 * (1 + sd[k + '.running_mean'].abs().max()), k
+        assert ((b.running_var - sd[k + '.running_var']).abs() / (sd[k + '.running_var'] + 1e-3)).max() <= 2e-3, k
+    x = torch.randn(4, 3, 96, 96, generator=torch.Generator().manual_seed(0))
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    with torch.no_grad():
+        want = ref(x)
+    got = m.feature_extractor(x.to(cuda_device)).cpu()
+    assert (got - want).abs().max() <= 2e-5 * max(1.0, want.abs().max().item())
+    assert want.abs().max() < 20 and want.std() > 1e-3      # well-conditioned synthetic checkpoint
