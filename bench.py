@@ -251,12 +251,13 @@ def main():
     value = world / (ms_per_step / 1e3)
 
     # ---- roofline of the dominant kernel family, timed live with CUDA events on the launch stream ----------
-    fe.set_option('profile', 1)
+    fe.set_option('profile', 1 if args.profile_steps else 0)
     torch.cuda.synchronize(dev)
     for i in range(args.profile_steps):
         step_device(i)
     prof = fe.profile_read()
     fe.set_option('profile', 0)
+    args.profile_steps = max(1, args.profile_steps)
     total_ms = sum(p['ms'] for p in prof.values()) or 1.0
     dom = max(prof, key=lambda k: prof[k]['ms'])
     peaks = {}
