@@ -79,6 +79,32 @@ int orbit_head_predict(const float* frame_feats, int num_clips, int clip_length,
                        const float* weight, const float* bias, int num_classes, int metric,
                        float logit_scale, float* logits, int32_t* argmax, void* stream);
 
+/* FineTuner inner loop in one launch. Replaces the num_grad_steps x batches loop of
+ * MultiStepFewShotRecogniser.personalise (few_shot_recognisers.py:231-246) for the default FineTuner (frozen
+ * extractor, so the clip features are loop-invariant): LinearClassifier.predict + cross_entropy (mean, each
+ * batch re-weighted by batch_len/N  ==  mean over all N clips) + torch.optim.Adam / SGD (utils/optim.py:8-32).
+ *   clip_feats [num_clips, feat_dim] pooled support features; class_index as in orbit_proto_configure
+ *   optimizer 0 = Adam(lr, betas, eps, weight_decay), 1 = SGD(lr, momentum, weight_decay)
+ *   weight [num_classes, feat_dim], bias [num_classes]: in = initial head (zeros, classifier_heads.py:59-60),
+ *   out = personalised head.  scratch >= orbit_linear_finetune_scratch_bytes().                        */
+int64_t orbit_linear_finetune_scratch_bytes(int num_clips, int feat_dim, int num_classes);
+int orbit_linear_finetune(const float* clip_feats, const int32_t* class_index, int num_clips, int feat_dim,
+                          int num_classes, int num_grad_steps, int optimizer, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, float momentum, float logit_scale, float* weight,
+                          float* bias, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Single layer entry point (what the engine runs for every conv_pw / conv_pwl / conv_head + BatchNormAct2d
+ * of the timm extractor, few_shot_recognisers.py:114-117): 1x1 convolution on NHWC activations as a GEMM,
+ *   out[M,N] = act( (A[M,K] * gate[m / rows_per_frame, k]) . W[N,K]^T * scale[n] + shift[n] ) (+ residual[M,N])
+ * act: 0 none, 1 SiLU, 2 ReLU.  gate / residual may be NULL.
+ * mode 0: fp32 FFMA tiles; mode 1: tcgen05 3xTF32 (fp32-grade); mode 2: tcgen05 single-pass TF32.
+ * w_split: scratch of 2*N*K floats (modes 1,2; receives the tf32 hi/lo split of W), may be NULL in mode 0.
+ * ---------------------------------------------------------------------------------------------- */
+int orbit_pointwise_conv(const float* A, const float* W, const float* scale, const float* shift,
+                         const float* gate, const float* residual, float* out, int M, int N, int K,
+                         int rows_per_frame, int act, int mode, float* w_split, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backbone engine: the feature extractor forward (reference: timm model called at
  * few_shot_recognisers.py:114-117,143-146, with FiLM by functional_call parameter substitution).

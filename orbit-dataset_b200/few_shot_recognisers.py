@@ -308,7 +308,7 @@ class MultiStepFewShotRecogniser(FewShotRecogniser):
         features = self._get_features_in_batches(context_clips, ops_counter=ops_counter)
         features = self._pool_features(features)
         finetune_linear_head(self.classifier, features, context_labels, self.batch_size, num_grad_steps,
-                             learning_rate, optimizer, learning_args, self.logit_scale)
+                             learning_rate, optimizer, dict(learning_args), self.logit_scale)
 
     def predict(self, clips, ops_counter=None):
         """few_shot_recognisers.py:248-258."""

@@ -101,3 +101,31 @@ def test_device_calibration_matches_oracle(cuda_device):
     got = m.feature_extractor(x.to(cuda_device)).cpu()
     assert (got - want).abs().max() <= 2e-5 * max(1.0, want.abs().max().item())
     assert want.abs().max() < 20 and want.std() > 1e-3      # well-conditioned synthetic checkpoint
+
+
+def test_finetuner_matches_oracle(cuda_device):
+    """MultiStepFewShotRecogniser.personalise (device-side Adam loop on the linear head) vs the oracle's
+    torch.optim.Adam loop, then predict(): logits within 1e-3, identical arg-max."""
+    import orbit_b200
+    from oracle.recogniser import OracleRecogniser
+    from orbit_b200.synthetic import EpisodeSpec, calibration_frames, make_episode
+    spec = EpisodeSpec(4, 3, 3, 1, 64)
+    oracle = OracleRecogniser('efficientnet_b0', False, 'linear', 1, 5, 1.0, 1991, calibration_frames(64))
+    ctx, ctx_y, tgt, _ = make_episode(spec, index=2)
+    m = orbit_b200.MultiStepFewShotRecogniser('efficientnet_b0', False, 'linear', 1, 5, False)
+    m.load_state_dict(oracle.state_dict(), strict=True)
+    m._set_device(cuda_device)
+    m._send_to_device()
+    for opt, lr, steps in (('adam', 0.1, 5), ('adam', 1e-3, 50), ('sgd', 0.5, 10)):
+        oracle.personalise_finetune(ctx, ctx_y, num_grad_steps=steps, learning_rate=lr, optimizer=opt, momentum=0.9)
+        ref = oracle.predict(tgt)
+        args = {'num_grad_steps': steps, 'learning_rate': lr, 'optimizer': opt, 'loss_fn': None,
+                'extractor_lr_scale': 0.1, 'epsilon': 1e-8, 'weight_decay': 0.0, 'betas': (0.9, 0.999), 'momentum': 0.9}
+        m.personalise(ctx, ctx_y, args)       # CPU clips + CPU labels, as multi-step-learner.py:147 passes them
+        logits = m.predict(tgt).cpu()
+        err_w = (m.classifier.weight.detach().cpu() - oracle.head[0]).abs().max().item()
+        err = (logits - ref).abs().max().item()
+        print(f"{opt} lr={lr} steps={steps}: max|dW|={err_w:.2e} max|dlogit|={err:.2e} max|logit|={ref.abs().max():.2f}")
+        assert err <= 1e-3 * max(1.0, ref.abs().max().item())
+        assert torch.equal(logits.argmax(1), ref.argmax(1))
+        m._reset()

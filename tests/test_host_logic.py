@@ -1,0 +1,89 @@
+"""CPU-only tests of the host-side mirror of the reference interface (no kernels run)."""
+import pytest
+import torch
+
+import orbit_b200
+from orbit_b200 import OrbitError
+
+
+def make(classifier='proto', adapt=False):
+    return orbit_b200.SingleStepFewShotRecogniser('efficientnet_b0', adapt, classifier, 2, 4, False, 16)
+
+
+def test_constructor_surface_and_errors():
+    m = make()
+    assert m.clip_length == 2 and m.batch_size == 4 and m.logit_scale == 1.0
+    assert m.classifier_name == 'proto' and m.film_parameter_names is None
+    assert m.film_generator.regularization_term() == 0
+    with pytest.raises(ValueError, match="Classifier bogus not valid"):
+        make('bogus')
+    with pytest.raises(ValueError, match="Invalid feature_extractor_name"):
+        orbit_b200.SingleStepFewShotRecogniser('resnet50', False, 'proto', 1, 1, False, 16)
+
+
+def test_no_cpu_fallback():
+    """The product must fail loudly off-GPU instead of silently computing on the CPU."""
+    m = make()
+    m.set_test_mode(True)
+    clips, labels = torch.zeros(4, 2, 3, 64, 64), torch.tensor([0, 0, 1, 1])
+    with pytest.raises(OrbitError, match="no CPU fallback"):
+        m.personalise(clips, labels)
+    with pytest.raises(OrbitError):
+        m.feature_extractor(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(OrbitError):
+        orbit_b200.PrototypicalClassifier().configure(torch.zeros(4, 8), labels)
+
+
+def test_predict_before_personalise_raises_attribute_error():
+    head = orbit_b200.PrototypicalClassifier()
+    with pytest.raises(AttributeError, match="is model personalised"):
+        head.predict(torch.zeros(2, 8))
+
+
+def test_state_dict_roundtrip_and_reset():
+    a, b = make(), make()
+    with torch.no_grad():
+        for p in a.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    b.load_state_dict(a.state_dict(), strict=True)
+    assert torch.equal(a.feature_extractor._blob, b.feature_extractor._blob)
+    assert all(not p.requires_grad for p in a.feature_extractor.parameters())   # learn_extractor=False freezes
+    a._reset()
+    assert a.film_dict is None and a.classifier.weight is None
+
+
+def test_batch_indices_and_frame_history():
+    from orbit_b200 import attach_frame_history, get_batch_indices
+    assert get_batch_indices(0, 10, 4) == (0, 4)
+    assert get_batch_indices(2, 10, 4) == (8, 10)
+    fr = torch.arange(5, dtype=torch.float32).reshape(5, 1, 1, 1)
+    h = attach_frame_history(fr, 3)
+    assert h.shape == (5, 3, 1, 1, 1)
+    assert h[:, :, 0, 0, 0].tolist() == [[0, 0, 0], [0, 0, 1], [0, 1, 2], [1, 2, 3], [2, 3, 4]]
+
+
+def test_class_index_follows_torch_unique_order():
+    from orbit_b200.classifier_heads import _class_index
+    labels = torch.tensor([107, 100, 114, 100, 107])
+    classes, idx = _class_index(labels)
+    assert classes.tolist() == torch.unique(labels).tolist() == [100, 107, 114]
+    assert idx.tolist() == [1, 0, 2, 0, 1]
+
+
+def test_multistep_pops_learning_args_like_the_reference():
+    m = orbit_b200.MultiStepFewShotRecogniser('efficientnet_b0', False, 'linear', 1, 4, False)
+    args = {'num_grad_steps': 2, 'learning_rate': 0.1, 'optimizer': 'adam', 'loss_fn': None, 'extractor_lr_scale': 0.1,
+            'epsilon': 1e-8}
+    with pytest.raises(OrbitError):     # CPU tensors are refused, but only after the dict was consumed
+        m.personalise(torch.zeros(2, 1, 3, 64, 64), torch.tensor([0, 1]), args)
+    assert 'num_grad_steps' not in args and 'epsilon' in args   # few_shot_recognisers.py:218-223 mutates the dict
+
+
+def test_synthetic_episode_shapes():
+    from orbit_b200.synthetic import S2, EpisodeSpec, make_episode
+    assert S2.way * S2.support_clips_per_class == 200 and S2.way * S2.query_clips_per_class == 80
+    ctx, cy, tgt, ty = make_episode(EpisodeSpec(5, 2, 3, 2, 32), index=4)
+    assert ctx.shape == (10, 2, 3, 32, 32) and tgt.shape == (15, 2, 3, 32, 32)
+    assert sorted(cy.tolist()) == [0, 0, 1, 1, 2, 2, 3, 3, 4, 4]
+    ctx2, *_ = make_episode(EpisodeSpec(5, 2, 3, 2, 32), index=4)
+    assert torch.equal(ctx, ctx2)
