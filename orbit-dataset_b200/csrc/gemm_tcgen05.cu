@@ -4,16 +4,16 @@
 // model/few_shot_recognisers.py:114-117,143-146 (88% of EfficientNet-B0's MACs); the
 // FiLM gamma'/beta' (model/film.py, feature_adapters.py:66-78) arrive folded into `scale`/`shift`.
 //
-// Design (one persistent CTA per SM, warp-specialised, 512 threads):
+// Design (one persistent CTA per SM, warp-specialised, 768 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B, zero OOB fill) of the fp32 A tile
 //               [128 rows x 32 k] and the weight tiles [BN x 32 k] (tf32 hi and lo parts) into a
 //               multi-stage shared-memory ring, completion on mbarriers.
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) with the
 //               accumulator in TMEM (double buffered, 2 x BN columns); tcgen05.commit frees ring slots.
-//   warps 12-15 A transform: multiply the landed tile by the squeeze-excite gate (per frame, per input
+//   warps 4-11  A transform: multiply the landed tile by the squeeze-excite gate (per frame, per input
 //               channel) and split it into tf32 hi / lo parts in shared memory (3xTF32: hi*hi + hi*lo + lo*hi
 //               gives fp32-grade products; the tensor core accumulates in fp32), then fence.proxy.async.
-//   warps 4-11  epilogue: tcgen05.ld the accumulator rows, apply folded BN/FiLM scale-shift, SiLU, residual,
+//   warps 12-23 epilogue: tcgen05.ld the accumulator rows, apply folded BN/FiLM scale-shift, SiLU, residual,
 //               and store fp32 rows (16-byte vector stores).
 // The kernel is HBM-bound by design (A read once, out written once); the tensor pipe has the headroom
 // for the three passes.
@@ -23,14 +23,20 @@
 
 namespace orbit {
 
+// fp32 -> tf32 (10-bit mantissa) with round-to-nearest, returned in an fp32 container
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
 __global__ void tf32_split_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float v = w[i];
-    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-    const float lo = v - hi;  // exact
+    const float hi = to_tf32(v);       // round-to-nearest tf32: |v - hi| <= 2^-12 |v|
     out[i] = hi;
-    out[n + i] = __uint_as_float(__float_as_uint(lo) & 0xffffe000u);
+    out[n + i] = to_tf32(v - hi);      // v - hi is exact in fp32; rounding it to tf32 leaves ~2^-23 |v|
 }
 
 int launch_tf32_split(const float* w, int64_t n, float* out, cudaStream_t st) {
@@ -45,11 +51,15 @@ constexpr int BM = 128;          // rows per tile (= UMMA M, one TMEM lane per r
 constexpr int BK = 32;           // fp32 elements per k-block = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction along K
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
-constexpr int NUM_THREADS = 512;
-constexpr int EPI_WARP0 = 4, NUM_EPI_WARPS = 8;
-constexpr int XF_WARP0 = 12, NUM_XF_WARPS = 4;
+// Warp roles. The hardware arbiter favours higher warp ids, so the epilogue (the role with real ALU work)
+// sits last; its first warp id must be a multiple of 4 (a warp reaches TMEM lanes 32*(warp%4)..+31).
+constexpr int XF_WARP0 = 4, NUM_XF_WARPS = 8;
+constexpr int EPI_WARP0 = 12, NUM_EPI_WARPS = 12, EPI_SPLIT = NUM_EPI_WARPS / 4;   // 4 lane groups x 3 column shares
+constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 768
 constexpr int MAX_STAGES = 8;
-constexpr int TMEM_COLS = 256;   // 2 accumulators x BN (<= 128) fp32 columns
+constexpr int TMEM_COLS = 512;   // main accumulator x2 + correction accumulator x2, BN (<= 128) fp32 columns each
+constexpr int SLAB_BYTES = 32 * 128;       // epilogue staging slab: 32 rows x 32 fp32, SWIZZLE_128B (1 or 2 per warp)
+constexpr int L2_PREFETCH_DISTANCE = 12;   // k-blocks (16 KB of A each) requested into L2 ahead of the smem ring
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -62,22 +72,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
+// Blocking wait with a hardware suspend-time hint: the warp sleeps inside try_wait until the phase completes
+// (or ~20 us pass) instead of burning issue slots in a polling loop. Bounded: a protocol bug must surface
+// as a trap (launch failure), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    long long t0 = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if ((spin & 1023u) == 1023u) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();   // ~2 s: deadlock => launch failure, not a hang
-        }
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+        if (spin > 400000u) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -85,6 +92,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -129,37 +147,45 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// x * sigmoid(x) with the SFU approximations (ex2.approx, rcp.approx): ~3e-7 relative error, 2 MUFU ops.
+// The accurate expf + IEEE division cost ~30 issue slots per output and made the epilogue the bottleneck.
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
 struct Params {
     const float* scale;
     const float* shift;
     const float* gate;       // [frames, K] or null
-    const float* residual;   // [M, N] or null
-    float* out;              // [M, N]
+    int has_residual;
     int M, N, K, rows_per_frame, act, passes;
     int BN, n_tiles, m_tiles, stages;
-    int b_tile_bytes;        // BN * 128 rounded up to 1024
+    int b_tile_bytes;        // BN * 128 (multiple of 2048)
+    int slabs_per_warp;      // 1 or 2 staging slabs per epilogue warp
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                  const __grid_constant__ CUtensorMap map_blo, const Params p) {
+                  const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
+                  const __grid_constant__ CUtensorMap map_res, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const bool split = p.passes == 3;
     const bool transform = split || p.gate != nullptr;
     const int a_bytes = A_TILE_BYTES * (split ? 2 : 1);
     const int stage_bytes = a_bytes + p.b_tile_bytes * (split ? 2 : 1);
-    auto stage_a_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
-    auto stage_a_lo = [&](int s) { return smem + (size_t)s * stage_bytes + A_TILE_BYTES; };
-    auto stage_b_hi = [&](int s) { return smem + (size_t)s * stage_bytes + a_bytes; };
-    auto stage_b_lo = [&](int s) { return smem + (size_t)s * stage_bytes + a_bytes + p.b_tile_bytes; };
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint8_t* staging = smem;                                  // [NUM_EPI_WARPS][slabs_per_warp][32 rows][128 B]
+    uint8_t* ring = smem + (size_t)NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES;
+    auto stage_a_hi = [&](int s) { return ring + (size_t)s * stage_bytes; };
+    auto stage_a_lo = [&](int s) { return ring + (size_t)s * stage_bytes + A_TILE_BYTES; };
+    auto stage_b_hi = [&](int s) { return ring + (size_t)s * stage_bytes + a_bytes; };
+    auto stage_b_lo = [&](int s) { return ring + (size_t)s * stage_bytes + a_bytes + p.b_tile_bytes; };
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;                      // [stages] TMA landed
     uint64_t* ready = bars + MAX_STAGES;        // [stages] transform done
     uint64_t* empty = bars + 2 * MAX_STAGES;    // [stages] MMAs that read the slot retired
     uint64_t* tmem_full = bars + 3 * MAX_STAGES;       // [2]
     uint64_t* tmem_empty = bars + 3 * MAX_STAGES + 2;  // [2]
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+    uint64_t* res_bar = bars + 3 * MAX_STAGES + 4;     // [NUM_EPI_WARPS] residual slab landed
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4 + NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = ceil_div(p.K, BK);
@@ -168,6 +194,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], NUM_XF_WARPS); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], NUM_EPI_WARPS); }
+        for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -179,16 +206,29 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    // TMEM columns: main accumulator of buffer a at a*BN, correction (hi*lo + lo*hi) accumulator at (2+a)*BN.
+    // Keeping the 2^-11-scaled correction terms out of the main accumulator cuts the number of (truncating)
+    // tensor-core accumulations into it by 3x.
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             uint32_t it = 0;
             const uint32_t tx = A_TILE_BYTES + (uint32_t)p.BN * BK * 4 * (split ? 2 : 1);
+            // L2 prefetch cursor: runs L2_PREFETCH_DISTANCE k-blocks ahead of the shared-memory ring, so that HBM
+            // latency is covered by requests that cost no shared memory (the ring only has to cover L2 latency).
+            int pf_tile = blockIdx.x, pf_kb = 0;
+            auto prefetch_next = [&]() {
+                if (pf_tile >= num_tiles) return;
+                tma_prefetch_l2_2d(&map_a, pf_kb * BK, (pf_tile / p.n_tiles) * BM);
+                if (++pf_kb == num_k) { pf_kb = 0; pf_tile += gridDim.x; }
+            };
+            for (int i = 0; i < L2_PREFETCH_DISTANCE; ++i) prefetch_next();
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const int s = it % p.stages;
+                    prefetch_next();
                     mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
                     mbar_expect_tx(&full[s], tx);
                     tma_load_2d(stage_a_hi(s), &map_a, &full[s], kb * BK, m0);
@@ -206,7 +246,8 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int acc = tcount & 1;
                 mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + (uint32_t)(acc * p.BN);
+                const uint32_t d_main = tmem_base + (uint32_t)(acc * p.BN);
+                const uint32_t d_corr = tmem_base + (uint32_t)((2 + acc) * p.BN);
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
@@ -222,52 +263,50 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per k step inside the swizzle row
                         const uint32_t first = (kb | k) ? 1u : 0u;
                         if (split) {
-                            umma_tf32(d_addr, a_lo + adv, b_hi + adv, idesc, first);
-                            umma_tf32(d_addr, a_hi + adv, b_lo + adv, idesc, 1u);
-                            umma_tf32(d_addr, a_hi + adv, b_hi + adv, idesc, 1u);
-                        } else {
-                            umma_tf32(d_addr, a_hi + adv, b_hi + adv, idesc, first);
+                            umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, first);
+                            umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
                         }
+                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, first);
                     }
                     umma_commit(&empty[s]);                       // slot reusable once these MMAs retire
-                    if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+                    if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulators complete
                 }
             }
         }
-    } else if (warp >= XF_WARP0) {
+    } else if (warp >= XF_WARP0 && warp < XF_WARP0 + NUM_XF_WARPS) {
         // ================================ A transform ================================
         if (transform) {
-            const int t = threadIdx.x - XF_WARP0 * 32;       // 0..127
+            const int t = threadIdx.x - XF_WARP0 * 32;       // 0..255
             const int pchunk = t & 7;                        // physical 16-byte chunk inside the 128-byte row
-            const int rbase = t >> 3;                        // rows rbase + 16*i
+            const int rbase = t >> 3;                        // rows rbase + 32*i
             const int jchunk = pchunk ^ (rbase & 7);         // logical chunk (SWIZZLE_128B: chunk ^= row & 7)
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / p.n_tiles) * BM;
+                int frame[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) frame[i] = min(m0 + rbase + 32 * i, p.M - 1) / p.rows_per_frame;
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const int s = it % p.stages;
+                    const int kcol = kb * BK + jchunk * 4;
+                    float4 g[4];
+                    const bool gated = p.gate != nullptr && kcol < p.K;
+                    if (gated) {                                 // issue the gate loads before blocking on the TMA
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) g[i] = ldg4(p.gate + (int64_t)frame[i] * p.K + kcol);
+                    }
                     mbar_wait(&full[s], (it / p.stages) & 1);
                     float4* hi = reinterpret_cast<float4*>(stage_a_hi(s));
                     float4* lo = reinterpret_cast<float4*>(stage_a_lo(s));
-                    const int kcol = kb * BK + jchunk * 4;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = rbase + 16 * i;
-                        const int idx = row * 8 + pchunk;
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = (rbase + 32 * i) * 8 + pchunk;
                         float4 v = hi[idx];
-                        if (p.gate && kcol < p.K) {
-                            const int m = min(m0 + row, p.M - 1);
-                            const float4 g = ldg4(p.gate + (int64_t)(m / p.rows_per_frame) * p.K + kcol);
-                            v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
-                        }
+                        if (gated) { v.x *= g[i].x; v.y *= g[i].y; v.z *= g[i].z; v.w *= g[i].w; }
                         if (split) {
-                            float4 h;
-                            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                            const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
                             hi[idx] = h;
-                            lo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                            lo[idx] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
                         } else {
                             hi[idx] = v;
                         }
@@ -280,46 +319,105 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else if (warp >= EPI_WARP0) {
         // ================================ epilogue ================================
-        const int ew = warp - EPI_WARP0;            // 0..7
+        // warp -> TMEM lane group (warp % 4) x column parity; 32 rows x 32 columns slabs go through a swizzled
+        // shared-memory staging buffer and leave with one TMA store (coalesced, clipped at the M / N edges);
+        // the residual slab arrives the same way.
+        const int ew = warp - EPI_WARP0;            // 0..11
         const int lane_grp = warp & 3;              // TMEM lanes 32*lane_grp .. +31 are accessible to this warp
-        const int col_half = ew >> 2;               // two warps share a lane group and split the columns
-        const int row_in_tile = lane_grp * 32 + lane;
-        uint32_t tcount = 0;
+        const int share = ew >> 2;                  // the EPI_SPLIT warps of a lane group share the tile's column slabs
+        const int nbuf = p.slabs_per_warp;
+        uint8_t* my_staging = staging + (size_t)ew * nbuf * SLAB_BYTES;
+        const int sw = lane & 7;
+        const int n_slabs = ceil_div(p.BN, 32);
+        uint32_t tcount = 0, res_phase = 0, slab_count = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int acc = tcount & 1;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
+            const int row0 = m0 + lane_grp * 32;
+            // slab sl belongs to share (sl + tile counter) % EPI_SPLIT: uneven slab counts even out over tiles
+            const int first_slab = (share + EPI_SPLIT - (int)(tcount % EPI_SPLIT)) % EPI_SPLIT;
+            bool res_issued = false;
+            auto slab_live = [&](int sl) { return row0 < p.M && n0 + sl * 32 < p.N; };
+            auto wait_staging_free = [&]() { if (nbuf == 2) tma_store_wait_read1(); else tma_store_wait_read0(); };
+            auto issue_residual = [&](int sl) {   // TMA-load the residual slab into the staging buffer it will be added in
+                float4* st = reinterpret_cast<float4*>(my_staging + (size_t)(slab_count % nbuf) * SLAB_BYTES);
+                if (lane == 0) {
+                    wait_staging_free();
+                    mbar_expect_tx(&res_bar[ew], SLAB_BYTES);
+                    tma_load_2d(st, &map_res, &res_bar[ew], n0 + sl * 32, row0);
+                }
+                __syncwarp();
+            };
+            if (p.has_residual && first_slab < n_slabs && slab_live(first_slab)) { issue_residual(first_slab); res_issued = true; }
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
             tc_fence_after();
-            const int64_t row = (int64_t)m0 + row_in_tile;
-            const int n_groups = p.BN / 16;
-            for (int g = col_half; g < n_groups; g += 2) {
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN + g * 16), v);
-                const int col = n0 + g * 16;
-                if (row < p.M) {
+            const uint32_t t_main = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN);
+            const uint32_t t_corr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((2 + acc) * p.BN);
+            for (int sl = first_slab; sl < n_slabs; sl += EPI_SPLIT) {
+                const int c0 = sl * 32;
+                const int width = min(32, p.BN - c0);          // 32, or 16 in the last slab of a single n-tile
+                const bool live = slab_live(sl);               // slab entirely outside the tensor: nothing to store
+                float4* stage = reinterpret_cast<float4*>(my_staging + (size_t)(slab_count % nbuf) * SLAB_BYTES);
+                if (live) {
+                    if (p.has_residual) {
+                        if (!res_issued) issue_residual(sl);
+                        res_issued = false;
+                        mbar_wait(&res_bar[ew], res_phase);
+                        res_phase ^= 1;
+                    } else {
+                        if (lane == 0) wait_staging_free();
+                        __syncwarp();
+                    }
+                }
+                const bool interior = n0 + c0 + 32 <= p.N;     // no column predicates needed
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                  // two 16-column halves of the slab
+                    if (h * 16 >= width) {
+                        if (live) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) stage[lane * 8 + ((h * 4 + q) ^ sw)] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        continue;
+                    }
+                    float v[16];
+                    tmem_ld16(t_main + c0 + h * 16, v);
+                    if (split) {
+                        float u[16];
+                        tmem_ld16(t_corr + c0 + h * 16, u);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += u[i];
+                    }
+                    if (!live) continue;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int c = col + q * 4;
-                        if (c < p.N) {
+                        const int c = n0 + c0 + h * 16 + q * 4;
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (interior || c < p.N) {
                             const float4 sc = ldg4(p.scale + c), sh = ldg4(p.shift + c);
-                            float4 o;
                             o.x = fmaf(v[q * 4 + 0], sc.x, sh.x); o.y = fmaf(v[q * 4 + 1], sc.y, sh.y);
                             o.z = fmaf(v[q * 4 + 2], sc.z, sh.z); o.w = fmaf(v[q * 4 + 3], sc.w, sh.w);
-                            if (p.act == 1) { o.x = siluf_(o.x); o.y = siluf_(o.y); o.z = siluf_(o.z); o.w = siluf_(o.w); }
+                            if (p.act == 1) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
                             else if (p.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                            if (p.residual) {
-                                const float4 r = ldg4_stream(p.residual + row * p.N + c);
+                            if (p.has_residual) {
+                                const float4 r = stage[lane * 8 + ((h * 4 + q) ^ sw)];
                                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                             }
-                            *reinterpret_cast<float4*>(p.out + row * p.N + c) = o;
                         }
+                        stage[lane * 8 + ((h * 4 + q) ^ sw)] = o;
                     }
+                }
+                if (live) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&map_out, stage, n0 + c0, row0);
+                    ++slab_count;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -370,25 +468,33 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     if (K % 4 || N % 4 || (passes != 1 && passes != 3)) return ORBIT_ERR_UNSUPPORTED;
     if (M <= 0) return ORBIT_OK;
     Params p;
-    p.scale = scale; p.shift = shift; p.gate = gate; p.residual = residual; p.out = out;
+    p.scale = scale; p.shift = shift; p.gate = gate; p.has_residual = residual != nullptr;
     p.M = M; p.N = N; p.K = K; p.rows_per_frame = rows_per_frame; p.act = act; p.passes = passes;
+    // n-tiles of at most 128 columns; with several n-tiles BN must be a multiple of the 32-column store slab
     p.n_tiles = ceil_div(N, 128);
-    p.BN = ceil_div(ceil_div(N, p.n_tiles), 16) * 16;
+    p.BN = p.n_tiles > 1 ? ceil_div(ceil_div(N, p.n_tiles), 32) * 32 : ceil_div(N, 16) * 16;
     p.m_tiles = ceil_div(M, BM);
-    p.b_tile_bytes = ceil_div(p.BN * BK * 4, 1024) * 1024;
+    p.b_tile_bytes = p.BN * BK * 4;
     const int stage_bytes = (A_TILE_BYTES + p.b_tile_bytes) * (passes == 3 ? 2 : 1);
-    const int bar_bytes = (3 * MAX_STAGES + 4) * 8 + 16;
+    const int bar_bytes = (3 * MAX_STAGES + 4 + NUM_EPI_WARPS) * 8 + 16;
     const int budget = 227 * 1024 - 1024 /*alignment slack*/ - bar_bytes;
-    p.stages = std::min(MAX_STAGES, budget / stage_bytes);
+    // double-buffered epilogue staging when that still leaves a 4-deep operand ring
+    p.slabs_per_warp = (budget - 2 * NUM_EPI_WARPS * SLAB_BYTES) / stage_bytes >= 4 ? 2 : 1;
+    const int staging_bytes = NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES;
+    p.stages = std::min(MAX_STAGES, (budget - staging_bytes) / stage_bytes);
     if (p.stages < 2) return ORBIT_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)p.stages * stage_bytes + bar_bytes + 1024;
+    const size_t smem = (size_t)staging_bytes + (size_t)p.stages * stage_bytes + bar_bytes + 1024;
 
-    CUtensorMap map_a, map_bhi, map_blo;
+    CUtensorMap map_a, map_bhi, map_blo, map_out, map_res;
     int rc = make_map(&map_a, A, M, K, BM);
     if (rc) return rc;
     rc = make_map(&map_bhi, w_split, N, K, p.BN);
     if (rc) return rc;
     rc = make_map(&map_blo, w_split + (int64_t)N * K, N, K, p.BN);
+    if (rc) return rc;
+    rc = make_map(&map_out, out, M, N, 32);
+    if (rc) return rc;
+    rc = make_map(&map_res, residual ? residual : out, M, N, 32);
     if (rc) return rc;
 
     static int num_sms = 0;
@@ -399,7 +505,7 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
         ORBIT_CUDA(cudaFuncSetAttribute(pw_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     const int grid = std::min(p.m_tiles * p.n_tiles, num_sms);
-    pw_tcgen05_kernel<<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+    pw_tcgen05_kernel<<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_out, map_res, p);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }

@@ -5,7 +5,7 @@
 
 namespace orbit {
 
-// w [n] fp32 -> out [2][n]: hi = w with the low 13 mantissa bits cleared (exactly tf32), lo = tf32(w - hi)
+// w [n] fp32 -> out [2][n]: hi = tf32(w) (round to nearest), lo = tf32(w - hi)
 int launch_tf32_split(const float* w, int64_t n, float* out, cudaStream_t st);
 
 // out[M,N] = act((A[M,K] (*gate)) W[N,K]^T * scale + shift) (+ residual); w_split = [hi | lo] from launch_tf32_split.

@@ -17,7 +17,7 @@ def _product(oracle, cuda_device, clip_length=2):
 
 
 @pytest.mark.parametrize("size,n", [(224, 5), (84, 7), (64, 3), (96, 33)])
-@pytest.mark.parametrize("gemm", [0])
+@pytest.mark.parametrize("gemm", [0, 1])
 def test_efficientnet_features_match_oracle(cuda_device, oracle_effnet, size, n, gemm):
     m = _product(oracle_effnet, cuda_device)
     m.feature_extractor.set_option('gemm', gemm)
@@ -30,7 +30,7 @@ def test_efficientnet_features_match_oracle(cuda_device, oracle_effnet, size, n,
     scale = ref.abs().max().item()
     print(f"size={size} n={n} max|err|={err:.3e} max|ref|={scale:.3f}")
     assert out.shape == ref.shape
-    assert err <= 2e-5 * max(1.0, scale)
+    assert err <= (2e-5 if gemm == 0 else 5e-5) * max(1.0, scale)
 
 
 def test_chunking_is_invisible(cuda_device, oracle_effnet):
@@ -56,12 +56,13 @@ def test_episode_logits_and_argmax(cuda_device, oracle_effnet):
 
     m = _product(oracle_effnet, cuda_device)
     m.stage_slice_frames = 8
-    for clips_dev in (False, True):
+    for clips_dev, gemm in ((False, 0), (True, 0), (True, 1), (False, 1)):
+        m.feature_extractor.set_option('gemm', gemm)
         c, t = (ctx.to(cuda_device), tgt.to(cuda_device)) if clips_dev else (ctx, tgt)
         m.personalise(c, ctx_y.to(cuda_device))
         logits, am = m.predict(t, want_argmax=True)
         err = (logits.cpu() - ref).abs().max().item()
-        print(f"device_clips={clips_dev} max|dlogit|={err:.3e} max|logit|={ref.abs().max().item():.2f}")
+        print(f"device_clips={clips_dev} gemm={gemm} max|dlogit|={err:.3e} max|logit|={ref.abs().max().item():.2f}")
         assert err <= 1e-3
         assert torch.equal(am.cpu().long(), ref.argmax(dim=1))
         m._reset()
