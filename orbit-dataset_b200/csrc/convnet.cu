@@ -175,109 +175,176 @@ int launch_stem(const float* x, const float* w, const float* scale, const float*
 }
 
 // ------------------------------------------------------------------------------------------------
-// Depthwise KxK conv + folded BN/FiLM + activation, NHWC. A thread owns 4 channels (one 128-bit
-// lane) and a strip of TW output pixels along x; neighbouring taps are reused from registers.
-// grid (tiles, channel chunks, frames); block = LX lanes x LY strips.
-// Epilogue: the activated outputs are summed per (frame, tile, channel) for the SE squeeze with a
+// Depthwise KxK conv + folded BN/FiLM + activation, NHWC, HBM-bound.
+// A thread owns 4 channels (one 128-bit lane) and a strip of TW=4 output columns, and WALKS DOWN the rows of
+// its tile with rolling accumulators: every input row is loaded once (SPAN 128-bit loads), and scattered into
+// the R = ceil(K/S) output rows it contributes to, which live in registers; an output row is written when its
+// last input row has been consumed. Loads per output drop from K*SPAN/TW (row-at-a-time) to SPAN/TW.
+// Everything about the ring (which slot a (row phase, ky) pair hits, which slot completes) is resolved at
+// compile time by unrolling over the P = R*S row phases.
+// grid (tiles * strip_blocks, channel chunks, frames); block = LX lanes x LY strips.
+// Epilogue: the activated outputs are summed per (frame, block, channel) for the SE squeeze with a
 // fixed-order shared-memory reduction (deterministic; no atomics).
 // ------------------------------------------------------------------------------------------------
 constexpr int kDwTW = 4;
 
-template <int K, int S>
-__global__ void __launch_bounds__(256)
+__host__ __device__ constexpr int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+__host__ __device__ constexpr int floor_mod(int a, int b) { return a - floor_div(a, b) * b; }
+
+struct DwPlan {
+    int VEC, LX, LY, nchunks, tiles, rows_per_tile, strip_blocks, groups;
+};
+
+// K=3: 4 channels per thread (128-bit accesses); K=5: 2 channels per thread (64-bit) so that the 25 taps,
+// the rolling accumulators and the streamed row all stay in registers (~110) without spilling.
+static DwPlan dw_plan(int C, int Ho, int Wo, int k, int stride) {
+    DwPlan p;
+    p.VEC = k == 3 ? 4 : 2;
+    const int Cv = C / p.VEC;
+    p.nchunks = ceil_div(Cv, 32);
+    p.LX = ceil_div(Cv, p.nchunks);
+    const int strips = ceil_div(Wo, kDwTW);
+    p.LY = std::max(1, std::min(256 / p.LX, strips));
+    p.strip_blocks = ceil_div(strips, p.LY);
+    const int R = ceil_div(k, stride);
+    const int want_tiles = std::min(ceil_div(Ho, R), Ho >= 56 ? 4 : (Ho >= 14 ? 2 : 1));
+    p.rows_per_tile = ceil_div(ceil_div(Ho, want_tiles), R) * R;   // multiple of R: tiles start on a ring boundary
+    p.tiles = ceil_div(Ho, p.rows_per_tile);
+    p.groups = p.tiles * p.strip_blocks;
+    return p;
+}
+
+int dw_partial_groups(int C, int Ho, int Wo, int k, int stride) { return dw_plan(C, Ho, Wo, k, stride).groups; }
+
+template <int VEC> struct VecIO;
+template <> struct VecIO<4> {
+    static __device__ __forceinline__ void load(const float* p, float* v) { const float4 t = ldg4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct VecIO<2> {
+    static __device__ __forceinline__ void load(const float* p, float* v) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
+    static __device__ __forceinline__ void store(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+
+template <int K, int S, int VEC>
+__global__ void __launch_bounds__(256, 2)
 dw_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
           const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C,
-          int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile) {
-    extern __shared__ __align__(16) float4 s_dw[];  // weights [K*K][LX] then reduction [LY][LX]
-    float4* s_w = s_dw;
-    float4* s_red = s_dw + K * K * LX;
-    const int tile = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z, tiles = gridDim.x;
+          int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile, int strip_blocks) {
+    constexpr int TW = kDwTW, R = (K + S - 1) / S, P = R * S, SPAN = (TW - 1) * S + K;
+    extern __shared__ __align__(16) float s_red[];  // [LY][LX][VEC] partial-sum reduction
+    const int tile = blockIdx.x / strip_blocks, sb = blockIdx.x % strip_blocks, chunk = blockIdx.y, b = blockIdx.z;
+    const int groups = gridDim.x;
     const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
-    const int C4 = C >> 2;
-    const int c4 = chunk * LX + lx;
-    const bool live = c4 < C4;
-    for (int i = threadIdx.x; i < K * K * LX; i += blockDim.x) {
-        const int t = i / LX, cc = chunk * LX + (i % LX);
-        s_w[i] = cc < C4 ? ldg4(wt + (int64_t)t * C + cc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc, sum = sc;
-    if (live) { sc = ldg4(scale + c4 * 4); sh = ldg4(shift + c4 * 4); }
+    const int Cv = C / VEC;
+    const int cv = chunk * LX + lx;
+    const int strip = sb * LY + ly;
+    const bool live = cv < Cv && strip * TW < Wo;
+    float sum[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) sum[e] = 0.f;
     const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
-    const int strips_per_row = ceil_div(Wo, kDwTW);
-    const int nstrips = (row1 - row0) * strips_per_row;
-    constexpr int SPAN = (kDwTW - 1) * S + K;
-    if (live) {
-        const float* xb = x + (int64_t)b * H * W * C + c4 * 4;
-        float* yb = y + (int64_t)b * Ho * Wo * C + c4 * 4;
-        for (int s = ly; s < nstrips; s += LY) {
-            const int oy = row0 + s / strips_per_row, ox0 = (s % strips_per_row) * kDwTW;
-            float4 o[kDwTW];
+    if (live && row0 < row1) {
+        float wreg[K * K][VEC], sc[VEC], sh[VEC];
 #pragma unroll
-            for (int t = 0; t < kDwTW; ++t) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < K * K; ++t) VecIO<VEC>::load(wt + (int64_t)t * C + cv * VEC, wreg[t]);
+        VecIO<VEC>::load(scale + cv * VEC, sc);
+        VecIO<VEC>::load(shift + cv * VEC, sh);
+        const float* xb = x + (int64_t)b * H * W * C + cv * VEC;
+        float* yb = y + (int64_t)b * Ho * Wo * C + cv * VEC;
+        const int ox0 = strip * TW, ixb = ox0 * S - pad_l;
+        float acc[R][TW][VEC];
 #pragma unroll
-            for (int ky = 0; ky < K; ++ky) {
-                const int iy = oy * S - pad_t + ky;
-                if (iy < 0 || iy >= H) continue;
-                const float* rowp = xb + (int64_t)iy * W * C;
-                const int ixb = ox0 * S - pad_l;
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-                for (int j = 0; j < SPAN; ++j) {
-                    const int ix = ixb + j;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ix >= 0 && ix < W) v = ldg4(rowp + (int64_t)ix * C);
+            for (int t = 0; t < TW; ++t)
 #pragma unroll
-                    for (int t = 0; t < kDwTW; ++t) {
-                        const int kx = j - t * S;
-                        if (kx >= 0 && kx < K) fma4(o[t], v, s_w[(ky * K + kx) * LX + lx]);
+                for (int e = 0; e < VEC; ++e) acc[r][t][e] = 0.f;
+        const int vy_last = (row1 - 1) * S + K - 1;     // virtual row vy = input row + pad_t = oy*S + ky
+        for (int vyb = row0 * S; vyb <= vy_last; vyb += P) {
+#pragma unroll
+            for (int ph = 0; ph < P; ++ph) {
+                const int vy = vyb + ph;
+                if (vy > vy_last) break;
+                const int iy = vy - pad_t;
+                if (iy >= 0 && iy < H) {
+                    const float* rowp = xb + (int64_t)iy * W * C;
+#pragma unroll
+                    for (int j = 0; j < SPAN; ++j) {
+                        const int ix = ixb + j;
+                        float v[VEC];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) v[e] = 0.f;
+                        if (ix >= 0 && ix < W) VecIO<VEC>::load(rowp + (int64_t)ix * C, v);
+#pragma unroll
+                        for (int ky = 0; ky < K; ++ky) {
+                            if (floor_mod(ph - ky, S) != 0) continue;                  // compile-time after unrolling
+                            const int slot = floor_mod(floor_div(ph - ky, S), R);     // compile-time
+#pragma unroll
+                            for (int t = 0; t < TW; ++t) {
+                                const int kx = j - t * S;
+                                if (kx >= 0 && kx < K) {
+#pragma unroll
+                                    for (int e = 0; e < VEC; ++e) acc[slot][t][e] = fmaf(v[e], wreg[ky * K + kx][e], acc[slot][t][e]);
+                                }
+                            }
+                        }
                     }
                 }
-            }
+                if (floor_mod(ph - (K - 1), S) == 0) {   // an output row has now seen all K of its input rows
+                    const int rel = floor_div(ph - (K - 1), S);
+                    const int slot = floor_mod(rel, R);
+                    const int oy = vyb / S + rel;
+                    if (oy >= row0 && oy < row1) {
 #pragma unroll
-            for (int t = 0; t < kDwTW; ++t) {
-                if (ox0 + t < Wo) {
-                    float4 r;
-                    r.x = apply_act(fmaf(o[t].x, sc.x, sh.x), act); r.y = apply_act(fmaf(o[t].y, sc.y, sh.y), act);
-                    r.z = apply_act(fmaf(o[t].z, sc.z, sh.z), act); r.w = apply_act(fmaf(o[t].w, sc.w, sh.w), act);
-                    *reinterpret_cast<float4*>(yb + ((int64_t)oy * Wo + ox0 + t) * C) = r;
-                    add4(sum, r);
+                        for (int t = 0; t < TW; ++t) {
+                            if (ox0 + t < Wo) {
+                                float r[VEC];
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) { r[e] = apply_act(fmaf(acc[slot][t][e], sc[e], sh[e]), act); sum[e] += r[e]; }
+                                VecIO<VEC>::store(yb + ((int64_t)oy * Wo + ox0 + t) * C, r);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < TW; ++t)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[slot][t][e] = 0.f;
                 }
             }
         }
     }
     if (partial) {
-        s_red[ly * LX + lx] = sum;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s_red[(ly * LX + lx) * VEC + e] = sum[e];
         __syncthreads();
-        if (ly == 0 && live) {
-            float4 t = s_red[lx];
-            for (int r = 1; r < LY; ++r) add4(t, s_red[r * LX + lx]);
-            *reinterpret_cast<float4*>(partial + ((int64_t)b * tiles + tile) * C + c4 * 4) = t;
+        if (ly == 0 && cv < Cv) {
+            float t[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) t[e] = s_red[lx * VEC + e];
+            for (int r = 1; r < LY; ++r)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) t[e] += s_red[(r * LX + lx) * VEC + e];
+            VecIO<VEC>::store(partial + ((int64_t)b * groups + blockIdx.x) * C + cv * VEC, t);
         }
     }
 }
-
-int dw_num_tiles(int Ho) { return std::min(Ho, 8); }
 
 int launch_depthwise(const float* x, const float* wt, const float* scale, const float* shift, float* y, float* partial,
                      int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, int act,
                      cudaStream_t st) {
     if (C % 4) return ORBIT_ERR_UNSUPPORTED;
-    const int C4 = C / 4;
-    const int nchunks = ceil_div(C4, 32);
-    const int LX = ceil_div(C4, nchunks);
-    const int LY = std::max(1, 256 / LX);
-    const int tiles = dw_num_tiles(Ho);
-    const int rows_per_tile = ceil_div(Ho, tiles);
-    dim3 grid(tiles, nchunks, B), block(LX * LY);
-    const size_t smem = sizeof(float4) * ((size_t)k * k * LX + (size_t)LY * LX);
-#define ORBIT_DW_CASE(KK, SS)                                                                                         \
+    const DwPlan pl = dw_plan(C, Ho, Wo, k, stride);
+    dim3 grid(pl.groups, pl.nchunks, B), block(pl.LX * pl.LY);
+    const size_t smem = sizeof(float) * (size_t)pl.LY * pl.LX * pl.VEC;
+#define ORBIT_DW_CASE(KK, SS, VV)                                                                                     \
     if (k == KK && stride == SS) {                                                                                    \
-        dw_kernel<KK, SS><<<grid, block, smem, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t, pad_l,  \
-                                                    act, LX, LY, rows_per_tile);                                      \
+        dw_kernel<KK, SS, VV><<<grid, block, smem, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t,     \
+                                                        pad_l, act, pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks); \
         ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                              \
         return ORBIT_OK;                                                                                              \
     }
-    ORBIT_DW_CASE(3, 1) ORBIT_DW_CASE(3, 2) ORBIT_DW_CASE(5, 1) ORBIT_DW_CASE(5, 2)
+    ORBIT_DW_CASE(3, 1, 4) ORBIT_DW_CASE(3, 2, 4) ORBIT_DW_CASE(5, 1, 2) ORBIT_DW_CASE(5, 2, 2)
 #undef ORBIT_DW_CASE
     return ORBIT_ERR_UNSUPPORTED;
 }

@@ -32,8 +32,8 @@ int launch_stem(const float* x, const float* w, const float* scale, const float*
                 int Ho, int Wo, int pad_t, int pad_l, int cout, int act, cudaStream_t st);
 
 // depthwise kxk: x [B,H,W,C] -> y [B,Ho,Wo,C]; wt is [k*k][C]; also writes per-(frame,tile,channel) sums
-// of the activated output into partial [B][tiles][C] (deterministic SE squeeze); returns tiles via *tiles_out
-int dw_num_tiles(int Ho);
+// of the activated output into partial [B][groups][C] (deterministic SE squeeze), groups = dw_partial_groups(...)
+int dw_partial_groups(int C, int Ho, int Wo, int k, int stride);
 int launch_depthwise(const float* x, const float* wt, const float* scale, const float* shift, float* y, float* partial,
                      int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, int act,
                      cudaStream_t st);

@@ -203,7 +203,7 @@ static int plan_buffers(const orbit_engine* e, int H, int W, BufSizes* bs) {
                 h = ho; w = wo;
                 if (h < 1 || w < 1) return ORBIT_ERR_UNSUPPORTED;
                 need(op.out, (int64_t)h * w * op.cout);
-                if (op.kind == OP_DW) need(BUF_PARTIAL, (int64_t)dw_num_tiles(h) * op.cout);
+                if (op.kind == OP_DW) need(BUF_PARTIAL, (int64_t)dw_partial_groups(op.cout, h, w, op.k, op.stride) * op.cout);
                 break;
             }
             case OP_SE: need(BUF_GATE, op.cout); break;
@@ -390,7 +390,7 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                         rc = launch_depthwise(ptr(op.in), derived + op.dw_wt, scale, shift, ptr(op.out),
                                               raw ? nullptr : buf[BUF_PARTIAL], B, h, w, op.cin, ho, wo, op.k, op.stride, pt,
                                               pl, act, st);
-                        se_tiles = dw_num_tiles(ho); se_hw = ho * wo;
+                        se_tiles = dw_partial_groups(op.cin, ho, wo, op.k, op.stride); se_hw = ho * wo;
                         p_bytes = 4.0 * B * op.cin * ((double)h * w + (double)ho * wo + se_tiles);
                         p_flops = 2.0 * op.k * op.k * op.cin * (double)B * ho * wo;
                         break;

@@ -57,7 +57,7 @@ constexpr int XF_WARP0 = 4, NUM_XF_WARPS = 8;
 constexpr int EPI_WARP0 = 12, NUM_EPI_WARPS = 12, EPI_SPLIT = NUM_EPI_WARPS / 4;   // 4 lane groups x 3 column shares
 constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 768
 constexpr int MAX_STAGES = 8;
-constexpr int TMEM_COLS = 512;   // main accumulator x2 + correction accumulator x2, BN (<= 128) fp32 columns each
+constexpr int TMEM_COLS = 512;   // main accumulator x2 + correction accumulator x2, BN (<= 96) fp32 columns each
 constexpr int SLAB_BYTES = 32 * 128;       // epilogue staging slab: 32 rows x 32 fp32, SWIZZLE_128B (1 or 2 per warp)
 constexpr int L2_PREFETCH_DISTANCE = 12;   // k-blocks (16 KB of A each) requested into L2 ahead of the smem ring
 
@@ -147,6 +147,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {   // no wait: pair with tmem_ld_wait()
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // x * sigmoid(x) with the SFU approximations (ex2.approx, rcp.approx): ~3e-7 relative error, 2 MUFU ops.
 // The accurate expf + IEEE division cost ~30 issue slots per output and made the epilogue the bottleneck.
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
@@ -182,10 +194,12 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t* full = bars;                      // [stages] TMA landed
     uint64_t* ready = bars + MAX_STAGES;        // [stages] transform done
     uint64_t* empty = bars + 2 * MAX_STAGES;    // [stages] MMAs that read the slot retired
-    uint64_t* tmem_full = bars + 3 * MAX_STAGES;       // [2]
-    uint64_t* tmem_empty = bars + 3 * MAX_STAGES + 2;  // [2]
-    uint64_t* res_bar = bars + 3 * MAX_STAGES + 4;     // [NUM_EPI_WARPS] residual slab landed
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4 + NUM_EPI_WARPS);
+    uint64_t* tmem_full = bars + 3 * MAX_STAGES;       // [2] correction accumulator of a tile complete
+    uint64_t* tmem_empty = bars + 3 * MAX_STAGES + 2;  // [2] ... drained by the epilogue
+    uint64_t* main_full = bars + 3 * MAX_STAGES + 4;   // [2] main accumulator of one k-block complete
+    uint64_t* main_empty = bars + 3 * MAX_STAGES + 6;  // [2] ... added into the epilogue's registers
+    uint64_t* res_bar = bars + 3 * MAX_STAGES + 8;     // [NUM_EPI_WARPS] residual slab landed
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 8 + NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = ceil_div(p.K, BK);
@@ -193,7 +207,10 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], NUM_XF_WARPS); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], NUM_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], NUM_EPI_WARPS);
+            mbar_init(&main_full[a], 1); mbar_init(&main_empty[a], NUM_EPI_WARPS);
+        }
         for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
@@ -206,10 +223,17 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
-    // TMEM columns: main accumulator of buffer a at a*BN, correction (hi*lo + lo*hi) accumulator at (2+a)*BN.
-    // Keeping the 2^-11-scaled correction terms out of the main accumulator cuts the number of (truncating)
-    // tensor-core accumulations into it by 3x.
+    // TMEM columns: main accumulators (hi*hi) at {0,1}*BN, correction accumulators (hi*lo + lo*hi) at {2,3}*BN.
+    // The tensor core adds into its fp32 accumulator with TRUNCATION (measured: -0.45 ulp per accumulation, a
+    // systematic bias that grows with K and compounds over the network's ~33 GEMM layers). So the main accumulator
+    // only ever holds ONE k-block (4 MMAs): the epilogue warps add it into fp32 registers with round-to-nearest
+    // every k-block (double-buffered against the MMAs), and the 2^-11-scaled correction terms -- whose truncation
+    // error is negligible -- accumulate over the whole tile in their own accumulator.
 
+    // Register budget: 768 threads x 80 at launch. The control and transform warps need few registers; the
+    // epilogue warps keep up to 64 running sums per thread. (setmaxnreg works on aligned groups of 4 warps.)
+    if (warp < XF_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
@@ -241,19 +265,20 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(BM, p.BN);
-            uint32_t it = 0, tcount = 0;
+            uint32_t it = 0, tcount = 0;        // it = global k-block counter (ring slot AND main-accumulator parity)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
                 const int acc = tcount & 1;
-                mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_main = tmem_base + (uint32_t)(acc * p.BN);
+                if (split) mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
                 const uint32_t d_corr = tmem_base + (uint32_t)((2 + acc) * p.BN);
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
+                    const int mb = it & 1;
+                    mbar_wait(&main_empty[mb], ((it >> 1) & 1) ^ 1);
                     mbar_wait(&full[s], ph);
                     if (transform) mbar_wait(&ready[s], ph);
                     tc_fence_after();
+                    const uint32_t d_main = tmem_base + (uint32_t)(mb * p.BN);
                     const uint64_t a_hi = make_desc_sw128(smem_u32(stage_a_hi(s)));
                     const uint64_t b_hi = make_desc_sw128(smem_u32(stage_b_hi(s)));
                     const uint64_t a_lo = make_desc_sw128(smem_u32(stage_a_lo(s)));
@@ -261,19 +286,21 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per k step inside the swizzle row
-                        const uint32_t first = (kb | k) ? 1u : 0u;
                         if (split) {
-                            umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, first);
+                            umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
                             umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
                         }
-                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, first);
+                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, k ? 1u : 0u);
                     }
-                    umma_commit(&empty[s]);                       // slot reusable once these MMAs retire
-                    if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulators complete
+                    umma_commit(&empty[s]);          // ring slot reusable once these MMAs retire
+                    umma_commit(&main_full[mb]);     // this k-block's main accumulator is complete (and, after the
+                                                     // last k-block, the tile's correction accumulator too)
                 }
             }
         }
-    } else if (warp >= XF_WARP0 && warp < XF_WARP0 + NUM_XF_WARPS) {
+    }
+    } else if (warp < EPI_WARP0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ================================ A transform ================================
         if (transform) {
             const int t = threadIdx.x - XF_WARP0 * 32;       // 0..255
@@ -329,7 +356,10 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         uint8_t* my_staging = staging + (size_t)ew * nbuf * SLAB_BYTES;
         const int sw = lane & 7;
         const int n_slabs = ceil_div(p.BN, 32);
-        uint32_t tcount = 0, res_phase = 0, slab_count = 0;
+        constexpr int MAXS = 1;                     // BN <= 96 -> <= 3 slabs -> one per warp of a lane group (keeps the
+                                                    // unrolled epilogue small: a 2-slab version thrashed the I-cache, 2.7x slower)
+        const uint32_t t_lane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        uint32_t tcount = 0, res_phase = 0, slab_count = 0, it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int acc = tcount & 1;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
@@ -349,73 +379,87 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 __syncwarp();
             };
             if (p.has_residual && first_slab < n_slabs && slab_live(first_slab)) { issue_residual(first_slab); res_issued = true; }
-            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
-            tc_fence_after();
-            const uint32_t t_main = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN);
-            const uint32_t t_corr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((2 + acc) * p.BN);
-            for (int sl = first_slab; sl < n_slabs; sl += EPI_SPLIT) {
-                const int c0 = sl * 32;
-                const int width = min(32, p.BN - c0);          // 32, or 16 in the last slab of a single n-tile
-                const bool live = slab_live(sl);               // slab entirely outside the tensor: nothing to store
-                float4* stage = reinterpret_cast<float4*>(my_staging + (size_t)(slab_count % nbuf) * SLAB_BYTES);
-                if (live) {
-                    if (p.has_residual) {
-                        if (!res_issued) issue_residual(sl);
-                        res_issued = false;
-                        mbar_wait(&res_bar[ew], res_phase);
-                        res_phase ^= 1;
-                    } else {
-                        if (lane == 0) wait_staging_free();
-                        __syncwarp();
+
+            // ---- fp32 (round-to-nearest) accumulation of the per-k-block main accumulators ----
+            float sum[MAXS][32];
+#pragma unroll
+            for (int i = 0; i < MAXS; ++i)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[i][j] = 0.f;
+            auto add_from_tmem = [&](uint32_t col_base) {
+#pragma unroll
+                for (int i = 0; i < MAXS; ++i) {
+                    const int sl = first_slab + i * EPI_SPLIT;
+                    if (sl < n_slabs) {
+                        const int c0 = sl * 32;
+                        float u[32];
+                        tmem_ld16_issue(t_lane + col_base + c0, u);
+                        if (p.BN - c0 > 16) tmem_ld16_issue(t_lane + col_base + c0 + 16, u + 16);
+                        else {
+#pragma unroll
+                            for (int j = 16; j < 32; ++j) u[j] = 0.f;
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum[i][j] += u[j];
                     }
+                }
+            };
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int mb = it & 1;
+                mbar_wait(&main_full[mb], (it >> 1) & 1);
+                tc_fence_after();
+                add_from_tmem((uint32_t)(mb * p.BN));
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&main_empty[mb]);
+            }
+            if (split) {   // tcgen05.commit covers ALL earlier MMAs: the last main_full also completed the correction terms
+                add_from_tmem((uint32_t)((2 + acc) * p.BN));
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+
+            // ---- scale/shift, activation, residual, store ----
+#pragma unroll
+            for (int i = 0; i < MAXS; ++i) {
+                const int sl = first_slab + i * EPI_SPLIT;
+                if (sl >= n_slabs || !slab_live(sl)) continue;
+                const int c0 = sl * 32;
+                float4* stage = reinterpret_cast<float4*>(my_staging + (size_t)(slab_count % nbuf) * SLAB_BYTES);
+                if (p.has_residual) {
+                    if (!res_issued) issue_residual(sl);
+                    res_issued = false;
+                    mbar_wait(&res_bar[ew], res_phase);
+                    res_phase ^= 1;
+                } else {
+                    if (lane == 0) wait_staging_free();
+                    __syncwarp();
                 }
                 const bool interior = n0 + c0 + 32 <= p.N;     // no column predicates needed
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {                  // two 16-column halves of the slab
-                    if (h * 16 >= width) {
-                        if (live) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) stage[lane * 8 + ((h * 4 + q) ^ sw)] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 8; ++q) {
+                    const int c = n0 + c0 + q * 4;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (interior || c < p.N) {
+                        const float4 sc = ldg4(p.scale + c), sh = ldg4(p.shift + c);
+                        o.x = fmaf(sum[i][q * 4 + 0], sc.x, sh.x); o.y = fmaf(sum[i][q * 4 + 1], sc.y, sh.y);
+                        o.z = fmaf(sum[i][q * 4 + 2], sc.z, sh.z); o.w = fmaf(sum[i][q * 4 + 3], sc.w, sh.w);
+                        if (p.act == 1) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
+                        else if (p.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        if (p.has_residual) {
+                            const float4 r = stage[lane * 8 + (q ^ sw)];
+                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                         }
-                        continue;
                     }
-                    float v[16];
-                    tmem_ld16(t_main + c0 + h * 16, v);
-                    if (split) {
-                        float u[16];
-                        tmem_ld16(t_corr + c0 + h * 16, u);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += u[i];
-                    }
-                    if (!live) continue;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c = n0 + c0 + h * 16 + q * 4;
-                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (interior || c < p.N) {
-                            const float4 sc = ldg4(p.scale + c), sh = ldg4(p.shift + c);
-                            o.x = fmaf(v[q * 4 + 0], sc.x, sh.x); o.y = fmaf(v[q * 4 + 1], sc.y, sh.y);
-                            o.z = fmaf(v[q * 4 + 2], sc.z, sh.z); o.w = fmaf(v[q * 4 + 3], sc.w, sh.w);
-                            if (p.act == 1) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
-                            else if (p.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                            if (p.has_residual) {
-                                const float4 r = stage[lane * 8 + ((h * 4 + q) ^ sw)];
-                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                            }
-                        }
-                        stage[lane * 8 + ((h * 4 + q) ^ sw)] = o;
-                    }
+                    stage[lane * 8 + (q ^ sw)] = o;
                 }
-                if (live) {
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) tma_store_2d(&map_out, stage, n0 + c0, row0);
-                    ++slab_count;
-                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tma_store_2d(&map_out, stage, n0 + c0, row0);
+                ++slab_count;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         if (lane == 0) tma_store_wait_all();
     }
@@ -470,13 +514,14 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     Params p;
     p.scale = scale; p.shift = shift; p.gate = gate; p.has_residual = residual != nullptr;
     p.M = M; p.N = N; p.K = K; p.rows_per_frame = rows_per_frame; p.act = act; p.passes = passes;
-    // n-tiles of at most 128 columns; with several n-tiles BN must be a multiple of the 32-column store slab
-    p.n_tiles = ceil_div(N, 128);
+    // n-tiles of at most 96 columns (3 store slabs = one per epilogue warp of a lane group); with several n-tiles
+    // BN must be a multiple of the 32-column store slab
+    p.n_tiles = ceil_div(N, 96);
     p.BN = p.n_tiles > 1 ? ceil_div(ceil_div(N, p.n_tiles), 32) * 32 : ceil_div(N, 16) * 16;
     p.m_tiles = ceil_div(M, BM);
     p.b_tile_bytes = p.BN * BK * 4;
     const int stage_bytes = (A_TILE_BYTES + p.b_tile_bytes) * (passes == 3 ? 2 : 1);
-    const int bar_bytes = (3 * MAX_STAGES + 4 + NUM_EPI_WARPS) * 8 + 16;
+    const int bar_bytes = (3 * MAX_STAGES + 8 + NUM_EPI_WARPS) * 8 + 16;
     const int budget = 227 * 1024 - 1024 /*alignment slack*/ - bar_bytes;
     // double-buffered epilogue staging when that still leaves a 4-deep operand ring
     p.slabs_per_warp = (budget - 2 * NUM_EPI_WARPS * SLAB_BYTES) / stage_bytes >= 4 ? 2 : 1;

@@ -7,7 +7,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liborbit_b200.so")
+LIB_PATH = os.environ.get("ORBIT_B200_LIB", os.path.join(HERE, "liborbit_b200.so"))   # override: dev A/B builds
 
 _i, _i64, _f, _p = C.c_int, C.c_int64, C.c_float, C.c_void_p
 _SIGNATURES = {
