@@ -48,8 +48,8 @@ struct orbit_engine {
     int max_c = 0;
     std::vector<FoldEntry> folds;
     std::vector<Op> ops;
-    int chunk_frames = 16;
-    int gemm_mode = 0;
+    int chunk_frames = 256;   // frames per pass through the layer plan (workspace ~10 MB per 224-px frame)
+    int gemm_mode = 1;        // tcgen05 3xTF32
     mutable std::atomic<int64_t> last_launches{0};
     // optional per-launch CUDA-event timing (option "profile"): one event before every launch + one at the end
     int profile = 0;
