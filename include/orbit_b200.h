@@ -45,6 +45,12 @@ const char* orbit_error_string(int code);
 /* 0 if the current CUDA device is sm_100 and the library's kernels can run, else ORBIT_ERR_NO_DEVICE */
 int         orbit_device_check(void);
 
+/* Process-wide numerics options. "tc_debias_x1000": kappa*1000 of the truncation de-biasing of the tcgen05
+ * 3xTF32 GEMM (every tcgen05.mma result is truncated, not rounded, to fp32; kappa*ulp is added back to each
+ * promoted k-block partial).                                                                            */
+int orbit_set_global_option(const char* key, int value);
+int orbit_get_global_option(const char* key, int* value);
+
 /* ------------------------------------------------------------------------------------------------
  * Head: frame pooling + prototype build + all-pairs scoring.
  * ---------------------------------------------------------------------------------------------- */

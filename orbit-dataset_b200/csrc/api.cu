@@ -1,4 +1,5 @@
 // Library-level entry points of the C ABI (include/orbit_b200.h).
+#include <cstring>
 #include "convnet.cuh"
 #include "gemm_tcgen05.cuh"
 
@@ -37,4 +38,15 @@ extern "C" int orbit_pointwise_conv(const float* A, const float* W, const float*
     if (rc) return rc;
     return launch_pointwise_tcgen05(A, w_split, scale, shift, gate, residual, out, M, N, K, rows_per_frame, act,
                                     mode == 1 ? 3 : 1, st);
+}
+
+extern "C" int orbit_set_global_option(const char* key, int value) {
+    if (!key) return ORBIT_ERR_ARG;
+    if (!strcmp(key, "tc_debias_x1000")) { orbit::set_tcgen05_debias((float)value / 1000.0f); return ORBIT_OK; }
+    return ORBIT_ERR_UNSUPPORTED;
+}
+extern "C" int orbit_get_global_option(const char* key, int* value) {
+    if (!key || !value) return ORBIT_ERR_ARG;
+    if (!strcmp(key, "tc_debias_x1000")) { *value = (int)(orbit::get_tcgen05_debias() * 1000.0f + 0.5f); return ORBIT_OK; }
+    return ORBIT_ERR_UNSUPPORTED;
 }

@@ -161,7 +161,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // x * sigmoid(x) with the SFU approximations (ex2.approx, rcp.approx): ~3e-7 relative error, 2 MUFU ops.
 // The accurate expf + IEEE division cost ~30 issue slots per output and made the epilogue the bottleneck.
+#if defined(ORBIT_SILU_ACCURATE)
+__device__ __forceinline__ float silu_fast(float x) { return x / (1.0f + expf(-x)); }
+#elif defined(ORBIT_SILU_MID)
+__device__ __forceinline__ float silu_fast(float x) { return x * __frcp_rn(1.0f + expf(-x)); }
+#else
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+#endif
 
 struct Params {
     const float* scale;
@@ -172,6 +178,7 @@ struct Params {
     int BN, n_tiles, m_tiles, stages;
     int b_tile_bytes;        // BN * 128 (multiple of 2048)
     int slabs_per_warp;      // 1 or 2 staging slabs per epilogue warp
+    float debias;            // kappa * 2^-23: expected truncation loss of a promoted k-block partial, in units of its exponent
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -386,7 +393,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int i = 0; i < MAXS; ++i)
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sum[i][j] = 0.f;
-            auto add_from_tmem = [&](uint32_t col_base) {
+            auto add_from_tmem = [&](uint32_t col_base, float debias) {
 #pragma unroll
                 for (int i = 0; i < MAXS; ++i) {
                     const int sl = first_slab + i * EPI_SPLIT;
@@ -400,8 +407,14 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             for (int j = 16; j < 32; ++j) u[j] = 0.f;
                         }
                         tmem_ld_wait();
+                        // Every tcgen05.mma result is TRUNCATED to fp32 (measured): the k-block partial u
+                        // is short by 0.5 ulp(u) in expectation for its last MMA, plus the earlier ones at their
+                        // smaller magnitudes. Adding kappa * ulp(u) * sign(u) back removes the systematic part.
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) sum[i][j] += u[j];
+                        for (int j = 0; j < 32; ++j) {
+                            const float pow2 = __uint_as_float(__float_as_uint(u[j]) & 0xff800000u);   // sign * 2^exponent
+                            sum[i][j] += fmaf(pow2, debias, u[j]);
+                        }
                     }
                 }
             };
@@ -409,13 +422,13 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int mb = it & 1;
                 mbar_wait(&main_full[mb], (it >> 1) & 1);
                 tc_fence_after();
-                add_from_tmem((uint32_t)(mb * p.BN));
+                add_from_tmem((uint32_t)(mb * p.BN), p.debias);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&main_empty[mb]);
             }
             if (split) {   // tcgen05.commit covers ALL earlier MMAs: the last main_full also completed the correction terms
-                add_from_tmem((uint32_t)((2 + acc) * p.BN));
+                add_from_tmem((uint32_t)((2 + acc) * p.BN), 0.f);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -505,6 +518,10 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 
 }  // namespace tc
 
+static float g_debias_kappa = 1.0f;   // one ulp of every promoted k-block partial (4 truncating MMAs: 0.5*(1+.75+.5+.25) ulp expected loss)
+void set_tcgen05_debias(float kappa) { g_debias_kappa = kappa; }
+float get_tcgen05_debias() { return g_debias_kappa; }
+
 int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* scale, const float* shift,
                              const float* gate, const float* residual, float* out, int M, int N, int K,
                              int rows_per_frame, int act, int passes, cudaStream_t st) {
@@ -514,6 +531,7 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     Params p;
     p.scale = scale; p.shift = shift; p.gate = gate; p.has_residual = residual != nullptr;
     p.M = M; p.N = N; p.K = K; p.rows_per_frame = rows_per_frame; p.act = act; p.passes = passes;
+    p.debias = passes == 3 ? g_debias_kappa * 1.1920929e-07f : 0.f;
     // n-tiles of at most 96 columns (3 store slabs = one per epilogue warp of a lane group); with several n-tiles
     // BN must be a multiple of the 32-column store slab
     p.n_tiles = ceil_div(N, 96);

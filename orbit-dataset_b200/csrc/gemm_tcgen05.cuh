@@ -14,4 +14,8 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
                              const float* gate, const float* residual, float* out, int M, int N, int K,
                              int rows_per_frame, int act, int passes, cudaStream_t st);
 
+// kappa of the truncation de-biasing applied to every promoted k-block partial in 3xTF32 mode (process-wide)
+void set_tcgen05_debias(float kappa);
+float get_tcgen05_debias();
+
 }  // namespace orbit

@@ -14,6 +14,8 @@ _SIGNATURES = {
     "orbit_abi_version": (_i, []),
     "orbit_error_string": (C.c_char_p, [_i]),
     "orbit_device_check": (_i, []),
+    "orbit_set_global_option": (_i, [C.c_char_p, _i]),
+    "orbit_get_global_option": (_i, [C.c_char_p, C.POINTER(_i)]),
     "orbit_pool_clips": (_i, [_p, _i, _i, _i, _p, _p]),
     "orbit_proto_configure_scratch_bytes": (_i64, [_i, _i]),
     "orbit_proto_configure": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),

@@ -112,7 +112,7 @@ def test_finetune_kernel_matches_torch_optimisers(cuda_device):
     from oracle.recogniser import OracleRecogniser
     g = torch.Generator().manual_seed(0)
     feats = torch.randn(12, 256, generator=g) * 0.5 + 0.2
-    labels = torch.tensor([0, 1, 2, 3] * 3)[torch.randperm(12, generator=g)] + 10     # arbitrary label values
+    labels = torch.tensor([0, 1, 2, 3] * 3)[torch.randperm(12, generator=g)]           # 0..C-1 as F.cross_entropy needs
     oracle = OracleRecogniser.__new__(OracleRecogniser)
     oracle.batch_size, oracle.feat_dim, oracle.logit_scale, oracle.clip_length = 5, 256, 1.5, 1
     oracle._features = lambda clips, film=None: clips                                   # features are given
