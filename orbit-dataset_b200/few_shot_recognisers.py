@@ -120,7 +120,7 @@ class FewShotRecogniser(nn.Module):
         self.frame_pooler = MeanPooler(T=self.clip_length)
         self.device = torch.device('cpu')
         self._stager = None
-        self.stage_slice_frames = 64  # frames per overlapped H2D slice for CPU-resident clips
+        self.stage_slice_frames = 320  # frames per overlapped H2D slice for CPU-resident clips (193 MB at 224 px)
 
     def _set_device(self, device):
         self.device = torch.device(device)

@@ -106,13 +106,17 @@ def test_device_calibration_matches_oracle(cuda_device):
 
 def test_finetune_kernel_matches_torch_optimisers(cuda_device):
     """orbit_linear_finetune on IDENTICAL features vs torch.optim.Adam / SGD driven through the oracle's
-    batch loop (batch_size 5 over 12 clips => batches of 5,5,2 re-weighted by batch_len/N)."""
+    batch loop (batch_size 5 over 13 clips => batches of 5,5,3 re-weighted by batch_len/N)."""
     import orbit_b200
     from orbit_b200.finetune import finetune_linear_head
     from oracle.recogniser import OracleRecogniser
     g = torch.Generator().manual_seed(0)
-    feats = torch.randn(12, 256, generator=g) * 0.5 + 0.2
-    labels = torch.tensor([0, 1, 2, 3] * 3)[torch.randperm(12, generator=g)]           # 0..C-1 as F.cross_entropy needs
+    feats = torch.randn(13, 256, generator=g) * 0.5 + 0.2
+    # 0..C-1 as F.cross_entropy needs; class counts (5,4,2,2) deliberately != N/C: for a class with exactly N/C
+    # clips the first bias gradient of the zero-initialised head is exactly 0, and Adam's g/(|g|+eps) then turns
+    # torch's ~7e-9 rounding noise into a +-0.04 update -- an ill-conditioned quantity that no other summation
+    # order (CPU fp64, or this kernel) reproduces.
+    labels = torch.tensor([0] * 5 + [1] * 4 + [2] * 2 + [3] * 2)[torch.randperm(13, generator=g)]
     oracle = OracleRecogniser.__new__(OracleRecogniser)
     oracle.batch_size, oracle.feat_dim, oracle.logit_scale, oracle.clip_length = 5, 256, 1.5, 1
     oracle._features = lambda clips, film=None: clips                                   # features are given
@@ -140,6 +144,7 @@ def test_finetuner_matches_oracle(cuda_device):
     spec = EpisodeSpec(4, 3, 3, 1, 64)
     oracle = OracleRecogniser('efficientnet_b0', False, 'linear', 1, 5, 1.0, 1991, calibration_frames(64))
     ctx, ctx_y, tgt, _ = make_episode(spec, index=2)
+    ctx, ctx_y = ctx[:-1], ctx_y[:-1]          # unbalanced classes (see test_finetune_kernel_matches_torch_optimisers)
     m = orbit_b200.MultiStepFewShotRecogniser('efficientnet_b0', False, 'linear', 1, 5, False)
     m.load_state_dict(oracle.state_dict(), strict=True)
     m._set_device(cuda_device)
