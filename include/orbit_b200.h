@@ -37,6 +37,8 @@ extern "C" {
 #define ORBIT_ARCH_VIT_B_32        2 /* feature_extractors.py:54-58                             */
 #define ORBIT_ARCH_VIT_B_32_CLIP   3 /* feature_extractors.py:59-64                             */
 #define ORBIT_ARCH_RESNET18        4 /* BASELINE.json extension (not in the reference)          */
+#define ORBIT_ARCH_SET_ENCODER   100 /* SetEncoder / SimplePrePoolNet (model/set_encoders.py:34-120): frames ->
+                                        64-d per-frame embedding, run through the same engine API               */
 
 #define ORBIT_MAX_CLASSES 64
 
@@ -85,6 +87,22 @@ int orbit_head_predict(const float* frame_feats, int num_clips, int clip_length,
                        const float* weight, const float* bias, int num_classes, int metric,
                        float logit_scale, float* logits, int32_t* argmax, void* stream);
 
+/* FiLM parameter generator in ONE launch. Replaces FilmParameterGenerator.forward (model/feature_adapters.py:66-78):
+ * per FiLM tensor i (sorted-name order) g = Linear(hidden,size_i)(ReLU(LayerNorm(Linear(hidden,hidden)(z)))),
+ * gamma' = gamma0*(g*r+1) for '...weight', beta' = beta0 + g*r for '...bias'; written at film[out_i ...].
+ *   gen_params: flat fp32 blob of all generators; table: num_tensors device records of
+ *   orbit_film_table_entry_bytes() bytes = {int64 w1,b1,ln_w,ln_b,w2,b2,reg,init,out; int32 size,is_weight}
+ *   (offsets into gen_params / film); task_embedding z [hidden] (set_encoders.py:61-75 aggregate).         */
+int orbit_film_table_entry_bytes(void);
+int orbit_film_generate(const float* gen_params, const void* table, int num_tensors, int max_size,
+                        const float* task_embedding, int hidden, float* film, void* stream);
+
+/* out[r, o] = act(in[r, :] . weight[o, :] + bias[o]) (+ skip[r, o]) for r < rows <= 64. act: 0 none, 2 ReLU,
+ * 3 ELU. The dense layers of DenseResidualBlock (model/mlps.py:33-50) used by VersaClassifier.configure
+ * (classifier_heads.py:171-180) on the class-mean rows.                                                   */
+int orbit_dense_rows(const float* in, const float* weight, const float* bias, const float* skip, float* out,
+                     int rows, int in_dim, int out_dim, int act, void* stream);
+
 /* FineTuner inner loop in one launch. Replaces the num_grad_steps x batches loop of
  * MultiStepFewShotRecogniser.personalise (few_shot_recognisers.py:231-246) for the default FineTuner (frozen
  * extractor, so the clip features are loop-invariant): LinearClassifier.predict + cross_entropy (mean, each
@@ -126,6 +144,7 @@ int  orbit_engine_feat_dim(const orbit_engine* e);
 int     orbit_engine_num_params(const orbit_engine* e);
 int     orbit_engine_param_info(const orbit_engine* e, int i, char* name, int name_cap,
                                 int64_t* numel, int64_t* offset);
+int     orbit_engine_param_shape(const orbit_engine* e, int i, int* ndim, int64_t* dims4);
 int64_t orbit_engine_param_floats(const orbit_engine* e);
 
 /* FiLM tensors (reference model/film.py:38-74), in the SORTED-name order the reference's generator

@@ -30,8 +30,9 @@ bn_fold_kernel(FoldTable tab, const float* __restrict__ params, const float* __r
         const float b = (film && e.film_beta >= 0) ? film[e.film_beta + c] : params[e.beta + c];
         const float inv = 1.0f / sqrtf(params[e.var + c] + e.eps);
         const float sc = g * inv;
+        const float cb = e.conv_bias >= 0 ? params[e.conv_bias + c] : 0.f;
         derived[e.out + c] = sc;
-        derived[e.out + e.channels + c] = b - params[e.mean + c] * sc;
+        derived[e.out + e.channels + c] = b + (cb - params[e.mean + c]) * sc;
     }
 }
 
@@ -45,6 +46,16 @@ int launch_bn_fold(const FoldEntry* entries, int n, const float* params, const f
         bn_fold_kernel<<<grid, 256, 0, st>>>(tab, params, film, derived);
         ORBIT_RETURN_IF_LAUNCH_FAILED();
     }
+    return ORBIT_OK;
+}
+
+__global__ void add_vec_kernel(float* __restrict__ a, const float* __restrict__ b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += b[i];
+}
+int launch_add_vec(float* a, const float* b, int n, cudaStream_t st) {
+    add_vec_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, n);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }
 
@@ -553,6 +564,77 @@ int launch_pointwise_ffma(const float* A, const float* Wt, const float* scale, c
                                                             rows_per_frame, act);
     ORBIT_PW_CASE(16) ORBIT_PW_CASE(32) ORBIT_PW_CASE(64) ORBIT_PW_CASE(128)
 #undef ORBIT_PW_CASE
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 convolution of the set encoder (reference model/set_encoders.py:91-120) = im2col + the pointwise GEMM
+// (tensor cores) + 2x2 max pool. The im2col matrix is written once and read once; at the CNAPs support-set sizes
+// (<= 150 frames) that is a few GB of traffic, far below the GEMM time.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int Kpad, int nchw) {
+    const int64_t total = (int64_t)B * H * W * Kpad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kpad);
+        const int64_t pix = i / Kpad;
+        const int xx = (int)(pix % W), yy = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
+        float v = 0.f;
+        if (k < 9 * C) {
+            const int c = nchw ? k / 9 : k % C, tap = nchw ? k % 9 : k / C;
+            const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                v = nchw ? __ldg(x + (((int64_t)b * C + c) * H + iy) * W + ix) : __ldg(x + (((int64_t)b * H + iy) * W + ix) * C + c);
+        }
+        col[i] = v;
+    }
+}
+int launch_im2col3x3(const float* x, float* col, int B, int H, int W, int C, int Kpad, int nchw, cudaStream_t st) {
+    const int64_t total = (int64_t)B * H * W * Kpad;
+    im2col3x3_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(x, col, B, H, W, C, Kpad, nchw);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+__global__ void conv3x3_weight_relayout_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int Kpad, int nchw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout * Kpad) return;
+    const int co = i / Kpad, k = i % Kpad;
+    float v = 0.f;
+    if (k < 9 * Cin) {
+        const int c = nchw ? k / 9 : k % Cin, tap = nchw ? k % 9 : k / Cin;
+        v = w[((int64_t)co * Cin + c) * 9 + tap];
+    }
+    out[i] = v;
+}
+int launch_conv3x3_weight_relayout(const float* w, float* out, int Cout, int Cin, int Kpad, int nchw, cudaStream_t st) {
+    conv3x3_weight_relayout_kernel<<<ceil_div(Cout * Kpad, 256), 256, 0, st>>>(w, out, Cout, Cin, Kpad, nchw);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+__global__ void __launch_bounds__(256)
+maxpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, C4 = C >> 2;
+    const int64_t total = (int64_t)B * Ho * Wo * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % C4);
+        const int64_t pix = i / C4;
+        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
+        const float* p = x + (((int64_t)b * H + oy * 2) * W + ox * 2) * C + q * 4;
+        const float4 a = ldg4(p), bb = ldg4(p + C), c = ldg4(p + (int64_t)W * C), d = ldg4(p + (int64_t)W * C + C);
+        float4 m;
+        m.x = fmaxf(fmaxf(a.x, bb.x), fmaxf(c.x, d.x)); m.y = fmaxf(fmaxf(a.y, bb.y), fmaxf(c.y, d.y));
+        m.z = fmaxf(fmaxf(a.z, bb.z), fmaxf(c.z, d.z)); m.w = fmaxf(fmaxf(a.w, bb.w), fmaxf(c.w, d.w));
+        *reinterpret_cast<float4*>(y + pix * C + q * 4) = m;
+    }
+}
+int launch_maxpool2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st) {
+    if (C % 4) return ORBIT_ERR_UNSUPPORTED;
+    const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (C / 4);
+    if (total == 0) return ORBIT_OK;
+    maxpool2_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(x, y, B, H, W, C);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }

@@ -10,6 +10,7 @@ enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2 };
 struct FoldEntry {
     int64_t gamma, beta, mean, var;  // offsets into the params blob
     int64_t film_gamma, film_beta;   // offsets into the film blob, or -1
+    int64_t conv_bias;               // offset of the preceding conv's bias in params (folded into shift), or -1
     int64_t out;                     // offset into derived: scale[C] then shift[C]
     int channels;
     float eps;
@@ -17,6 +18,9 @@ struct FoldEntry {
 
 int launch_bn_fold(const FoldEntry* entries_host, int n, const float* params, const float* film, float* derived,
                    cudaStream_t st);
+
+// a[i] += b[i]
+int launch_add_vec(float* a, const float* b, int n, cudaStream_t st);
 
 // out = [ones(n) | zeros(n)]
 int launch_fill_identity(float* out, int n, cudaStream_t st);
@@ -46,6 +50,14 @@ int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, con
 int launch_pointwise_ffma(const float* A, const float* Wt, const float* scale, const float* shift, const float* gate,
                           const float* residual, float* out, int M, int N, int K, int rows_per_frame, int act,
                           cudaStream_t st);
+
+// 3x3 / pad 1 / stride 1 im2col. nchw=1: x [B,C,H,W] -> col [B*H*W, Kpad], k = c*9 + tap (timm/torch weight order);
+// nchw=0: x [B,H,W,C] -> col [B*H*W, 9*C], k = tap*C + c. Columns >= 9*C are zero.
+int launch_im2col3x3(const float* x, float* col, int B, int H, int W, int C, int Kpad, int nchw, cudaStream_t st);
+// conv weight [Cout, Cin, 3, 3] -> [Cout, Kpad] in the im2col k-order above
+int launch_conv3x3_weight_relayout(const float* w, float* out, int Cout, int Cin, int Kpad, int nchw, cudaStream_t st);
+// 2x2 / stride 2 max pool (floor), NHWC
+int launch_maxpool2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st);
 
 // spatial mean: x [B,HW,C] -> y [B,C]
 int launch_spatial_mean(const float* x, float* y, int B, int HW, int C, cudaStream_t st);

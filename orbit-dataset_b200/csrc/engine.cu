@@ -17,10 +17,12 @@ namespace orbit {
 struct ParamInfo {
     std::string name;
     int64_t numel, offset;
+    int ndim = 1;
+    int64_t dims[4] = {0, 0, 0, 0};
 };
 
-enum OpKind { OP_STEM, OP_DW, OP_SE, OP_PW, OP_SPATIAL_MEAN };
-enum Buf { BUF_X0 = 0, BUF_X1, BUF_E, BUF_D, BUF_H, BUF_PARTIAL, BUF_GATE, BUF_COUNT, BUF_INPUT = 100, BUF_OUTPUT = 101, BUF_NONE = -1 };
+enum OpKind { OP_STEM, OP_DW, OP_SE, OP_PW, OP_SPATIAL_MEAN, OP_CONV3, OP_MAXPOOL };
+enum Buf { BUF_X0 = 0, BUF_X1, BUF_E, BUF_D, BUF_H, BUF_PARTIAL, BUF_GATE, BUF_COL, BUF_COUNT, BUF_INPUT = 100, BUF_OUTPUT = 101, BUF_NONE = -1 };
 
 struct Op {
     OpKind kind;
@@ -33,6 +35,9 @@ struct Op {
     int fold_idx = -1;          // index into orbit_engine::folds
     int64_t dw_wt = -1;         // derived offset of re-laid-out depthwise weights
     int64_t w_split = -1;       // derived offset of tf32 hi/lo split weights (PW, tcgen05 path)
+    int64_t w_gemm = -1;        // CONV3: derived offset of the weights re-laid-out to [cout, kpad] (im2col k-order)
+    int kpad = 0;               // CONV3: im2col row length (9*cin rounded up to a multiple of 4)
+    bool nchw_in = false;       // CONV3: input is the fp32 NCHW frame tensor
     int se_reduce = 0;
 };
 
@@ -59,10 +64,16 @@ struct orbit_engine {
     mutable size_t prof_used = 0;
     mutable std::vector<size_t> prof_ends;   // index of the closing event of each forward call
 
-    int64_t add_param(const std::string& name, int64_t numel) {
-        params.push_back({name, numel, param_floats});
-        param_floats += (numel + 3) / 4 * 4;  // every tensor starts 16-byte aligned (128-bit loads)
-        return params.back().offset;
+    int64_t add_param(const std::string& name, int64_t d0, int64_t d1 = 0, int64_t d2 = 0, int64_t d3 = 0) {
+        ParamInfo pi;
+        pi.name = name;
+        pi.dims[0] = d0; pi.dims[1] = d1; pi.dims[2] = d2; pi.dims[3] = d3;
+        pi.ndim = d1 == 0 ? 1 : (d2 == 0 ? 2 : 4);
+        pi.numel = d0 * (d1 ? d1 : 1) * (d2 ? d2 : 1) * (d3 ? d3 : 1);
+        pi.offset = param_floats;
+        params.push_back(pi);
+        param_floats += (pi.numel + 3) / 4 * 4;  // every tensor starts 16-byte aligned (128-bit loads)
+        return pi.offset;
     }
     int64_t add_derived(int64_t numel) {
         const int64_t o = derived_floats;
@@ -79,6 +90,7 @@ struct orbit_engine {
         f.mean = add_param(name + ".running_mean", c);
         f.var = add_param(name + ".running_var", c);
         f.film_gamma = f.film_beta = -1;
+        f.conv_bias = -1;
         f.channels = c;
         f.eps = eps;
         f.out = add_derived(2 * (int64_t)c);
@@ -115,7 +127,7 @@ static void build_efficientnet_b0(orbit_engine* e) {
     e->feat_dim = 1280;
     {
         Op op; op.kind = OP_STEM; op.in = BUF_INPUT; op.out = BUF_X0; op.cin = 3; op.cout = 32; op.k = 3; op.stride = 2; op.act = ACT_SILU;
-        op.w = e->add_param("conv_stem.weight", 32 * 27);
+        op.w = e->add_param("conv_stem.weight", 32, 3, 3, 3);
         op.fold = e->add_bn("bn1", 32, eps, true, &op);
         e->ops.push_back(op);
     }
@@ -129,7 +141,7 @@ static void build_efficientnet_b0(orbit_engine* e) {
             int dw_in = cur;
             if (!ds) {  // expand 1x1 + bn1 + SiLU
                 Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_E; op.cin = cin; op.cout = mid; op.act = ACT_SILU;
-                op.w = e->add_param(p + "conv_pw.weight", (int64_t)mid * cin);
+                op.w = e->add_param(p + "conv_pw.weight", mid, cin, 1, 1);
                 op.fold = e->add_bn(p + "bn1", mid, eps, false, &op);
                 op.w_split = e->add_derived(2 * (int64_t)mid * cin);
                 e->ops.push_back(op);
@@ -137,7 +149,7 @@ static void build_efficientnet_b0(orbit_engine* e) {
             }
             {   // depthwise + bn + SiLU (the FiLM site of InvertedResidual: bn2)
                 Op op; op.kind = OP_DW; op.in = dw_in; op.out = BUF_D; op.cin = op.cout = mid; op.k = k; op.stride = stride; op.act = ACT_SILU;
-                op.w = e->add_param(p + "conv_dw.weight", (int64_t)mid * k * k);
+                op.w = e->add_param(p + "conv_dw.weight", mid, 1, k, k);
                 op.fold = e->add_bn(p + (ds ? "bn1" : "bn2"), mid, eps, !ds, &op);
                 op.dw_wt = e->add_derived((int64_t)mid * k * k);
                 e->ops.push_back(op);
@@ -145,9 +157,9 @@ static void build_efficientnet_b0(orbit_engine* e) {
             {   // squeeze-excite gate
                 Op op; op.kind = OP_SE; op.in = BUF_PARTIAL; op.out = BUF_GATE; op.cin = op.cout = mid;
                 op.se_reduce = std::max(1, cin / 4);
-                op.w = e->add_param(p + "se.conv_reduce.weight", (int64_t)op.se_reduce * mid);
+                op.w = e->add_param(p + "se.conv_reduce.weight", op.se_reduce, mid, 1, 1);
                 op.b = e->add_param(p + "se.conv_reduce.bias", op.se_reduce);
-                op.w2 = e->add_param(p + "se.conv_expand.weight", (int64_t)mid * op.se_reduce);
+                op.w2 = e->add_param(p + "se.conv_expand.weight", mid, op.se_reduce, 1, 1);
                 op.b2 = e->add_param(p + "se.conv_expand.bias", mid);
                 e->ops.push_back(op);
             }
@@ -155,7 +167,7 @@ static void build_efficientnet_b0(orbit_engine* e) {
                 Op op; op.kind = OP_PW; op.in = BUF_D; op.cin = mid; op.cout = cout; op.act = ACT_NONE; op.gated = true;
                 op.out = cur == BUF_X0 ? BUF_X1 : BUF_X0;
                 if (stride == 1 && cin == cout) op.res = cur;
-                op.w = e->add_param(p + (ds ? "conv_pw.weight" : "conv_pwl.weight"), (int64_t)cout * mid);
+                op.w = e->add_param(p + (ds ? "conv_pw.weight" : "conv_pwl.weight"), cout, mid, 1, 1);
                 op.fold = e->add_bn(p + (ds ? "bn2" : "bn3"), cout, eps, false, &op);
                 op.w_split = e->add_derived(2 * (int64_t)cout * mid);
                 e->ops.push_back(op);
@@ -166,7 +178,7 @@ static void build_efficientnet_b0(orbit_engine* e) {
     }
     {   // conv_head + bn2 (FiLM, root) + SiLU, then global average pool
         Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_H; op.cin = cin; op.cout = 1280; op.act = ACT_SILU;
-        op.w = e->add_param("conv_head.weight", (int64_t)1280 * cin);
+        op.w = e->add_param("conv_head.weight", 1280, cin, 1, 1);
         op.fold = e->add_bn("bn2", 1280, eps, true, &op);
         op.w_split = e->add_derived(2 * (int64_t)1280 * cin);
         e->ops.push_back(op);
@@ -174,6 +186,36 @@ static void build_efficientnet_b0(orbit_engine* e) {
         e->ops.push_back(pool);
     }
     e->finalize_film();
+    e->ident = e->add_derived(2 * (int64_t)e->max_c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Set encoder plan (reference model/set_encoders.py:81-120 SimplePrePoolNet): 5 x [conv3x3(pad 1, bias) +
+// BatchNorm2d(eps 1e-5) + ReLU + maxpool 2x2] + global average pool -> 64-d per frame. State-dict keys as in the
+// reference: encoder.layer{i}.0.{weight,bias}, encoder.layer{i}.1.{weight,bias,running_mean,running_var}.
+// ------------------------------------------------------------------------------------------------
+static void build_set_encoder(orbit_engine* e) {
+    e->feat_dim = 64;
+    int cin = 3, cur = BUF_INPUT;
+    for (int i = 1; i <= 5; ++i) {
+        const std::string p = "encoder.layer" + std::to_string(i) + ".";
+        Op op; op.kind = OP_CONV3; op.in = cur; op.out = BUF_E; op.cin = cin; op.cout = 64; op.k = 3; op.act = ACT_RELU;
+        op.nchw_in = (i == 1);
+        op.kpad = (9 * cin + 3) / 4 * 4;
+        op.w = e->add_param(p + "0.weight", 64, cin, 3, 3);
+        op.b = e->add_param(p + "0.bias", 64);
+        op.fold = e->add_bn(p + "1", 64, 1e-5f, false, &op);
+        e->folds[op.fold_idx].conv_bias = op.b;
+        op.w_gemm = e->add_derived((int64_t)64 * op.kpad);
+        op.w_split = e->add_derived(2 * (int64_t)64 * op.kpad);
+        e->ops.push_back(op);
+        Op pool; pool.kind = OP_MAXPOOL; pool.in = BUF_E; pool.out = (i % 2) ? BUF_X0 : BUF_X1; pool.cin = pool.cout = 64;
+        e->ops.push_back(pool);
+        cur = pool.out;
+        cin = 64;
+    }
+    Op mean; mean.kind = OP_SPATIAL_MEAN; mean.in = cur; mean.out = BUF_OUTPUT; mean.cin = mean.cout = 64;
+    e->ops.push_back(mean);
     e->ident = e->add_derived(2 * (int64_t)e->max_c);
 }
 
@@ -208,6 +250,15 @@ static int plan_buffers(const orbit_engine* e, int H, int W, BufSizes* bs) {
             }
             case OP_SE: need(BUF_GATE, op.cout); break;
             case OP_PW: need(op.out, (int64_t)h * w * op.cout); break;
+            case OP_CONV3:
+                need(BUF_COL, (int64_t)h * w * op.kpad);
+                need(op.out, (int64_t)h * w * op.cout);
+                break;
+            case OP_MAXPOOL:
+                h /= 2; w /= 2;
+                if (h < 1 || w < 1) return ORBIT_ERR_UNSUPPORTED;
+                need(op.out, (int64_t)h * w * op.cout);
+                break;
             case OP_SPATIAL_MEAN: break;
         }
     }
@@ -220,6 +271,7 @@ extern "C" int orbit_engine_create(orbit_engine** out, int arch) {
     e->arch = arch;
     switch (arch) {
         case ORBIT_ARCH_EFFICIENTNET_B0: build_efficientnet_b0(e); break;
+        case ORBIT_ARCH_SET_ENCODER: build_set_encoder(e); break;
         default: delete e; return ORBIT_ERR_UNSUPPORTED;
     }
     *out = e;
@@ -248,6 +300,12 @@ static int info(const std::vector<ParamInfo>& v, int i, char* name, int cap, int
 }
 extern "C" int orbit_engine_param_info(const orbit_engine* e, int i, char* name, int cap, int64_t* numel, int64_t* offset) {
     return e ? info(e->params, i, name, cap, numel, offset) : ORBIT_ERR_ARG;
+}
+extern "C" int orbit_engine_param_shape(const orbit_engine* e, int i, int* ndim, int64_t* dims4) {
+    if (!e || !ndim || !dims4 || i < 0 || i >= (int)e->params.size()) return ORBIT_ERR_ARG;
+    *ndim = e->params[i].ndim;
+    for (int d = 0; d < 4; ++d) dims4[d] = e->params[i].dims[d];
+    return ORBIT_OK;
 }
 extern "C" int orbit_engine_film_info(const orbit_engine* e, int i, char* name, int cap, int64_t* numel, int64_t* offset) {
     return e ? info(e->film, i, name, cap, numel, offset) : ORBIT_ERR_ARG;
@@ -283,6 +341,11 @@ extern "C" int orbit_engine_prepare(const orbit_engine* e, const float* params, 
             if (rc) return rc;
         } else if (op.kind == OP_PW && op.w_split >= 0) {
             rc = launch_tf32_split(params + op.w, (int64_t)op.cout * op.cin, derived + op.w_split, st);
+            if (rc) return rc;
+        } else if (op.kind == OP_CONV3) {
+            rc = launch_conv3x3_weight_relayout(params + op.w, derived + op.w_gemm, op.cout, op.cin, op.kpad, op.nchw_in, st);
+            if (rc) return rc;
+            rc = launch_tf32_split(derived + op.w_gemm, (int64_t)op.cout * op.kpad, derived + op.w_split, st);
             if (rc) return rc;
         }
     }
@@ -418,6 +481,27 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                         p_flops = 2.0 * M * (double)op.cin * op.cout;
                         break;
                     }
+                    case OP_CONV3: {
+                        const int M = B * h * w;
+                        rc = launch_im2col3x3(ptr(op.in), buf[BUF_COL], B, h, w, op.cin, op.kpad, op.nchw_in, st);
+                        if (rc) return rc;
+                        ++launches;
+                        if (e->profile) { e->prof_recs.push_back({(int)OP_STEM, 4.0 * M * (op.cin + (double)op.kpad), 0.0}); rc = prof_mark(e, st); if (rc) return rc; }
+                        if (e->gemm_mode == 0 || raw)
+                            rc = launch_pointwise_ffma(buf[BUF_COL], derived + op.w_gemm, scale, shift, nullptr, nullptr, ptr(op.out),
+                                                       M, op.cout, op.kpad, h * w, act, st);
+                        else
+                            rc = launch_pointwise_tcgen05(buf[BUF_COL], derived + op.w_split, scale, shift, nullptr, nullptr,
+                                                          ptr(op.out), M, op.cout, op.kpad, h * w, act, e->gemm_mode == 1 ? 3 : 1, st);
+                        p_bytes = 4.0 * ((double)M * op.kpad + (double)M * op.cout + (double)op.kpad * op.cout);
+                        p_flops = 2.0 * M * (double)op.kpad * op.cout;
+                        break;
+                    }
+                    case OP_MAXPOOL:
+                        rc = launch_maxpool2(ptr(op.in), ptr(op.out), B, h, w, op.cin, st);
+                        ho = h / 2; wo = w / 2;
+                        p_bytes = 4.0 * B * op.cin * ((double)h * w + (double)ho * wo);
+                        break;
                     case OP_SPATIAL_MEAN:
                         rc = launch_spatial_mean(ptr(op.in), ptr(op.out), B, h * w, op.cin, st);
                         p_bytes = 4.0 * B * op.cin * (h * w + 1.0);
@@ -426,12 +510,16 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                 }
                 if (rc) return rc;
                 ++launches;
-                if (e->profile) e->prof_recs.push_back({(int)op.kind, p_bytes, p_flops});
+                if (e->profile) e->prof_recs.push_back({op.kind == OP_CONV3 ? (int)OP_PW : (op.kind == OP_MAXPOOL ? (int)OP_SPATIAL_MEAN : (int)op.kind), p_bytes, p_flops});
                 if (raw) {
                     const FoldEntry& fe = e->folds[op.fold_idx];
                     if (e->profile) { rc = prof_mark(e, st); if (rc) return rc; e->prof_recs.push_back({5, 0.0, 0.0}); }
                     rc = launch_channel_stats(ptr(op.out), (int64_t)B * ho * wo, op.cout, calib + fe.mean, calib + fe.var, st);
                     if (rc) return rc;
+                    if (fe.conv_bias >= 0) {   // statistics were taken before the conv bias: BN sees conv + bias
+                        rc = launch_add_vec(calib + fe.mean, calib + fe.conv_bias, op.cout, st);
+                        if (rc) return rc;
+                    }
                     rc = launch_bn_fold(&fe, 1, calib, nullptr, derived, st);
                     if (rc) return rc;
                     launches += 2;

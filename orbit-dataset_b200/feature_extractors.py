@@ -14,6 +14,7 @@ import torch.nn as nn
 from . import lib as L
 
 ARCH_IDS = {
+    'set_encoder': 100,   # not an extractor string of the reference: the SetEncoder runs through the same engine
     'efficientnet_b0': 0,
     'vit_s_32': 1,
     'vit_b_32': 2,
@@ -35,10 +36,6 @@ def _engine_table(engine, count_fn, info_fn):
         L.check(info_fn(engine, i, name, 256, C.byref(numel), C.byref(offset)), "param_info")
         out.append((name.value.decode(), numel.value, offset.value))
     return out
-
-
-_SHAPES_4D = ('conv_stem.weight', 'conv_dw.weight', 'conv_pw.weight', 'conv_pwl.weight', 'conv_head.weight',
-              'se.conv_reduce.weight', 'se.conv_expand.weight')
 
 
 class FeatureExtractor(nn.Module):
@@ -70,33 +67,12 @@ class FeatureExtractor(nn.Module):
 
     # ---- parameter tree ------------------------------------------------------------------------
     def _build_tree(self):
-        # 4-D conv shapes are recovered from the channel counts of the adjacent norm / bias entries.
-        sizes = {n: k for n, k, _ in self._table}
-        for name, numel, offset in self._table:
-            shape = (numel,)
-            if name == 'conv_stem.weight':
-                shape = (numel // 27, 3, 3, 3)
-            elif name.endswith('conv_dw.weight'):
-                pre = name[:-len('conv_dw.weight')]
-                c = sizes[pre + ('bn2.weight' if pre + 'bn3.weight' in sizes else 'bn1.weight')]
-                k = int(round((numel // c) ** 0.5))
-                shape = (c, 1, k, k)
-            elif name.endswith('se.conv_reduce.weight'):
-                r = sizes[name[:-len('weight')] + 'bias']
-                shape = (r, numel // r, 1, 1)
-            elif name.endswith('se.conv_expand.weight'):
-                c = sizes[name[:-len('weight')] + 'bias']
-                shape = (c, numel // c, 1, 1)
-            elif name.endswith(('conv_pw.weight', 'conv_pwl.weight', 'conv_head.weight')):
-                pre = name.rsplit('conv_', 1)[0]
-                kind = name.rsplit('.', 2)[-2]
-                if kind == 'conv_head':
-                    cout = sizes['bn2.weight']
-                elif kind == 'conv_pwl':
-                    cout = sizes[pre + 'bn3.weight']
-                else:  # conv_pw: expand (-> bn1) in InvertedResidual, project (-> bn2) in DepthwiseSeparable
-                    cout = sizes[pre + ('bn1.weight' if pre + 'conv_pwl.weight' in sizes else 'bn2.weight')]
-                shape = (cout, numel // cout, 1, 1)
+        """Reproduces the reference/timm module tree (dotted names) with parameters that are views of the blob."""
+        lib = L.load()
+        ndim, dims = C.c_int(), (C.c_int64 * 4)()
+        for i, (name, numel, offset) in enumerate(self._table):
+            L.check(lib.orbit_engine_param_shape(self._engine, i, C.byref(ndim), dims), "orbit_engine_param_shape")
+            shape = tuple(int(dims[d]) for d in range(ndim.value))
             self._shapes[name] = shape
             parent = self
             parts = name.split('.')
@@ -151,6 +127,11 @@ class FeatureExtractor(nn.Module):
             elif leaf == 'bias':
                 dst.copy_((0.1 if name.rsplit('.', 2)[-2].startswith(('bn', 'norm')) else 0.05) *
                           torch.randn(numel, generator=g))
+            elif len(shape) == 4 and shape[1] != 1 and shape[2] == 3 and shape[0] > shape[1] * 9:
+                # first 3x3 conv of the set encoder (64 filters over 27 inputs): orthonormal columns
+                flat = torch.empty(shape[0], numel // shape[0])
+                nn.init.orthogonal_(flat, generator=g)
+                dst.copy_(flat.flatten())
             elif len(shape) == 4 and shape[1] == 1:            # depthwise
                 k = shape[2]
                 w = torch.randn(shape, generator=g) * (0.2 / k)

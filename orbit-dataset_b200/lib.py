@@ -20,6 +20,9 @@ _SIGNATURES = {
     "orbit_proto_configure_scratch_bytes": (_i64, [_i, _i]),
     "orbit_proto_configure": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "orbit_head_predict": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _f, _p, _p, _p]),
+    "orbit_film_table_entry_bytes": (_i, []),
+    "orbit_film_generate": (_i, [_p, _p, _i, _i, _p, _i, _p, _p]),
+    "orbit_dense_rows": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "orbit_linear_finetune_scratch_bytes": (_i64, [_i, _i, _i]),
     "orbit_linear_finetune": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _f, _p, _p, _p, _p]),
     "orbit_pointwise_conv": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
@@ -28,6 +31,7 @@ _SIGNATURES = {
     "orbit_engine_feat_dim": (_i, [_p]),
     "orbit_engine_num_params": (_i, [_p]),
     "orbit_engine_param_info": (_i, [_p, _i, C.c_char_p, _i, C.POINTER(_i64), C.POINTER(_i64)]),
+    "orbit_engine_param_shape": (_i, [_p, _i, C.POINTER(_i), C.POINTER(_i64)]),
     "orbit_engine_param_floats": (_i64, [_p]),
     "orbit_engine_num_film": (_i, [_p]),
     "orbit_engine_film_info": (_i, [_p, _i, C.c_char_p, _i, C.POINTER(_i64), C.POINTER(_i64)]),
