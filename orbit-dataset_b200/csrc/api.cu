@@ -29,7 +29,7 @@ extern "C" int orbit_pointwise_conv(const float* A, const float* W, const float*
                                     int rows_per_frame, int act, int mode, float* w_split, void* stream) {
     using namespace orbit;
     if (!A || !W || !scale || !shift || !out || M < 0 || N <= 0 || K <= 0 || rows_per_frame <= 0) return ORBIT_ERR_ARG;
-    if (mode < 0 || mode > 2 || act < 0 || act > 2) return ORBIT_ERR_ARG;
+    if (mode < 0 || mode > 2 || act < 0 || act > 4 || act == 3) return ORBIT_ERR_ARG;
     if (!aligned16(A) || !aligned16(W) || !aligned16(out) || !aligned16(scale) || !aligned16(shift)) return ORBIT_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) return launch_pointwise_ffma(A, W, scale, shift, gate, residual, out, M, N, K, rows_per_frame, act, st);

@@ -119,6 +119,7 @@ int launch_dw_relayout(const float* w, int C, int kk, float* out, cudaStream_t s
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == ACT_SILU) return siluf_(v);
     if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));   // exact (erf) GELU, as timm's nn.GELU
     return v;
 }
 

@@ -4,7 +4,7 @@
 
 namespace orbit {
 
-enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2 };
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_ELU = 3, ACT_GELU = 4 };
 
 // One BatchNorm (or FiLM-modulated BatchNorm) to fold into per-channel scale/shift.
 struct FoldEntry {

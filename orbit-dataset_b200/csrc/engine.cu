@@ -11,6 +11,7 @@
 
 #include "convnet.cuh"
 #include "gemm_tcgen05.cuh"
+#include "vit.cuh"
 
 namespace orbit {
 
@@ -21,7 +22,7 @@ struct ParamInfo {
     int64_t dims[4] = {0, 0, 0, 0};
 };
 
-enum OpKind { OP_STEM, OP_DW, OP_SE, OP_PW, OP_SPATIAL_MEAN, OP_CONV3, OP_MAXPOOL };
+enum OpKind { OP_STEM, OP_DW, OP_SE, OP_PW, OP_SPATIAL_MEAN, OP_CONV3, OP_MAXPOOL, OP_PATCH, OP_ASSEMBLE, OP_LN, OP_ATTN };
 enum Buf { BUF_X0 = 0, BUF_X1, BUF_E, BUF_D, BUF_H, BUF_PARTIAL, BUF_GATE, BUF_COL, BUF_COUNT, BUF_INPUT = 100, BUF_OUTPUT = 101, BUF_NONE = -1 };
 
 struct Op {
@@ -38,6 +39,11 @@ struct Op {
     int64_t w_gemm = -1;        // CONV3: derived offset of the weights re-laid-out to [cout, kpad] (im2col k-order)
     int kpad = 0;               // CONV3: im2col row length (9*cin rounded up to a multiple of 4)
     bool nchw_in = false;       // CONV3: input is the fp32 NCHW frame tensor
+    bool bias_only = false;     // PW: a Linear layer: scale = 1, shift = bias (params + b)
+    int ln = -1;                // LN: index into orbit_engine::lns
+    bool cls_only = false;      // LN: normalise token 0 of every frame only and write [frames, dim] (final norm + token pooling)
+    int heads = 0, patch = 0;   // ATTN / PATCH
+    float eps = 0.f;
     int se_reduce = 0;
 };
 
@@ -52,6 +58,9 @@ struct orbit_engine {
     int64_t ident = -1;  // derived offset of [ones(max_c) | zeros(max_c)] (identity scale/shift for calibration)
     int max_c = 0;
     std::vector<FoldEntry> folds;
+    struct LnEntry { int64_t gamma, beta, film_gamma, film_beta, out; int dim; };
+    std::vector<LnEntry> lns;   // LayerNorms: effective (FiLM-substituted) gamma/beta are copied to derived[out]
+    int tokens = 0;             // ViT: tokens per frame (patches + class token)
     std::vector<Op> ops;
     int chunk_frames = 256;   // frames per pass through the layer plan (workspace ~10 MB per 224-px frame)
     int gemm_mode = 1;        // tcgen05 3xTF32
@@ -68,7 +77,7 @@ struct orbit_engine {
         ParamInfo pi;
         pi.name = name;
         pi.dims[0] = d0; pi.dims[1] = d1; pi.dims[2] = d2; pi.dims[3] = d3;
-        pi.ndim = d1 == 0 ? 1 : (d2 == 0 ? 2 : 4);
+        pi.ndim = d1 == 0 ? 1 : (d2 == 0 ? 2 : (d3 == 0 ? 3 : 4));
         pi.numel = d0 * (d1 ? d1 : 1) * (d2 ? d2 : 1) * (d3 ? d3 : 1);
         pi.offset = param_floats;
         params.push_back(pi);
@@ -101,6 +110,22 @@ struct orbit_engine {
         folds.push_back(f);
         return f.out;
     }
+    // LayerNorm: registers weight/bias; FiLM site when `film_site` (model/film.py:57-66); returns index into lns
+    int add_ln(const std::string& name, int dim, bool film_site) {
+        LnEntry l;
+        l.gamma = add_param(name + ".weight", dim);
+        l.beta = add_param(name + ".bias", dim);
+        l.film_gamma = l.film_beta = -1;
+        l.out = add_derived(2 * (int64_t)dim);
+        l.dim = dim;
+        lns.push_back(l);
+        if (film_site) {
+            ParamInfo a; a.name = name + ".weight"; a.numel = dim; a.offset = -(int64_t)lns.size();
+            ParamInfo b = a; b.name = name + ".bias";
+            film.push_back(a); film.push_back(b);
+        }
+        return (int)lns.size() - 1;
+    }
     void finalize_film() {
         // generator order = sorted names (feature_adapters.py:43-44); remember which fold entry each feeds
         std::sort(film.begin(), film.end(), [](const ParamInfo& a, const ParamInfo& b) { return a.name < b.name; });
@@ -109,7 +134,8 @@ struct orbit_engine {
             const int64_t fold_idx = f.offset;
             f.offset = off;
             const bool is_weight = f.name.size() > 7 && f.name.compare(f.name.size() - 7, 7, ".weight") == 0;
-            if (is_weight) folds[fold_idx].film_gamma = off; else folds[fold_idx].film_beta = off;
+            if (fold_idx >= 0) { if (is_weight) folds[fold_idx].film_gamma = off; else folds[fold_idx].film_beta = off; }
+            else { LnEntry& l = lns[-fold_idx - 1]; if (is_weight) l.film_gamma = off; else l.film_beta = off; }
             off += f.numel;
         }
         film_floats = off;
@@ -219,6 +245,60 @@ static void build_set_encoder(orbit_engine* e) {
     e->ident = e->add_derived(2 * (int64_t)e->max_c);
 }
 
+// ------------------------------------------------------------------------------------------------
+// ViT plan (timm 0.6.12 vit_{small,base}_patch32_224*, num_classes=0, token pooling). State-dict keys as timm:
+// patch_embed.proj.*, cls_token, pos_embed, [norm_pre.*], blocks.i.{norm1,attn.qkv,attn.proj,norm2,mlp.fc1,mlp.fc2}.*,
+// norm.*. FiLM sites: every LayerNorm called norm/norm1/norm2 (model/film.py:57-66).
+// ------------------------------------------------------------------------------------------------
+static void build_vit(orbit_engine* e, int dim, int depth, int heads, float eps, bool pre_norm) {
+    const int P = 32, np = 49, T = np + 1;
+    e->feat_dim = dim;
+    e->tokens = T;
+    auto linear = [&](const std::string& name, int in_buf, int out_buf, int cin, int cout, int act, int res) {
+        Op op; op.kind = OP_PW; op.in = in_buf; op.out = out_buf; op.res = res; op.cin = cin; op.cout = cout; op.act = act;
+        op.bias_only = true;
+        op.w = e->add_param(name + ".weight", cout, cin);
+        op.b = e->add_param(name + ".bias", cout);
+        op.w_split = e->add_derived(2 * (int64_t)cout * cin);
+        e->max_c = std::max(e->max_c, cout);
+        e->ops.push_back(op);
+    };
+    {
+        Op col; col.kind = OP_PATCH; col.in = BUF_INPUT; col.out = BUF_COL; col.patch = P; col.cin = 3; col.cout = 3 * P * P;
+        e->ops.push_back(col);
+        Op op; op.kind = OP_PW; op.in = BUF_COL; op.out = BUF_D; op.cin = 3 * P * P; op.cout = dim; op.act = ACT_NONE; op.bias_only = true;
+        op.w = e->add_param("patch_embed.proj.weight", dim, 3, P, P);
+        op.b = e->add_param("patch_embed.proj.bias", dim);
+        op.w_split = e->add_derived(2 * (int64_t)dim * 3 * P * P);
+        op.patch = P;   // marks "rows = frames * patches" for this GEMM
+        e->max_c = std::max(e->max_c, dim);
+        e->ops.push_back(op);
+        Op as; as.kind = OP_ASSEMBLE; as.in = BUF_D; as.out = BUF_X0; as.cin = as.cout = dim;
+        as.w = e->add_param("cls_token", 1, 1, dim);
+        as.b = e->add_param("pos_embed", 1, T, dim);
+        e->ops.push_back(as);
+    }
+    auto layernorm = [&](const std::string& name, int in_buf, int out_buf, bool film_site, bool cls_only) {
+        Op op; op.kind = OP_LN; op.in = in_buf; op.out = out_buf; op.cin = op.cout = dim; op.eps = eps; op.cls_only = cls_only;
+        op.ln = e->add_ln(name, dim, film_site);
+        e->ops.push_back(op);
+    };
+    if (pre_norm) layernorm("norm_pre", BUF_X0, BUF_X0, false, false);
+    for (int i = 0; i < depth; ++i) {
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        layernorm(p + "norm1", BUF_X0, BUF_X1, true, false);
+        linear(p + "attn.qkv", BUF_X1, BUF_E, dim, 3 * dim, ACT_NONE, BUF_NONE);
+        { Op at; at.kind = OP_ATTN; at.in = BUF_E; at.out = BUF_D; at.cin = at.cout = dim; at.heads = heads; e->ops.push_back(at); }
+        linear(p + "attn.proj", BUF_D, BUF_X0, dim, dim, ACT_NONE, BUF_X0);       // x += proj(attn)   (in-place residual)
+        layernorm(p + "norm2", BUF_X0, BUF_X1, true, false);
+        linear(p + "mlp.fc1", BUF_X1, BUF_E, dim, 4 * dim, ACT_GELU, BUF_NONE);
+        linear(p + "mlp.fc2", BUF_E, BUF_X0, 4 * dim, dim, ACT_NONE, BUF_X0);    // x += fc2(gelu(fc1))
+    }
+    layernorm("norm", BUF_X0, BUF_OUTPUT, true, true);
+    e->finalize_film();
+    e->ident = e->add_derived(2 * (int64_t)e->max_c);
+}
+
 // TF "SAME" geometry: out = ceil(in/s), pad_before = total/2 (stride 1 => symmetric (k-1)/2)
 static void same_geometry(int in, int k, int s, int* out, int* pad_before) {
     *out = (in + s - 1) / s;
@@ -249,7 +329,7 @@ static int plan_buffers(const orbit_engine* e, int H, int W, BufSizes* bs) {
                 break;
             }
             case OP_SE: need(BUF_GATE, op.cout); break;
-            case OP_PW: need(op.out, (int64_t)h * w * op.cout); break;
+            case OP_PW: need(op.out, (int64_t)(e->tokens ? e->tokens : h * w) * op.cout); break;
             case OP_CONV3:
                 need(BUF_COL, (int64_t)h * w * op.kpad);
                 need(op.out, (int64_t)h * w * op.cout);
@@ -260,6 +340,15 @@ static int plan_buffers(const orbit_engine* e, int H, int W, BufSizes* bs) {
                 need(op.out, (int64_t)h * w * op.cout);
                 break;
             case OP_SPATIAL_MEAN: break;
+            case OP_PATCH:
+                if (H % op.patch || W % op.patch || (H / op.patch) * (W / op.patch) + 1 != e->tokens) return ORBIT_ERR_UNSUPPORTED;
+                need(op.out, (int64_t)(e->tokens - 1) * op.cout);
+                break;
+            case OP_ASSEMBLE:
+            case OP_LN:
+            case OP_ATTN:
+                need(op.out, (int64_t)e->tokens * op.cout);
+                break;
         }
     }
     return ORBIT_OK;
@@ -272,6 +361,9 @@ extern "C" int orbit_engine_create(orbit_engine** out, int arch) {
     switch (arch) {
         case ORBIT_ARCH_EFFICIENTNET_B0: build_efficientnet_b0(e); break;
         case ORBIT_ARCH_SET_ENCODER: build_set_encoder(e); break;
+        case ORBIT_ARCH_VIT_S_32: build_vit(e, 384, 12, 6, 1e-6f, false); break;
+        case ORBIT_ARCH_VIT_B_32: build_vit(e, 768, 12, 12, 1e-6f, false); break;
+        case ORBIT_ARCH_VIT_B_32_CLIP: build_vit(e, 768, 12, 12, 1e-5f, true); break;
         default: delete e; return ORBIT_ERR_UNSUPPORTED;
     }
     *out = e;
@@ -333,6 +425,11 @@ extern "C" int orbit_engine_prepare(const orbit_engine* e, const float* params, 
     if (rc) return rc;
     if (e->ident >= 0) {
         rc = launch_fill_identity(derived + e->ident, e->max_c, st);
+        if (rc) return rc;
+    }
+    for (const orbit_engine::LnEntry& l : e->lns) {
+        rc = launch_ln_affine((film && l.film_gamma >= 0) ? film + l.film_gamma : params + l.gamma,
+                              (film && l.film_beta >= 0) ? film + l.film_beta : params + l.beta, derived + l.out, l.dim, st);
         if (rc) return rc;
     }
     for (const Op& op : e->ops) {
@@ -430,8 +527,8 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
             int ho = h, wo = w;
             for (int pass = 0; pass < passes; ++pass) {
                 const bool raw = passes == 2 && pass == 0;
-                const float* scale = raw ? derived + e->ident : derived + op.fold;
-                const float* shift = raw ? derived + e->ident + e->max_c : derived + op.fold + op.cout;
+                const float* scale = (raw || op.bias_only) ? derived + e->ident : derived + op.fold;
+                const float* shift = raw ? derived + e->ident + e->max_c : (op.bias_only ? params + op.b : derived + op.fold + op.cout);
                 const int act = raw ? ACT_NONE : op.act;
                 double p_bytes = 0, p_flops = 0;
                 if (e->profile) { rc = prof_mark(e, st); if (rc) return rc; }
@@ -464,8 +561,32 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                         p_bytes = 4.0 * (B * op.cin * (se_tiles + 1.0) + 2.0 * op.cin * op.se_reduce);
                         p_flops = 4.0 * B * op.cin * op.se_reduce;
                         break;
+                    case OP_PATCH:
+                        rc = launch_patch_im2col(ptr(op.in), ptr(op.out), B, h, w, op.patch, st);
+                        p_bytes = 8.0 * B * 3.0 * h * w;
+                        break;
+                    case OP_ASSEMBLE:
+                        rc = launch_assemble_tokens(ptr(op.in), params + op.w, params + op.b, ptr(op.out), B, e->tokens - 1, op.cout, st);
+                        p_bytes = 8.0 * B * e->tokens * op.cout;
+                        break;
+                    case OP_LN: {
+                        const orbit_engine::LnEntry& l = e->lns[op.ln];
+                        if (op.cls_only)
+                            rc = launch_layernorm(ptr(op.in), (int64_t)e->tokens * op.cin, derived + l.out, derived + l.out + l.dim, op.eps,
+                                                  ptr(op.out), op.cout, B, op.cin, st);
+                        else
+                            rc = launch_layernorm(ptr(op.in), op.cin, derived + l.out, derived + l.out + l.dim, op.eps, ptr(op.out),
+                                                  op.cout, B * e->tokens, op.cin, st);
+                        p_bytes = 8.0 * B * (op.cls_only ? 1 : e->tokens) * op.cin;
+                        break;
+                    }
+                    case OP_ATTN:
+                        rc = launch_attention(ptr(op.in), ptr(op.out), B, e->tokens, op.heads, op.cin / op.heads, st);
+                        p_bytes = 16.0 * B * e->tokens * op.cin;
+                        p_flops = 4.0 * B * e->tokens * e->tokens * op.cin;
+                        break;
                     case OP_PW: {
-                        const int M = B * h * w;
+                        const int M = e->tokens ? B * (op.patch ? e->tokens - 1 : e->tokens) : B * h * w;
                         const float* gate = op.gated ? buf[BUF_GATE] : nullptr;
                         const float* res = raw ? nullptr : ptr(op.res);
                         if (e->gemm_mode == 0 || raw) {
@@ -510,7 +631,14 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                 }
                 if (rc) return rc;
                 ++launches;
-                if (e->profile) e->prof_recs.push_back({op.kind == OP_CONV3 ? (int)OP_PW : (op.kind == OP_MAXPOOL ? (int)OP_SPATIAL_MEAN : (int)op.kind), p_bytes, p_flops});
+                if (e->profile) {
+                    int fam = (int)op.kind;
+                    if (op.kind == OP_CONV3) fam = OP_PW;
+                    else if (op.kind == OP_MAXPOOL || op.kind == OP_LN || op.kind == OP_ASSEMBLE) fam = OP_SPATIAL_MEAN;
+                    else if (op.kind == OP_PATCH) fam = OP_STEM;
+                    else if (op.kind == OP_ATTN) fam = OP_SE;
+                    e->prof_recs.push_back({fam, p_bytes, p_flops});
+                }
                 if (raw) {
                     const FoldEntry& fe = e->folds[op.fold_idx];
                     if (e->profile) { rc = prof_mark(e, st); if (rc) return rc; e->prof_recs.push_back({5, 0.0, 0.0}); }

@@ -169,6 +169,8 @@ __device__ __forceinline__ float silu_fast(float x) { return x * __frcp_rn(1.0f 
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 #endif
 
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
 struct Params {
     const float* scale;
     const float* shift;
@@ -461,6 +463,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         o.z = fmaf(sum[i][q * 4 + 2], sc.z, sh.z); o.w = fmaf(sum[i][q * 4 + 3], sc.w, sh.w);
                         if (p.act == 1) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
                         else if (p.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        else if (p.act == 4) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
                         if (p.has_residual) {
                             const float4 r = stage[lane * 8 + (q ^ sw)];
                             o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
