@@ -129,6 +129,16 @@ int orbit_pointwise_conv(const float* A, const float* W, const float* scale, con
                          const float* gate, const float* residual, float* out, int M, int N, int K,
                          int rows_per_frame, int act, int mode, float* w_split, void* stream);
 
+/* Depthwise k x k convolution (k in {3,5}, stride in {1,2}, TF "SAME" padding) on NHWC activations with the folded
+ * BatchNorm/FiLM scale-shift and activation fused: timm conv_dw + BatchNormAct2d of every MBConv block.
+ *   x [B,H,W,C] -> y [B,ceil(H/s),ceil(W/s),C]; weight [C,1,k,k] (torch layout); weight_scratch: k*k*C floats.
+ *   partial (nullable): [B][groups][C] per-block channel sums of y (the squeeze-excite squeeze), groups*C*B =
+ *   orbit_depthwise_partial_floats().                                                                    */
+int64_t orbit_depthwise_partial_floats(int B, int H, int W, int C, int k, int stride);
+int orbit_depthwise_conv(const float* x, const float* weight, const float* scale, const float* shift, float* y,
+                         float* partial, float* weight_scratch, int B, int H, int W, int C, int k, int stride,
+                         int act, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backbone engine: the feature extractor forward (reference: timm model called at
  * few_shot_recognisers.py:114-117,143-146, with FiLM by functional_call parameter substitution).

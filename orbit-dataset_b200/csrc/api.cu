@@ -50,3 +50,31 @@ extern "C" int orbit_get_global_option(const char* key, int* value) {
     if (!strcmp(key, "tc_debias_x1000")) { *value = (int)(orbit::get_tcgen05_debias() * 1000.0f + 0.5f); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
+
+static void same_geom(int in, int k, int s, int* out, int* pad_before) {
+    *out = (in + s - 1) / s;
+    const int total = (*out - 1) * s + k - in;
+    *pad_before = (total > 0 ? total : 0) / 2;
+}
+
+extern "C" int64_t orbit_depthwise_partial_floats(int B, int H, int W, int C, int k, int stride) {
+    int ho, wo, p;
+    same_geom(H, k, stride, &ho, &p); same_geom(W, k, stride, &wo, &p);
+    return (int64_t)B * orbit::dw_partial_groups(C, ho, wo, k, stride) * C;
+}
+
+extern "C" int orbit_depthwise_conv(const float* x, const float* weight, const float* scale, const float* shift, float* y,
+                                    float* partial, float* weight_scratch, int B, int H, int W, int C, int k, int stride,
+                                    int act, void* stream) {
+    using namespace orbit;
+    if (!x || !weight || !scale || !shift || !y || !weight_scratch || B < 0 || H <= 0 || W <= 0 || C <= 0) return ORBIT_ERR_ARG;
+    if ((k != 3 && k != 5) || (stride != 1 && stride != 2) || C % 4) return ORBIT_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(y) || !aligned16(scale) || !aligned16(shift) || !aligned16(weight_scratch)) return ORBIT_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    int ho, wo, pt, pl;
+    same_geom(H, k, stride, &ho, &pt); same_geom(W, k, stride, &wo, &pl);
+    int rc = launch_dw_relayout(weight, C, k * k, weight_scratch, st);
+    if (rc) return rc;
+    if (B == 0) return ORBIT_OK;
+    return launch_depthwise(x, weight_scratch, scale, shift, y, partial, B, H, W, C, ho, wo, k, stride, pt, pl, act, st);
+}

@@ -123,6 +123,16 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// x * sigmoid(x) with the SFU approximations (ex2.approx, rcp.approx; ~3e-7 relative error). ncu showed the
+// depthwise kernels to be ISSUE-bound, not memory-bound, with the accurate expf + IEEE division taking ~30 of
+// the ~85 instructions per output.
+__device__ __forceinline__ float act_fast(float v, int act) {
+    if (act == ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // Stem: 3x3 stride-2 conv on the fp32 NCHW frames, one output pixel (all COUT channels) per thread.
 // The NCHW->NHWC change of layout is fused here so the frames are read exactly once.
@@ -169,10 +179,10 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
 #pragma unroll
     for (int q = 0; q < COUT / 4; ++q) {
         float4 o;
-        o.x = apply_act(fmaf(acc[4 * q + 0], s_sc[4 * q + 0], s_sh[4 * q + 0]), act);
-        o.y = apply_act(fmaf(acc[4 * q + 1], s_sc[4 * q + 1], s_sh[4 * q + 1]), act);
-        o.z = apply_act(fmaf(acc[4 * q + 2], s_sc[4 * q + 2], s_sh[4 * q + 2]), act);
-        o.w = apply_act(fmaf(acc[4 * q + 3], s_sc[4 * q + 3], s_sh[4 * q + 3]), act);
+        o.x = act_fast(fmaf(acc[4 * q + 0], s_sc[4 * q + 0], s_sh[4 * q + 0]), act);
+        o.y = act_fast(fmaf(acc[4 * q + 1], s_sc[4 * q + 1], s_sh[4 * q + 1]), act);
+        o.z = act_fast(fmaf(acc[4 * q + 2], s_sc[4 * q + 2], s_sh[4 * q + 2]), act);
+        o.w = act_fast(fmaf(acc[4 * q + 3], s_sc[4 * q + 3], s_sh[4 * q + 3]), act);
         yp[q] = o;
     }
 }
@@ -238,9 +248,124 @@ template <> struct VecIO<2> {
     static __device__ __forceinline__ void store(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
 };
 
+// Rolling accumulators, ONE iteration = S input rows = one finished output row (the ring is rotated through
+// registers instead of unrolling over its phases: 3-5x less code, the unrolled version stalled on instruction
+// fetch). Pending output rows o_old .. o_old+R-1 live in acc[0..R-1]; virtual input row vy (= input row + pad_t)
+// feeds output row (vy - ky)/S for every ky of matching parity.
 template <int K, int S, int VEC>
 __global__ void __launch_bounds__(256, 2)
 dw_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
+          const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C,
+          int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile, int strip_blocks) {
+    constexpr int TW = kDwTW, R = (K + S - 1) / S, SPAN = (TW - 1) * S + K, HALF = (K - 1) / S;
+    extern __shared__ __align__(16) float s_red[];  // [LY][LX][VEC] partial-sum reduction
+    const int tile = blockIdx.x / strip_blocks, sb = blockIdx.x % strip_blocks, chunk = blockIdx.y, b = blockIdx.z;
+    const int groups = gridDim.x;
+    const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
+    const int Cv = C / VEC;
+    const int cv = chunk * LX + lx;
+    const int strip = sb * LY + ly;
+    const bool live = cv < Cv && strip * TW < Wo;
+    float sum[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) sum[e] = 0.f;
+    const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
+    if (live && row0 < row1) {
+        float wreg[K * K][VEC], sc[VEC], sh[VEC];
+#pragma unroll
+        for (int t = 0; t < K * K; ++t) VecIO<VEC>::load(wt + (int64_t)t * C + cv * VEC, wreg[t]);
+        VecIO<VEC>::load(scale + cv * VEC, sc);
+        VecIO<VEC>::load(shift + cv * VEC, sh);
+        const float* xb = x + (int64_t)b * H * W * C + cv * VEC;
+        float* yb = y + (int64_t)b * Ho * Wo * C + cv * VEC;
+        const int ox0 = strip * TW, ixb = ox0 * S - pad_l;
+        float acc[R][TW][VEC];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int t = 0; t < TW; ++t)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[r][t][e] = 0.f;
+        // iteration m handles virtual rows m*S .. m*S+S-1; the oldest pending output row is o_old = m - HALF
+        // (HALF = (K-1)/S) and it is complete after the virtual row o_old*S + K-1, i.e. inside this iteration.
+        for (int m = row0; m < row1 + HALF; ++m) {
+#pragma unroll
+            for (int sub = 0; sub < S; ++sub) {
+                const int vy = m * S + sub;
+                const int iy = vy - pad_t;
+                if (iy >= 0 && iy < H) {
+                    const float* rowp = xb + (int64_t)iy * W * C;
+#pragma unroll
+                    for (int j = 0; j < SPAN; ++j) {
+                        const int ix = ixb + j;
+                        float v[VEC];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) v[e] = 0.f;
+                        if (ix >= 0 && ix < W) VecIO<VEC>::load(rowp + (int64_t)ix * C, v);
+#pragma unroll
+                        for (int ky = sub; ky < K; ky += S) {          // ky with (vy - ky) divisible by S
+                            const int slot = HALF - (ky - sub) / S;    // output row m - (ky-sub)/S, relative to o_old
+#pragma unroll
+                            for (int t = 0; t < TW; ++t) {
+                                const int kx = j - t * S;
+                                if (kx >= 0 && kx < K) {
+#pragma unroll
+                                    for (int e = 0; e < VEC; ++e) acc[slot][t][e] = fmaf(v[e], wreg[ky * K + kx][e], acc[slot][t][e]);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (sub == (K - 1) % S) {      // the oldest pending output row has now seen its last input row
+                    const int oy = m - HALF;
+                    if (oy >= row0 && oy < row1) {
+#pragma unroll
+                        for (int t = 0; t < TW; ++t) {
+                            if (ox0 + t < Wo) {
+                                float r[VEC];
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) { r[e] = act_fast(fmaf(acc[0][t][e], sc[e], sh[e]), act); sum[e] += r[e]; }
+                                VecIO<VEC>::store(yb + ((int64_t)oy * Wo + ox0 + t) * C, r);
+                            }
+                        }
+                    }
+                }
+            }
+            // rotate the ring: slot r <- slot r+1, newest slot cleared (rows above the tile accumulate garbage that is
+            // rotated out without ever being stored)
+#pragma unroll
+            for (int r = 0; r + 1 < R; ++r)
+#pragma unroll
+                for (int t = 0; t < TW; ++t)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[r][t][e] = acc[r + 1][t][e];
+#pragma unroll
+            for (int t = 0; t < TW; ++t)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[R - 1][t][e] = 0.f;
+        }
+    }
+    if (partial) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s_red[(ly * LX + lx) * VEC + e] = sum[e];
+        __syncthreads();
+        if (ly == 0 && cv < Cv) {
+            float t[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) t[e] = s_red[lx * VEC + e];
+            for (int r = 1; r < LY; ++r)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) t[e] += s_red[(r * LX + lx) * VEC + e];
+            VecIO<VEC>::store(partial + ((int64_t)b * groups + blockIdx.x) * C + cv * VEC, t);
+        }
+    }
+}
+
+// Variant that unrolls over the P = R*S phases of the accumulator ring instead of rotating it through registers;
+// faster for K=3, S=2 (measured), slower elsewhere (instruction-fetch bound).
+template <int K, int S, int VEC>
+__global__ void __launch_bounds__(256, 2)
+dw_kernel_unrolled(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
           const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C,
           int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile, int strip_blocks) {
     constexpr int TW = kDwTW, R = (K + S - 1) / S, P = R * S, SPAN = (TW - 1) * S + K;
@@ -313,7 +438,7 @@ dw_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float
                             if (ox0 + t < Wo) {
                                 float r[VEC];
 #pragma unroll
-                                for (int e = 0; e < VEC; ++e) { r[e] = apply_act(fmaf(acc[slot][t][e], sc[e], sh[e]), act); sum[e] += r[e]; }
+                                for (int e = 0; e < VEC; ++e) { r[e] = act_fast(fmaf(acc[slot][t][e], sc[e], sh[e]), act); sum[e] += r[e]; }
                                 VecIO<VEC>::store(yb + ((int64_t)oy * Wo + ox0 + t) * C, r);
                             }
                         }
@@ -356,7 +481,13 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
         ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                              \
         return ORBIT_OK;                                                                                              \
     }
-    ORBIT_DW_CASE(3, 1, 4) ORBIT_DW_CASE(3, 2, 4) ORBIT_DW_CASE(5, 1, 2) ORBIT_DW_CASE(5, 2, 2)
+    if (k == 3 && stride == 2) {
+        dw_kernel_unrolled<3, 2, 4><<<grid, block, smem, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t, pad_l, act,
+                                                              pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks);
+        ORBIT_RETURN_IF_LAUNCH_FAILED();
+        return ORBIT_OK;
+    }
+    ORBIT_DW_CASE(3, 1, 4) ORBIT_DW_CASE(5, 1, 2) ORBIT_DW_CASE(5, 2, 2)
 #undef ORBIT_DW_CASE
     return ORBIT_ERR_UNSUPPORTED;
 }
