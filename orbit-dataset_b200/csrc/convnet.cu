@@ -668,12 +668,16 @@ pw_ffma_kernel(const float* __restrict__ A, const float* __restrict__ Wt, const 
             if (row >= M) continue;
             float v[GW];
 #pragma unroll
-            for (int j = 0; j < GW; ++j) v[j] = apply_act(fmaf(acc[i][g * 4 + j], sc[j], sh[j]), act);
+            for (int j = 0; j < GW; ++j) v[j] = apply_act(fmaf(acc[i][g * 4 + j], sc[j], sh[j]), act < 16 ? act : ACT_NONE);
             float* op = out + row * N + col0;
             if (residual) {
                 const float* rp = residual + row * N + col0;
 #pragma unroll
                 for (int j = 0; j < GW; ++j) v[j] += __ldg(rp + j);
+            }
+            if (act >= 16) {
+#pragma unroll
+                for (int j = 0; j < GW; ++j) v[j] = apply_act(v[j], act - 16);
             }
             if constexpr (GW == 4) *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
             else if constexpr (GW == 2) *reinterpret_cast<float2*>(op) = make_float2(v[0], v[1]);
@@ -706,67 +710,79 @@ int launch_pointwise_ffma(const float* A, const float* Wt, const float* scale, c
 // (<= 150 frames) that is a few GB of traffic, far below the GEMM time.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-im2col3x3_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int Kpad, int nchw) {
-    const int64_t total = (int64_t)B * H * W * Kpad;
+im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int k, int stride, int pad,
+              int Ho, int Wo, int Kpad, int nchw) {
+    const int kk = k * k;
+    const int64_t total = (int64_t)B * Ho * Wo * Kpad;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(i % Kpad);
+        const int kc = (int)(i % Kpad);
         const int64_t pix = i / Kpad;
-        const int xx = (int)(pix % W), yy = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
+        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
         float v = 0.f;
-        if (k < 9 * C) {
-            const int c = nchw ? k / 9 : k % C, tap = nchw ? k % 9 : k / C;
-            const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+        if (kc < kk * C) {
+            const int c = nchw ? kc / kk : kc % C, tap = nchw ? kc % kk : kc / C;
+            const int iy = oy * stride - pad + tap / k, ix = ox * stride - pad + tap % k;
             if (iy >= 0 && iy < H && ix >= 0 && ix < W)
                 v = nchw ? __ldg(x + (((int64_t)b * C + c) * H + iy) * W + ix) : __ldg(x + (((int64_t)b * H + iy) * W + ix) * C + c);
         }
         col[i] = v;
     }
 }
-int launch_im2col3x3(const float* x, float* col, int B, int H, int W, int C, int Kpad, int nchw, cudaStream_t st) {
-    const int64_t total = (int64_t)B * H * W * Kpad;
-    im2col3x3_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(x, col, B, H, W, C, Kpad, nchw);
+int launch_im2col(const float* x, float* col, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                  int Kpad, int nchw, cudaStream_t st) {
+    const int64_t total = (int64_t)B * Ho * Wo * Kpad;
+    if (total == 0) return ORBIT_OK;
+    im2col_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(x, col, B, H, W, C, k, stride, pad, Ho, Wo, Kpad, nchw);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }
 
-__global__ void conv3x3_weight_relayout_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int Kpad, int nchw) {
+__global__ void conv_weight_relayout_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kk, int Kpad, int nchw) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Cout * Kpad) return;
-    const int co = i / Kpad, k = i % Kpad;
+    const int co = i / Kpad, kc = i % Kpad;
     float v = 0.f;
-    if (k < 9 * Cin) {
-        const int c = nchw ? k / 9 : k % Cin, tap = nchw ? k % 9 : k / Cin;
-        v = w[((int64_t)co * Cin + c) * 9 + tap];
+    if (kc < kk * Cin) {
+        const int c = nchw ? kc / kk : kc % Cin, tap = nchw ? kc % kk : kc / Cin;
+        v = w[((int64_t)co * Cin + c) * kk + tap];
     }
     out[i] = v;
 }
-int launch_conv3x3_weight_relayout(const float* w, float* out, int Cout, int Cin, int Kpad, int nchw, cudaStream_t st) {
-    conv3x3_weight_relayout_kernel<<<ceil_div(Cout * Kpad, 256), 256, 0, st>>>(w, out, Cout, Cin, Kpad, nchw);
+int launch_conv_weight_relayout(const float* w, float* out, int Cout, int Cin, int kk, int Kpad, int nchw, cudaStream_t st) {
+    conv_weight_relayout_kernel<<<ceil_div(Cout * Kpad, 256), 256, 0, st>>>(w, out, Cout, Cin, kk, Kpad, nchw);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }
 
 __global__ void __launch_bounds__(256)
-maxpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
-    const int Ho = H / 2, Wo = W / 2, C4 = C >> 2;
+maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C, int k, int stride, int pad,
+               int Ho, int Wo) {
+    const int C4 = C >> 2;
     const int64_t total = (int64_t)B * Ho * Wo * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int q = (int)(i % C4);
         const int64_t pix = i / C4;
         const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
-        const float* p = x + (((int64_t)b * H + oy * 2) * W + ox * 2) * C + q * 4;
-        const float4 a = ldg4(p), bb = ldg4(p + C), c = ldg4(p + (int64_t)W * C), d = ldg4(p + (int64_t)W * C + C);
-        float4 m;
-        m.x = fmaxf(fmaxf(a.x, bb.x), fmaxf(c.x, d.x)); m.y = fmaxf(fmaxf(a.y, bb.y), fmaxf(c.y, d.y));
-        m.z = fmaxf(fmaxf(a.z, bb.z), fmaxf(c.z, d.z)); m.w = fmaxf(fmaxf(a.w, bb.w), fmaxf(c.w, d.w));
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int ky = 0; ky < k; ++ky) {
+            const int iy = oy * stride - pad + ky;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < k; ++kx) {
+                const int ix = ox * stride - pad + kx;
+                if (ix < 0 || ix >= W) continue;
+                const float4 v = ldg4(x + (((int64_t)b * H + iy) * W + ix) * C + q * 4);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
         *reinterpret_cast<float4*>(y + pix * C + q * 4) = m;
     }
 }
-int launch_maxpool2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st) {
+int launch_maxpool(const float* x, float* y, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                   cudaStream_t st) {
     if (C % 4) return ORBIT_ERR_UNSUPPORTED;
-    const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (C / 4);
+    const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
     if (total == 0) return ORBIT_OK;
-    maxpool2_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(x, y, B, H, W, C);
+    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(x, y, B, H, W, C, k, stride, pad, Ho, Wo);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }

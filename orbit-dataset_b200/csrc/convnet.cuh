@@ -47,17 +47,20 @@ int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, con
                    const float* b2, float* gate, int B, int C, int R, cudaStream_t st);
 
 // pointwise conv as GEMM: out[M,N] = act((A[M,K] (*gate[m/rows_per_frame, k])) W[N,K]^T * scale[n] + shift[n]) (+res)
+// act >= 16: (act - 16) is applied AFTER the residual add (ResNet BasicBlock: relu(bn(conv) + identity))
 int launch_pointwise_ffma(const float* A, const float* Wt, const float* scale, const float* shift, const float* gate,
                           const float* residual, float* out, int M, int N, int K, int rows_per_frame, int act,
                           cudaStream_t st);
 
-// 3x3 / pad 1 / stride 1 im2col. nchw=1: x [B,C,H,W] -> col [B*H*W, Kpad], k = c*9 + tap (timm/torch weight order);
-// nchw=0: x [B,H,W,C] -> col [B*H*W, 9*C], k = tap*C + c. Columns >= 9*C are zero.
-int launch_im2col3x3(const float* x, float* col, int B, int H, int W, int C, int Kpad, int nchw, cudaStream_t st);
-// conv weight [Cout, Cin, 3, 3] -> [Cout, Kpad] in the im2col k-order above
-int launch_conv3x3_weight_relayout(const float* w, float* out, int Cout, int Cin, int Kpad, int nchw, cudaStream_t st);
-// 2x2 / stride 2 max pool (floor), NHWC
-int launch_maxpool2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st);
+// k x k / stride / symmetric pad im2col. nchw=1: x [B,C,H,W] -> col [B*Ho*Wo, Kpad], col index = c*k*k + tap (torch
+// weight order); nchw=0: x [B,H,W,C] -> col index = tap*C + c. Columns >= k*k*C are zero.
+int launch_im2col(const float* x, float* col, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                  int Kpad, int nchw, cudaStream_t st);
+// conv weight [Cout, Cin, k, k] -> [Cout, Kpad] in the im2col column order above
+int launch_conv_weight_relayout(const float* w, float* out, int Cout, int Cin, int kk, int Kpad, int nchw, cudaStream_t st);
+// k x k / stride max pool with symmetric padding (floor mode), NHWC: (2,2,0) for the set encoder, (3,2,1) for resnet
+int launch_maxpool(const float* x, float* y, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                   cudaStream_t st);
 
 // spatial mean: x [B,HW,C] -> y [B,C]
 int launch_spatial_mean(const float* x, float* y, int B, int HW, int C, cudaStream_t st);

@@ -37,7 +37,9 @@ struct Op {
     int64_t dw_wt = -1;         // derived offset of re-laid-out depthwise weights
     int64_t w_split = -1;       // derived offset of tf32 hi/lo split weights (PW, tcgen05 path)
     int64_t w_gemm = -1;        // CONV3: derived offset of the weights re-laid-out to [cout, kpad] (im2col k-order)
-    int kpad = 0;               // CONV3: im2col row length (9*cin rounded up to a multiple of 4)
+    int kpad = 0;               // CONV3: im2col row length (k*k*cin rounded up to a multiple of 4)
+    int pad = 1;                // CONV3 / MAXPOOL: symmetric padding
+    int save = BUF_NONE;        // CONV3: unused; PW-free resnet plumbing uses explicit buffers
     bool nchw_in = false;       // CONV3: input is the fp32 NCHW frame tensor
     bool bias_only = false;     // PW: a Linear layer: scale = 1, shift = bias (params + b)
     int ln = -1;                // LN: index into orbit_engine::lns
@@ -228,6 +230,7 @@ static void build_set_encoder(orbit_engine* e) {
         Op op; op.kind = OP_CONV3; op.in = cur; op.out = BUF_E; op.cin = cin; op.cout = 64; op.k = 3; op.act = ACT_RELU;
         op.nchw_in = (i == 1);
         op.kpad = (9 * cin + 3) / 4 * 4;
+        op.pad = 1;
         op.w = e->add_param(p + "0.weight", 64, cin, 3, 3);
         op.b = e->add_param(p + "0.bias", 64);
         op.fold = e->add_bn(p + "1", 64, 1e-5f, false, &op);
@@ -236,6 +239,7 @@ static void build_set_encoder(orbit_engine* e) {
         op.w_split = e->add_derived(2 * (int64_t)64 * op.kpad);
         e->ops.push_back(op);
         Op pool; pool.kind = OP_MAXPOOL; pool.in = BUF_E; pool.out = (i % 2) ? BUF_X0 : BUF_X1; pool.cin = pool.cout = 64;
+        pool.k = 2; pool.stride = 2; pool.pad = 0;
         e->ops.push_back(pool);
         cur = pool.out;
         cin = 64;
@@ -299,6 +303,53 @@ static void build_vit(orbit_engine* e, int dim, int depth, int heads, float eps,
     e->ident = e->add_derived(2 * (int64_t)e->max_c);
 }
 
+// ------------------------------------------------------------------------------------------------
+// ResNet-18 plan (torchvision resnet18 with fc = Identity; BASELINE.json extension, not in the reference at this
+// commit -- SURVEY.md F6). Every conv = im2col + GEMM with the folded BatchNorm (eps 1e-5) in the epilogue;
+// BasicBlock: relu(bn2(conv2(relu(bn1(conv1 x)))) + shortcut(x)). FiLM sites (extension, by the reference's mechanism
+// of substituting BatchNorm affine parameters): bn1 / bn2 of every BasicBlock.
+// ------------------------------------------------------------------------------------------------
+static void build_resnet18(orbit_engine* e) {
+    const float eps = 1e-5f;
+    e->feat_dim = 512;
+    auto conv = [&](const std::string& wname, const std::string& bnname, int in_buf, int out_buf, int cin, int cout, int k,
+                    int stride, int pad, int act, int res, bool film_site, bool nchw) {
+        Op op; op.kind = OP_CONV3; op.in = in_buf; op.out = out_buf; op.res = res; op.cin = cin; op.cout = cout; op.k = k;
+        op.stride = stride; op.pad = pad; op.act = act; op.nchw_in = nchw;
+        op.kpad = (k * k * cin + 3) / 4 * 4;
+        op.w = e->add_param(wname, cout, cin, k, k);
+        op.fold = e->add_bn(bnname, cout, eps, film_site, &op);
+        op.w_gemm = e->add_derived((int64_t)cout * op.kpad);
+        op.w_split = e->add_derived(2 * (int64_t)cout * op.kpad);
+        e->ops.push_back(op);
+    };
+    conv("conv1.weight", "bn1", BUF_INPUT, BUF_E, 3, 64, 7, 2, 3, ACT_RELU, BUF_NONE, false, true);
+    { Op pool; pool.kind = OP_MAXPOOL; pool.in = BUF_E; pool.out = BUF_X0; pool.cin = pool.cout = 64; pool.k = 3; pool.stride = 2; pool.pad = 1; e->ops.push_back(pool); }
+    int cin = 64, cur = BUF_X0;
+    const int widths[4] = {64, 128, 256, 512};
+    for (int l = 0; l < 4; ++l) {
+        for (int b = 0; b < 2; ++b) {
+            const std::string p = "layer" + std::to_string(l + 1) + "." + std::to_string(b) + ".";
+            const int cout = widths[l], stride = (l > 0 && b == 0) ? 2 : 1;
+            const int other = cur == BUF_X0 ? BUF_X1 : BUF_X0;
+            int shortcut = cur;
+            if (stride != 1 || cin != cout) {   // first: it must see the block INPUT geometry (writing BUF_D does not advance h, w)
+                conv(p + "downsample.0.weight", p + "downsample.1", cur, BUF_D, cin, cout, 1, stride, 0, ACT_NONE, BUF_NONE, false, false);
+                shortcut = BUF_D;
+            }
+            conv(p + "conv1.weight", p + "bn1", cur, BUF_E, cin, cout, 3, stride, 1, ACT_RELU, BUF_NONE, true, false);
+            conv(p + "conv2.weight", p + "bn2", BUF_E, other, cout, cout, 3, 1, 1, 16 + ACT_RELU, shortcut, true, false);
+            // torchvision registers conv1, bn1, conv2, bn2, downsample: param ORDER differs here, names are what matter
+            cur = other;
+            cin = cout;
+        }
+    }
+    Op mean; mean.kind = OP_SPATIAL_MEAN; mean.in = cur; mean.out = BUF_OUTPUT; mean.cin = mean.cout = 512;
+    e->ops.push_back(mean);
+    e->finalize_film();
+    e->ident = e->add_derived(2 * (int64_t)e->max_c);
+}
+
 // TF "SAME" geometry: out = ceil(in/s), pad_before = total/2 (stride 1 => symmetric (k-1)/2)
 static void same_geometry(int in, int k, int s, int* out, int* pad_before) {
     *out = (in + s - 1) / s;
@@ -330,12 +381,16 @@ static int plan_buffers(const orbit_engine* e, int H, int W, BufSizes* bs) {
             }
             case OP_SE: need(BUF_GATE, op.cout); break;
             case OP_PW: need(op.out, (int64_t)(e->tokens ? e->tokens : h * w) * op.cout); break;
-            case OP_CONV3:
-                need(BUF_COL, (int64_t)h * w * op.kpad);
-                need(op.out, (int64_t)h * w * op.cout);
+            case OP_CONV3: {
+                const int ho = (h + 2 * op.pad - op.k) / op.stride + 1, wo = (w + 2 * op.pad - op.k) / op.stride + 1;
+                if (ho < 1 || wo < 1) return ORBIT_ERR_UNSUPPORTED;
+                need(BUF_COL, (int64_t)ho * wo * op.kpad);
+                need(op.out, (int64_t)ho * wo * op.cout);
+                if (op.out != BUF_D) { h = ho; w = wo; }     // the downsample branch does not advance the main path
                 break;
+            }
             case OP_MAXPOOL:
-                h /= 2; w /= 2;
+                h = (h + 2 * op.pad - op.k) / op.stride + 1; w = (w + 2 * op.pad - op.k) / op.stride + 1;
                 if (h < 1 || w < 1) return ORBIT_ERR_UNSUPPORTED;
                 need(op.out, (int64_t)h * w * op.cout);
                 break;
@@ -361,6 +416,7 @@ extern "C" int orbit_engine_create(orbit_engine** out, int arch) {
     switch (arch) {
         case ORBIT_ARCH_EFFICIENTNET_B0: build_efficientnet_b0(e); break;
         case ORBIT_ARCH_SET_ENCODER: build_set_encoder(e); break;
+        case ORBIT_ARCH_RESNET18: build_resnet18(e); break;
         case ORBIT_ARCH_VIT_S_32: build_vit(e, 384, 12, 6, 1e-6f, false); break;
         case ORBIT_ARCH_VIT_B_32: build_vit(e, 768, 12, 12, 1e-6f, false); break;
         case ORBIT_ARCH_VIT_B_32_CLIP: build_vit(e, 768, 12, 12, 1e-5f, true); break;
@@ -440,7 +496,7 @@ extern "C" int orbit_engine_prepare(const orbit_engine* e, const float* params, 
             rc = launch_tf32_split(params + op.w, (int64_t)op.cout * op.cin, derived + op.w_split, st);
             if (rc) return rc;
         } else if (op.kind == OP_CONV3) {
-            rc = launch_conv3x3_weight_relayout(params + op.w, derived + op.w_gemm, op.cout, op.cin, op.kpad, op.nchw_in, st);
+            rc = launch_conv_weight_relayout(params + op.w, derived + op.w_gemm, op.cout, op.cin, op.k * op.k, op.kpad, op.nchw_in, st);
             if (rc) return rc;
             rc = launch_tf32_split(derived + op.w_gemm, (int64_t)op.cout * op.kpad, derived + op.w_split, st);
             if (rc) return rc;
@@ -603,24 +659,28 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                         break;
                     }
                     case OP_CONV3: {
-                        const int M = B * h * w;
-                        rc = launch_im2col3x3(ptr(op.in), buf[BUF_COL], B, h, w, op.cin, op.kpad, op.nchw_in, st);
+                        const int cho = (h + 2 * op.pad - op.k) / op.stride + 1, cwo = (w + 2 * op.pad - op.k) / op.stride + 1;
+                        const int M = B * cho * cwo;
+                        rc = launch_im2col(ptr(op.in), buf[BUF_COL], B, h, w, op.cin, op.k, op.stride, op.pad, cho, cwo, op.kpad,
+                                           op.nchw_in, st);
                         if (rc) return rc;
                         ++launches;
                         if (e->profile) { e->prof_recs.push_back({(int)OP_STEM, 4.0 * M * (op.cin + (double)op.kpad), 0.0}); rc = prof_mark(e, st); if (rc) return rc; }
+                        const float* res = raw ? nullptr : ptr(op.res);
                         if (e->gemm_mode == 0 || raw)
-                            rc = launch_pointwise_ffma(buf[BUF_COL], derived + op.w_gemm, scale, shift, nullptr, nullptr, ptr(op.out),
-                                                       M, op.cout, op.kpad, h * w, act, st);
+                            rc = launch_pointwise_ffma(buf[BUF_COL], derived + op.w_gemm, scale, shift, nullptr, res, ptr(op.out),
+                                                       M, op.cout, op.kpad, cho * cwo, act, st);
                         else
-                            rc = launch_pointwise_tcgen05(buf[BUF_COL], derived + op.w_split, scale, shift, nullptr, nullptr,
-                                                          ptr(op.out), M, op.cout, op.kpad, h * w, act, e->gemm_mode == 1 ? 3 : 1, st);
-                        p_bytes = 4.0 * ((double)M * op.kpad + (double)M * op.cout + (double)op.kpad * op.cout);
+                            rc = launch_pointwise_tcgen05(buf[BUF_COL], derived + op.w_split, scale, shift, nullptr, res,
+                                                          ptr(op.out), M, op.cout, op.kpad, cho * cwo, act, e->gemm_mode == 1 ? 3 : 1, st);
+                        p_bytes = 4.0 * ((double)M * op.kpad + (double)M * op.cout * (res ? 2 : 1) + (double)op.kpad * op.cout);
                         p_flops = 2.0 * M * (double)op.kpad * op.cout;
+                        if (op.out != BUF_D) { ho = cho; wo = cwo; }    // the downsample branch keeps the main path's geometry
                         break;
                     }
                     case OP_MAXPOOL:
-                        rc = launch_maxpool2(ptr(op.in), ptr(op.out), B, h, w, op.cin, st);
-                        ho = h / 2; wo = w / 2;
+                        ho = (h + 2 * op.pad - op.k) / op.stride + 1; wo = (w + 2 * op.pad - op.k) / op.stride + 1;
+                        rc = launch_maxpool(ptr(op.in), ptr(op.out), B, h, w, op.cin, op.k, op.stride, op.pad, ho, wo, st);
                         p_bytes = 4.0 * B * op.cin * ((double)h * w + (double)ho * wo);
                         break;
                     case OP_SPATIAL_MEAN:

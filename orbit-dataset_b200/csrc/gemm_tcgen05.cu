@@ -468,6 +468,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             const float4 r = stage[lane * 8 + (q ^ sw)];
                             o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                         }
+                        if (p.act == 16 + 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     }
                     stage[lane * 8 + (q ^ sw)] = o;
                 }
