@@ -103,6 +103,21 @@ int orbit_film_generate(const float* gen_params, const void* table, int num_tens
 int orbit_dense_rows(const float* in, const float* weight, const float* bias, const float* skip, float* out,
                      int rows, int in_dim, int out_dim, int act, void* stream);
 
+/* Mahalanobis head (Simple CNAPs). Replaces MahalanobisClassifier.configure/predict/_estimate_cov
+ * (classifier_heads.py:282-368): Sigma_c = n_c/(n_c+1) cov(class c) + 1/(n_c+1) cov(all) + I, P_c = Sigma_c^-1,
+ * logits[n,c] = -logit_scale (mu_c - q_n)^T P_c (mu_c - q_n); a one-clip class uses the reference's scalar estimate.
+ *   clip_feats [num_clips, feat_dim] pooled features; order [num_clips] int32 (device): clip indices grouped by class
+ *   rank; counts_host [num_classes] (HOST): clips per class. means [C,D], precisions [C,D,D], task_mean [D],
+ *   task_precision [D,D] = (cov(all) + I)^-1 (place it at precisions + C*D*D to invert all matrices in one sweep).  */
+int64_t orbit_mahalanobis_configure_workspace_bytes(int num_clips, int feat_dim, int num_classes);
+int orbit_mahalanobis_configure(const float* clip_feats, const int32_t* order, const int32_t* counts_host, int num_clips,
+                                int feat_dim, int num_classes, float* means, float* precisions, float* task_mean,
+                                float* task_precision, void* workspace, void* stream);
+int64_t orbit_mahalanobis_predict_workspace_bytes(int num_clips, int feat_dim);
+int orbit_mahalanobis_predict(const float* clip_feats, int num_clips, int feat_dim, const float* means,
+                              const float* precisions, int num_classes, float logit_scale, float* logits,
+                              void* workspace, void* stream);
+
 /* FineTuner inner loop in one launch. Replaces the num_grad_steps x batches loop of
  * MultiStepFewShotRecogniser.personalise (few_shot_recognisers.py:231-246) for the default FineTuner (frozen
  * extractor, so the clip features are loop-invariant): LinearClassifier.predict + cross_entropy (mean, each

@@ -1,5 +1,5 @@
-"""Versa head (reference model/classifier_heads.py:121-180, model/mlps.py:33-50) on the native kernels.
-The Mahalanobis head (classifier_heads.py:265-368) needs per-class DxD inverses and is not implemented yet."""
+"""Versa head (reference model/classifier_heads.py:121-180, model/mlps.py:33-50) and Mahalanobis head
+(classifier_heads.py:265-368) on the native kernels."""
 import torch
 import torch.nn as nn
 
@@ -100,5 +100,71 @@ class VersaClassifier(HeadClassifier):
 
 
 class MahalanobisClassifier(HeadClassifier):
+    """classifier_heads.py:265-368 (Simple CNAPs): per-class regularised covariances -> precisions; logits are
+    negative Mahalanobis distances. Attributes as in the reference: means, precisions, task_mean, task_precision."""
+
     def __init__(self, logit_scale: float = 1.0):
-        raise NotImplementedError("the Mahalanobis head (per-class DxD inverses) is not implemented on the B200 path yet")
+        super().__init__(logit_scale)
+        self.reset()
+
+    def reset(self):
+        self.means = None
+        self.precisions = None
+        self.task_mean = None
+        self.task_precision = None
+
+    @staticmethod
+    def _pool(features, clip_length):
+        if clip_length == 1:
+            return features.contiguous().float()
+        n, d = features.shape[0] // clip_length, features.shape[1]
+        out = torch.empty(n, d, dtype=torch.float32, device=features.device)
+        f = features.contiguous().float()
+        L.check(L.load().orbit_pool_clips(L.ptr(f), n, clip_length, d, L.ptr(out), L.stream_ptr(f.device)), "orbit_pool_clips")
+        L.count_launches(1)
+        return out
+
+    def configure(self, context_features, context_labels, ops_counter=None, clip_length=1):
+        import ctypes as C
+        import numpy as np
+        L.require_cuda(context_features, "context_features")
+        assert context_features.size(0) == context_labels.size(0) * clip_length, \
+            "context features and labels are different sizes!"
+        lib = L.load()
+        feats = self._pool(context_features, clip_length)
+        dev = feats.device
+        classes, idx = _class_index(context_labels)
+        c, (n, d) = len(classes), feats.shape
+        order = np.argsort(idx, kind='stable').astype(np.int32)
+        counts = np.bincount(idx, minlength=c).astype(np.int32)
+        order_dev = torch.from_numpy(order).to(dev)
+        mats = torch.empty(c + 1, d, d, dtype=torch.float32, device=dev)     # class precisions, then the task precision
+        means = torch.empty(c, d, dtype=torch.float32, device=dev)
+        task_mean = torch.empty(d, dtype=torch.float32, device=dev)
+        ws = torch.empty(lib.orbit_mahalanobis_configure_workspace_bytes(n, d, c), dtype=torch.uint8, device=dev)
+        L.check(lib.orbit_mahalanobis_configure(L.ptr(feats), L.ptr(order_dev), counts.ctypes.data_as(C.c_void_p), n, d, c,
+                                                L.ptr(means), L.ptr(mats), L.ptr(task_mean), L.ptr(mats[c]), L.ptr(ws),
+                                                L.stream_ptr(dev)), "orbit_mahalanobis_configure")
+        L.count_launches(2 * d + 8 * (c + 1))
+        self.means = nn.Parameter(means)
+        self.task_mean = nn.Parameter(task_mean)
+        self.precisions = nn.Parameter(mats[:c])
+        self.task_precision = nn.Parameter(mats[c])
+
+    def predict(self, target_features, ops_counter=None, clip_length=1, want_argmax=False):
+        if self.means is None or self.precisions is None:
+            raise AttributeError("Means and/or precisions not set - is model personalised?")
+        L.require_cuda(target_features, "target_features")
+        lib = L.load()
+        q = self._pool(target_features, clip_length)
+        nq, d = q.shape
+        c = self.means.shape[0]
+        logits = torch.empty(nq, c, dtype=torch.float32, device=q.device)
+        ws = torch.empty(max(1, lib.orbit_mahalanobis_predict_workspace_bytes(nq, d)), dtype=torch.uint8, device=q.device)
+        L.check(lib.orbit_mahalanobis_predict(L.ptr(q), nq, d, L.ptr(self.means.detach()), L.ptr(self.precisions.detach()), c,
+                                              float(self.logit_scale), L.ptr(logits), L.ptr(ws), L.stream_ptr(q.device)),
+                "orbit_mahalanobis_predict")
+        L.count_launches(4 * c + 2)
+        if want_argmax:
+            return logits, logits.argmax(dim=1).int()
+        return logits

@@ -23,6 +23,10 @@ _SIGNATURES = {
     "orbit_film_table_entry_bytes": (_i, []),
     "orbit_film_generate": (_i, [_p, _p, _i, _i, _p, _i, _p, _p]),
     "orbit_dense_rows": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "orbit_mahalanobis_configure_workspace_bytes": (_i64, [_i, _i, _i]),
+    "orbit_mahalanobis_configure": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "orbit_mahalanobis_predict_workspace_bytes": (_i64, [_i, _i]),
+    "orbit_mahalanobis_predict": (_i, [_p, _i, _i, _p, _p, _i, _f, _p, _p, _p]),
     "orbit_linear_finetune_scratch_bytes": (_i64, [_i, _i, _i]),
     "orbit_linear_finetune": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _f, _p, _p, _p, _p]),
     "orbit_pointwise_conv": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -70,3 +70,43 @@ def test_cnaps_episode_matches_oracle(cuda_device, head, way, size):
         assert torch.equal(am.cpu().long(), ref.argmax(1))
         m._reset()
         assert m.film_dict is None and m.classifier.weight is None
+
+
+@pytest.mark.parametrize("d,counts", [(128, [6, 5, 4, 3]), (512, [3, 1, 4]), (1280, [4, 4, 3])])
+def test_mahalanobis_head_matches_oracle(cuda_device, d, counts):
+    """Simple-CNAPs head on given features (incl. a one-clip class: the reference's scalar covariance branch)."""
+    from orbit_b200.classifier_heads_ext import MahalanobisClassifier
+    g = torch.Generator().manual_seed(d)
+    labels = torch.cat([torch.full((n,), 3 * c + 1) for c, n in enumerate(counts)])
+    labels = labels[torch.randperm(len(labels), generator=g)]
+    feats = torch.randn(len(labels), d, generator=g) * 0.5 + 0.3 * torch.randn(1, d, generator=g)
+    q = torch.randn(9, d, generator=g) * 0.5
+    means, precs = parts.mahalanobis_configure(feats, labels)
+    ref = parts.mahalanobis_predict(q, means, precs, 2.0)
+    head = MahalanobisClassifier(2.0)
+    head.configure(feats.to(cuda_device), labels.to(cuda_device))
+    logits, am = head.predict(q.to(cuda_device), want_argmax=True)
+    perr = (head.precisions.detach().cpu() - precs).abs().max().item()
+    err = (logits.cpu() - ref).abs().max().item()
+    print(f"mahalanobis D={d}: max|dP|={perr:.2e} max|dlogit|={err:.2e} max|logit|={ref.abs().max():.2f}")
+    assert (head.means.detach().cpu() - means).abs().max() <= 1e-5
+    assert perr <= 1e-4
+    assert err <= 2e-4 * max(1.0, ref.abs().max().item())
+    assert torch.equal(am.cpu().long(), ref.argmax(1))
+    head.reset()
+    with pytest.raises(AttributeError):
+        head.predict(q.to(cuda_device))
+
+
+def test_simple_cnaps_episode_matches_oracle(cuda_device):
+    oracle, m = _pair(cuda_device, 'mahalanobis', 64, clip_length=1)
+    spec = EpisodeSpec(3, 3, 2, 1, 64)
+    ctx, ctx_y, tgt, _ = make_episode(spec, index=1)
+    oracle.personalise(ctx, ctx_y)
+    ref = oracle.predict(tgt)
+    m.personalise(ctx.to(cuda_device), ctx_y.to(cuda_device))
+    logits = m.predict(tgt.to(cuda_device))
+    err = (logits.cpu() - ref).abs().max().item()
+    print(f"SimpleCNAPs episode: max|dlogit|={err:.2e} max|logit|={ref.abs().max():.2f}")
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item())
+    assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1))
