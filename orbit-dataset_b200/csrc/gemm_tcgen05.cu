@@ -87,22 +87,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spin > 400000u) __trap();
     }
 }
-// Relaxed wait for the many-warp roles (transform, epilogue): back off between probes so that waiting warps do not
-// eat the issue slots of the warps with real work (ncu: 30-45 % of all issued instructions were mbarrier polling).
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
-        if (!done) __nanosleep(96);
-        if (spin > 400000u) __trap();
-    }
-}
-
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -347,7 +331,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 4; ++i) g[i] = ldg4(p.gate + (int64_t)frame[i] * p.K + kcol);
                     }
-                    mbar_wait_relaxed(&full[s], (it / p.stages) & 1);
+                    mbar_wait(&full[s], (it / p.stages) & 1);
                     float4* hi = reinterpret_cast<float4*>(stage_a_hi(s));
                     float4* lo = reinterpret_cast<float4*>(stage_a_lo(s));
 #pragma unroll
@@ -438,7 +422,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             };
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const int mb = it & 1;
-                mbar_wait_relaxed(&main_full[mb], (it >> 1) & 1);
+                mbar_wait(&main_full[mb], (it >> 1) & 1);
                 tc_fence_after();
                 add_from_tmem((uint32_t)(mb * p.BN), p.debias);
                 tc_fence_before();

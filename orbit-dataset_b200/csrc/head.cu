@@ -202,7 +202,9 @@ using namespace orbit;
 
 extern "C" int orbit_pool_clips(const float* frame_feats, int num_clips, int clip_length, int feat_dim,
                                 float* clip_feats, void* stream) {
-    if (!frame_feats || !clip_feats || num_clips < 0 || clip_length <= 0 || feat_dim <= 0) return ORBIT_ERR_ARG;
+    if (num_clips < 0 || clip_length <= 0 || feat_dim <= 0) return ORBIT_ERR_ARG;
+    if (num_clips == 0) return ORBIT_OK;
+    if (!frame_feats || !clip_feats) return ORBIT_ERR_ARG;
     if (feat_dim % 4 || !aligned16(frame_feats) || !aligned16(clip_feats)) return ORBIT_ERR_UNSUPPORTED;
     if (num_clips == 0) return ORBIT_OK;
     const int64_t total = (int64_t)num_clips * (feat_dim / 4);
@@ -237,8 +239,9 @@ extern "C" int orbit_proto_configure(const float* frame_feats, const int32_t* cl
 extern "C" int orbit_head_predict(const float* frame_feats, int num_clips, int clip_length, int feat_dim,
                                   const float* weight, const float* bias, int num_classes, int metric,
                                   float logit_scale, float* logits, int32_t* argmax, void* stream) {
-    if (!frame_feats || !weight || !logits) return ORBIT_ERR_ARG;
     if (num_clips < 0 || clip_length <= 0 || feat_dim <= 0 || num_classes <= 0) return ORBIT_ERR_ARG;
+    if (num_clips == 0 && weight) return ORBIT_OK;       // empty query set: nothing to write (pointers may be null)
+    if (!frame_feats || !weight || !logits) return ORBIT_ERR_ARG;
     if (metric != ORBIT_METRIC_EUCLIDEAN && metric != ORBIT_METRIC_COSINE) return ORBIT_ERR_ARG;
     if (num_classes > ORBIT_MAX_CLASSES || feat_dim % 4) return ORBIT_ERR_UNSUPPORTED;
     if (!aligned16(frame_feats) || !aligned16(weight)) return ORBIT_ERR_UNSUPPORTED;

@@ -42,6 +42,7 @@ def test_error_strings_and_argument_validation_without_gpu():
     assert b"workspace" in lib.orbit_error_string(-3)
     # null pointers / bad sizes are refused before anything is launched
     assert lib.orbit_pool_clips(None, 1, 1, 4, None, None) == -1
+    assert lib.orbit_pool_clips(None, 0, 1, 4, None, None) == 0          # empty input is legal
     assert lib.orbit_proto_configure(None, None, 1, 1, 4, 1, 0, None, None, None, None, None) == -1
     assert lib.orbit_head_predict(None, 1, 1, 4, None, None, 1, 0, 1.0, None, None, None) == -1
     assert lib.orbit_engine_forward(None, None, None, None, 1, 8, 8, None, None, 0, None) == -1

@@ -161,3 +161,30 @@ def test_finetuner_matches_oracle(cuda_device):
         assert err <= 1e-3 * max(1.0, ref.abs().max().item())
         assert torch.equal(logits.argmax(1), ref.argmax(1))
         m._reset()
+
+
+def test_ragged_batches_and_frame_history(cuda_device, oracle_effnet):
+    """batch_size that does not divide the clip count (3 + 3 + 1 clips), a video turned into causal clips with
+    attach_frame_history (data/utils.py:8-28), and an empty video."""
+    from orbit_b200 import attach_frame_history
+    from orbit_b200.synthetic import EpisodeSpec, make_episode
+    m = _product(oracle_effnet, cuda_device)
+    m.batch_size = 3
+    oracle_effnet.batch_size = 3
+    spec = EpisodeSpec(way=7, support_clips_per_class=1, query_clips_per_class=1, clip_length=2, frame_size=64)
+    ctx, ctx_y, tgt, _ = make_episode(spec, index=11)
+    video = tgt[:, 0]                                   # 7 frames of one "video"
+    clips = attach_frame_history(video, 2)
+    assert clips.shape == (7, 2, 3, 64, 64)
+    try:
+        oracle_effnet.reset()
+        oracle_effnet.personalise(ctx, ctx_y)
+        ref = oracle_effnet.predict(clips)
+        m.personalise(ctx, ctx_y.to(cuda_device))
+        logits = m.predict(clips.to(cuda_device))
+        assert (logits.cpu() - ref).abs().max().item() <= 1e-3
+        assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1))
+        empty = m.predict(clips[:0].to(cuda_device))
+        assert empty.shape == (0, 7)
+    finally:
+        oracle_effnet.batch_size = 256

@@ -87,3 +87,26 @@ def test_cpu_tensor_is_refused():
     from orbit_b200 import MeanPooler, OrbitError
     with pytest.raises(OrbitError):
         MeanPooler(2)(torch.randn(4, 8))
+
+
+def test_edge_cases_empty_query_single_class_max_classes(cuda_device):
+    """Empty query set -> [0, C] logits; one class; the 64-class maximum; 65 classes refused (ValueError)."""
+    from orbit_b200 import PrototypicalClassifier
+    g = torch.Generator().manual_seed(9)
+    sf = torch.randn(12, 64, generator=g)
+    head = PrototypicalClassifier()
+    head.configure(sf.to(cuda_device), torch.zeros(12, dtype=torch.long))
+    assert head.weight.shape == (1, 64)
+    out = head.predict(torch.empty(0, 64, device=cuda_device))
+    assert out.shape == (0, 1)
+    lg, am = head.predict(sf.to(cuda_device), want_argmax=True)
+    assert lg.shape == (12, 1) and int(am.max()) == 0
+    many = torch.randn(130, 64, generator=g)
+    labels = torch.arange(130) % 64
+    head.configure(many.to(cuda_device), labels.to(cuda_device))
+    w_ref, b_ref = parts.proto_configure(many, labels)
+    assert (head.weight.cpu() - w_ref).abs().max() <= 1e-5 and head.weight.shape[0] == 64
+    with pytest.raises(ValueError):
+        head.configure(many.to(cuda_device), (torch.arange(130) % 65).to(cuda_device))
+    with pytest.raises(AssertionError):
+        head.configure(many.to(cuda_device), labels[:100].to(cuda_device))   # classifier_heads.py:240
