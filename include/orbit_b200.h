@@ -37,6 +37,7 @@ extern "C" {
 #define ORBIT_ARCH_VIT_B_32        2 /* feature_extractors.py:54-58                             */
 #define ORBIT_ARCH_VIT_B_32_CLIP   3 /* feature_extractors.py:59-64                             */
 #define ORBIT_ARCH_RESNET18        4 /* BASELINE.json extension (not in the reference)          */
+#define ORBIT_ARCH_EFFICIENTNET_V2_S 5 /* timm tf_efficientnetv2_s_in21k (feature_extractors.py:44-48) */
 #define ORBIT_ARCH_SET_ENCODER   100 /* SetEncoder / SimplePrePoolNet (model/set_encoders.py:34-120): frames ->
                                         64-d per-frame embedding, run through the same engine API               */
 

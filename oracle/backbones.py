@@ -109,16 +109,38 @@ class InvertedResidual(nn.Module):
         return y + x if self.has_skip else y
 
 
-# the other timm block classes film.py:36 imports; never instantiated by B0
 class ConvBnAct(nn.Module):
-    pass
+    """timm 'cn' block (EfficientNet-V2 stage 0): conv3x3 + bn1(SiLU) (+ skip). ``bn1`` is the FiLM site (film.py:41-42)."""
 
+    def __init__(self, cin, cout, k, s, eps):
+        super().__init__()
+        self.conv = Conv2dSame(cin, cout, k, s, bias=False)
+        self.bn1 = BatchNormAct2d(cout, eps)
+        self.has_skip = (s == 1 and cin == cout)
 
-class CondConvResidual(nn.Module):
-    pass
+    def forward(self, x):
+        y = self.bn1(self.conv(x))
+        return y + x if self.has_skip else y
 
 
 class EdgeResidual(nn.Module):
+    """timm 'er' block (fused MBConv): conv_exp kxk + bn1(SiLU) -> conv_pwl 1x1 + bn2 (+ skip). FiLM site: ``bn1``."""
+
+    def __init__(self, cin, cout, k, s, expand, eps):
+        super().__init__()
+        mid = cin * expand
+        self.conv_exp = Conv2dSame(cin, mid, k, s, bias=False)
+        self.bn1 = BatchNormAct2d(mid, eps)
+        self.conv_pwl = nn.Conv2d(mid, cout, 1, bias=False)
+        self.bn2 = BatchNormAct2d(cout, eps, act=False)
+        self.has_skip = (s == 1 and cin == cout)
+
+    def forward(self, x):
+        y = self.bn2(self.conv_pwl(self.bn1(self.conv_exp(x))))
+        return y + x if self.has_skip else y
+
+
+class CondConvResidual(nn.Module):   # imported by film.py:36, never instantiated by the supported extractors
     pass
 
 
@@ -134,17 +156,34 @@ EFFNET_B0_STAGES = (
 )
 
 
+# (block type, repeats, kernel, stride, out channels, expand) per stage of timm tf_efficientnetv2_s
+EFFNET_V2S_STAGES = (
+    ('cn', 2, 3, 1, 24, 1),
+    ('er', 4, 3, 2, 48, 4),
+    ('er', 4, 3, 2, 64, 4),
+    ('ir', 6, 3, 2, 128, 4),
+    ('ir', 9, 3, 1, 160, 6),
+    ('ir', 15, 3, 2, 256, 6),
+)
+
+
 class EfficientNet(nn.Module):
     def __init__(self, eps=1e-3, stem=32, head=1280, stages=EFFNET_B0_STAGES):
         super().__init__()
         self.conv_stem = Conv2dSame(3, stem, 3, 2, bias=False)
         self.bn1 = BatchNormAct2d(stem, eps)
         blocks, cin = [], stem
-        for (r, k, s, cout, e) in stages:
+        for spec in stages:
+            kind = spec[0] if isinstance(spec[0], str) else None
+            (r, k, s, cout, e) = spec[1:] if kind else spec
             stage = []
             for j in range(r):
                 st = s if j == 0 else 1
-                if e == 1:
+                if kind == 'cn':
+                    stage.append(ConvBnAct(cin, cout, k, st, eps))
+                elif kind == 'er':
+                    stage.append(EdgeResidual(cin, cout, k, st, e, eps))
+                elif kind is None and e == 1:
                     stage.append(DepthwiseSeparableConv(cin, cout, k, st, eps))
                 else:
                     stage.append(InvertedResidual(cin, cout, k, st, e, eps))
@@ -247,6 +286,8 @@ def build(name: str) -> nn.Module:
     """Extractor strings of reference feature_extractors.py:39-66 (+ resnet18 extension)."""
     if name == 'efficientnet_b0':
         return EfficientNet()
+    if name == 'efficientnet_v2_s':
+        return EfficientNet(stem=24, stages=EFFNET_V2S_STAGES)
     if name == 'vit_s_32':
         return VisionTransformer(384, 12, 6)
     if name == 'vit_b_32':

@@ -205,9 +205,11 @@ def film_parameter_names(extractor_name: str, model: nn.Module):
         leaf = mname.split('.')[-1]
         parent = mname.rsplit('.', 1)[0] if '.' in mname else ''
         if 'efficientnet' in extractor_name:
+            ptype = type(model.get_submodule(parent)).__name__ if parent else ''
             if isinstance(mod, nn.BatchNorm2d) and (
                     (parent == '' and leaf in ('bn1', 'bn2')) or
-                    (leaf == 'bn2' and type(model.get_submodule(parent)).__name__ == 'InvertedResidual')):
+                    (leaf == 'bn2' and ptype == 'InvertedResidual') or
+                    (leaf == 'bn1' and ptype in ('EdgeResidual', 'ConvBnAct'))):
                 names += [mname + '.weight', mname + '.bias']
         elif 'vit' in extractor_name:
             if isinstance(mod, nn.LayerNorm) and leaf in ('norm', 'norm1', 'norm2'):

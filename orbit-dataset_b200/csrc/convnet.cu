@@ -710,8 +710,8 @@ int launch_pointwise_ffma(const float* A, const float* Wt, const float* scale, c
 // (<= 150 frames) that is a few GB of traffic, far below the GEMM time.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int k, int stride, int pad,
-              int Ho, int Wo, int Kpad, int nchw) {
+im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int k, int stride, int pad_t,
+              int pad_l, int Ho, int Wo, int Kpad, int nchw) {
     const int kk = k * k;
     const int64_t total = (int64_t)B * Ho * Wo * Kpad;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -721,18 +721,18 @@ im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H
         float v = 0.f;
         if (kc < kk * C) {
             const int c = nchw ? kc / kk : kc % C, tap = nchw ? kc % kk : kc / C;
-            const int iy = oy * stride - pad + tap / k, ix = ox * stride - pad + tap % k;
+            const int iy = oy * stride - pad_t + tap / k, ix = ox * stride - pad_l + tap % k;
             if (iy >= 0 && iy < H && ix >= 0 && ix < W)
                 v = nchw ? __ldg(x + (((int64_t)b * C + c) * H + iy) * W + ix) : __ldg(x + (((int64_t)b * H + iy) * W + ix) * C + c);
         }
         col[i] = v;
     }
 }
-int launch_im2col(const float* x, float* col, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
-                  int Kpad, int nchw, cudaStream_t st) {
+int launch_im2col(const float* x, float* col, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho,
+                  int Wo, int Kpad, int nchw, cudaStream_t st) {
     const int64_t total = (int64_t)B * Ho * Wo * Kpad;
     if (total == 0) return ORBIT_OK;
-    im2col_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(x, col, B, H, W, C, k, stride, pad, Ho, Wo, Kpad, nchw);
+    im2col_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(x, col, B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo, Kpad, nchw);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }

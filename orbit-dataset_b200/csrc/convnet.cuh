@@ -52,10 +52,10 @@ int launch_pointwise_ffma(const float* A, const float* Wt, const float* scale, c
                           const float* residual, float* out, int M, int N, int K, int rows_per_frame, int act,
                           cudaStream_t st);
 
-// k x k / stride / symmetric pad im2col. nchw=1: x [B,C,H,W] -> col [B*Ho*Wo, Kpad], col index = c*k*k + tap (torch
+// k x k / stride im2col with top/left padding (pad_t, pad_l); taps beyond the bottom/right edge read zero. nchw=1: x [B,C,H,W] -> col [B*Ho*Wo, Kpad], col index = c*k*k + tap (torch
 // weight order); nchw=0: x [B,H,W,C] -> col index = tap*C + c. Columns >= k*k*C are zero.
-int launch_im2col(const float* x, float* col, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
-                  int Kpad, int nchw, cudaStream_t st);
+int launch_im2col(const float* x, float* col, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho,
+                  int Wo, int Kpad, int nchw, cudaStream_t st);
 // conv weight [Cout, Cin, k, k] -> [Cout, Kpad] in the im2col column order above
 int launch_conv_weight_relayout(const float* w, float* out, int Cout, int Cin, int kk, int Kpad, int nchw, cudaStream_t st);
 // k x k / stride max pool with symmetric padding (floor mode), NHWC: (2,2,0) for the set encoder, (3,2,1) for resnet

@@ -38,6 +38,7 @@ struct Op {
     int64_t w_split = -1;       // derived offset of tf32 hi/lo split weights (PW, tcgen05 path)
     int64_t w_gemm = -1;        // CONV3: derived offset of the weights re-laid-out to [cout, kpad] (im2col k-order)
     int kpad = 0;               // CONV3: im2col row length (k*k*cin rounded up to a multiple of 4)
+    bool same_pad = false;      // CONV3: TF SAME geometry (asymmetric for stride 2) instead of the symmetric `pad`
     int pad = 1;                // CONV3 / MAXPOOL: symmetric padding
     int save = BUF_NONE;        // CONV3: unused; PW-free resnet plumbing uses explicit buffers
     bool nchw_in = false;       // CONV3: input is the fp32 NCHW frame tensor
@@ -144,6 +145,50 @@ struct orbit_engine {
     }
 };
 
+// One timm DepthwiseSeparableConv (expand == 1) / InvertedResidual block: [expand 1x1 + bn1 + SiLU] -> depthwise kxk +
+// bn (FiLM site of InvertedResidual: bn2, model/film.py:39-40) + SiLU -> squeeze-excite (reduce = cin/4) -> gated
+// project 1x1 + bn (+ skip). `*cur` is the buffer holding the block input; it is advanced to the block output.
+static void add_mbconv(orbit_engine* e, const std::string& p, int cin, int cout, int k, int stride, int expand, float eps, int* cur_io) {
+    const int cur = *cur_io;
+    const int mid = cin * expand;
+    const bool ds = expand == 1;
+    int dw_in = cur;
+    if (!ds) {  // expand 1x1 + bn1 + SiLU
+        Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_E; op.cin = cin; op.cout = mid; op.act = ACT_SILU;
+        op.w = e->add_param(p + "conv_pw.weight", mid, cin, 1, 1);
+        op.fold = e->add_bn(p + "bn1", mid, eps, false, &op);
+        op.w_split = e->add_derived(2 * (int64_t)mid * cin);
+        e->ops.push_back(op);
+        dw_in = BUF_E;
+    }
+    {   // depthwise + bn + SiLU
+        Op op; op.kind = OP_DW; op.in = dw_in; op.out = BUF_D; op.cin = op.cout = mid; op.k = k; op.stride = stride; op.act = ACT_SILU;
+        op.w = e->add_param(p + "conv_dw.weight", mid, 1, k, k);
+        op.fold = e->add_bn(p + (ds ? "bn1" : "bn2"), mid, eps, !ds, &op);
+        op.dw_wt = e->add_derived((int64_t)mid * k * k);
+        e->ops.push_back(op);
+    }
+    {   // squeeze-excite gate
+        Op op; op.kind = OP_SE; op.in = BUF_PARTIAL; op.out = BUF_GATE; op.cin = op.cout = mid;
+        op.se_reduce = std::max(1, cin / 4);
+        op.w = e->add_param(p + "se.conv_reduce.weight", op.se_reduce, mid, 1, 1);
+        op.b = e->add_param(p + "se.conv_reduce.bias", op.se_reduce);
+        op.w2 = e->add_param(p + "se.conv_expand.weight", mid, op.se_reduce, 1, 1);
+        op.b2 = e->add_param(p + "se.conv_expand.bias", mid);
+        e->ops.push_back(op);
+    }
+    {   // project 1x1 (gated input) + bn (+ residual)
+        Op op; op.kind = OP_PW; op.in = BUF_D; op.cin = mid; op.cout = cout; op.act = ACT_NONE; op.gated = true;
+        op.out = cur == BUF_X0 ? BUF_X1 : BUF_X0;
+        if (stride == 1 && cin == cout) op.res = cur;
+        op.w = e->add_param(p + (ds ? "conv_pw.weight" : "conv_pwl.weight"), cout, mid, 1, 1);
+        op.fold = e->add_bn(p + (ds ? "bn2" : "bn3"), cout, eps, false, &op);
+        op.w_split = e->add_derived(2 * (int64_t)cout * mid);
+        e->ops.push_back(op);
+        *cur_io = op.out;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // EfficientNet-B0 plan (timm tf_efficientnet_b0: TF SAME padding, BN eps 1e-3, SiLU, SE reduce = cin/4)
 // ------------------------------------------------------------------------------------------------
@@ -163,48 +208,76 @@ static void build_efficientnet_b0(orbit_engine* e) {
     for (int s = 0; s < 7; ++s) {
         for (int j = 0; j < stages[s].repeats; ++j) {
             const std::string p = "blocks." + std::to_string(s) + "." + std::to_string(j) + ".";
-            const int stride = j == 0 ? stages[s].stride : 1, k = stages[s].k, cout = stages[s].cout;
-            const int mid = cin * stages[s].expand;
-            const bool ds = stages[s].expand == 1;
-            int dw_in = cur;
-            if (!ds) {  // expand 1x1 + bn1 + SiLU
-                Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_E; op.cin = cin; op.cout = mid; op.act = ACT_SILU;
-                op.w = e->add_param(p + "conv_pw.weight", mid, cin, 1, 1);
-                op.fold = e->add_bn(p + "bn1", mid, eps, false, &op);
-                op.w_split = e->add_derived(2 * (int64_t)mid * cin);
-                e->ops.push_back(op);
-                dw_in = BUF_E;
-            }
-            {   // depthwise + bn + SiLU (the FiLM site of InvertedResidual: bn2)
-                Op op; op.kind = OP_DW; op.in = dw_in; op.out = BUF_D; op.cin = op.cout = mid; op.k = k; op.stride = stride; op.act = ACT_SILU;
-                op.w = e->add_param(p + "conv_dw.weight", mid, 1, k, k);
-                op.fold = e->add_bn(p + (ds ? "bn1" : "bn2"), mid, eps, !ds, &op);
-                op.dw_wt = e->add_derived((int64_t)mid * k * k);
-                e->ops.push_back(op);
-            }
-            {   // squeeze-excite gate
-                Op op; op.kind = OP_SE; op.in = BUF_PARTIAL; op.out = BUF_GATE; op.cin = op.cout = mid;
-                op.se_reduce = std::max(1, cin / 4);
-                op.w = e->add_param(p + "se.conv_reduce.weight", op.se_reduce, mid, 1, 1);
-                op.b = e->add_param(p + "se.conv_reduce.bias", op.se_reduce);
-                op.w2 = e->add_param(p + "se.conv_expand.weight", mid, op.se_reduce, 1, 1);
-                op.b2 = e->add_param(p + "se.conv_expand.bias", mid);
-                e->ops.push_back(op);
-            }
-            {   // project 1x1 (gated input) + bn (+ residual)
-                Op op; op.kind = OP_PW; op.in = BUF_D; op.cin = mid; op.cout = cout; op.act = ACT_NONE; op.gated = true;
-                op.out = cur == BUF_X0 ? BUF_X1 : BUF_X0;
-                if (stride == 1 && cin == cout) op.res = cur;
-                op.w = e->add_param(p + (ds ? "conv_pw.weight" : "conv_pwl.weight"), cout, mid, 1, 1);
-                op.fold = e->add_bn(p + (ds ? "bn2" : "bn3"), cout, eps, false, &op);
+            add_mbconv(e, p, cin, stages[s].cout, stages[s].k, j == 0 ? stages[s].stride : 1, stages[s].expand, eps, &cur);
+            cin = stages[s].cout;
+        }
+    }
+    {   // conv_head + bn2 (FiLM, root) + SiLU, then global average pool
+        Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_H; op.cin = cin; op.cout = 1280; op.act = ACT_SILU;
+        op.w = e->add_param("conv_head.weight", 1280, cin, 1, 1);
+        op.fold = e->add_bn("bn2", 1280, eps, true, &op);
+        op.w_split = e->add_derived(2 * (int64_t)1280 * cin);
+        e->ops.push_back(op);
+        Op pool; pool.kind = OP_SPATIAL_MEAN; pool.in = BUF_H; pool.out = BUF_OUTPUT; pool.cin = pool.cout = 1280;
+        e->ops.push_back(pool);
+    }
+    e->finalize_film();
+    e->ident = e->add_derived(2 * (int64_t)e->max_c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EfficientNet-V2-S plan (timm tf_efficientnetv2_s: TF SAME padding, BN eps 1e-3, SiLU; reference
+// model/feature_extractors.py:16-19). Stages: cn r2 k3 s1 c24 | er r4 k3 s2 e4 c48 | er r4 k3 s2 e4 c64 |
+// ir r6 k3 s2 e4 c128 se | ir r9 k3 s1 e6 c160 se | ir r15 k3 s2 e6 c256 se | head 1280. The full 3x3 convs (stem, ConvBnAct,
+// EdgeResidual.conv_exp) run as im2col + the tcgen05 GEMM with BN/FiLM/SiLU/skip in its epilogue. FiLM sites
+// (model/film.py:38-46): root bn1/bn2, ConvBnAct.bn1, EdgeResidual.bn1, InvertedResidual.bn2.
+// ------------------------------------------------------------------------------------------------
+static void build_efficientnet_v2_s(orbit_engine* e) {
+    const float eps = 1e-3f;
+    e->feat_dim = 1280;
+    e->chunk_frames = 128;   // the 112x112x216 im2col matrix is 10.8 MB per frame
+    auto conv = [&](const std::string& wname, const std::string& bnname, int in_buf, int out_buf, int cin, int cout, int k,
+                    int stride, int act, int res, bool film_site, bool nchw) {
+        Op op; op.kind = OP_CONV3; op.in = in_buf; op.out = out_buf; op.res = res; op.cin = cin; op.cout = cout; op.k = k;
+        op.stride = stride; op.same_pad = true; op.act = act; op.nchw_in = nchw;
+        op.kpad = (k * k * cin + 3) / 4 * 4;
+        op.w = e->add_param(wname, cout, cin, k, k);
+        op.fold = e->add_bn(bnname, cout, eps, film_site, &op);
+        op.w_gemm = e->add_derived((int64_t)cout * op.kpad);
+        op.w_split = e->add_derived(2 * (int64_t)cout * op.kpad);
+        e->ops.push_back(op);
+    };
+    conv("conv_stem.weight", "bn1", BUF_INPUT, BUF_X0, 3, 24, 3, 2, ACT_SILU, BUF_NONE, true, true);
+    int cin = 24, cur = BUF_X0;
+    struct Stage { char type; int repeats, k, stride, cout, expand; };
+    const Stage stages[6] = {{'c', 2, 3, 1, 24, 1}, {'e', 4, 3, 2, 48, 4}, {'e', 4, 3, 2, 64, 4},
+                             {'i', 6, 3, 2, 128, 4}, {'i', 9, 3, 1, 160, 6}, {'i', 15, 3, 2, 256, 6}};
+    for (int s = 0; s < 6; ++s) {
+        for (int j = 0; j < stages[s].repeats; ++j) {
+            const std::string p = "blocks." + std::to_string(s) + "." + std::to_string(j) + ".";
+            const int stride = j == 0 ? stages[s].stride : 1, cout = stages[s].cout;
+            const int other = cur == BUF_X0 ? BUF_X1 : BUF_X0;
+            const bool skip = stride == 1 && cin == cout;
+            if (stages[s].type == 'c') {          // ConvBnAct: silu(bn1(conv x)) + x
+                conv(p + "conv.weight", p + "bn1", cur, other, cin, cout, 3, stride, ACT_SILU, skip ? cur : BUF_NONE, true, false);
+                cur = other;
+            } else if (stages[s].type == 'e') {   // EdgeResidual: bn2(conv_pwl(silu(bn1(conv_exp x)))) + x
+                const int mid = cin * stages[s].expand;
+                conv(p + "conv_exp.weight", p + "bn1", cur, BUF_E, cin, mid, 3, stride, ACT_SILU, BUF_NONE, true, false);
+                Op op; op.kind = OP_PW; op.in = BUF_E; op.out = other; op.cin = mid; op.cout = cout; op.act = ACT_NONE;
+                if (skip) op.res = cur;
+                op.w = e->add_param(p + "conv_pwl.weight", cout, mid, 1, 1);
+                op.fold = e->add_bn(p + "bn2", cout, eps, false, &op);
                 op.w_split = e->add_derived(2 * (int64_t)cout * mid);
                 e->ops.push_back(op);
-                cur = op.out;
+                cur = other;
+            } else {
+                add_mbconv(e, p, cin, cout, stages[s].k, stride, stages[s].expand, eps, &cur);
             }
             cin = cout;
         }
     }
-    {   // conv_head + bn2 (FiLM, root) + SiLU, then global average pool
+    {
         Op op; op.kind = OP_PW; op.in = cur; op.out = BUF_H; op.cin = cin; op.cout = 1280; op.act = ACT_SILU;
         op.w = e->add_param("conv_head.weight", 1280, cin, 1, 1);
         op.fold = e->add_bn("bn2", 1280, eps, true, &op);
@@ -357,6 +430,18 @@ static void same_geometry(int in, int k, int s, int* out, int* pad_before) {
     *pad_before = total / 2;
 }
 
+// output size and top/left padding of a full convolution: symmetric `pad` or TF SAME
+static void conv_geometry(const Op& op, int h, int w, int* ho, int* wo, int* pt, int* pl) {
+    if (op.same_pad) {
+        same_geometry(h, op.k, op.stride, ho, pt);
+        same_geometry(w, op.k, op.stride, wo, pl);
+    } else {
+        *ho = (h + 2 * op.pad - op.k) / op.stride + 1;
+        *wo = (w + 2 * op.pad - op.k) / op.stride + 1;
+        *pt = *pl = op.pad;
+    }
+}
+
 struct BufSizes {
     int64_t per_frame[BUF_COUNT];
 };
@@ -382,7 +467,8 @@ static int plan_buffers(const orbit_engine* e, int H, int W, BufSizes* bs) {
             case OP_SE: need(BUF_GATE, op.cout); break;
             case OP_PW: need(op.out, (int64_t)(e->tokens ? e->tokens : h * w) * op.cout); break;
             case OP_CONV3: {
-                const int ho = (h + 2 * op.pad - op.k) / op.stride + 1, wo = (w + 2 * op.pad - op.k) / op.stride + 1;
+                int ho, wo, pt, pl;
+                conv_geometry(op, h, w, &ho, &wo, &pt, &pl);
                 if (ho < 1 || wo < 1) return ORBIT_ERR_UNSUPPORTED;
                 need(BUF_COL, (int64_t)ho * wo * op.kpad);
                 need(op.out, (int64_t)ho * wo * op.cout);
@@ -415,6 +501,7 @@ extern "C" int orbit_engine_create(orbit_engine** out, int arch) {
     e->arch = arch;
     switch (arch) {
         case ORBIT_ARCH_EFFICIENTNET_B0: build_efficientnet_b0(e); break;
+        case ORBIT_ARCH_EFFICIENTNET_V2_S: build_efficientnet_v2_s(e); break;
         case ORBIT_ARCH_SET_ENCODER: build_set_encoder(e); break;
         case ORBIT_ARCH_RESNET18: build_resnet18(e); break;
         case ORBIT_ARCH_VIT_S_32: build_vit(e, 384, 12, 6, 1e-6f, false); break;
@@ -659,9 +746,10 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                         break;
                     }
                     case OP_CONV3: {
-                        const int cho = (h + 2 * op.pad - op.k) / op.stride + 1, cwo = (w + 2 * op.pad - op.k) / op.stride + 1;
+                        int cho, cwo, cpt, cpl;
+                        conv_geometry(op, h, w, &cho, &cwo, &cpt, &cpl);
                         const int M = B * cho * cwo;
-                        rc = launch_im2col(ptr(op.in), buf[BUF_COL], B, h, w, op.cin, op.k, op.stride, op.pad, cho, cwo, op.kpad,
+                        rc = launch_im2col(ptr(op.in), buf[BUF_COL], B, h, w, op.cin, op.k, op.stride, cpt, cpl, cho, cwo, op.kpad,
                                            op.nchw_in, st);
                         if (rc) return rc;
                         ++launches;

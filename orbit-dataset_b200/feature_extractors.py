@@ -20,6 +20,7 @@ ARCH_IDS = {
     'vit_b_32': 2,
     'vit_b_32_clip': 3,
     'resnet18': 4,  # BASELINE.json extension; not in the reference at this commit
+    'efficientnet_v2_s': 5,
 }
 
 

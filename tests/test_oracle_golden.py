@@ -153,3 +153,15 @@ def test_finetuner_vs_reference(gr):
         close(oracle.head[0], gr['finetune_weight'], 1e-4)
         close(oracle.head[1], gr['finetune_bias'], 1e-4)
         close(oracle.predict(tgt), gr['finetune_logits'], 1e-4)
+
+
+def test_efficientnet_v2_s_structure():
+    """tf_efficientnetv2_s with num_classes=0: 20,177,488 parameters (timm's published 21.46 M minus the 1280x1000+1000
+    classifier), 84 FiLM tensors (2 root + 2 ConvBnAct + 8 EdgeResidual + 30 InvertedResidual sites, weight + bias)."""
+    from oracle import backbones, parts
+    m = backbones.build('efficientnet_v2_s')
+    assert sum(p.numel() for p in m.parameters()) == 20177488
+    names = parts.film_parameter_names('efficientnet_v2_s', m)
+    assert len(names) == 84 and names[:2] == ['bn1.weight', 'bn1.bias'] and names[-2:] == ['bn2.weight', 'bn2.bias']
+    assert 'blocks.0.1.bn1.weight' in names and 'blocks.2.3.bn1.bias' in names and 'blocks.5.14.bn2.weight' in names
+    assert not any('.bn3.' in n for n in names)
