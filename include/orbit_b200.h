@@ -195,6 +195,11 @@ int orbit_engine_get_option(const orbit_engine* e, const char* key, int* value);
 
 int64_t orbit_engine_workspace_bytes(const orbit_engine* e, int height, int width);
 
+/* Multiply-accumulates of one forward pass over ONE height x width frame (convolutions, dense layers, attention
+ * matmuls, pooling adds; normalisation and activations are not counted). Replaces the thop trace behind
+ * OpsCounter.compute_macs (reference utils/ops_counter.py:82-88, few_shot_recognisers.py:119-120). Host-only; < 0 on error. */
+int64_t orbit_engine_macs(const orbit_engine* e, int height, int width);
+
 /* frames [num_frames,3,height,width] fp32 NCHW  ->  feats [num_frames, feat_dim] fp32.          */
 int orbit_engine_forward(const orbit_engine* e, const float* params, const float* derived,
                          const float* frames, int num_frames, int height, int width,

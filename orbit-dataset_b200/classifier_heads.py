@@ -76,6 +76,8 @@ class LinearClassifier(nn.Module):
     def predict(self, features, ops_counter=None, clip_length=1):
         if self.weight is None:
             raise AttributeError("Weight and/or bias not set - is model personalised?")
+        if ops_counter:   # classifier_heads.py:72-73
+            ops_counter.add_macs(self.weight.size(0) * (features.size(0) // clip_length) * self.feat_dim)
         return _head_predict(features, clip_length, self.weight, self.bias, 0, self.logit_scale)
 
     def reset(self):
@@ -87,6 +89,13 @@ class HeadClassifier(nn.Module):
     def __init__(self, logit_scale: float = 1.0):
         super().__init__()
         self.logit_scale = logit_scale
+
+    @staticmethod
+    def _count_class_reps(ops_counter, num_context, feat_dim, num_classes):
+        """MACs the reference adds in ``_build_class_reps`` (classifier_heads.py:101-103): per class, selecting its
+        rows (N) and mean-pooling them (n_c * D); summed over classes = C*N + N*D."""
+        if ops_counter:
+            ops_counter.add_macs(num_classes * num_context + num_context * feat_dim)
 
 
 class PrototypicalClassifier(HeadClassifier):
@@ -135,6 +144,9 @@ class PrototypicalClassifier(HeadClassifier):
         if euclid:
             self.bias = nn.Parameter(bias)
         self.classes = torch.from_numpy(classes)
+        self._count_class_reps(ops_counter, n, d, c)
+        if ops_counter:   # classifier_heads.py:256-259: 2*mu, mu.mu^T, negation -- D MACs each per class
+            ops_counter.add_macs(3 * c * d)
 
     def predict(self, features, ops_counter=None, clip_length=1, want_argmax=False):
         if self.weight is None or (self.distance_fn == 'euclidean' and self.bias is None):
@@ -142,5 +154,8 @@ class PrototypicalClassifier(HeadClassifier):
         if self.distance_fn not in _METRICS:
             raise ValueError(f"Distance function {self.distance_fn} not valid.")
         bias = self.bias if self.distance_fn == 'euclidean' else None
+        if ops_counter:   # classifier_heads.py:221-228
+            nq, d, c = features.size(0) // clip_length, features.size(1), self.weight.size(0)
+            ops_counter.add_macs(nq * d * c if self.distance_fn == 'euclidean' else 2 * nq * d * c + c * d + nq * d)
         return _head_predict(features, clip_length, self.weight, bias, _METRICS[self.distance_fn], self.logit_scale,
                              want_argmax)

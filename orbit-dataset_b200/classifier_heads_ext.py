@@ -17,6 +17,9 @@ class DenseResidualBlock(nn.Module):
         self.linear3 = nn.Linear(out_size, out_size)
         self.in_size, self.out_size = in_size, out_size
 
+    def count_macs(self, x):
+        return int(x.shape[0]) * (self.in_size * self.out_size + 2 * self.out_size * self.out_size)
+
     def forward(self, x):
         lib = L.load()
         L.require_cuda(x, "class representations")
@@ -97,6 +100,11 @@ class VersaClassifier(HeadClassifier):
         L.count_launches(1)
         self.weight = nn.Parameter(self.weight_processor(mu))
         self.bias = nn.Parameter(self.bias_processor(mu).reshape(c))
+        self._count_class_reps(ops_counter, n, d, c)
+        if ops_counter:   # classifier_heads.py:175-177: both hyper-networks traced once per class
+            for _ in range(c):
+                ops_counter.compute_macs(self.weight_processor, mu[:1])
+                ops_counter.compute_macs(self.bias_processor, mu[:1])
 
 
 class MahalanobisClassifier(HeadClassifier):
@@ -150,6 +158,13 @@ class MahalanobisClassifier(HeadClassifier):
         self.task_mean = nn.Parameter(task_mean)
         self.precisions = nn.Parameter(mats[:c])
         self.task_precision = nn.Parameter(mats[c])
+        if ops_counter:   # classifier_heads.py:296,308,314-320,363-366
+            def cov_macs(rows):
+                return rows * d + rows * rows * d + rows * d
+            ops_counter.add_macs(cov_macs(n))
+            for n_c in counts.tolist():
+                ops_counter.add_macs(cov_macs(n_c))
+                ops_counter.add_macs(n + n_c * d + 1 + 2 * d * d + (d ** 3) / 3 + d ** 2 - 4 * d / 3)
 
     def predict(self, target_features, ops_counter=None, clip_length=1, want_argmax=False):
         if self.means is None or self.precisions is None:

@@ -603,6 +603,47 @@ extern "C" int64_t orbit_engine_workspace_bytes(const orbit_engine* e, int heigh
     return total + 1024;
 }
 
+extern "C" int64_t orbit_engine_macs(const orbit_engine* e, int height, int width) {
+    if (!e || height <= 0 || width <= 0) return ORBIT_ERR_ARG;
+    BufSizes bs;
+    if (plan_buffers(e, height, width, &bs)) return ORBIT_ERR_UNSUPPORTED;
+    int64_t macs = 0;
+    int h = height, w = width;
+    for (const Op& op : e->ops) {
+        switch (op.kind) {
+            case OP_STEM:
+            case OP_DW: {
+                int ho, wo, p;
+                same_geometry(h, op.k, op.stride, &ho, &p);
+                same_geometry(w, op.k, op.stride, &wo, &p);
+                h = ho; w = wo;
+                macs += (int64_t)h * w * op.cout * op.k * op.k * (op.kind == OP_STEM ? op.cin : 1);
+                break;
+            }
+            case OP_SE: macs += (int64_t)h * w * op.cin + 2LL * op.cin * op.se_reduce; break;   // squeeze adds + 2 FCs
+            case OP_PW: {
+                const int64_t rows = e->tokens ? (op.patch ? e->tokens - 1 : e->tokens) : (int64_t)h * w;
+                macs += rows * op.cin * op.cout;
+                break;
+            }
+            case OP_CONV3: {
+                int ho, wo, pt, pl;
+                conv_geometry(op, h, w, &ho, &wo, &pt, &pl);
+                macs += (int64_t)ho * wo * op.k * op.k * op.cin * op.cout;
+                if (op.out != BUF_D) { h = ho; w = wo; }
+                break;
+            }
+            case OP_MAXPOOL:
+                h = (h + 2 * op.pad - op.k) / op.stride + 1; w = (w + 2 * op.pad - op.k) / op.stride + 1;
+                break;
+            case OP_SPATIAL_MEAN: macs += (int64_t)h * w * op.cin; break;
+            case OP_ATTN: macs += 2LL * e->tokens * e->tokens * op.cin; break;   // QK^T and PV
+            case OP_PATCH: case OP_ASSEMBLE: case OP_LN: break;
+        }
+    }
+    return macs;
+}
+
 static int prof_mark(const orbit_engine* e, cudaStream_t st) {
     if (e->prof_used == e->prof_events.size()) {
         cudaEvent_t ev;

@@ -20,6 +20,9 @@ class NullSetEncoder(nn.Module):
     def forward(self, x):
         return None
 
+    def count_macs(self, *inputs):
+        return 0
+
     def aggregate(self, x, aggregation='mean'):
         return None
 
@@ -33,6 +36,9 @@ class NullGenerator(nn.Module):
 
     def forward(self, x):
         return {}
+
+    def count_macs(self, *inputs):
+        return 0
 
     def regularization_term(self):
         return 0
@@ -51,6 +57,7 @@ class SetEncoder(FeatureExtractor):
         if x.dim() == 5:
             x = x.flatten(end_dim=1)
         return super().forward(x)
+    # count_macs: inherited from FeatureExtractor (the set encoder runs through the same engine)
 
     def aggregate(self, x, aggregation='mean'):
         if not isinstance(x, torch.Tensor):
@@ -75,6 +82,11 @@ _TABLE_DTYPE = np.dtype([(k, '<i8') for k in ('w1', 'b1', 'ln_w', 'ln_b', 'w2', 
 class FilmParameterGenerator(nn.Module):
     """feature_adapters.py:36-78. ``forward(z)`` returns the reference's ``{name: tensor}`` dict; the tensors are
     views of ONE film blob (sorted-name order, feature_adapters.py:43-44) that the extractor engine folds directly."""
+
+    def count_macs(self, *inputs):
+        """Dense-layer MACs of every DenseBlock (mlps.py:52-71: pooled->hidden, hidden->size) plus the regulariser
+        scale (one multiply per generated value, feature_adapters.py:62-66)."""
+        return sum(self.hidden * self.hidden + self.hidden * r['size'] + r['size'] for r in self._rows)
 
     def __init__(self, film_parameter_sizes, initial_film_parameters, pooled_size, hidden_size):
         super().__init__()

@@ -195,6 +195,15 @@ class FeatureExtractor(nn.Module):
         L.check(L.load().orbit_engine_get_option(self._engine, key.encode(), C.byref(v)), f"get_option({key})")
         return v.value
 
+    def count_macs(self, frames) -> int:
+        """MACs of one forward over ``frames`` [..., 3, H, W] (any leading dims); see ``ops_counter.py``."""
+        h, w = int(frames.shape[-2]), int(frames.shape[-1])
+        n = int(frames.numel() // (3 * h * w))
+        per_frame = L.load().orbit_engine_macs(self._engine, h, w)
+        if per_frame < 0:
+            L.check(int(per_frame), "orbit_engine_macs")
+        return n * int(per_frame)
+
     PROFILE_FAMILIES = ('stem_conv', 'depthwise_conv', 'se_gate', 'pointwise_gemm', 'spatial_mean', 'calibration')
 
     def profile_read(self):

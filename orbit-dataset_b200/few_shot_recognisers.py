@@ -153,6 +153,8 @@ class FewShotRecogniser(nn.Module):
         self._require_device()
         if len(clips.shape) == 5:
             clips = clips.reshape(clips.shape[0] * clips.shape[1], *clips.shape[2:])
+        if ops_counter:
+            ops_counter.compute_macs(self.feature_extractor, clips)
         return self._run_extractor(clips, film_dict)
 
     def _get_features_in_batches(self, clips, film_dict={}, ops_counter=None):
@@ -167,12 +169,16 @@ class FewShotRecogniser(nn.Module):
             if len(batch_clips.shape) == 5:
                 batch_clips = batch_clips.flatten(end_dim=1)
             features.append(self._run_extractor(batch_clips, film_dict))
+            if ops_counter:
+                ops_counter.compute_macs(self.feature_extractor, batch_clips)
         if not features:
             return torch.empty(0, self.feature_extractor.output_size, device=self.device)
         return features[0] if len(features) == 1 else torch.cat(features, dim=0)
 
     def _pool_features(self, features, ops_counter=None):
         """few_shot_recognisers.py:155-166."""
+        if ops_counter:
+            ops_counter.add_macs(features.size(0) * features.size(1))
         return self.frame_pooler(features)
 
     def set_test_mode(self, test_mode):
@@ -228,7 +234,9 @@ class SingleStepFewShotRecogniser(FewShotRecogniser):
         task_embedding = self._get_task_embedding_in_batches(context_clips, ops_counter)
         self.film_dict = self._generate_film_params(task_embedding, ops_counter)
         context_features = self._get_features_in_batches(context_clips, self.film_dict, ops_counter)
-        # pooling (poolers.py:13-16) is fused into the head's configure kernel
+        # pooling (poolers.py:13-16) is fused into the head's configure kernel; its MACs are still the reference's
+        if ops_counter:
+            ops_counter.add_macs(context_features.size(0) * context_features.size(1))
         self.classifier.configure(context_features, context_labels, ops_counter, clip_length=self.clip_length)
 
     def personalise_with_lite(self, context_clips, context_labels):
@@ -249,10 +257,14 @@ class SingleStepFewShotRecogniser(FewShotRecogniser):
             batch_start_index, batch_end_index = get_batch_indices(batch, num_clips, self.batch_size)
             batch_clips = context_clips[batch_start_index:batch_end_index].to(self.device, non_blocking=True)
             reps.append(self.set_encoder(batch_clips))
+            if ops_counter:
+                ops_counter.compute_macs(self.set_encoder, batch_clips)
         return self.set_encoder.aggregate(reps, aggregation=aggregation)
 
     def _generate_film_params(self, task_embedding, ops_counter=None):
         """few_shot_recognisers.py:439-451."""
+        if ops_counter:
+            ops_counter.compute_macs(self.film_generator, task_embedding)
         return self.film_generator(task_embedding)
 
     def predict(self, target_clips, want_argmax=False):
@@ -306,7 +318,10 @@ class MultiStepFewShotRecogniser(FewShotRecogniser):
         num_classes = len(torch.unique(context_labels))
         self.init_classifier(num_classes)
         features = self._get_features_in_batches(context_clips, ops_counter=ops_counter)
-        features = self._pool_features(features)
+        features = self._pool_features(features, ops_counter=ops_counter)
+        if ops_counter:   # the head's forward inside the loop (classifier_heads.py:72-73), once per clip per grad step;
+            # the extractor/pool MACs above are counted once because the frozen features are computed once
+            ops_counter.add_macs(num_grad_steps * num_classes * features.size(0) * features.size(1))
         finetune_linear_head(self.classifier, features, context_labels, self.batch_size, num_grad_steps,
                              learning_rate, optimizer, dict(learning_args), self.logit_scale)
 
@@ -314,7 +329,9 @@ class MultiStepFewShotRecogniser(FewShotRecogniser):
         """few_shot_recognisers.py:248-258."""
         self._set_batch_norm_state()
         features = self._get_features_in_batches(clips, ops_counter=ops_counter)
-        return self.classifier.predict(features, clip_length=self.clip_length)
+        if ops_counter:
+            ops_counter.add_macs(features.size(0) * features.size(1))      # pooling, fused into the head kernel
+        return self.classifier.predict(features, ops_counter=ops_counter, clip_length=self.clip_length)
 
     def personalise_with_lite(self, context_clips, context_labels):
         NotImplementedError

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "orbit_engine_set_option": (_i, [_p, C.c_char_p, _i]),
     "orbit_engine_get_option": (_i, [_p, C.c_char_p, C.POINTER(_i)]),
     "orbit_engine_workspace_bytes": (_i64, [_p, _i, _i]),
+    "orbit_engine_macs": (_i64, [_p, _i, _i]),
     "orbit_engine_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p]),
     "orbit_engine_calibrate": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p]),
     "orbit_engine_profile_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double),

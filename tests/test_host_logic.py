@@ -87,3 +87,47 @@ def test_synthetic_episode_shapes():
     assert sorted(cy.tolist()) == [0, 0, 1, 1, 2, 2, 3, 3, 4, 4]
     ctx2, *_ = make_episode(EpisodeSpec(5, 2, 3, 2, 32), index=4)
     assert torch.equal(ctx, ctx2)
+
+
+def test_engine_macs_match_published_model_costs():
+    """orbit_engine_macs (the analytic stand-in for the thop trace of utils/ops_counter.py:82-88) against the published
+    224x224 costs of the same architectures: EfficientNet-B0 0.39 GMACs, EfficientNetV2-S 8.4 GMACs @384 (x (224/384)^2),
+    ResNet-18 1.82 GMACs (incl. the 0.5 M fc), ViT-B/32 4.41 GMACs, ViT-S/32 1.15 GMACs (timm model cards)."""
+    import torch
+    from orbit_b200.feature_extractors import FeatureExtractor
+    published = {'efficientnet_b0': 0.39e9, 'efficientnet_v2_s': 8.44e9 * (224 / 384) ** 2, 'resnet18': 1.82e9,
+                 'vit_b_32': 4.41e9, 'vit_s_32': 1.15e9}
+    for name, want in published.items():
+        fe = FeatureExtractor(name)
+        got = fe.count_macs(torch.empty(1, 3, 224, 224))
+        assert abs(got - want) / want < 0.02, (name, got, want)
+        assert fe.count_macs(torch.empty(2, 5, 3, 224, 224)) == 10 * got      # clips x frames
+
+
+def test_ops_counter_interface_and_head_formulas():
+    """OpsCounter mirrors utils/ops_counter.py:10-99; head MACs follow the reference's hand-written counts."""
+    import torch
+    from orbit_b200 import OpsCounter
+    from orbit_b200.ops_counter import clever_format
+    from orbit_b200.classifier_heads import HeadClassifier
+
+    class Fake(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(7))
+
+        def count_macs(self, x):
+            return 100 * x.shape[0]
+
+    oc = OpsCounter(count_backward=True)
+    oc.compute_macs(Fake(), torch.zeros(3, 2))
+    assert oc.get_task_macs() == 600 and oc.task_params_counter == 7          # forward + backward multiplier
+    oc.add_macs(5)
+    assert oc.get_task_macs() == 605
+    HeadClassifier._count_class_reps(oc, 10, 4, 3)                            # C*N + N*D
+    assert oc.get_task_macs() == 605 + 30 + 40
+    oc.task_complete()
+    assert oc.get_task_macs() == 0 and oc.get_task_params() == oc.base_params_counter
+    with pytest.raises(TypeError):
+        oc.compute_macs(torch.nn.Linear(2, 2), torch.zeros(1, 2))
+    assert clever_format([4007548, 1234, 12]) == ('4.01M', '1.23K', '12.00B')
