@@ -62,6 +62,13 @@ int orbit_get_global_option(const char* key, int* value);
 int orbit_pool_clips(const float* frame_feats, int num_clips, int clip_length, int feat_dim,
                      float* clip_feats, void* stream);
 
+/* Sliding-window dedupe: clip features of attach_frame_history(frames, L) + MeanPooler
+ * (data/utils.py:8-28, model/poolers.py:13-16) from per-frame features computed ONCE:
+ *   clip_feats[t,:] = mean over l = 0..L-1 of frame_feats[max(t-L+1+l, 0),:]   (left-padded with frame 0).
+ * Bit-identical to orbit_pool_clips over the materialised [F, L] clips; must not run in place.      */
+int orbit_pool_history(const float* frame_feats, int num_frames, int history_length, int feat_dim,
+                       float* clip_feats, void* stream);
+
 /* Replaces FewShotRecogniser._pool_features + HeadClassifier._build_class_reps +
  * PrototypicalClassifier.configure (few_shot_recognisers.py:155-166; classifier_heads.py:94-105,
  * 232-263) in one launch.
@@ -224,6 +231,21 @@ int orbit_engine_profile_read(const orbit_engine* e, double* ms, int64_t* launch
 
 /* number of kernels the last orbit_engine_forward on this engine enqueued (for bench accounting) */
 int64_t orbit_engine_last_launches(const orbit_engine* e);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-side evaluator. Replaces the per-video statistics of the reference's
+ * Evaluator.get_frame_accuracy / get_frames_to_recognition / get_video_prediction and the softmax + .cpu() of
+ * TestEvaluator.append_video (utils/eval_metrics.py:27-68,260-276) for a batch of videos in one launch.
+ *   logits [rows, num_classes] fp32 (nullable) or predictions [rows] int32 (used when logits is NULL);
+ *   frame_index [video_offsets[V]] int32 (nullable): row of every scored frame, in order (the reference drops padded
+ *   duplicate frames with np.unique, eval_metrics.py:262-264); NULL = rows video_offsets[v] .. video_offsets[v+1]-1;
+ *   video_offsets [V+1], video_labels [V] int32 (device);
+ *   stats [V,4] int32 = {correct frames, frames, index of first correct frame (= frames if none), most frequent
+ *   prediction (lowest index on ties)}; pred_out [video_offsets[V]] int32 (nullable): arg-max per scored frame.
+ * num_classes <= 64.                                                                               */
+int orbit_video_stats(const float* logits, const int32_t* predictions, int num_classes, const int32_t* frame_index,
+                      const int32_t* video_offsets, const int32_t* video_labels, int num_videos, int32_t* stats,
+                      int32_t* pred_out, void* stream);
 
 #ifdef __cplusplus
 }

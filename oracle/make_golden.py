@@ -8,6 +8,7 @@ What comes from the reference itself (imported from /root/reference, not copied)
   * model/poolers.MeanPooler, model/classifier_heads.{Prototypical,Linear,Versa,Mahalanobis}Classifier
   * model/set_encoders.SetEncoder, model/feature_adapters.FilmParameterGenerator
   * data/utils.attach_frame_history
+  * utils/eval_metrics.TestEvaluator (thop, imported there only for the ops counter, is stubbed)
   * model/few_shot_recognisers.{SingleStep,MultiStep}FewShotRecogniser end to end, on top of
     oracle/timm_shim (timm itself is not installable here; the backbone arithmetic is the restatement)
 Inputs are regenerated from seeds by the tests (torch CPU RNG is deterministic for a fixed torch
@@ -182,9 +183,73 @@ def golden_recogniser():
     print('recogniser.npz', len(out), 'arrays')
 
 
+def evaluator_case(seed=1991):
+    """Seeded evaluator workload shared by make_golden and the tests: users -> tasks -> videos of (label, logits, paths).
+    Every video is padded to a multiple of 4 frames by repeating its last frame (as the reference's clip loader does),
+    which exercises the duplicate-frame removal of append_video; one video is never recognised."""
+    rng = np.random.RandomState(seed)
+    users = []
+    for u, num_tasks in enumerate((2, 3)):
+        tasks = []
+        for t in range(num_tasks):
+            videos = []
+            for v in range(3 + (t % 2)):
+                frames, label = int(rng.randint(5, 41)), int(rng.randint(0, 5))
+                logits = rng.randn(frames, 5).astype(np.float32)
+                logits[:, label] += 1.5
+                if (u, t, v) == (1, 1, 2):
+                    logits[:, label] = -100.0
+                paths = [f"user{u}/obj{label}/task{t}-video{v}/frame-{i:06d}.jpg" for i in range(frames)]
+                pad = (-frames) % 4
+                logits = np.concatenate([logits, np.repeat(logits[-1:], pad, axis=0)])
+                paths = paths + [paths[-1]] * pad
+                videos.append((label, logits, paths))
+            tasks.append(videos)
+        users.append(tasks)
+    return users
+
+
+def golden_evaluator():
+    import types
+    for name in ('thop', 'thop.profile', 'thop.vision', 'thop.vision.basic_hooks'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules['thop'].profile = lambda *a, **k: (0, 0)
+    sys.modules['thop'].clever_format = lambda v, f: tuple(str(x) for x in v)
+    sys.modules['thop.profile'].register_hooks = {}
+    sys.modules['thop.vision.basic_hooks'].count_convNd = None
+    from utils.eval_metrics import TestEvaluator
+    stats = ['frame_acc', 'frames_to_recognition']
+    ev = TestEvaluator(stats)
+    users = evaluator_case()
+    out = {}
+    for u, tasks in enumerate(users):
+        for t, videos in enumerate(tasks):
+            for label, logits, paths in videos:
+                ev.append_video(torch.from_numpy(logits), torch.tensor(label), np.array(paths))
+            if t + 1 < len(tasks):
+                ev.next_task()
+        ev.set_current_user(f"user{u}")
+        cur = ev.get_mean_stats(current_user=True)
+        for level, st in zip(('user', 'object', 'task', 'video'), cur):
+            for stat in stats:
+                out[f'current{u}.{level}.{stat}'] = np.array(st[stat], dtype=np.float64)
+        if u + 1 < len(users):
+            ev.next_user()
+    for level, st in zip(('user', 'object', 'task', 'video'), ev.get_mean_stats()):
+        for stat in stats:
+            out[f'all.{level}.{stat}'] = np.array(st[stat], dtype=np.float64)
+    out['input_checksum'] = np.array(sum(float(np.abs(lg).sum()) for tasks in users for videos in tasks for _, lg, _ in videos))
+    np.savez_compressed(os.path.join(OUT, 'evaluator.npz'), **out)
+    print('evaluator.npz', {k: v.tolist() for k, v in out.items() if k.startswith('all.')})
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if 'evaluator' in sys.argv[1:]:
+        golden_evaluator()
+        sys.exit(0)
     golden_parts()
     golden_recogniser()
+    golden_evaluator()

@@ -73,12 +73,12 @@ class LinearClassifier(nn.Module):
         self.weight = nn.Parameter(torch.zeros(num_classes, self.feat_dim), requires_grad=True)
         self.bias = nn.Parameter(torch.zeros(num_classes), requires_grad=True)
 
-    def predict(self, features, ops_counter=None, clip_length=1):
+    def predict(self, features, ops_counter=None, clip_length=1, want_argmax=False):
         if self.weight is None:
             raise AttributeError("Weight and/or bias not set - is model personalised?")
         if ops_counter:   # classifier_heads.py:72-73
             ops_counter.add_macs(self.weight.size(0) * (features.size(0) // clip_length) * self.feat_dim)
-        return _head_predict(features, clip_length, self.weight, self.bias, 0, self.logit_scale)
+        return _head_predict(features, clip_length, self.weight, self.bias, 0, self.logit_scale, want_argmax)
 
     def reset(self):
         self.weight = None

@@ -33,6 +33,29 @@ __global__ void __launch_bounds__(256) pool_clips_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// causal history pool: out[t,:] = mean_l in[max(t-L+1+l, 0),:], l = 0..L-1 -- the clip features of
+// attach_frame_history(frames, L) (reference data/utils.py:8-28) followed by MeanPooler (model/poolers.py:13-16),
+// from per-FRAME features computed once. Same summation order and division as pool_clips_kernel, so the result is
+// bit-identical to pooling the materialised clips.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_history_kernel(const float* __restrict__ in, int n_frames, int L, int D,
+                                                           float* __restrict__ out) {
+    const int d4 = D >> 2;
+    const int64_t total = (int64_t)n_frames * d4;
+    const float len = (float)L;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / d4), q = (int)(i % d4);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < L; ++l) {
+            const int src = max(t - L + 1 + l, 0);
+            add4(s, ldg4(in + (int64_t)src * D + q * 4));
+        }
+        s.x /= len; s.y /= len; s.z /= len; s.w /= len;
+        *reinterpret_cast<float4*>(out + (int64_t)t * D + q * 4) = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // configure: one launch builds mu_c, W = 2 mu_c, b = -mu_c.mu_c from support FRAME features.
 // grid (C, ceil(D/128)); block 256 = 8 row groups x 32 lanes, lane owns 4 consecutive columns.
 // ------------------------------------------------------------------------------------------------
@@ -210,6 +233,19 @@ extern "C" int orbit_pool_clips(const float* frame_feats, int num_clips, int cli
     const int64_t total = (int64_t)num_clips * (feat_dim / 4);
     const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 8);
     pool_clips_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(frame_feats, num_clips, clip_length, feat_dim, clip_feats);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
+extern "C" int orbit_pool_history(const float* frame_feats, int num_frames, int history_length, int feat_dim, float* clip_feats,
+                                  void* stream) {
+    if (num_frames < 0 || history_length <= 0 || feat_dim <= 0) return ORBIT_ERR_ARG;
+    if (num_frames == 0) return ORBIT_OK;
+    if (!frame_feats || !clip_feats || frame_feats == clip_feats) return ORBIT_ERR_ARG;
+    if (feat_dim % 4 || !aligned16(frame_feats) || !aligned16(clip_feats)) return ORBIT_ERR_UNSUPPORTED;
+    const int64_t total = (int64_t)num_frames * (feat_dim / 4);
+    const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 8);
+    pool_history_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(frame_feats, num_frames, history_length, feat_dim, clip_feats);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }

@@ -236,10 +236,10 @@ extern "C" int64_t orbit_mahalanobis_predict_workspace_bytes(int num_clips, int 
 extern "C" int orbit_mahalanobis_predict(const float* clip_feats, int num_clips, int feat_dim, const float* means,
                                          const float* precisions, int num_classes, float logit_scale, float* logits,
                                          void* workspace, void* stream) {
-    if (!clip_feats || !means || !precisions || !logits || !workspace) return ORBIT_ERR_ARG;
     if (num_clips < 0 || feat_dim <= 0 || num_classes <= 0) return ORBIT_ERR_ARG;
+    if (num_clips == 0) return ORBIT_OK;     // empty query set: nothing to score (pointers may be null)
+    if (!clip_feats || !means || !precisions || !logits || !workspace) return ORBIT_ERR_ARG;
     if (feat_dim % 4) return ORBIT_ERR_UNSUPPORTED;
-    if (num_clips == 0) return ORBIT_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int D = feat_dim, Nq = num_clips;
     float* ws = reinterpret_cast<float*>(workspace);

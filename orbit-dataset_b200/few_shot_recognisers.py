@@ -181,6 +181,31 @@ class FewShotRecogniser(nn.Module):
             ops_counter.add_macs(features.size(0) * features.size(1))
         return self.frame_pooler(features)
 
+    def predict_video(self, video_frames, want_argmax=False):
+        """Per-frame logits of one target video: equal (bit for bit) to
+        ``predict(attach_frame_history(video_frames, clip_length))`` -- the reference's test loop,
+        single-step-learner.py:327-332 -- but every frame goes through the extractor ONCE instead of ``clip_length``
+        times; the causal ``clip_length``-frame means are formed on the device from the per-frame features
+        (valid because the extractor is frame-wise and in eval mode). ``video_frames``: [F,3,H,W] on CPU or device."""
+        self._set_batch_norm_state()
+        self._require_device()
+        if video_frames.dim() != 4:
+            raise ValueError("predict_video expects the frames of one video, [F,3,H,W]")
+        film_dict = getattr(self, 'film_dict', None) or {}
+        step = self.batch_size * self.clip_length
+        feats = [self._run_extractor(video_frames[i:i + step], film_dict) for i in range(0, len(video_frames), step)]
+        if not feats:
+            feats = [torch.empty(0, self.feature_extractor.output_size, device=self.device)]
+        feats = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
+        if self.clip_length > 1 and len(feats):
+            pooled = torch.empty_like(feats)
+            L.check(L.load().orbit_pool_history(L.ptr(feats), feats.shape[0], self.clip_length, feats.shape[1], L.ptr(pooled),
+                                                L.stream_ptr(feats.device)), "orbit_pool_history")
+            L.count_launches(1)
+            feats = pooled
+        kwargs = {'want_argmax': True} if want_argmax else {}
+        return self.classifier.predict(feats, clip_length=1, **kwargs)
+
     def set_test_mode(self, test_mode):
         self.test_mode = test_mode
 

@@ -17,6 +17,7 @@ _SIGNATURES = {
     "orbit_set_global_option": (_i, [C.c_char_p, _i]),
     "orbit_get_global_option": (_i, [C.c_char_p, C.POINTER(_i)]),
     "orbit_pool_clips": (_i, [_p, _i, _i, _i, _p, _p]),
+    "orbit_pool_history": (_i, [_p, _i, _i, _i, _p, _p]),
     "orbit_proto_configure_scratch_bytes": (_i64, [_i, _i]),
     "orbit_proto_configure": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "orbit_head_predict": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _f, _p, _p, _p]),
@@ -48,6 +49,7 @@ _SIGNATURES = {
     "orbit_engine_get_option": (_i, [_p, C.c_char_p, C.POINTER(_i)]),
     "orbit_engine_workspace_bytes": (_i64, [_p, _i, _i]),
     "orbit_engine_macs": (_i64, [_p, _i, _i]),
+    "orbit_video_stats": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _p, _p]),
     "orbit_engine_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p]),
     "orbit_engine_calibrate": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p]),
     "orbit_engine_profile_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double),

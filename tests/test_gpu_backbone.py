@@ -188,3 +188,31 @@ def test_ragged_batches_and_frame_history(cuda_device, oracle_effnet):
         assert empty.shape == (0, 7)
     finally:
         oracle_effnet.batch_size = 256
+
+
+@pytest.mark.parametrize("head,adapt", [('proto', False), ('versa', True), ('mahalanobis', False)])
+def test_predict_video_dedupes_frame_history_bit_exactly(cuda_device, head, adapt):
+    """predict_video(frames) == predict(attach_frame_history(frames, L)) bit for bit, with F instead of
+    F*L frames through the extractor (reference test loop single-step-learner.py:327-332, data/utils.py:8-28)."""
+    import orbit_b200
+    from orbit_b200 import attach_frame_history
+    from orbit_b200 import lib as L
+    from orbit_b200.synthetic import EpisodeSpec, calibration_frames, make_episode
+    m = orbit_b200.SingleStepFewShotRecogniser('efficientnet_b0', adapt, head, 4, 8, False, 16)
+    m._set_device(cuda_device); m._send_to_device(); m.set_test_mode(True)
+    m.feature_extractor.calibrate_batchnorm(calibration_frames(64).to(cuda_device))
+    ctx, ctx_y, _, _ = make_episode(EpisodeSpec(3, 2, 1, 4, 64), index=11)
+    m.personalise(ctx.to(cuda_device), ctx_y.to(cuda_device))
+    video = calibration_frames(64)[:37].to(cuda_device) * 0.8           # 37 frames: ragged last extractor batch
+    before = L.launches()
+    ref_logits = m.predict(attach_frame_history(video, 4))
+    mid = L.launches()
+    logits, am = m.predict_video(video, want_argmax=True)
+    after = L.launches()
+    assert logits.shape == ref_logits.shape == (37, 3)
+    assert torch.equal(logits, ref_logits)
+    assert torch.equal(am.long(), ref_logits.argmax(1))
+    assert (after - mid) < (mid - before)                                # fewer launches: a quarter of the frames
+    # CPU-resident frames take the staged path and give the same bits
+    assert torch.equal(m.predict_video(video.cpu()), ref_logits)
+    assert m.predict_video(video[:0]).shape[0] == 0

@@ -165,3 +165,24 @@ def test_efficientnet_v2_s_structure():
     assert len(names) == 84 and names[:2] == ['bn1.weight', 'bn1.bias'] and names[-2:] == ['bn2.weight', 'bn2.bias']
     assert 'blocks.0.1.bn1.weight' in names and 'blocks.2.3.bn1.bias' in names and 'blocks.5.14.bn2.weight' in names
     assert not any('.bn3.' in n for n in names)
+
+
+def test_evaluator_oracle_matches_reference_golden():
+    """oracle/evaluator.py vs the reference TestEvaluator's own output (tests/golden/evaluator.npz)."""
+    import os
+    import numpy as np
+    from oracle import evaluator as ev
+    from oracle.make_golden import evaluator_case
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'evaluator.npz'))
+    users = evaluator_case()
+    assert abs(sum(float(np.abs(lg).sum()) for t in users for vs in t for _, lg, _ in vs) - float(g['input_checksum'])) < 1e-3
+    dedup = [[[(label, lg[np.unique(np.array(paths), return_index=True)[1]]) for label, lg, paths in videos]
+              for videos in tasks] for tasks in users]
+    for stat in ('frame_acc', 'frames_to_recognition'):
+        got = ev.mean_stats(stat, dedup)
+        for level in ('user', 'object', 'task', 'video'):
+            assert np.array_equal(np.array(got[level]), g[f'all.{level}.{stat}']), (stat, level)
+        for u in range(2):
+            got_u = ev.mean_stats(stat, dedup[u:u + 1])
+            for level in ('user', 'object', 'task', 'video'):
+                assert np.array_equal(np.array(got_u[level]), g[f'current{u}.{level}.{stat}']), (stat, level, u)
