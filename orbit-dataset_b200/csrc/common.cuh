@@ -28,6 +28,16 @@ __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { r
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x / (1.0f + expf(-x)); }
 
+// x * sigmoid(x) on the SFU: ex2.approx.ftz + rcp.approx.ftz (2 MUFU + 3 FP32 ops, ~3e-7 relative error). The
+// CUDA intrinsics __expf/__fdividef wrap the same two instructions in denormal-range fix-ups (~6 more issue slots
+// per element) that x*sigmoid(x) does not need: e underflows to 0 (result x) or overflows to inf (result -0).
+__device__ __forceinline__ float silu_sfu(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

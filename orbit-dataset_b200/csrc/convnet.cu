@@ -127,7 +127,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // depthwise kernels to be ISSUE-bound, not memory-bound, with the accurate expf + IEEE division taking ~30 of
 // the ~85 instructions per output.
 __device__ __forceinline__ float act_fast(float v, int act) {
-    if (act == ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
+    if (act == ACT_SILU) return silu_sfu(v);
     if (act == ACT_RELU) return fmaxf(v, 0.f);
     return v;
 }
@@ -467,6 +467,186 @@ dw_kernel_unrolled(const float* __restrict__ x, const float* __restrict__ wt, co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second-generation depthwise kernel (same tiling and rolling accumulators as dw_kernel above). ncu of the first
+// version on the K=5 layers: 98 thread-instructions per output of which only 25 were FFMAs -- 64-bit address
+// arithmetic (25 %), ring-rotation MOVs (13 %) and divergence bookkeeping made it ISSUE-bound at 1.3-1.7 TB/s.
+// Here: (i) channel PAIRS are processed with the Blackwell packed `fma.rn.f32x2` (two IEEE fp32 FMAs per issue
+// slot, bit-identical to two fmaf), (ii) column validity and column offsets are hoisted out of the row loop,
+// (iii) the k*k taps live in shared memory ([tap][lane], one conflict-free LDS per tap per row) instead of 50-100
+// registers, which pays for (iv) a register prefetch of the NEXT input row while the current one is consumed.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f2_t;   // two packed fp32
+__device__ __forceinline__ void f2_unpack(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+    f2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+template <int NP> struct PairIO;
+template <> struct PairIO<1> {
+    static __device__ __forceinline__ void load(const float* p, f2_t* v) { v[0] = __ldg(reinterpret_cast<const f2_t*>(p)); }
+    static __device__ __forceinline__ void load_shared(const float* p, f2_t* v) { v[0] = *reinterpret_cast<const f2_t*>(p); }
+    static __device__ __forceinline__ void store(float* p, const float* r) { *reinterpret_cast<float2*>(p) = make_float2(r[0], r[1]); }
+};
+template <> struct PairIO<2> {
+    static __device__ __forceinline__ void load(const float* p, f2_t* v) {
+        const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2*>(p)); v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void load_shared(const float* p, f2_t* v) {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p); v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void store(float* p, const float* r) { *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]); }
+};
+
+// CT = compile-time channel count (0: use the runtime C): column offsets j*C become load/store immediates.
+template <int K, int S, int VEC, int MINB, int CT>
+__global__ void __launch_bounds__(256, MINB)
+dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
+           const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C_rt,
+           int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile, int strip_blocks) {
+    constexpr int TW = kDwTW, R = (K + S - 1) / S, SPAN = (TW - 1) * S + K, HALF = (K - 1) / S, NP = VEC / 2;
+    const int C = CT ? CT : C_rt;
+    extern __shared__ __align__(16) float s_dyn[];
+    constexpr int LXS = 32;                               // lane stride of the tap table (LX <= 32): tap offsets are immediates
+    float* s_w = s_dyn;                                   // [K*K][LXS][VEC] taps of this block's channel chunk
+    float* s_red = s_dyn + K * K * LXS * VEC;              // [LY][LX][VEC] partial-sum reduction
+    const int tile = blockIdx.x / strip_blocks, sb = blockIdx.x % strip_blocks, chunk = blockIdx.y, b = blockIdx.z;
+    const int groups = gridDim.x;
+    const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
+    const int Cv = C / VEC;
+    const int cv = chunk * LX + lx;
+    const int strip = sb * LY + ly;
+    const bool live = cv < Cv && strip * TW < Wo;
+    for (int i = threadIdx.x; i < K * K * LXS; i += blockDim.x) {
+        const int t = i / LXS, l = i % LXS, c = chunk * LX + l;
+        float wv[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) wv[e] = 0.f;
+        if (l < LX && c < Cv) VecIO<VEC>::load(wt + (int64_t)t * C + c * VEC, wv);
+        VecIO<VEC>::store(s_w + (size_t)i * VEC, wv);
+    }
+    __syncthreads();
+    float sum[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) sum[e] = 0.f;
+    const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
+    if (live && row0 < row1) {
+        f2_t sc[NP], sh[NP];
+        PairIO<NP>::load(scale + cv * VEC, sc);
+        PairIO<NP>::load(shift + cv * VEC, sh);
+        const int ox0 = strip * TW, ixb = ox0 * S - pad_l;
+        unsigned cmask = 0;                               // bit j: input column ixb + j exists
+#pragma unroll
+        for (int j = 0; j < SPAN; ++j) cmask |= (ixb + j >= 0 && ixb + j < W) ? (1u << j) : 0u;
+        const int64_t row_stride = (int64_t)W * C;
+        const float* xcol = x + (int64_t)b * H * row_stride + (int64_t)ixb * C + cv * VEC;   // (row 0, column ixb): only valid columns are dereferenced
+        float* yb = y + ((int64_t)b * Ho * Wo + ox0) * C + cv * VEC;
+        const float* wlane = s_w + lx * VEC;
+        // virtual row vy = input row + pad_t; rows that exist and that this tile needs: [vy_lo, vy_hi]
+        const int vy_lo = pad_t, vy_hi = min(H - 1 + pad_t, (row1 - 1) * S + K - 1);
+        xcol -= pad_t * row_stride;
+        auto load_row = [&](int vy, f2_t (&dst)[SPAN][NP]) {
+            if (vy >= vy_lo && vy <= vy_hi) {
+                const float* rp = xcol + vy * row_stride;
+#pragma unroll
+                for (int j = 0; j < SPAN; ++j) {
+                    if (cmask & (1u << j)) PairIO<NP>::load(rp + j * C, dst[j]);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) dst[j][q] = 0ull;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < SPAN; ++j)
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) dst[j][q] = 0ull;
+            }
+        };
+        f2_t acc[R][TW][NP], v[SPAN][NP], vn[SPAN][NP];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int t = 0; t < TW; ++t)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) acc[r][t][q] = 0ull;
+        load_row(row0 * S, v);
+        // iteration m handles virtual rows m*S .. m*S+S-1; the oldest pending output row is m - HALF
+        for (int m = row0; m < row1 + HALF; ++m) {
+#pragma unroll
+            for (int sub = 0; sub < S; ++sub) {
+                load_row(m * S + sub + 1, vn);            // in flight while row m*S+sub is consumed
+#pragma unroll
+                for (int ky = sub; ky < K; ky += S) {      // ky with (vy - ky) divisible by S
+                    const int slot = HALF - (ky - sub) / S;
+#pragma unroll
+                    for (int kx = 0; kx < K; ++kx) {
+                        f2_t w[NP];
+                        PairIO<NP>::load_shared(wlane + (ky * K + kx) * LXS * VEC, w);
+#pragma unroll
+                        for (int t = 0; t < TW; ++t)
+#pragma unroll
+                            for (int q = 0; q < NP; ++q) acc[slot][t][q] = f2_fma(v[kx + t * S][q], w[q], acc[slot][t][q]);
+                    }
+                }
+                if (sub == (K - 1) % S) {      // the oldest pending output row has now seen its last input row
+                    const int oy = m - HALF;
+                    if (oy >= row0) {          // (oy < row1 by the loop bound)
+                        float* yrow = yb + (int64_t)oy * Wo * C;
+#pragma unroll
+                        for (int t = 0; t < TW; ++t) {
+                            if (ox0 + t < Wo) {
+                                float r[VEC];
+#pragma unroll
+                                for (int q = 0; q < NP; ++q) {
+                                    f2_unpack(f2_fma(acc[0][t][q], sc[q], sh[q]), r[2 * q], r[2 * q + 1]);
+                                    r[2 * q] = act_fast(r[2 * q], act); r[2 * q + 1] = act_fast(r[2 * q + 1], act);
+                                    sum[2 * q] += r[2 * q]; sum[2 * q + 1] += r[2 * q + 1];
+                                }
+                                PairIO<NP>::store(yrow + t * C, r);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < SPAN; ++j)
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) v[j][q] = vn[j][q];
+            }
+            // rotate the ring: slot r <- slot r+1, newest slot cleared
+#pragma unroll
+            for (int r = 0; r + 1 < R; ++r)
+#pragma unroll
+                for (int t = 0; t < TW; ++t)
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) acc[r][t][q] = acc[r + 1][t][q];
+#pragma unroll
+            for (int t = 0; t < TW; ++t)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) acc[R - 1][t][q] = 0ull;
+        }
+    }
+    if (partial) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s_red[(ly * LX + lx) * VEC + e] = sum[e];
+        __syncthreads();
+        if (ly == 0 && cv < Cv) {
+            float t[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) t[e] = s_red[lx * VEC + e];
+            for (int r = 1; r < LY; ++r)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) t[e] += s_red[(r * LX + lx) * VEC + e];
+            VecIO<VEC>::store(partial + ((int64_t)b * groups + blockIdx.x) * C + cv * VEC, t);
+        }
+    }
+}
+
+static int g_dw_variant = 2;   // 1 = first-generation kernels (kept for A/B), 2 = packed-FMA kernels
+void set_dw_variant(int v) { g_dw_variant = v; }
+int get_dw_variant() { return g_dw_variant; }
+
 int launch_depthwise(const float* x, const float* wt, const float* scale, const float* shift, float* y, float* partial,
                      int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, int act,
                      cudaStream_t st) {
@@ -480,6 +660,26 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
                                                         pad_l, act, pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks); \
         ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                              \
         return ORBIT_OK;                                                                                              \
+    }
+    if (g_dw_variant >= 2) {
+        const size_t smem2 = smem + sizeof(float) * (size_t)k * k * 32 * pl.VEC;
+#define ORBIT_DW2_LAUNCH(KK, SS, VV, MB, CC)                                                                           \
+        {                                                                                                             \
+            dw2_kernel<KK, SS, VV, MB, CC><<<grid, block, smem2, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho,  \
+                                                                       Wo, pad_t, pad_l, act, pl.LX, pl.LY,           \
+                                                                       pl.rows_per_tile, pl.strip_blocks);            \
+            ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                          \
+            return ORBIT_OK;                                                                                          \
+        }
+#define ORBIT_DW2_CT(KK, SS, VV, CC) if (k == KK && stride == SS && C == CC) ORBIT_DW2_LAUNCH(KK, SS, VV, 2, CC)
+#define ORBIT_DW2_ANY(KK, SS, VV) if (k == KK && stride == SS) ORBIT_DW2_LAUNCH(KK, SS, VV, 2, 0)
+        // the EfficientNet-B0 depthwise shapes get compile-time channel counts; everything else the generic kernels
+        ORBIT_DW2_CT(5, 2, 2, 144) ORBIT_DW2_CT(5, 2, 2, 672)
+        ORBIT_DW2_CT(5, 1, 2, 240) ORBIT_DW2_CT(5, 1, 2, 480) ORBIT_DW2_CT(5, 1, 2, 672) ORBIT_DW2_CT(5, 1, 2, 1152)
+        ORBIT_DW2_ANY(3, 1, 4) ORBIT_DW2_ANY(3, 2, 4) ORBIT_DW2_ANY(5, 1, 2) ORBIT_DW2_ANY(5, 2, 2)
+#undef ORBIT_DW2_CT
+#undef ORBIT_DW2_ANY
+#undef ORBIT_DW2_LAUNCH
     }
     if (k == 3 && stride == 2) {
         dw_kernel_unrolled<3, 2, 4><<<grid, block, smem, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t, pad_l, act,

@@ -42,6 +42,10 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
                      int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, int act,
                      cudaStream_t st);
 
+// depthwise kernel generation: 1 = first kernels (A/B only), 2 = packed fma.rn.f32x2 kernels (default)
+void set_dw_variant(int v);
+int get_dw_variant();
+
 // squeeze-excite gate: partial [B][tiles][C] -> gate [B][C] = sigmoid(W2 silu(W1 mean + b1) + b2)
 int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2,
                    const float* b2, float* gate, int B, int C, int R, cudaStream_t st);

@@ -166,7 +166,7 @@ __device__ __forceinline__ float silu_fast(float x) { return x / (1.0f + expf(-x
 #elif defined(ORBIT_SILU_MID)
 __device__ __forceinline__ float silu_fast(float x) { return x * __frcp_rn(1.0f + expf(-x)); }
 #else
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return silu_sfu(x); }
 #endif
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }

@@ -5,6 +5,7 @@ import torch
 from orbit_b200 import lib as L
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 lib = L.load(); dev = torch.device('cuda:0')
+if os.environ.get('DWV'): assert lib.orbit_set_global_option(b'dw_variant', int(os.environ['DWV'])) == 0
 layers = [(112, 32, 3, 1), (112, 96, 3, 2), (56, 144, 3, 1), (56, 144, 5, 2), (28, 240, 5, 1), (28, 240, 3, 2), (14, 480, 3, 1),
           (14, 480, 5, 1), (14, 672, 5, 1), (14, 672, 5, 2), (7, 1152, 5, 1), (7, 1152, 3, 1)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -18,7 +19,7 @@ for H, C, k, s in layers:
     scratch = torch.empty(k * k * C, device=dev)
     ts = []
     for it in range(4):
-        flush.zero_()
+        if not os.environ.get("NOFLUSH"): flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = lib.orbit_depthwise_conv(L.ptr(x), L.ptr(w), L.ptr(sc), L.ptr(sh), L.ptr(y), L.ptr(partial), L.ptr(scratch), B, H, H, C, k, s, 1,
