@@ -63,38 +63,39 @@ constexpr int L2_PREFETCH_DISTANCE = 12;   // k-blocks (16 KB of A each) request
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// All shared-memory traffic of this kernel uses explicit shared-state-space instructions on 32-bit addresses:
+// through generic pointers the compiler emitted LD.E/ST.E with 64-bit address arithmetic (ncu, round 1).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Blocking wait with a hardware suspend-time hint: the warp sleeps inside try_wait until the phase completes
 // (or ~20 us pass) instead of burning issue slots in a polling loop. Bounded: a protocol bug must surface
 // as a trap (launch failure), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
         if (spin > 400000u) __trap();
     }
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
@@ -107,6 +108,26 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32u(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// fp32 -> tf32 with round-to-nearest (ties away), identical to cvt.rna.tf32.f32 on finite inputs: add half a
+// tf32 ulp to the magnitude and clear the 13 low mantissa bits. (The cvt instruction is emulated on sm_100 with
+// these two operations plus an inf/NaN guard per element; activations here are finite.)
+__device__ __forceinline__ float rna_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -114,8 +135,8 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -135,18 +156,6 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {   // no wait: pair with tmem_ld_wait()
     uint32_t r[16];
     asm volatile(
@@ -163,8 +172,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // The accurate expf + IEEE division cost ~30 issue slots per output and made the epilogue the bottleneck.
 #if defined(ORBIT_SILU_ACCURATE)
 __device__ __forceinline__ float silu_fast(float x) { return x / (1.0f + expf(-x)); }
-#elif defined(ORBIT_SILU_MID)
-__device__ __forceinline__ float silu_fast(float x) { return x * __frcp_rn(1.0f + expf(-x)); }
 #else
 __device__ __forceinline__ float silu_fast(float x) { return silu_sfu(x); }
 #endif
@@ -176,62 +183,66 @@ struct Params {
     const float* shift;
     const float* gate;       // [frames, K] or null
     int has_residual;
-    int M, N, K, rows_per_frame, act, passes;
+    int M, N, K, rows_per_frame, act;
     int BN, n_tiles, m_tiles, stages;
     int b_tile_bytes;        // BN * 128 (multiple of 2048)
     int slabs_per_warp;      // 1 or 2 staging slabs per epilogue warp
     float debias;            // kappa * 2^-23: expected truncation loss of a promoted k-block partial, in units of its exponent
 };
 
+constexpr int SS_BYTES = 256;   // per epilogue warp: scale[32] | shift[32] of the slab it is finishing
+
+// Template parameters fix at compile time what round 1 decided per element at run time (ncu: the epilogue ran
+// 1050 and the transform 530 instructions per warp per 128-row step, 2.5-4x the arithmetic actually needed):
+//   SPLIT  3xTF32 (hi/lo) or plain TF32;  GATED / RES  0, 1, or -1 = look at the arguments;  ACT  activation or -1.
+template <bool SPLIT, int GATED, int ACT, int RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ CUtensorMap map_res, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const bool split = p.passes == 3;
-    const bool transform = split || p.gate != nullptr;
-    const int a_bytes = A_TILE_BYTES * (split ? 2 : 1);
-    const int stage_bytes = a_bytes + p.b_tile_bytes * (split ? 2 : 1);
-    uint8_t* staging = smem;                                  // [NUM_EPI_WARPS][slabs_per_warp][32 rows][128 B]
-    uint8_t* ring = smem + (size_t)NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES;
-    auto stage_a_hi = [&](int s) { return ring + (size_t)s * stage_bytes; };
-    auto stage_a_lo = [&](int s) { return ring + (size_t)s * stage_bytes + A_TILE_BYTES; };
-    auto stage_b_hi = [&](int s) { return ring + (size_t)s * stage_bytes + a_bytes; };
-    auto stage_b_lo = [&](int s) { return ring + (size_t)s * stage_bytes + a_bytes + p.b_tile_bytes; };
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes);
-    uint64_t* full = bars;                      // [stages] TMA landed
-    uint64_t* ready = bars + MAX_STAGES;        // [stages] transform done
-    uint64_t* empty = bars + 2 * MAX_STAGES;    // [stages] MMAs that read the slot retired
-    uint64_t* tmem_full = bars + 3 * MAX_STAGES;       // [2] correction accumulator of a tile complete
-    uint64_t* tmem_empty = bars + 3 * MAX_STAGES + 2;  // [2] ... drained by the epilogue
-    uint64_t* main_full = bars + 3 * MAX_STAGES + 4;   // [2] main accumulator of one k-block complete
-    uint64_t* main_empty = bars + 3 * MAX_STAGES + 6;  // [2] ... added into the epilogue's registers
-    uint64_t* res_bar = bars + 3 * MAX_STAGES + 8;     // [NUM_EPI_WARPS] residual slab landed
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 8 + NUM_EPI_WARPS);
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const bool gated = GATED < 0 ? p.gate != nullptr : GATED != 0;
+    const bool has_res = RES < 0 ? p.has_residual != 0 : RES != 0;
+    const int act = ACT < 0 ? p.act : ACT;
+    const bool transform = SPLIT || gated;
+    const uint32_t a_bytes = A_TILE_BYTES * (SPLIT ? 2 : 1);
+    const uint32_t stage_bytes = a_bytes + (uint32_t)p.b_tile_bytes * (SPLIT ? 2 : 1);
+    const uint32_t staging = smem;                                   // [NUM_EPI_WARPS][slabs_per_warp][32 rows][128 B]
+    const uint32_t sstab = staging + (uint32_t)(NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES);   // [NUM_EPI_WARPS][SS_BYTES]
+    const uint32_t ring = sstab + NUM_EPI_WARPS * SS_BYTES;          // (3 KB: the ring stays 1024-byte aligned)
+    const uint32_t bars = ring + (uint32_t)p.stages * stage_bytes;
+    auto full = [&](uint32_t s) { return bars + 8u * s; };                              // TMA landed
+    auto ready = [&](uint32_t s) { return bars + 8u * (MAX_STAGES + s); };              // transform done
+    auto empty = [&](uint32_t s) { return bars + 8u * (2 * MAX_STAGES + s); };          // MMAs that read the slot retired
+    auto tmem_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 2 + a); }; // correction accumulator drained
+    auto main_full = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 4 + a); };  // main accumulator of one k-block complete
+    auto main_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 6 + a); }; // ... added into the epilogue's registers
+    auto res_bar = [&](uint32_t w) { return bars + 8u * (3 * MAX_STAGES + 8 + w); };    // residual slab landed
+    const uint32_t tmem_base_slot = bars + 8u * (3 * MAX_STAGES + 8 + NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = ceil_div(p.K, BK);
     const int num_tiles = p.m_tiles * p.n_tiles;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], NUM_XF_WARPS); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(ready(s), NUM_XF_WARPS); mbar_init(empty(s), 1); }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], NUM_EPI_WARPS);
-            mbar_init(&main_full[a], 1); mbar_init(&main_empty[a], NUM_EPI_WARPS);
+            mbar_init(tmem_empty(a), NUM_EPI_WARPS);
+            mbar_init(main_full(a), 1); mbar_init(main_empty(a), NUM_EPI_WARPS);
         }
-        for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
+        for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_base_slot), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_base_slot;
+    const uint32_t tmem_base = lds32u(tmem_base_slot);
     // TMEM columns: main accumulators (hi*hi) at {0,1}*BN, correction accumulators (hi*lo + lo*hi) at {2,3}*BN.
     // The tensor core adds into its fp32 accumulator with TRUNCATION (measured: -0.45 ulp per accumulation, a
     // systematic bias that grows with K and compounds over the network's ~33 GEMM layers). So the main accumulator
@@ -239,15 +250,15 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // every k-block (double-buffered against the MMAs), and the 2^-11-scaled correction terms -- whose truncation
     // error is negligible -- accumulate over the whole tile in their own accumulator.
 
-    // Register budget: 768 threads x 80 at launch. The control and transform warps need few registers; the
-    // epilogue warps keep up to 64 running sums per thread. (setmaxnreg works on aligned groups of 4 warps.)
+    // Register budget: 768 threads x 80 at launch; the control and transform warps give registers back to the CTA
+    // pool (setmaxnreg works on aligned groups of 4 warps; an .inc can only claim what the CTA's own .dec freed --
+    // 29 per epilogue thread here -- and the epilogue fits in 80, so it does not ask).
     if (warp < XF_WARP0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            uint32_t it = 0;
-            const uint32_t tx = A_TILE_BYTES + (uint32_t)p.BN * BK * 4 * (split ? 2 : 1);
+            const uint32_t tx = A_TILE_BYTES + (uint32_t)p.BN * BK * 4 * (SPLIT ? 2 : 1);
             // L2 prefetch cursor: runs L2_PREFETCH_DISTANCE k-blocks ahead of the shared-memory ring, so that HBM
             // latency is covered by requests that cost no shared memory (the ring only has to cover L2 latency).
             int pf_tile = blockIdx.x, pf_kb = 0;
@@ -257,16 +268,18 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++pf_kb == num_k) { pf_kb = 0; pf_tile += gridDim.x; }
             };
             for (int i = 0; i < L2_PREFETCH_DISTANCE; ++i) prefetch_next();
+            uint32_t s = 0, ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const int s = it % p.stages;
+                for (int kb = 0; kb < num_k; ++kb) {
                     prefetch_next();
-                    mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], tx);
-                    tma_load_2d(stage_a_hi(s), &map_a, &full[s], kb * BK, m0);
-                    tma_load_2d(stage_b_hi(s), &map_bhi, &full[s], kb * BK, n0);
-                    if (split) tma_load_2d(stage_b_lo(s), &map_blo, &full[s], kb * BK, n0);
+                    mbar_wait(empty(s), ph ^ 1);
+                    mbar_expect_tx(full(s), tx);
+                    const uint32_t st = ring + s * stage_bytes;
+                    tma_load_2d(st, &map_a, full(s), kb * BK, m0);
+                    tma_load_2d(st + a_bytes, &map_bhi, full(s), kb * BK, n0);
+                    if (SPLIT) tma_load_2d(st + a_bytes + p.b_tile_bytes, &map_blo, full(s), kb * BK, n0);
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -274,36 +287,36 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(BM, p.BN);
-            uint32_t it = 0, tcount = 0;        // it = global k-block counter (ring slot AND main-accumulator parity)
+            uint32_t it = 0, tcount = 0, s = 0, ph = 0;   // it = global k-block counter (main-accumulator parity)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-                const int acc = tcount & 1;
-                if (split) mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
-                const uint32_t d_corr = tmem_base + (uint32_t)((2 + acc) * p.BN);
+                const uint32_t acc = tcount & 1;
+                if (SPLIT) mbar_wait(tmem_empty(acc), ((tcount >> 1) & 1) ^ 1);
+                const uint32_t d_corr = tmem_base + (2 + acc) * (uint32_t)p.BN;
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
-                    const int mb = it & 1;
-                    mbar_wait(&main_empty[mb], ((it >> 1) & 1) ^ 1);
-                    mbar_wait(&full[s], ph);
-                    if (transform) mbar_wait(&ready[s], ph);
+                    const uint32_t mb = it & 1;
+                    mbar_wait(main_empty(mb), ((it >> 1) & 1) ^ 1);
+                    mbar_wait(full(s), ph);
+                    if (transform) mbar_wait(ready(s), ph);
                     tc_fence_after();
-                    const uint32_t d_main = tmem_base + (uint32_t)(mb * p.BN);
-                    const uint64_t a_hi = make_desc_sw128(smem_u32(stage_a_hi(s)));
-                    const uint64_t b_hi = make_desc_sw128(smem_u32(stage_b_hi(s)));
-                    const uint64_t a_lo = make_desc_sw128(smem_u32(stage_a_lo(s)));
-                    const uint64_t b_lo = make_desc_sw128(smem_u32(stage_b_lo(s)));
+                    const uint32_t d_main = tmem_base + mb * (uint32_t)p.BN;
+                    const uint32_t st = ring + s * stage_bytes;
+                    const uint64_t a_hi = make_desc_sw128(st);
+                    const uint64_t a_lo = make_desc_sw128(st + A_TILE_BYTES);
+                    const uint64_t b_hi = make_desc_sw128(st + a_bytes);
+                    const uint64_t b_lo = make_desc_sw128(st + a_bytes + p.b_tile_bytes);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per k step inside the swizzle row
-                        if (split) {
+                        if (SPLIT) {
                             umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
                             umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
                         }
                         umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, k ? 1u : 0u);
                     }
-                    umma_commit(&empty[s]);          // ring slot reusable once these MMAs retire
-                    umma_commit(&main_full[mb]);     // this k-block's main accumulator is complete (and, after the
+                    umma_commit(empty(s));           // ring slot reusable once these MMAs retire
+                    umma_commit(main_full(mb));      // this k-block's main accumulator is complete (and, after the
                                                      // last k-block, the tile's correction accumulator too)
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -311,172 +324,176 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else if (warp < EPI_WARP0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ================================ A transform ================================
+        // 256 threads; thread t owns the 16-byte chunk (t & 7) of rows (t >> 3) + 32 i: multiply by the squeeze-excite
+        // gate and split into tf32 hi / lo in place (3xTF32). Conflict-free: 8 consecutive threads cover one 128-byte row.
         if (transform) {
             const int t = threadIdx.x - XF_WARP0 * 32;       // 0..255
             const int pchunk = t & 7;                        // physical 16-byte chunk inside the 128-byte row
             const int rbase = t >> 3;                        // rows rbase + 32*i
             const int jchunk = pchunk ^ (rbase & 7);         // logical chunk (SWIZZLE_128B: chunk ^= row & 7)
-            uint32_t it = 0;
+            const uint32_t toff = (uint32_t)(rbase * 128 + pchunk * 16);
+            uint32_t s = 0, ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.n_tiles) * BM;
-                int frame[4];
+                const float* grow[4];
+                if (gated) {
+                    const int m0 = (tile / p.n_tiles) * BM;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) frame[i] = min(m0 + rbase + 32 * i, p.M - 1) / p.rows_per_frame;
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const int kcol = kb * BK + jchunk * 4;
+                    for (int i = 0; i < 4; ++i)
+                        grow[i] = p.gate + (int64_t)(min(m0 + rbase + 32 * i, p.M - 1) / p.rows_per_frame) * p.K + jchunk * 4;
+                }
+                for (int kb = 0; kb < num_k; ++kb) {
                     float4 g[4];
-                    const bool gated = p.gate != nullptr && kcol < p.K;
-                    if (gated) {                                 // issue the gate loads before blocking on the TMA
+                    const bool g_on = gated && kb * BK + jchunk * 4 < p.K;
+                    if (g_on) {                                  // issue the gate loads before blocking on the TMA
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) g[i] = ldg4(p.gate + (int64_t)frame[i] * p.K + kcol);
+                        for (int i = 0; i < 4; ++i) g[i] = ldg4(grow[i] + kb * BK);
                     }
-                    mbar_wait(&full[s], (it / p.stages) & 1);
-                    float4* hi = reinterpret_cast<float4*>(stage_a_hi(s));
-                    float4* lo = reinterpret_cast<float4*>(stage_a_lo(s));
+                    mbar_wait(full(s), ph);
+                    const uint32_t a = ring + s * stage_bytes + toff;
+                    float4 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = lds128(a + i * 4096);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int idx = (rbase + 32 * i) * 8 + pchunk;
-                        float4 v = hi[idx];
-                        if (gated) { v.x *= g[i].x; v.y *= g[i].y; v.z *= g[i].z; v.w *= g[i].w; }
-                        if (split) {
-                            const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-                            hi[idx] = h;
-                            lo[idx] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+                        if (g_on) { v[i].x *= g[i].x; v[i].y *= g[i].y; v[i].z *= g[i].z; v[i].w *= g[i].w; }
+                        if (SPLIT) {
+                            const float4 h = make_float4(rna_tf32(v[i].x), rna_tf32(v[i].y), rna_tf32(v[i].z), rna_tf32(v[i].w));
+                            sts128(a + i * 4096, h);
+                            sts128(a + A_TILE_BYTES + i * 4096,
+                                   make_float4(rna_tf32(v[i].x - h.x), rna_tf32(v[i].y - h.y), rna_tf32(v[i].z - h.z), rna_tf32(v[i].w - h.w)));
                         } else {
-                            hi[idx] = v;
+                            sts128(a + i * 4096, v[i]);
                         }
                     }
                     fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ready[s]);
+                    if (lane == 0) mbar_arrive(ready(s));
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    } else {
         // ================================ epilogue ================================
-        // warp -> TMEM lane group (warp % 4) x column parity; 32 rows x 32 columns slabs go through a swizzled
+        // warp -> TMEM lane group (warp % 4) x column share; 32 rows x 32 columns slabs go through a swizzled
         // shared-memory staging buffer and leave with one TMA store (coalesced, clipped at the M / N edges);
         // the residual slab arrives the same way.
         const int ew = warp - EPI_WARP0;            // 0..11
         const int lane_grp = warp & 3;              // TMEM lanes 32*lane_grp .. +31 are accessible to this warp
         const int share = ew >> 2;                  // the EPI_SPLIT warps of a lane group share the tile's column slabs
         const int nbuf = p.slabs_per_warp;
-        uint8_t* my_staging = staging + (size_t)ew * nbuf * SLAB_BYTES;
+        const uint32_t my_staging = staging + (uint32_t)(ew * nbuf * SLAB_BYTES);
+        const uint32_t my_ss = sstab + (uint32_t)(ew * SS_BYTES);
         const int sw = lane & 7;
-        const int n_slabs = ceil_div(p.BN, 32);
-        constexpr int MAXS = 1;                     // BN <= 96 -> <= 3 slabs -> one per warp of a lane group (keeps the
-                                                    // unrolled epilogue small: a 2-slab version thrashed the I-cache, 2.7x slower)
+        const int n_slabs = ceil_div(p.BN, 32);     // BN <= 96 -> <= 3 slabs -> one per warp of a lane group
         const uint32_t t_lane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         uint32_t tcount = 0, res_phase = 0, slab_count = 0, it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-            const int acc = tcount & 1;
+            const uint32_t acc = tcount & 1;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
             const int row0 = m0 + lane_grp * 32;
             // slab sl belongs to share (sl + tile counter) % EPI_SPLIT: uneven slab counts even out over tiles
-            const int first_slab = (share + EPI_SPLIT - (int)(tcount % EPI_SPLIT)) % EPI_SPLIT;
-            bool res_issued = false;
-            auto slab_live = [&](int sl) { return row0 < p.M && n0 + sl * 32 < p.N; };
+            const int sl = (share + EPI_SPLIT - (int)(tcount % EPI_SPLIT)) % EPI_SPLIT;
+            const int c0 = sl * 32;
+            const bool have = sl < n_slabs;                                  // this warp holds a slab of the tile
+            const bool live = have && row0 < p.M && n0 + c0 < p.N;           // ... that has rows / columns to store
+            const bool wide = p.BN - c0 > 16;                                // the slab's second 16 columns exist in TMEM
+            const uint32_t stage = my_staging + (slab_count % nbuf) * SLAB_BYTES;
             auto wait_staging_free = [&]() { if (nbuf == 2) tma_store_wait_read1(); else tma_store_wait_read0(); };
-            auto issue_residual = [&](int sl) {   // TMA-load the residual slab into the staging buffer it will be added in
-                float4* st = reinterpret_cast<float4*>(my_staging + (size_t)(slab_count % nbuf) * SLAB_BYTES);
+            // per-column scale / shift of this slab: one coalesced load per lane now, parked in shared memory after the
+            // accumulation (columns beyond N get 0/0: their outputs are exact zeros and the TMA store clips them)
+            float my_sc = 0.f, my_sh = 0.f;
+            if (live && n0 + c0 + lane < p.N) { my_sc = __ldg(p.scale + n0 + c0 + lane); my_sh = __ldg(p.shift + n0 + c0 + lane); }
+            if (has_res && live) {            // TMA-load the residual slab into the staging buffer it will be added in
                 if (lane == 0) {
                     wait_staging_free();
-                    mbar_expect_tx(&res_bar[ew], SLAB_BYTES);
-                    tma_load_2d(st, &map_res, &res_bar[ew], n0 + sl * 32, row0);
+                    mbar_expect_tx(res_bar(ew), SLAB_BYTES);
+                    tma_load_2d(stage, &map_res, res_bar(ew), n0 + c0, row0);
                 }
                 __syncwarp();
-            };
-            if (p.has_residual && first_slab < n_slabs && slab_live(first_slab)) { issue_residual(first_slab); res_issued = true; }
+            }
 
             // ---- fp32 (round-to-nearest) accumulation of the per-k-block main accumulators ----
-            float sum[MAXS][32];
+            float sum[32];
 #pragma unroll
-            for (int i = 0; i < MAXS; ++i)
+            for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const uint32_t mb = it & 1;
+                mbar_wait(main_full(mb), (it >> 1) & 1);
+                tc_fence_after();
+                if (have) {
+                    float u[32];
+                    const uint32_t col = t_lane + mb * (uint32_t)p.BN + c0;
+                    tmem_ld16_issue(col, u);
+                    if (wide) tmem_ld16_issue(col + 16, u + 16);
+                    else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[i][j] = 0.f;
-            auto add_from_tmem = [&](uint32_t col_base, float debias) {
+                        for (int j = 16; j < 32; ++j) u[j] = 0.f;
+                    }
+                    tmem_ld_wait();
+                    // Every tcgen05.mma result is TRUNCATED to fp32 (measured): the k-block partial u
+                    // is short by 0.5 ulp(u) in expectation for its last MMA, plus the earlier ones at their
+                    // smaller magnitudes. Adding kappa * ulp(u) * sign(u) back removes the systematic part.
 #pragma unroll
-                for (int i = 0; i < MAXS; ++i) {
-                    const int sl = first_slab + i * EPI_SPLIT;
-                    if (sl < n_slabs) {
-                        const int c0 = sl * 32;
-                        float u[32];
-                        tmem_ld16_issue(t_lane + col_base + c0, u);
-                        if (p.BN - c0 > 16) tmem_ld16_issue(t_lane + col_base + c0 + 16, u + 16);
-                        else {
-#pragma unroll
-                            for (int j = 16; j < 32; ++j) u[j] = 0.f;
-                        }
-                        tmem_ld_wait();
-                        // Every tcgen05.mma result is TRUNCATED to fp32 (measured): the k-block partial u
-                        // is short by 0.5 ulp(u) in expectation for its last MMA, plus the earlier ones at their
-                        // smaller magnitudes. Adding kappa * ulp(u) * sign(u) back removes the systematic part.
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float pow2 = __uint_as_float(__float_as_uint(u[j]) & 0xff800000u);   // sign * 2^exponent
-                            sum[i][j] += fmaf(pow2, debias, u[j]);
-                        }
+                    for (int j = 0; j < 32; ++j) {
+                        const float pow2 = __uint_as_float(__float_as_uint(u[j]) & 0xff800000u);   // sign * 2^exponent
+                        sum[j] += fmaf(pow2, p.debias, u[j]);
                     }
                 }
-            };
-            for (int kb = 0; kb < num_k; ++kb, ++it) {
-                const int mb = it & 1;
-                mbar_wait(&main_full[mb], (it >> 1) & 1);
-                tc_fence_after();
-                add_from_tmem((uint32_t)(mb * p.BN), p.debias);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&main_empty[mb]);
+                if (lane == 0) mbar_arrive(main_empty(mb));
             }
-            if (split) {   // tcgen05.commit covers ALL earlier MMAs: the last main_full also completed the correction terms
-                add_from_tmem((uint32_t)((2 + acc) * p.BN), 0.f);
+            if (SPLIT) {   // tcgen05.commit covers ALL earlier MMAs: the last main_full also completed the correction terms
+                if (have) {
+                    float u[32];
+                    const uint32_t col = t_lane + (2 + acc) * (uint32_t)p.BN + c0;
+                    tmem_ld16_issue(col, u);
+                    if (wide) tmem_ld16_issue(col + 16, u + 16);
+                    else {
+#pragma unroll
+                        for (int j = 16; j < 32; ++j) u[j] = 0.f;
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[j] += u[j];
+                }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) mbar_arrive(tmem_empty(acc));
             }
+            if (!live) continue;
 
             // ---- scale/shift, activation, residual, store ----
-#pragma unroll
-            for (int i = 0; i < MAXS; ++i) {
-                const int sl = first_slab + i * EPI_SPLIT;
-                if (sl >= n_slabs || !slab_live(sl)) continue;
-                const int c0 = sl * 32;
-                float4* stage = reinterpret_cast<float4*>(my_staging + (size_t)(slab_count % nbuf) * SLAB_BYTES);
-                if (p.has_residual) {
-                    if (!res_issued) issue_residual(sl);
-                    res_issued = false;
-                    mbar_wait(&res_bar[ew], res_phase);
-                    res_phase ^= 1;
-                } else {
-                    if (lane == 0) wait_staging_free();
-                    __syncwarp();
-                }
-                const bool interior = n0 + c0 + 32 <= p.N;     // no column predicates needed
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int c = n0 + c0 + q * 4;
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (interior || c < p.N) {
-                        const float4 sc = ldg4(p.scale + c), sh = ldg4(p.shift + c);
-                        o.x = fmaf(sum[i][q * 4 + 0], sc.x, sh.x); o.y = fmaf(sum[i][q * 4 + 1], sc.y, sh.y);
-                        o.z = fmaf(sum[i][q * 4 + 2], sc.z, sh.z); o.w = fmaf(sum[i][q * 4 + 3], sc.w, sh.w);
-                        if (p.act == 1) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
-                        else if (p.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        else if (p.act == 4) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
-                        if (p.has_residual) {
-                            const float4 r = stage[lane * 8 + (q ^ sw)];
-                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                        }
-                        if (p.act == 16 + 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    }
-                    stage[lane * 8 + (q ^ sw)] = o;
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tma_store_2d(&map_out, stage, n0 + c0, row0);
-                ++slab_count;
+            sts32(my_ss + lane * 4, my_sc);
+            sts32(my_ss + 128 + lane * 4, my_sh);
+            if (has_res) {
+                mbar_wait(res_bar(ew), res_phase);
+                res_phase ^= 1;
+            } else {
+                if (lane == 0) wait_staging_free();
             }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 sc = lds128(my_ss + q * 16), sh = lds128(my_ss + 128 + q * 16);
+                float4 o;
+                o.x = fmaf(sum[q * 4 + 0], sc.x, sh.x); o.y = fmaf(sum[q * 4 + 1], sc.y, sh.y);
+                o.z = fmaf(sum[q * 4 + 2], sc.z, sh.z); o.w = fmaf(sum[q * 4 + 3], sc.w, sh.w);
+                if (act == 1) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
+                else if (act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                else if (act == 4) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
+                const uint32_t saddr = stage + (uint32_t)((lane * 8 + (q ^ sw)) * 16);
+                if (has_res) {
+                    const float4 r = lds128(saddr);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                if (act == 16 + 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                sts128(saddr, o);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&map_out, stage, n0 + c0, row0);
+            ++slab_count;
         }
         if (lane == 0) tma_store_wait_all();
     }
@@ -534,7 +551,7 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     if (M <= 0) return ORBIT_OK;
     Params p;
     p.scale = scale; p.shift = shift; p.gate = gate; p.has_residual = residual != nullptr;
-    p.M = M; p.N = N; p.K = K; p.rows_per_frame = rows_per_frame; p.act = act; p.passes = passes;
+    p.M = M; p.N = N; p.K = K; p.rows_per_frame = rows_per_frame; p.act = act;
     p.debias = passes == 3 ? g_debias_kappa * 1.1920929e-07f : 0.f;
     // n-tiles of at most 96 columns (3 store slabs = one per epilogue warp of a lane group); with several n-tiles
     // BN must be a multiple of the 32-column store slab
@@ -544,13 +561,13 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     p.b_tile_bytes = p.BN * BK * 4;
     const int stage_bytes = (A_TILE_BYTES + p.b_tile_bytes) * (passes == 3 ? 2 : 1);
     const int bar_bytes = (3 * MAX_STAGES + 8 + NUM_EPI_WARPS) * 8 + 16;
-    const int budget = 227 * 1024 - 1024 /*alignment slack*/ - bar_bytes;
+    const int budget = 227 * 1024 - 1024 /*alignment slack*/ - bar_bytes - NUM_EPI_WARPS * SS_BYTES;
     // double-buffered epilogue staging when that still leaves a 4-deep operand ring
     p.slabs_per_warp = (budget - 2 * NUM_EPI_WARPS * SLAB_BYTES) / stage_bytes >= 4 ? 2 : 1;
     const int staging_bytes = NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES;
     p.stages = std::min(MAX_STAGES, (budget - staging_bytes) / stage_bytes);
     if (p.stages < 2) return ORBIT_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)staging_bytes + (size_t)p.stages * stage_bytes + bar_bytes + 1024;
+    const size_t smem = (size_t)staging_bytes + NUM_EPI_WARPS * SS_BYTES + (size_t)p.stages * stage_bytes + bar_bytes + 1024;
 
     CUtensorMap map_a, map_bhi, map_blo, map_out, map_res;
     int rc = make_map(&map_a, A, M, K, BM);
@@ -564,15 +581,33 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     rc = make_map(&map_res, residual ? residual : out, M, N, 32);
     if (rc) return rc;
 
+    // specialisations for the shapes the backbones use; anything else runs the run-time-dispatch instance
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+    KernelFn fn = nullptr;
+    const bool g = gate != nullptr, r = residual != nullptr;
+    if (passes == 3) {
+        if (g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 1, 0, 0>;          // MBConv project
+        else if (g && act == 0 && r) fn = pw_tcgen05_kernel<true, 1, 0, 1>;      // MBConv project + skip
+        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0>;    // MBConv expand / conv_head (SiLU)
+        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0>;    // Linear / downsample
+        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1>;     // Linear + residual (ViT), EdgeResidual project
+        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0>;    // conv + ReLU
+        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0>;    // Linear + GELU
+        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1>;   // BasicBlock: relu(bn(conv) + identity)
+        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1>;     // ConvBnAct + skip (EfficientNet-V2)
+        else fn = pw_tcgen05_kernel<true, -1, -1, -1>;
+    } else {
+        fn = pw_tcgen05_kernel<false, -1, -1, -1>;
+    }
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
         ORBIT_CUDA(cudaGetDevice(&dev));
         ORBIT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        ORBIT_CUDA(cudaFuncSetAttribute(pw_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
+    ORBIT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = std::min(p.m_tiles * p.n_tiles, num_sms);
-    pw_tcgen05_kernel<<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_out, map_res, p);
+    fn<<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_out, map_res, p);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }
