@@ -37,7 +37,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='orbit_b200', choices=['orbit_b200', 'reference'])
     ap.add_argument('--gemm', type=int, default=int(os.environ.get('ORBIT_GEMM', '1')))
-    ap.add_argument('--chunk', type=int, default=int(os.environ.get('ORBIT_CHUNK', '640')))
+    ap.add_argument('--chunk', type=int, default=int(os.environ.get('ORBIT_CHUNK', '1600')))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--profile-steps', type=int, default=2)

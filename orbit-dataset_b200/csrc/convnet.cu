@@ -137,22 +137,37 @@ __device__ __forceinline__ float act_fast(float v, int act) {
 // Stem: 3x3 stride-2 conv on the fp32 NCHW frames, one output pixel (all COUT channels) per thread.
 // The NCHW->NHWC change of layout is fused here so the frames are read exactly once.
 // ------------------------------------------------------------------------------------------------
+// Two horizontally adjacent output pixels per thread (they share one of their three input columns and every
+// weight fetch), channel pairs on the packed fma.rn.f32x2 pipe: 27 x (8 LDS.128 + 32 FFMA2) per pixel pair instead
+// of 2 x 27 x (8 LDS.128 + 32 FFMA) in round 1.
+typedef unsigned long long stem_f2_t;
+__device__ __forceinline__ stem_f2_t stem_dup(float v) { stem_f2_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v)); return r; }
+__device__ __forceinline__ stem_f2_t stem_fma2(stem_f2_t a, stem_f2_t b, stem_f2_t c) {
+    stem_f2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 template <int COUT>
 __global__ void __launch_bounds__(128)
 stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
             const float* __restrict__ shift, float* __restrict__ y, int B, int H, int W, int Ho, int Wo, int pad_t,
             int pad_l, int act) {
+    constexpr int NP = COUT / 2;
     __shared__ __align__(16) float s_w[27 * COUT];  // [tap][co]
     __shared__ __align__(16) float s_sc[COUT], s_sh[COUT];
     for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) { const int tap = i / COUT, co = i % COUT; s_w[i] = w[co * 27 + tap]; }
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) { s_sc[i] = scale[i]; s_sh[i] = shift[i]; }
     __syncthreads();
+    const int Wp = (Wo + 1) / 2;                      // pixel pairs per output row
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)B * Ho * Wo) return;
-    const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho), b = (int)(idx / ((int64_t)Wo * Ho));
-    float acc[COUT];
+    if (idx >= (int64_t)B * Ho * Wp) return;
+    const int ox = 2 * (int)(idx % Wp), oy = (int)((idx / Wp) % Ho), b = (int)(idx / ((int64_t)Wp * Ho));
+    const bool second = ox + 1 < Wo;
+    stem_f2_t acc[2][NP];
 #pragma unroll
-    for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NP; ++i) { acc[0][i] = 0ull; acc[1][i] = 0ull; }
+    const int ix0 = ox * 2 - pad_l;                   // input columns ix0 .. ix0+4 feed the two outputs
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
         const float* xp = x + ((int64_t)b * 3 + ci) * H * W;
@@ -160,37 +175,47 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = oy * 2 - pad_t + ky;
             if (iy < 0 || iy >= H) continue;
+            const float* rp = xp + (int64_t)iy * W + ix0;
+            float v[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) v[j] = (ix0 + j >= 0 && ix0 + j < W) ? __ldg(rp + j) : 0.f;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * 2 - pad_l + kx;
-                if (ix < 0 || ix >= W) continue;
-                const float v = __ldg(xp + (int64_t)iy * W + ix);
-                const float4* wp = reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * COUT);
+                const stem_f2_t v0 = stem_dup(v[kx]), v1 = stem_dup(v[kx + 2]);
+                const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_w + (ci * 9 + ky * 3 + kx) * COUT);
 #pragma unroll
                 for (int q = 0; q < COUT / 4; ++q) {
-                    const float4 w4 = wp[q];
-                    acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+                    const ulonglong2 w2 = wp[q];
+                    acc[0][2 * q] = stem_fma2(v0, w2.x, acc[0][2 * q]); acc[0][2 * q + 1] = stem_fma2(v0, w2.y, acc[0][2 * q + 1]);
+                    acc[1][2 * q] = stem_fma2(v1, w2.x, acc[1][2 * q]); acc[1][2 * q + 1] = stem_fma2(v1, w2.y, acc[1][2 * q + 1]);
                 }
             }
         }
     }
-    float4* yp = reinterpret_cast<float4*>(y + idx * COUT);
+    const int64_t pix = ((int64_t)b * Ho + oy) * Wo + ox;
 #pragma unroll
-    for (int q = 0; q < COUT / 4; ++q) {
-        float4 o;
-        o.x = act_fast(fmaf(acc[4 * q + 0], s_sc[4 * q + 0], s_sh[4 * q + 0]), act);
-        o.y = act_fast(fmaf(acc[4 * q + 1], s_sc[4 * q + 1], s_sh[4 * q + 1]), act);
-        o.z = act_fast(fmaf(acc[4 * q + 2], s_sc[4 * q + 2], s_sh[4 * q + 2]), act);
-        o.w = act_fast(fmaf(acc[4 * q + 3], s_sc[4 * q + 3], s_sh[4 * q + 3]), act);
-        yp[q] = o;
+    for (int px = 0; px < 2; ++px) {
+        if (px == 1 && !second) break;
+        float4* yp = reinterpret_cast<float4*>(y + (pix + px) * COUT);
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+            float a0, a1, a2, a3;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc[px][2 * q]));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(a2), "=f"(a3) : "l"(acc[px][2 * q + 1]));
+            float4 o;
+            o.x = act_fast(fmaf(a0, s_sc[4 * q + 0], s_sh[4 * q + 0]), act);
+            o.y = act_fast(fmaf(a1, s_sc[4 * q + 1], s_sh[4 * q + 1]), act);
+            o.z = act_fast(fmaf(a2, s_sc[4 * q + 2], s_sh[4 * q + 2]), act);
+            o.w = act_fast(fmaf(a3, s_sc[4 * q + 3], s_sh[4 * q + 3]), act);
+            yp[q] = o;
+        }
     }
 }
 
 int launch_stem(const float* x, const float* w, const float* scale, const float* shift, float* y, int B, int H, int W,
                 int Ho, int Wo, int pad_t, int pad_l, int cout, int act, cudaStream_t st) {
     if (cout != 32) return ORBIT_ERR_UNSUPPORTED;
-    const int64_t total = (int64_t)B * Ho * Wo;
+    const int64_t total = (int64_t)B * Ho * ((Wo + 1) / 2);
     stem_kernel<32><<<(unsigned)ceil_div64(total, 128), 128, 0, st>>>(x, w, scale, shift, y, B, H, W, Ho, Wo, pad_t, pad_l, act);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
@@ -693,43 +718,78 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Squeeze-excite gate, one block per frame.
+// Squeeze-excite gate. One block handles kSeFrames frames so that the two FC weight matrices (up to 2 x 221 KB in
+// EfficientNet-B0) are fetched once per 8 frames instead of once per frame (round 1: one block per frame, 39 us per
+// launch, all of it L2 traffic for the weights), with 1024 threads and deeply unrolled independent weight loads:
+// the kernel is a chain of L2 latencies, so what matters is how many loads each SM keeps in flight.
+// Per-frame arithmetic order is unchanged.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kSeFrames = 8;
+
+__global__ void __launch_bounds__(1024)
 se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const float* __restrict__ w1,
-               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-               float* __restrict__ gate, int C, int R) {
-    extern __shared__ float s_se[];  // mean[C], hidden[R]
+               const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
+               float* __restrict__ gate, int B, int C, int R, int F) {
+    extern __shared__ float s_se[];  // mean[F][C], hidden[F][R]
     float* s_mean = s_se;
-    float* s_hid = s_se + C;
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const float* pb = partial + (int64_t)b * tiles * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float* s_hid = s_se + F * C;
+    const int f0 = blockIdx.x * F, nf = min(F, B - f0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < nf * C; i += blockDim.x) {
+        const int f = i / C, c = i - f * C;
+        const float* pb = partial + (int64_t)(f0 + f) * tiles * C + c;
         float s = 0.f;
-        for (int t = 0; t < tiles; ++t) s += pb[(int64_t)t * C + c];
-        s_mean[c] = s * inv_hw;
+        for (int t = 0; t < tiles; ++t) s += pb[(int64_t)t * C];
+        s_mean[i] = s * inv_hw;
     }
     __syncthreads();
     for (int r = warp; r < R; r += n_warps) {
-        float s = 0.f;
+        float s[kSeFrames];
+#pragma unroll
+        for (int f = 0; f < kSeFrames; ++f) s[f] = 0.f;
         const float* wr = w1 + (int64_t)r * C;
-        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + c), s_mean[c], s);
-        s = warp_sum(s);
-        if (lane == 0) s_hid[r] = siluf_(s + __ldg(b1 + r));
+#pragma unroll 12
+        for (int c = lane; c < C; c += 32) {
+            const float w = __ldg(wr + c);
+#pragma unroll
+            for (int f = 0; f < kSeFrames; ++f)
+                if (f < nf) s[f] = fmaf(w, s_mean[f * C + c], s[f]);
+        }
+        const float bias = __ldg(b1 + r);
+#pragma unroll
+        for (int f = 0; f < kSeFrames; ++f) {
+            if (f < nf) {
+                const float t = warp_sum(s[f]);
+                if (lane == 0) s_hid[f * R + r] = siluf_(t + bias);
+            }
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = __ldg(b2 + c);
-        const float* wr = w2 + (int64_t)c * R;
-        for (int r = 0; r < R; ++r) s = fmaf(__ldg(wr + r), s_hid[r], s);
-        gate[(int64_t)b * C + c] = sigmoidf_(s);
+        float s[kSeFrames];
+        const float bias = __ldg(b2 + c);
+#pragma unroll
+        for (int f = 0; f < kSeFrames; ++f) s[f] = bias;
+#pragma unroll 8
+        for (int r = 0; r < R; ++r) {
+            const float w = __ldg(w2t + (int64_t)r * C + c);     // transposed [R][C]: coalesced, independent loads
+#pragma unroll
+            for (int f = 0; f < kSeFrames; ++f)
+                if (f < nf) s[f] = fmaf(w, s_hid[f * R + r], s[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < kSeFrames; ++f)
+            if (f < nf) gate[(int64_t)(f0 + f) * C + c] = sigmoidf_(s[f]);
     }
 }
 
-int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2,
+int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2t,
                    const float* b2, float* gate, int B, int C, int R, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (size_t)(C + R);
-    se_gate_kernel<<<B, 256, smem, st>>>(partial, tiles, 1.0f / (float)hw, w1, b1, w2, b2, gate, C, R);
+    if (B <= 0) return ORBIT_OK;
+    int F = kSeFrames;
+    while (F > 1 && sizeof(float) * (size_t)F * (C + R) > 44 * 1024) F >>= 1;   // stay inside the default 48 KB
+    const size_t smem = sizeof(float) * (size_t)F * (C + R);
+    se_gate_kernel<<<ceil_div(B, F), C >= 256 ? 1024 : 256, smem, st>>>(partial, tiles, 1.0f / (float)hw, w1, b1, w2t, b2, gate, B, C, R, F);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }

@@ -46,8 +46,9 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
 void set_dw_variant(int v);
 int get_dw_variant();
 
-// squeeze-excite gate: partial [B][tiles][C] -> gate [B][C] = sigmoid(W2 silu(W1 mean + b1) + b2)
-int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2,
+// squeeze-excite gate: partial [B][tiles][C] -> gate [B][C] = sigmoid(W2 silu(W1 mean + b1) + b2);
+// w2t = the expand weight [C][R] transposed to [R][C] (launch_dw_relayout(w2, C, R, w2t))
+int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2t,
                    const float* b2, float* gate, int B, int C, int R, cudaStream_t st);
 
 // pointwise conv as GEMM: out[M,N] = act((A[M,K] (*gate[m/rows_per_frame, k])) W[N,K]^T * scale[n] + shift[n]) (+res)

@@ -175,6 +175,7 @@ static void add_mbconv(orbit_engine* e, const std::string& p, int cin, int cout,
         op.b = e->add_param(p + "se.conv_reduce.bias", op.se_reduce);
         op.w2 = e->add_param(p + "se.conv_expand.weight", mid, op.se_reduce, 1, 1);
         op.b2 = e->add_param(p + "se.conv_expand.bias", mid);
+        op.dw_wt = e->add_derived((int64_t)mid * op.se_reduce);   // expand weight transposed to [reduce][mid]
         e->ops.push_back(op);
     }
     {   // project 1x1 (gated input) + bn (+ residual)
@@ -579,6 +580,9 @@ extern "C" int orbit_engine_prepare(const orbit_engine* e, const float* params, 
         if (op.kind == OP_DW) {
             rc = launch_dw_relayout(params + op.w, op.cin, op.k * op.k, derived + op.dw_wt, st);
             if (rc) return rc;
+        } else if (op.kind == OP_SE) {
+            rc = launch_dw_relayout(params + op.w2, op.cin, op.se_reduce, derived + op.dw_wt, st);
+            if (rc) return rc;
         } else if (op.kind == OP_PW && op.w_split >= 0) {
             rc = launch_tf32_split(params + op.w, (int64_t)op.cout * op.cin, derived + op.w_split, st);
             if (rc) return rc;
@@ -740,7 +744,7 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                         break;
                     }
                     case OP_SE:
-                        rc = launch_se_gate(buf[BUF_PARTIAL], se_tiles, se_hw, params + op.w, params + op.b, params + op.w2,
+                        rc = launch_se_gate(buf[BUF_PARTIAL], se_tiles, se_hw, params + op.w, params + op.b, derived + op.dw_wt,
                                             params + op.b2, buf[BUF_GATE], B, op.cin, op.se_reduce, st);
                         p_bytes = 4.0 * (B * op.cin * (se_tiles + 1.0) + 2.0 * op.cin * op.se_reduce);
                         p_flops = 4.0 * B * op.cin * op.se_reduce;

@@ -22,67 +22,97 @@ from .feature_extractors import (create_feature_extractor, get_film_parameter_si
 
 
 class _HostStager:
-    """Moves CPU-resident clips to the device in slices on a side stream so the copy of slice i+1
-    overlaps the backbone pass of slice i (reference: ``clips.to(self.device, non_blocking=True)``
-    from pageable memory, few_shot_recognisers.py:112,142)."""
+    """Moves CPU-resident clips to the device on a side stream while the backbone runs (reference:
+    ``clips.to(self.device, non_blocking=True)`` from pageable memory, few_shot_recognisers.py:112,142).
 
-    def __init__(self, device, slice_frames):
+    One call = one whole-call device buffer (two are kept and alternate between calls), so the copy engine never
+    waits for the backbone inside a call and the NEXT call's copy (e.g. the query set while the support set is still
+    being processed) starts as soon as it is issued. The backbone consumes the buffer in chunks that only wait for
+    their own bytes: a short ramp (96, 224, 480 frames) so that the first kernels start after ~1 ms of copy, then
+    chunks of ``chunk_frames``. Pageable sources are staged through two pinned slices."""
+
+    def __init__(self, device, chunk_frames, copy_frames=160):
         self.device = device
-        self.slice_frames = slice_frames
+        self.chunk_frames = chunk_frames
+        self.copy_frames = copy_frames          # granularity of the async copies (97 MB at 224 px)
         self.copy_stream = torch.cuda.Stream(device)
-        self.dev = [None, None]
+        self.dev = [None, None]                 # whole-call device buffers
+        self.done = [None, None]                # the backbone finished reading dev[i]
         self.pinned = [None, None]
-        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
-        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
-        self.h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
-        self.used = [False, False]
+        self.pinned_free = [None, None]
+        self.calls = 0
         self.bytes_copied = 0
+        self.ramp = (96, 224, 480)
 
-    def _buffers(self, i, shape):
-        n = int(np.prod(shape))
-        if self.dev[i] is None or self.dev[i].numel() < n:
-            self.dev[i] = torch.empty(n, dtype=torch.float32, device=self.device)
-        return self.dev[i][:n].view(shape)
+    def _plan(self, total):
+        sizes, pos, k = [], 0, 0
+        while pos < total:
+            n = min(self.ramp[k], self.chunk_frames) if k < len(self.ramp) else self.chunk_frames
+            n = min(n, total - pos)
+            sizes.append(n)
+            pos += n
+            k += 1
+        if len(sizes) > 1 and sizes[-1] < 64:   # no tiny tail pass
+            tail = sizes.pop()
+            sizes[-1] += tail
+        return sizes
 
     def stream(self, frames_cpu):
-        """Yields device views of consecutive slices of ``frames_cpu`` [F,3,H,W]; each view is valid
-        until the next iteration's forward has been enqueued."""
+        """Yields device views of consecutive chunks of ``frames_cpu`` [F,3,H,W]; a view stays valid until the
+        call after next."""
         compute = torch.cuda.current_stream(self.device)
         total = frames_cpu.shape[0]
-        starts = list(range(0, total, self.slice_frames))
+        if total == 0:
+            return
+        i = self.calls % 2
+        self.calls += 1
+        per_frame = int(np.prod(frames_cpu.shape[1:]))
+        need = total * per_frame
+        if self.dev[i] is None or self.dev[i].numel() < need:
+            if self.done[i] is not None:
+                self.done[i].synchronize()
+            self.dev[i] = torch.empty(max(need, self.chunk_frames * per_frame), dtype=torch.float32, device=self.device)
+            # the allocator may hand back memory an earlier kernel on the compute stream still uses
+            ev = torch.cuda.Event(); ev.record(compute); self.copy_stream.wait_event(ev)
+        elif self.done[i] is not None:
+            self.copy_stream.wait_event(self.done[i])
+        dst = self.dev[i][:need].view(frames_cpu.shape)
+        sizes = self._plan(total)
         pinned_src = frames_cpu.is_pinned()
-
-        def issue(j):
-            i = j % 2
-            src = frames_cpu[starts[j]:starts[j] + self.slice_frames]
-            dst = self._buffers(i, src.shape)
-            if not pinned_src:
-                n = src.numel()
-                if self.pinned[i] is None or self.pinned[i].numel() < n:
-                    self.pinned[i] = torch.empty(n, dtype=torch.float32).pin_memory()
-                if self.used[i]:
-                    self.h2d_done[i].synchronize()  # staging buffer still in flight
-                stage = self.pinned[i][:n].view(src.shape)
-                stage.copy_(src)
-                src = stage
-            if self.used[i]:
-                self.copy_stream.wait_event(self.consumed[i])  # device buffer free again
-            with torch.cuda.stream(self.copy_stream):
-                dst.copy_(src, non_blocking=True)
-                self.h2d_done[i].record(self.copy_stream)
-                self.ready[i].record(self.copy_stream)
-            self.used[i] = True
-            self.bytes_copied += src.numel() * 4
-            return dst
-
-        pending = issue(0) if starts else None
-        for j in range(len(starts)):
-            cur, i = pending, j % 2
-            if j + 1 < len(starts):
-                pending = issue(j + 1)
-            compute.wait_event(self.ready[i])
-            yield cur
-            self.consumed[i].record(compute)
+        events, pos, j = [], 0, 0
+        for n in sizes:
+            end = pos + n
+            while pos < end:
+                m = min(self.copy_frames, end - pos)
+                src = frames_cpu[pos:pos + m]
+                if not pinned_src:
+                    k = j % 2
+                    j += 1
+                    if self.pinned[k] is None or self.pinned[k].numel() < m * per_frame:
+                        self.pinned[k] = torch.empty(self.copy_frames * per_frame, dtype=torch.float32).pin_memory()
+                        self.pinned_free[k] = None
+                    if self.pinned_free[k] is not None:
+                        self.pinned_free[k].synchronize()   # staging slice still in flight
+                    stage = self.pinned[k][:m * per_frame].view(src.shape)
+                    stage.copy_(src)
+                    src = stage
+                with torch.cuda.stream(self.copy_stream):
+                    dst[pos:pos + m].copy_(src, non_blocking=True)
+                    if not pinned_src:
+                        self.pinned_free[k] = torch.cuda.Event()
+                        self.pinned_free[k].record(self.copy_stream)
+                pos += m
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+            events.append(ev)
+        self.bytes_copied += need * 4
+        pos = 0
+        for n, ev in zip(sizes, events):
+            compute.wait_event(ev)
+            yield dst[pos:pos + n]
+            pos += n
+        self.done[i] = torch.cuda.Event()
+        self.done[i].record(compute)
 
 
 class FewShotRecogniser(nn.Module):
@@ -120,7 +150,8 @@ class FewShotRecogniser(nn.Module):
         self.frame_pooler = MeanPooler(T=self.clip_length)
         self.device = torch.device('cpu')
         self._stager = None
-        self.stage_slice_frames = 320  # frames per overlapped H2D slice for CPU-resident clips (193 MB at 224 px)
+        self.stage_copy_frames = 160      # frames per async H2D copy for CPU-resident clips (97 MB at 224 px)
+        self.stage_ramp = (96, 224, 480)  # sizes of the first backbone passes of a call (frames)
 
     def _set_device(self, device):
         self.device = torch.device(device)
@@ -142,9 +173,10 @@ class FewShotRecogniser(nn.Module):
         blob = self._film_blob(film_dict) if film_dict else None
         if frames.is_cuda:
             return self.feature_extractor(frames, blob)
-        if self._stager is None or self._stager.device != self.device or \
-                self._stager.slice_frames != self.stage_slice_frames:
-            self._stager = _HostStager(self.device, self.stage_slice_frames)
+        chunk = self.feature_extractor.get_option('chunk_frames')
+        if self._stager is None or self._stager.device != self.device or self._stager.chunk_frames != chunk:
+            self._stager = _HostStager(self.device, chunk)
+        self._stager.copy_frames, self._stager.ramp = self.stage_copy_frames, tuple(self.stage_ramp)
         outs = [self.feature_extractor(dev_frames, blob) for dev_frames in self._stager.stream(frames.float())]
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 

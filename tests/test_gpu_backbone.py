@@ -55,7 +55,7 @@ def test_episode_logits_and_argmax(cuda_device, oracle_effnet):
     ref = oracle_effnet.predict(tgt)
 
     m = _product(oracle_effnet, cuda_device)
-    m.stage_slice_frames = 8
+    m.stage_copy_frames, m.stage_ramp = 3, (4, 6)   # several copies per pass, several passes per call
     for clips_dev, gemm in ((False, 0), (True, 0), (True, 1), (False, 1)):
         m.feature_extractor.set_option('gemm', gemm)
         c, t = (ctx.to(cuda_device), tgt.to(cuda_device)) if clips_dev else (ctx, tgt)
