@@ -123,6 +123,33 @@ __device__ __forceinline__ uint32_t lds32u(uint32_t addr) {
     return v;
 }
 
+// Packed fp32x2 arithmetic (Blackwell): two IEEE round-to-nearest fp32 operations per issue slot. The epilogue is
+// issue-bound on the HBM-shaped layers, and every value it touches comes in adjacent-column pairs.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ void lds128_f2(uint32_t addr, f2_t& a, f2_t& b) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts128_f2(uint32_t addr, f2_t a, f2_t b) {
+    asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+}
+// x * sigmoid(x) on a pair: the two MUFU ops per element stay scalar, the three fp32 ops around them are packed
+__device__ __forceinline__ f2_t f2_silu(f2_t x) {
+    float t0, t1, e0, e1, r0, r1;
+    f2_unpack(f2_mul(x, f2_pack(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+    f2_unpack(f2_add(f2_pack(e0, e1), f2_pack(1.0f, 1.0f)), t0, t1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+    return f2_mul(x, f2_pack(r0, r1));
+}
+__device__ __forceinline__ f2_t f2_relu(f2_t x) { float a, b; f2_unpack(x, a, b); return f2_pack(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
+
 // fp32 -> tf32 with round-to-nearest (ties away), identical to cvt.rna.tf32.f32 on finite inputs: add half a
 // tf32 ulp to the magnitude and clear the 13 low mantissa bits. (The cvt instruction is emulated on sm_100 with
 // these two operations plus an inf/NaN guard per element; activations here are finite.)
@@ -413,9 +440,10 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
 
             // ---- fp32 (round-to-nearest) accumulation of the per-k-block main accumulators ----
-            float sum[32];
+            f2_t sum[16];                                  // 32 columns as adjacent pairs
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+            for (int j = 0; j < 16; ++j) sum[j] = 0ull;
+            const f2_t debias2 = f2_pack(p.debias, p.debias);
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const uint32_t mb = it & 1;
                 mbar_wait(main_full(mb), (it >> 1) & 1);
@@ -434,9 +462,10 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     // is short by 0.5 ulp(u) in expectation for its last MMA, plus the earlier ones at their
                     // smaller magnitudes. Adding kappa * ulp(u) * sign(u) back removes the systematic part.
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float pow2 = __uint_as_float(__float_as_uint(u[j]) & 0xff800000u);   // sign * 2^exponent
-                        sum[j] += fmaf(pow2, p.debias, u[j]);
+                    for (int j = 0; j < 16; ++j) {
+                        const f2_t up = f2_pack(u[2 * j], u[2 * j + 1]);
+                        const f2_t pow2 = up & 0xff800000ff800000ull;            // sign * 2^exponent of each half
+                        sum[j] = f2_add(sum[j], f2_fma(pow2, debias2, up));
                     }
                 }
                 tc_fence_before();
@@ -455,7 +484,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sum[j] += u[j];
+                    for (int j = 0; j < 16; ++j) sum[j] = f2_add(sum[j], f2_pack(u[2 * j], u[2 * j + 1]));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -473,22 +502,31 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) wait_staging_free();
             }
             __syncwarp();
+            f2_t sc[2], sh[2], rr[2] = {0ull, 0ull};       // software pipeline: the loads of step q+1 are issued before step q computes
+            lds128_f2(my_ss, sc[0], sc[1]);
+            lds128_f2(my_ss + 128, sh[0], sh[1]);
+            if (has_res) lds128_f2(stage + (uint32_t)((lane * 8 + sw) * 16), rr[0], rr[1]);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 sc = lds128(my_ss + q * 16), sh = lds128(my_ss + 128 + q * 16);
-                float4 o;
-                o.x = fmaf(sum[q * 4 + 0], sc.x, sh.x); o.y = fmaf(sum[q * 4 + 1], sc.y, sh.y);
-                o.z = fmaf(sum[q * 4 + 2], sc.z, sh.z); o.w = fmaf(sum[q * 4 + 3], sc.w, sh.w);
-                if (act == 1) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
-                else if (act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                else if (act == 4) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
-                const uint32_t saddr = stage + (uint32_t)((lane * 8 + (q ^ sw)) * 16);
-                if (has_res) {
-                    const float4 r = lds128(saddr);
-                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                f2_t scn[2] = {0ull, 0ull}, shn[2] = {0ull, 0ull}, rn[2] = {0ull, 0ull};
+                if (q < 7) {
+                    lds128_f2(my_ss + (q + 1) * 16, scn[0], scn[1]);
+                    lds128_f2(my_ss + 128 + (q + 1) * 16, shn[0], shn[1]);
+                    if (has_res) lds128_f2(stage + (uint32_t)((lane * 8 + ((q + 1) ^ sw)) * 16), rn[0], rn[1]);
                 }
-                if (act == 16 + 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                sts128(saddr, o);
+                f2_t o[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    o[h] = f2_fma(sum[2 * q + h], sc[h], sh[h]);
+                    if (act == 1) o[h] = f2_silu(o[h]);
+                    else if (act == 2) o[h] = f2_relu(o[h]);
+                    else if (act == 4) { float x0, x1; f2_unpack(o[h], x0, x1); o[h] = f2_pack(gelu_erf(x0), gelu_erf(x1)); }
+                    if (has_res) o[h] = f2_add(o[h], rr[h]);
+                    if (act == 16 + 2) o[h] = f2_relu(o[h]);
+                }
+                sts128_f2(stage + (uint32_t)((lane * 8 + (q ^ sw)) * 16), o[0], o[1]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { sc[h] = scn[h]; sh[h] = shn[h]; rr[h] = rn[h]; }
             }
             fence_proxy_async();
             __syncwarp();
