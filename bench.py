@@ -279,6 +279,18 @@ def main():
                                  "launches_per_step": v['launches'] // args.profile_steps}
                              for k, v in prof.items() if v['launches']}}
 
+    # DRAM traffic of the dominant kernel family per launch, from the committed ncu capture of this same command
+    # (profiles/<round>_traffic.json, written by scripts/summarise_profiles.py; ncu numbers never come from this run)
+    try:
+        import glob
+        tf = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')))[-1]
+        fam = json.load(open(tf))['families'].get(dom)
+        if fam:
+            roofline["traffic"] = fam['dram_bytes_per_launch']
+            roofline["traffic_source"] = os.path.relpath(tf, ROOT) + " (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    except Exception:
+        pass
+
     # ---- end to end through the public API with pinned host clips -----------------------------------------
     e2e = None
     if not args.no_e2e:
