@@ -53,6 +53,9 @@ int         orbit_device_check(void);
  * promoted k-block partial).                                                                            */
 int orbit_set_global_option(const char* key, int value);
 int orbit_get_global_option(const char* key, int* value);
+/* Development aid: device buffer of 256 x 16 uint32 that CTA 0 of every following tcgen05 GEMM launch fills with
+ * per-role clock stamps per k-block step (0/1 TMA producer, 2/3 transform, 4-7 MMA issuer, 8/9 epilogue); NULL = off. */
+int orbit_debug_set_gemm_trace(void* dev_buffer);
 
 /* ------------------------------------------------------------------------------------------------
  * Head: frame pooling + prototype build + all-pairs scoring.

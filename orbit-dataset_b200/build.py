@@ -24,7 +24,8 @@ def build_library(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("ORBIT_NVCC_EXTRA", "").split()      # e.g. -DORBIT_GEMM_TRACE for scripts/gemm_trace.py
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-lcuda"] if os.environ.get("ORBIT_LINK_LIBCUDA") else []
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

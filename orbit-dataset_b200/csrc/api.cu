@@ -40,6 +40,8 @@ extern "C" int orbit_pointwise_conv(const float* A, const float* W, const float*
                                     mode == 1 ? 3 : 1, st);
 }
 
+extern "C" int orbit_debug_set_gemm_trace(void* dev_buffer) { orbit::set_tcgen05_trace(static_cast<unsigned*>(dev_buffer)); return ORBIT_OK; }
+
 extern "C" int orbit_set_global_option(const char* key, int value) {
     if (!key) return ORBIT_ERR_ARG;
     if (!strcmp(key, "tc_debias_x1000")) { orbit::set_tcgen05_debias((float)value / 1000.0f); return ORBIT_OK; }

@@ -53,11 +53,12 @@ constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction along K
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
 // Warp roles. The hardware arbiter favours higher warp ids, so the epilogue (the role with real ALU work)
 // sits last; its first warp id must be a multiple of 4 (a warp reaches TMEM lanes 32*(warp%4)..+31).
-constexpr int XF_WARP0 = 4, NUM_XF_WARPS = 8;
-constexpr int EPI_WARP0 = 12, NUM_EPI_WARPS = 12, EPI_SPLIT = NUM_EPI_WARPS / 4;   // 4 lane groups x 3 column shares
-constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 768
+constexpr int XF_WARP0 = 4;       // transform warps: XFW = 4 (ungated: ~100 instructions per k-block) or 8 (gated K-heavy layers), template parameter
+constexpr int NUM_EPI_WARPS = 12, EPI_SPLIT = NUM_EPI_WARPS / 4;    // 4 lane groups x 3 column shares (first epilogue warp id: a multiple of 4)
+constexpr int num_threads(int xfw) { return (XF_WARP0 + xfw + NUM_EPI_WARPS) * 32; }   // 640 (<= 102 registers) or 768 (<= 85)
 constexpr int MAX_STAGES = 8;
-constexpr int TMEM_COLS = 512;   // main accumulator x2 + correction accumulator x2, BN (<= 96) fp32 columns each
+constexpr int NMAIN = 3;          // main (per-k-block) accumulators in flight: the MMA issuer may run this far ahead of the epilogue
+constexpr int TMEM_COLS = 512;   // main accumulator x NMAIN + correction accumulator x2, BN (<= 96) fp32 columns each: 480
 constexpr int SLAB_BYTES = 32 * 128;       // epilogue staging slab: 32 rows x 32 fp32, SWIZZLE_128B (1 or 2 per warp)
 constexpr int L2_PREFETCH_DISTANCE = 12;   // k-blocks (16 KB of A each) requested into L2 ahead of the smem ring
 
@@ -87,6 +88,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
         if (spin > 400000u) __trap();
     }
+}
+// Spinning wait (mbarrier.test_wait, no suspend) for the two waits on the per-k-block MMA <-> epilogue round trip.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+#if defined(ORBIT_NO_SPIN)
+    mbar_wait(bar, parity);
+#else
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > 200000000u) __trap();
+    }
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -214,19 +231,29 @@ struct Params {
     int BN, n_tiles, m_tiles, stages;
     int b_tile_bytes;        // BN * 128 (multiple of 2048)
     int slabs_per_warp;      // 1 or 2 staging slabs per epilogue warp
-    float debias;            // kappa * 2^-23: expected truncation loss of a promoted k-block partial, in units of its exponent
+    float debias;            // kappa: expected truncation loss of a promoted k-block partial, in ulps of that partial
+    unsigned* trace;         // dev aid (orbit_debug_set_gemm_trace): per-role clock stamps of CTA 0, [kTraceSteps][16]; else null
 };
 
+constexpr int kTraceSteps = 256;   // k-block steps of CTA 0 recorded when Params::trace is set
+#if defined(ORBIT_GEMM_TRACE)   // build with ORBIT_NVCC_EXTRA=-DORBIT_GEMM_TRACE (costs registers: not in the shipped library)
+__device__ __forceinline__ void trace_stamp(unsigned* trace, uint32_t step, int slot) {
+    if (trace && blockIdx.x == 0 && step < (uint32_t)kTraceSteps) trace[step * 16 + slot] = (unsigned)clock64();
+}
+#else
+__device__ __forceinline__ void trace_stamp(unsigned*, uint32_t, int) {}
+#endif
 constexpr int SS_BYTES = 256;   // per epilogue warp: scale[32] | shift[32] of the slab it is finishing
 
 // Template parameters fix at compile time what round 1 decided per element at run time (ncu: the epilogue ran
 // 1050 and the transform 530 instructions per warp per 128-row step, 2.5-4x the arithmetic actually needed):
 //   SPLIT  3xTF32 (hi/lo) or plain TF32;  GATED / RES  0, 1, or -1 = look at the arguments;  ACT  activation or -1.
-template <bool SPLIT, int GATED, int ACT, int RES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool SPLIT, int GATED, int ACT, int RES, int XFW>
+__global__ void __launch_bounds__(num_threads(XFW), 1)
 pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ CUtensorMap map_res, const Params p) {
+    constexpr int NUM_XF_WARPS = XFW, EPI_WARP0 = XF_WARP0 + XFW;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const bool gated = GATED < 0 ? p.gate != nullptr : GATED != 0;
@@ -242,9 +269,9 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto full = [&](uint32_t s) { return bars + 8u * s; };                              // TMA landed
     auto ready = [&](uint32_t s) { return bars + 8u * (MAX_STAGES + s); };              // transform done
     auto empty = [&](uint32_t s) { return bars + 8u * (2 * MAX_STAGES + s); };          // MMAs that read the slot retired
-    auto tmem_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 2 + a); }; // correction accumulator drained
-    auto main_full = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 4 + a); };  // main accumulator of one k-block complete
-    auto main_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 6 + a); }; // ... added into the epilogue's registers
+    auto tmem_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + a); };     // [2] correction accumulator drained
+    auto main_full = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 2 + a); };  // [NMAIN] main accumulator of one k-block complete
+    auto main_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 5 + a); }; // [NMAIN] ... added into the epilogue's registers
     auto res_bar = [&](uint32_t w) { return bars + 8u * (3 * MAX_STAGES + 8 + w); };    // residual slab landed
     const uint32_t tmem_base_slot = bars + 8u * (3 * MAX_STAGES + 8 + NUM_EPI_WARPS);
 
@@ -254,10 +281,8 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(ready(s), NUM_XF_WARPS); mbar_init(empty(s), 1); }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tmem_empty(a), NUM_EPI_WARPS);
-            mbar_init(main_full(a), 1); mbar_init(main_empty(a), NUM_EPI_WARPS);
-        }
+        for (int a = 0; a < 2; ++a) mbar_init(tmem_empty(a), NUM_EPI_WARPS);
+        for (int a = 0; a < NMAIN; ++a) { mbar_init(main_full(a), 1); mbar_init(main_empty(a), NUM_EPI_WARPS); }
         for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
@@ -270,18 +295,19 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = lds32u(tmem_base_slot);
-    // TMEM columns: main accumulators (hi*hi) at {0,1}*BN, correction accumulators (hi*lo + lo*hi) at {2,3}*BN.
+    // TMEM columns: main accumulators (hi*hi) at {0,1,2}*BN, correction accumulators (hi*lo + lo*hi) at {3,4}*BN.
+    // (Three main buffers, not two: the per-role clock trace showed the MMA issuer idle for ~3 k-blocks at every tile
+    // boundary while the epilogue warps finish the previous tile's activation + store phase.)
     // The tensor core adds into its fp32 accumulator with TRUNCATION (measured: -0.45 ulp per accumulation, a
     // systematic bias that grows with K and compounds over the network's ~33 GEMM layers). So the main accumulator
     // only ever holds ONE k-block (4 MMAs): the epilogue warps add it into fp32 registers with round-to-nearest
     // every k-block (double-buffered against the MMAs), and the 2^-11-scaled correction terms -- whose truncation
     // error is negligible -- accumulate over the whole tile in their own accumulator.
 
-    // Register budget: 768 threads x 80 at launch; the control and transform warps give registers back to the CTA
-    // pool (setmaxnreg works on aligned groups of 4 warps; an .inc can only claim what the CTA's own .dec freed --
-    // 29 per epilogue thread here -- and the epilogue fits in 80, so it does not ask).
+    // Register budget: 640 threads x 96 (ptxas) for every role. Round 1 ran 768 threads x 80 and moved registers
+    // between roles with setmaxnreg; the epilogue then spilled as soon as it grew, and a .inc can only claim what the
+    // CTA's own .dec freed (asking for more deadlocks). Halving the transform warps pays for 96 everywhere.
     if (warp < XF_WARP0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
@@ -295,17 +321,19 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++pf_kb == num_k) { pf_kb = 0; pf_tile += gridDim.x; }
             };
             for (int i = 0; i < L2_PREFETCH_DISTANCE; ++i) prefetch_next();
-            uint32_t s = 0, ph = 0;
+            uint32_t s = 0, ph = 0, step = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
-                for (int kb = 0; kb < num_k; ++kb) {
+                for (int kb = 0; kb < num_k; ++kb, ++step) {
                     prefetch_next();
                     mbar_wait(empty(s), ph ^ 1);
+                    trace_stamp(p.trace, step, 0);
                     mbar_expect_tx(full(s), tx);
                     const uint32_t st = ring + s * stage_bytes;
                     tma_load_2d(st, &map_a, full(s), kb * BK, m0);
                     tma_load_2d(st + a_bytes, &map_bhi, full(s), kb * BK, n0);
                     if (SPLIT) tma_load_2d(st + a_bytes + p.b_tile_bytes, &map_blo, full(s), kb * BK, n0);
+                    trace_stamp(p.trace, step, 1);
                     if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -314,16 +342,17 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(BM, p.BN);
-            uint32_t it = 0, tcount = 0, s = 0, ph = 0;   // it = global k-block counter (main-accumulator parity)
+            uint32_t it = 0, tcount = 0, s = 0, ph = 0, mb = 0, mph = 0;   // it = global k-block counter; mb/mph = main buffer and its parity
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1;
                 if (SPLIT) mbar_wait(tmem_empty(acc), ((tcount >> 1) & 1) ^ 1);
-                const uint32_t d_corr = tmem_base + (2 + acc) * (uint32_t)p.BN;
+                const uint32_t d_corr = tmem_base + (NMAIN + acc) * (uint32_t)p.BN;
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const uint32_t mb = it & 1;
-                    mbar_wait(main_empty(mb), ((it >> 1) & 1) ^ 1);
-                    mbar_wait(full(s), ph);
-                    if (transform) mbar_wait(ready(s), ph);
+                    mbar_wait(main_empty(mb), mph ^ 1);
+                    trace_stamp(p.trace, it, 4);
+                    if (transform) mbar_wait(ready(s), ph);   // the transform warps saw `full` (A and B landed) before they arrived
+                    else mbar_wait(full(s), ph);
+                    trace_stamp(p.trace, it, 6);
                     tc_fence_after();
                     const uint32_t d_main = tmem_base + mb * (uint32_t)p.BN;
                     const uint32_t st = ring + s * stage_bytes;
@@ -343,58 +372,65 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     umma_commit(empty(s));           // ring slot reusable once these MMAs retire
                     umma_commit(main_full(mb));      // this k-block's main accumulator is complete (and, after the
                                                      // last k-block, the tile's correction accumulator too)
+                    trace_stamp(p.trace, it, 7);
                     if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                    if (++mb == NMAIN) { mb = 0; mph ^= 1; }
                 }
             }
         }
     }
     } else if (warp < EPI_WARP0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ================================ A transform ================================
-        // 256 threads; thread t owns the 16-byte chunk (t & 7) of rows (t >> 3) + 32 i: multiply by the squeeze-excite
+        // 128 threads; thread t owns the 16-byte chunk (t & 7) of rows (t >> 3) + 16 i: multiply by the squeeze-excite
         // gate and split into tf32 hi / lo in place (3xTF32). Conflict-free: 8 consecutive threads cover one 128-byte row.
         if (transform) {
-            const int t = threadIdx.x - XF_WARP0 * 32;       // 0..255
+            constexpr int XR = BM / (NUM_XF_WARPS * 4);      // rows per thread (8 or 4)
+            constexpr int XS = NUM_XF_WARPS * 4;             // row stride between them (16 or 32: multiples of the 8-row swizzle period)
+            const int t = threadIdx.x - XF_WARP0 * 32;       // 0..127
             const int pchunk = t & 7;                        // physical 16-byte chunk inside the 128-byte row
-            const int rbase = t >> 3;                        // rows rbase + 32*i
+            const int rbase = t >> 3;                        // rows rbase + XS*i
             const int jchunk = pchunk ^ (rbase & 7);         // logical chunk (SWIZZLE_128B: chunk ^= row & 7)
             const uint32_t toff = (uint32_t)(rbase * 128 + pchunk * 16);
-            uint32_t s = 0, ph = 0;
+            uint32_t s = 0, ph = 0, xstep = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const float* grow[4];
+                const float* grow[XR];
                 if (gated) {
                     const int m0 = (tile / p.n_tiles) * BM;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        grow[i] = p.gate + (int64_t)(min(m0 + rbase + 32 * i, p.M - 1) / p.rows_per_frame) * p.K + jchunk * 4;
+                    for (int i = 0; i < XR; ++i)
+                        grow[i] = p.gate + (int64_t)(min(m0 + rbase + XS * i, p.M - 1) / p.rows_per_frame) * p.K + jchunk * 4;
                 }
                 for (int kb = 0; kb < num_k; ++kb) {
-                    float4 g[4];
+                    float4 g[XR];
                     const bool g_on = gated && kb * BK + jchunk * 4 < p.K;
                     if (g_on) {                                  // issue the gate loads before blocking on the TMA
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) g[i] = ldg4(grow[i] + kb * BK);
+                        for (int i = 0; i < XR; ++i) g[i] = ldg4(grow[i] + kb * BK);
                     }
                     mbar_wait(full(s), ph);
+                    if (t == 0) trace_stamp(p.trace, xstep, 2);
                     const uint32_t a = ring + s * stage_bytes + toff;
-                    float4 v[4];
+                    float4 v[XR];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = lds128(a + i * 4096);
+                    for (int i = 0; i < XR; ++i) v[i] = lds128(a + i * (XS * 128));
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < XR; ++i) {
                         if (g_on) { v[i].x *= g[i].x; v[i].y *= g[i].y; v[i].z *= g[i].z; v[i].w *= g[i].w; }
                         if (SPLIT) {
                             const float4 h = make_float4(rna_tf32(v[i].x), rna_tf32(v[i].y), rna_tf32(v[i].z), rna_tf32(v[i].w));
-                            sts128(a + i * 4096, h);
-                            sts128(a + A_TILE_BYTES + i * 4096,
-                                   make_float4(rna_tf32(v[i].x - h.x), rna_tf32(v[i].y - h.y), rna_tf32(v[i].z - h.z), rna_tf32(v[i].w - h.w)));
+                            sts128(a + i * (XS * 128), h);
+                            // lo = v - hi is exact in fp32 and has <= 13 significant bits; the tensor core reads its top 11
+                            // (at most half an fp32 ulp of v is dropped, with the sign of lo, i.e. unbiased w.r.t. v)
+                            sts128(a + A_TILE_BYTES + i * (XS * 128), make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w));
                         } else {
-                            sts128(a + i * 4096, v[i]);
+                            sts128(a + i * (XS * 128), v[i]);
                         }
                     }
                     fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
                     __syncwarp();
+                    if (t == 0) trace_stamp(p.trace, xstep, 3);
                     if (lane == 0) mbar_arrive(ready(s));
+                    ++xstep;
                     if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -413,7 +449,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int sw = lane & 7;
         const int n_slabs = ceil_div(p.BN, 32);     // BN <= 96 -> <= 3 slabs -> one per warp of a lane group
         const uint32_t t_lane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-        uint32_t tcount = 0, res_phase = 0, slab_count = 0, it = 0;
+        uint32_t tcount = 0, res_phase = 0, slab_count = 0, it = 0, mb = 0, mph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t acc = tcount & 1;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
@@ -443,10 +479,9 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             f2_t sum[16];                                  // 32 columns as adjacent pairs
 #pragma unroll
             for (int j = 0; j < 16; ++j) sum[j] = 0ull;
-            const f2_t debias2 = f2_pack(p.debias, p.debias);
             for (int kb = 0; kb < num_k; ++kb, ++it) {
-                const uint32_t mb = it & 1;
-                mbar_wait(main_full(mb), (it >> 1) & 1);
+                mbar_wait(main_full(mb), mph);
+                if (ew == 0 && lane == 0) trace_stamp(p.trace, it, 8);
                 tc_fence_after();
                 if (have) {
                     float u[32];
@@ -460,22 +495,34 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tmem_ld_wait();
                     // Every tcgen05.mma result is TRUNCATED to fp32 (measured): the k-block partial u
                     // is short by 0.5 ulp(u) in expectation for its last MMA, plus the earlier ones at their
-                    // smaller magnitudes. Adding kappa * ulp(u) * sign(u) back removes the systematic part.
+                    // smaller magnitudes. Adding kappa * ulp(u) * sign(u) back removes the systematic part. For the
+                    // default kappa = 1 that is "the next float away from zero", i.e. +1 on the bit pattern: one
+                    // 64-bit integer add per column pair (no carry can cross the halves: the low word is never
+                    // 0xffffffff) instead of round 1's mask + FMA per element.
+                    if (p.debias == 1.0f) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const f2_t up = f2_pack(u[2 * j], u[2 * j + 1]);
-                        const f2_t pow2 = up & 0xff800000ff800000ull;            // sign * 2^exponent of each half
-                        sum[j] = f2_add(sum[j], f2_fma(pow2, debias2, up));
+                        for (int j = 0; j < 16; ++j)
+                            sum[j] = f2_add(sum[j], f2_pack(u[2 * j], u[2 * j + 1]) + 0x0000000100000001ull);
+                    } else {
+                        const f2_t debias2 = f2_pack(p.debias * 1.1920929e-07f, p.debias * 1.1920929e-07f);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const f2_t up = f2_pack(u[2 * j], u[2 * j + 1]);
+                            const f2_t pow2 = up & 0xff800000ff800000ull;            // sign * 2^exponent of each half
+                            sum[j] = f2_add(sum[j], f2_fma(pow2, debias2, up));
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
+                if (ew == 0 && lane == 0) trace_stamp(p.trace, it, 9);
                 if (lane == 0) mbar_arrive(main_empty(mb));
+                if (++mb == NMAIN) { mb = 0; mph ^= 1; }
             }
             if (SPLIT) {   // tcgen05.commit covers ALL earlier MMAs: the last main_full also completed the correction terms
                 if (have) {
                     float u[32];
-                    const uint32_t col = t_lane + (2 + acc) * (uint32_t)p.BN + c0;
+                    const uint32_t col = t_lane + (NMAIN + acc) * (uint32_t)p.BN + c0;
                     tmem_ld16_issue(col, u);
                     if (wide) tmem_ld16_issue(col + 16, u + 16);
                     else {
@@ -578,6 +625,8 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 }  // namespace tc
 
 static float g_debias_kappa = 1.0f;   // one ulp of every promoted k-block partial (4 truncating MMAs: 0.5*(1+.75+.5+.25) ulp expected loss)
+static unsigned* g_gemm_trace = nullptr;
+void set_tcgen05_trace(unsigned* dev_buffer) { g_gemm_trace = dev_buffer; }
 void set_tcgen05_debias(float kappa) { g_debias_kappa = kappa; }
 float get_tcgen05_debias() { return g_debias_kappa; }
 
@@ -590,7 +639,8 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     Params p;
     p.scale = scale; p.shift = shift; p.gate = gate; p.has_residual = residual != nullptr;
     p.M = M; p.N = N; p.K = K; p.rows_per_frame = rows_per_frame; p.act = act;
-    p.debias = passes == 3 ? g_debias_kappa * 1.1920929e-07f : 0.f;
+    p.debias = passes == 3 ? g_debias_kappa : 0.f;
+    p.trace = g_gemm_trace;
     // n-tiles of at most 96 columns (3 store slabs = one per epilogue warp of a lane group); with several n-tiles
     // BN must be a multiple of the 32-column store slab
     p.n_tiles = ceil_div(N, 96);
@@ -622,20 +672,22 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     // specialisations for the shapes the backbones use; anything else runs the run-time-dispatch instance
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
     KernelFn fn = nullptr;
+    int xfw = 4;
     const bool g = gate != nullptr, r = residual != nullptr;
     if (passes == 3) {
-        if (g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 1, 0, 0>;          // MBConv project
-        else if (g && act == 0 && r) fn = pw_tcgen05_kernel<true, 1, 0, 1>;      // MBConv project + skip
-        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0>;    // MBConv expand / conv_head (SiLU)
-        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0>;    // Linear / downsample
-        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1>;     // Linear + residual (ViT), EdgeResidual project
-        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0>;    // conv + ReLU
-        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0>;    // Linear + GELU
-        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1>;   // BasicBlock: relu(bn(conv) + identity)
-        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1>;     // ConvBnAct + skip (EfficientNet-V2)
-        else fn = pw_tcgen05_kernel<true, -1, -1, -1>;
+        if (g && act == 0 && !r && K <= BK) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4>;          // MBConv project, one k-block per tile
+        else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8>; xfw = 8; }   // MBConv project
+        else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8>; xfw = 8; }    // MBConv project + skip
+        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4>;    // MBConv expand / conv_head (SiLU)
+        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4>;    // Linear / downsample
+        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4>;     // Linear + residual (ViT), EdgeResidual project
+        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4>;    // conv + ReLU
+        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0, 4>;    // Linear + GELU
+        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4>;   // BasicBlock: relu(bn(conv) + identity)
+        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1, 4>;     // ConvBnAct + skip (EfficientNet-V2)
+        else fn = pw_tcgen05_kernel<true, -1, -1, -1, 4>;
     } else {
-        fn = pw_tcgen05_kernel<false, -1, -1, -1>;
+        fn = pw_tcgen05_kernel<false, -1, -1, -1, 4>;
     }
     static int num_sms = 0;
     if (!num_sms) {
@@ -645,7 +697,7 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     }
     ORBIT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = std::min(p.m_tiles * p.n_tiles, num_sms);
-    fn<<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_out, map_res, p);
+    fn<<<grid, num_threads(xfw), smem, st>>>(map_a, map_bhi, map_blo, map_out, map_res, p);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }

@@ -16,6 +16,7 @@ _SIGNATURES = {
     "orbit_device_check": (_i, []),
     "orbit_set_global_option": (_i, [C.c_char_p, _i]),
     "orbit_get_global_option": (_i, [C.c_char_p, C.POINTER(_i)]),
+    "orbit_debug_set_gemm_trace": (_i, [_p]),
     "orbit_pool_clips": (_i, [_p, _i, _i, _i, _p, _p]),
     "orbit_pool_history": (_i, [_p, _i, _i, _i, _p, _p]),
     "orbit_proto_configure_scratch_bytes": (_i64, [_i, _i]),
