@@ -57,6 +57,7 @@ constexpr int XF_WARP0 = 4;       // transform warps: XFW = 4 (ungated: ~100 ins
 constexpr int NUM_EPI_WARPS = 12, EPI_SPLIT = NUM_EPI_WARPS / 4;    // 4 lane groups x 3 column shares (first epilogue warp id: a multiple of 4)
 constexpr int num_threads(int xfw) { return (XF_WARP0 + xfw + NUM_EPI_WARPS) * 32; }   // 640 (<= 102 registers) or 768 (<= 85)
 constexpr int MAX_STAGES = 8;
+constexpr int ATM_XFW = 4;        // transform warps of the A-in-TMEM variant
 constexpr int NMAIN = 3;          // main (per-k-block) accumulators in flight: the MMA issuer may run this far ahead of the epilogue
 constexpr int TMEM_COLS = 512;   // main accumulator x NMAIN + correction accumulator x2, BN (<= 96) fp32 columns each: 480
 constexpr int SLAB_BYTES = 32 * 128;       // epilogue staging slab: 32 rows x 32 fp32, SWIZZLE_128B (1 or 2 per warp)
@@ -179,6 +180,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lanes = rows, one tf32 per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -248,19 +267,25 @@ constexpr int SS_BYTES = 256;   // per epilogue warp: scale[32] | shift[32] of t
 // Template parameters fix at compile time what round 1 decided per element at run time (ncu: the epilogue ran
 // 1050 and the transform 530 instructions per warp per 128-row step, 2.5-4x the arithmetic actually needed):
 //   SPLIT  3xTF32 (hi/lo) or plain TF32;  GATED / RES  0, 1, or -1 = look at the arguments;  ACT  activation or -1.
-template <bool SPLIT, int GATED, int ACT, int RES, int XFW>
+//   XFW    transform warps (4 or 8);  ATM  the transform warps write A's hi/lo parts to TENSOR MEMORY (tcgen05.st) and the
+//          MMAs take A from there: per k-block the shared-memory port then carries TMA 40 KB + one 16 KB read of A +
+//          12 x 3 KB of B instead of 172 KB (the per-role trace put the K-heavy layers on that port), and a ring slot
+//          shrinks from 56 to 40 KB (4 stages instead of 3). Costs the third main accumulator (TMEM is 512 columns).
+template <bool SPLIT, int GATED, int ACT, int RES, int XFW, bool ATM>
 __global__ void __launch_bounds__(num_threads(XFW), 1)
 pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ CUtensorMap map_res, const Params p) {
     constexpr int NUM_XF_WARPS = XFW, EPI_WARP0 = XF_WARP0 + XFW;
+    constexpr int NM = ATM ? 2 : NMAIN;            // main accumulators in flight
+    static_assert(!ATM || SPLIT, "A-in-TMEM is the 3xTF32 path");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const bool gated = GATED < 0 ? p.gate != nullptr : GATED != 0;
     const bool has_res = RES < 0 ? p.has_residual != 0 : RES != 0;
     const int act = ACT < 0 ? p.act : ACT;
     const bool transform = SPLIT || gated;
-    const uint32_t a_bytes = A_TILE_BYTES * (SPLIT ? 2 : 1);
+    const uint32_t a_bytes = A_TILE_BYTES * ((SPLIT && !ATM) ? 2 : 1);
     const uint32_t stage_bytes = a_bytes + (uint32_t)p.b_tile_bytes * (SPLIT ? 2 : 1);
     const uint32_t staging = smem;                                   // [NUM_EPI_WARPS][slabs_per_warp][32 rows][128 B]
     const uint32_t sstab = staging + (uint32_t)(NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES);   // [NUM_EPI_WARPS][SS_BYTES]
@@ -273,7 +298,8 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto main_full = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 2 + a); };  // [NMAIN] main accumulator of one k-block complete
     auto main_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 5 + a); }; // [NMAIN] ... added into the epilogue's registers
     auto res_bar = [&](uint32_t w) { return bars + 8u * (3 * MAX_STAGES + 8 + w); };    // residual slab landed
-    const uint32_t tmem_base_slot = bars + 8u * (3 * MAX_STAGES + 8 + NUM_EPI_WARPS);
+    auto a_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 8 + NUM_EPI_WARPS + a); };   // [2] MMAs that read A-in-TMEM buffer a retired
+    const uint32_t tmem_base_slot = bars + 8u * (3 * MAX_STAGES + 10 + NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = ceil_div(p.K, BK);
@@ -282,7 +308,8 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(ready(s), NUM_XF_WARPS); mbar_init(empty(s), 1); }
         for (int a = 0; a < 2; ++a) mbar_init(tmem_empty(a), NUM_EPI_WARPS);
-        for (int a = 0; a < NMAIN; ++a) { mbar_init(main_full(a), 1); mbar_init(main_empty(a), NUM_EPI_WARPS); }
+        for (int a = 0; a < NM; ++a) { mbar_init(main_full(a), 1); mbar_init(main_empty(a), NUM_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) mbar_init(a_empty(a), 1);
         for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
@@ -346,7 +373,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1;
                 if (SPLIT) mbar_wait(tmem_empty(acc), ((tcount >> 1) & 1) ^ 1);
-                const uint32_t d_corr = tmem_base + (NMAIN + acc) * (uint32_t)p.BN;
+                const uint32_t d_corr = tmem_base + (NM + acc) * (uint32_t)p.BN;
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     mbar_wait(main_empty(mb), mph ^ 1);
                     trace_stamp(p.trace, it, 4);
@@ -360,6 +387,17 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     const uint64_t a_lo = make_desc_sw128(st + A_TILE_BYTES);
                     const uint64_t b_hi = make_desc_sw128(st + a_bytes);
                     const uint64_t b_lo = make_desc_sw128(st + a_bytes + p.b_tile_bytes);
+                    if (ATM) {
+                        const uint32_t a_t = tmem_base + (NM + 2) * (uint32_t)p.BN + (it & 1) * 64;   // hi at +0, lo at +32 columns
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            umma_tf32_ts(d_corr, a_t + 32 + k * UMMA_K, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                            umma_tf32_ts(d_corr, a_t + k * UMMA_K, b_lo + adv, idesc, 1u);
+                            umma_tf32_ts(d_main, a_t + k * UMMA_K, b_hi + adv, idesc, k ? 1u : 0u);
+                        }
+                        umma_commit(a_empty(it & 1));
+                    } else {
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per k step inside the swizzle row
@@ -369,12 +407,13 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         }
                         umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, k ? 1u : 0u);
                     }
+                    }
                     umma_commit(empty(s));           // ring slot reusable once these MMAs retire
                     umma_commit(main_full(mb));      // this k-block's main accumulator is complete (and, after the
                                                      // last k-block, the tile's correction accumulator too)
                     trace_stamp(p.trace, it, 7);
                     if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
-                    if (++mb == NMAIN) { mb = 0; mph ^= 1; }
+                    if (++mb == NM) { mb = 0; mph ^= 1; }
                 }
             }
         }
@@ -383,7 +422,58 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ================================ A transform ================================
         // 128 threads; thread t owns the 16-byte chunk (t & 7) of rows (t >> 3) + 16 i: multiply by the squeeze-excite
         // gate and split into tf32 hi / lo in place (3xTF32). Conflict-free: 8 consecutive threads cover one 128-byte row.
-        if (transform) {
+        if (ATM) {
+            // XFW/4 threads per tile row (= TMEM lane; warps w and w+4 reach the same lane quarter): read 16 or 32 k-values
+            // of the row from the swizzled slot, gate, split, tcgen05.st the hi and lo parts
+            constexpr int HPT = 8 / XFW;                     // 16-column halves per thread: 2 (4 warps) or 1 (8 warps)
+            const int t = threadIdx.x - XF_WARP0 * 32;
+            const int r = t & 127, half0 = (t >> 7) * HPT;
+            const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (NM + 2) * (uint32_t)p.BN;
+            uint32_t s = 0, ph = 0, xstep = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const float* grow = nullptr;
+                if (gated) grow = p.gate + (int64_t)(min((tile / p.n_tiles) * BM + r, p.M - 1) / p.rows_per_frame) * p.K + half0 * 16;
+                for (int kb = 0; kb < num_k; ++kb, ++xstep) {
+                    float4 g[4 * HPT];
+                    if (gated) {                                 // issue the gate loads before blocking on the TMA
+#pragma unroll
+                        for (int j = 0; j < 4 * HPT; ++j)
+                            g[j] = kb * BK + half0 * 16 + j * 4 < p.K ? ldg4(grow + kb * BK + j * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    }
+                    const uint32_t ab = xstep & 1;
+                    mbar_wait(full(s), ph);
+                    if (t == 0) trace_stamp(p.trace, xstep, 2);
+                    const uint32_t rowaddr = ring + s * stage_bytes + (uint32_t)r * 128u;
+                    const uint32_t acol = t_row + ab * 64;
+#pragma unroll
+                    for (int hh = 0; hh < HPT; ++hh) {
+                        const int half = half0 + hh;
+                        float hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = half * 4 + j;                                  // logical 16-byte chunk of the row
+                            float4 x = lds128(rowaddr + (uint32_t)((c ^ (r & 7)) * 16));
+                            if (gated) { const float4 gg = g[hh * 4 + j]; x.x *= gg.x; x.y *= gg.y; x.z *= gg.z; x.w *= gg.w; }
+                            hi[4 * j + 0] = rna_tf32(x.x); hi[4 * j + 1] = rna_tf32(x.y); hi[4 * j + 2] = rna_tf32(x.z); hi[4 * j + 3] = rna_tf32(x.w);
+                            lo[4 * j + 0] = x.x - hi[4 * j + 0]; lo[4 * j + 1] = x.y - hi[4 * j + 1];
+                            lo[4 * j + 2] = x.z - hi[4 * j + 2]; lo[4 * j + 3] = x.w - hi[4 * j + 3];
+                        }
+                        if (hh == 0) {           // the A buffer is free once the MMAs of two k-blocks ago retired
+                            mbar_wait(a_empty(ab), ((xstep >> 1) & 1) ^ 1);
+                            tc_fence_after();
+                        }
+                        tmem_st16(acol + half * 16, hi);
+                        tmem_st16(acol + 32 + half * 16, lo);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (t == 0) trace_stamp(p.trace, xstep, 3);
+                    if (lane == 0) mbar_arrive(ready(s));
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        } else if (transform) {
             constexpr int XR = BM / (NUM_XF_WARPS * 4);      // rows per thread (8 or 4)
             constexpr int XS = NUM_XF_WARPS * 4;             // row stride between them (16 or 32: multiples of the 8-row swizzle period)
             const int t = threadIdx.x - XF_WARP0 * 32;       // 0..127
@@ -410,6 +500,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     mbar_wait(full(s), ph);
                     if (t == 0) trace_stamp(p.trace, xstep, 2);
                     const uint32_t a = ring + s * stage_bytes + toff;
+#if !defined(ORBIT_EXPERIMENT_NO_XF)   // timing experiment only (wrong results): how much of a k-block is the transform's smem traffic?
                     float4 v[XR];
 #pragma unroll
                     for (int i = 0; i < XR; ++i) v[i] = lds128(a + i * (XS * 128));
@@ -426,6 +517,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             sts128(a + i * (XS * 128), v[i]);
                         }
                     }
+#endif
                     fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
                     __syncwarp();
                     if (t == 0) trace_stamp(p.trace, xstep, 3);
@@ -517,12 +609,12 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 __syncwarp();
                 if (ew == 0 && lane == 0) trace_stamp(p.trace, it, 9);
                 if (lane == 0) mbar_arrive(main_empty(mb));
-                if (++mb == NMAIN) { mb = 0; mph ^= 1; }
+                if (++mb == NM) { mb = 0; mph ^= 1; }
             }
             if (SPLIT) {   // tcgen05.commit covers ALL earlier MMAs: the last main_full also completed the correction terms
                 if (have) {
                     float u[32];
-                    const uint32_t col = t_lane + (NMAIN + acc) * (uint32_t)p.BN + c0;
+                    const uint32_t col = t_lane + (NM + acc) * (uint32_t)p.BN + c0;
                     tmem_ld16_issue(col, u);
                     if (wide) tmem_ld16_issue(col + 16, u + 16);
                     else {
@@ -625,6 +717,9 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 }  // namespace tc
 
 static float g_debias_kappa = 1.0f;   // one ulp of every promoted k-block partial (4 truncating MMAs: 0.5*(1+.75+.5+.25) ulp expected loss)
+static bool g_atm_enabled = true;
+void set_tcgen05_atm(bool on) { g_atm_enabled = on; }
+bool get_tcgen05_atm() { return g_atm_enabled; }
 static unsigned* g_gemm_trace = nullptr;
 void set_tcgen05_trace(unsigned* dev_buffer) { g_gemm_trace = dev_buffer; }
 void set_tcgen05_debias(float kappa) { g_debias_kappa = kappa; }
@@ -647,8 +742,11 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     p.BN = p.n_tiles > 1 ? ceil_div(ceil_div(N, p.n_tiles), 32) * 32 : ceil_div(N, 16) * 16;
     p.m_tiles = ceil_div(M, BM);
     p.b_tile_bytes = p.BN * BK * 4;
-    const int stage_bytes = (A_TILE_BYTES + p.b_tile_bytes) * (passes == 3 ? 2 : 1);
-    const int bar_bytes = (3 * MAX_STAGES + 8 + NUM_EPI_WARPS) * 8 + 16;
+    // A-in-TMEM for the K-heavy gated 3xTF32 layers (>= 8 k-blocks per tile: the MBConv projections of the 14x14 / 7x7 stages;
+    // measured slower on the ungated conv_head, which prefers the third main accumulator)
+    const bool atm = passes == 3 && K >= 8 * BK && gate != nullptr && act == 0 && g_atm_enabled;
+    const int stage_bytes = atm ? A_TILE_BYTES + 2 * p.b_tile_bytes : (A_TILE_BYTES + p.b_tile_bytes) * (passes == 3 ? 2 : 1);
+    const int bar_bytes = (3 * MAX_STAGES + 10 + NUM_EPI_WARPS) * 8 + 16;
     const int budget = 227 * 1024 - 1024 /*alignment slack*/ - bar_bytes - NUM_EPI_WARPS * SS_BYTES;
     // double-buffered epilogue staging when that still leaves a 4-deep operand ring
     p.slabs_per_warp = (budget - 2 * NUM_EPI_WARPS * SLAB_BYTES) / stage_bytes >= 4 ? 2 : 1;
@@ -675,19 +773,21 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     int xfw = 4;
     const bool g = gate != nullptr, r = residual != nullptr;
     if (passes == 3) {
-        if (g && act == 0 && !r && K <= BK) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4>;          // MBConv project, one k-block per tile
-        else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8>; xfw = 8; }   // MBConv project
-        else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8>; xfw = 8; }    // MBConv project + skip
-        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4>;    // MBConv expand / conv_head (SiLU)
-        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4>;    // Linear / downsample
-        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4>;     // Linear + residual (ViT), EdgeResidual project
-        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4>;    // conv + ReLU
-        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0, 4>;    // Linear + GELU
-        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4>;   // BasicBlock: relu(bn(conv) + identity)
-        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1, 4>;     // ConvBnAct + skip (EfficientNet-V2)
-        else fn = pw_tcgen05_kernel<true, -1, -1, -1, 4>;
+        if (atm && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, ATM_XFW, true>; xfw = ATM_XFW; }    // K-heavy MBConv project, A in TMEM
+        else if (atm && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, ATM_XFW, true>; xfw = ATM_XFW; } // ... + skip
+        else if (g && act == 0 && !r && K <= BK) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, false>;   // MBConv project, one k-block per tile
+        else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8, false>; xfw = 8; } // MBConv project
+        else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8, false>; xfw = 8; }  // MBConv project + skip
+        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, false>;    // MBConv expand / conv_head (SiLU)
+        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4, false>;    // Linear / downsample
+        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4, false>;     // Linear + residual (ViT), EdgeResidual project
+        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4, false>;    // conv + ReLU
+        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0, 4, false>;    // Linear + GELU
+        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4, false>;   // BasicBlock: relu(bn(conv) + identity)
+        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1, 4, false>;     // ConvBnAct + skip (EfficientNet-V2)
+        else fn = pw_tcgen05_kernel<true, -1, -1, -1, 4, false>;
     } else {
-        fn = pw_tcgen05_kernel<false, -1, -1, -1, 4>;
+        fn = pw_tcgen05_kernel<false, -1, -1, -1, 4, false>;
     }
     static int num_sms = 0;
     if (!num_sms) {

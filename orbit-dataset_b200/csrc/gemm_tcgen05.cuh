@@ -16,6 +16,9 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
 
 // kappa of the truncation de-biasing applied to every promoted k-block partial in 3xTF32 mode (process-wide)
 void set_tcgen05_debias(float kappa);
+// A-in-TMEM variant of the K-heavy 3xTF32 layers on/off (A/B switch; default on)
+void set_tcgen05_atm(bool on);
+bool get_tcgen05_atm();
 // dev aid: device buffer of 256 x 16 uint32 that CTA 0 of every following GEMM launch fills with per-role clock stamps (null = off)
 void set_tcgen05_trace(unsigned* dev_buffer);
 float get_tcgen05_debias();

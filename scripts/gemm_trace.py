@@ -6,6 +6,7 @@ import torch
 from orbit_b200 import lib as L
 B, hw, K, N, act, gated, resid = [int(a) for a in sys.argv[1:8]]
 lib = L.load(); dev = torch.device('cuda:0')
+if os.environ.get('ATM'): assert lib.orbit_set_global_option(b'tc_a_in_tmem', int(os.environ['ATM'])) == 0
 M = B * hw
 A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev) * K ** -0.5
 sc = torch.ones(N, device=dev); sh = torch.zeros(N, device=dev)
@@ -20,7 +21,7 @@ run(); torch.cuda.synchronize()
 lib.orbit_debug_set_gemm_trace(L.ptr(trace)); run(); torch.cuda.synchronize(); lib.orbit_debug_set_gemm_trace(None)
 t = trace.cpu().numpy().astype('uint32').astype('int64')
 t0 = int(t[0, 0])
-names = ['P:empty_ok', 'P:tma_issued', 'X:full_ok', 'X:ready', 'M:main_empty_ok', 'M:full_ok', 'M:ready_ok', 'M:committed', 'E:main_full_ok', 'E:arrived']
+names = ['P:empty_ok', 'P:tma_issued', 'X:full_ok', 'X:ready', 'M:main_empty_ok', '(unused)', 'M:ready_ok', 'M:committed', 'E:main_full_ok', 'E:arrived']
 num_k = (K + 31) // 32
 print(f"M={M} K={K} N={N} num_k={num_k}; clocks relative to the first producer stamp; one row per k-block step of CTA 0")
 print('step ' + ' '.join(f'{n:>15s}' for n in names))
@@ -34,5 +35,5 @@ for i, n in enumerate(names):
     print(f"{n:16s} mean period {d.mean():8.1f} clk")
 lat = lambda a, b: float((((t[sel, b] - t[sel, a]) & 0xffffffff).astype('int64')).mean())
 print(f"TMA issue -> X full_ok   {lat(1, 2):8.1f}\nX full_ok -> X ready      {lat(2, 3):8.1f}\nX ready -> M ready_ok     {lat(3, 6):8.1f}\n"
-      f"M ready_ok -> committed   {lat(6, 7):8.1f}\nM committed -> E full_ok  {lat(7, 8):8.1f}\nE full_ok -> E arrived    {lat(8, 9):8.1f}\n"
-      f"M main_empty_ok->full_ok  {lat(4, 5):8.1f}\nM full_ok -> ready_ok     {lat(5, 6):8.1f}")
+      f"M main_empty_ok->ready_ok {lat(4, 6):8.1f}\nM ready_ok -> committed   {lat(6, 7):8.1f}\nM committed -> E full_ok  {lat(7, 8):8.1f}\n"
+      f"E full_ok -> E arrived    {lat(8, 9):8.1f}\nP empty_ok -> tma_issued  {lat(0, 1):8.1f}")
