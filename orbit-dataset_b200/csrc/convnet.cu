@@ -254,7 +254,7 @@ static DwPlan dw_plan(int C, int Ho, int Wo, int k, int stride) {
     p.LY = std::max(1, std::min(256 / p.LX, strips));
     p.strip_blocks = ceil_div(strips, p.LY);
     const int R = ceil_div(k, stride);
-    const int want_tiles = std::min(ceil_div(Ho, R), Ho >= 56 ? 4 : (Ho >= 14 ? 2 : 1));
+    const int want_tiles = std::min(ceil_div(Ho, R), Ho >= 112 ? 4 : (Ho >= 56 ? 2 : 1));   // few, tall tiles: every tile re-reads K-1 halo rows
     p.rows_per_tile = ceil_div(ceil_div(Ho, want_tiles), R) * R;   // multiple of R: tiles start on a ring boundary
     p.tiles = ceil_div(Ho, p.rows_per_tile);
     p.groups = p.tiles * p.strip_blocks;
