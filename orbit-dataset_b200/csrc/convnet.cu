@@ -168,20 +168,27 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
 #pragma unroll
     for (int i = 0; i < NP; ++i) { acc[0][i] = 0ull; acc[1][i] = 0ull; }
     const int ix0 = ox * 2 - pad_l;                   // input columns ix0 .. ix0+4 feed the two outputs
+    // all 45 input values first (one exposed HBM latency instead of nine), then the 27 x 32 packed FMAs
+    float vin[3][3][5];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
         const float* xp = x + ((int64_t)b * 3 + ci) * H * W;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = oy * 2 - pad_t + ky;
-            if (iy < 0 || iy >= H) continue;
+            const bool rok = iy >= 0 && iy < H;
             const float* rp = xp + (int64_t)iy * W + ix0;
-            float v[5];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) v[j] = (ix0 + j >= 0 && ix0 + j < W) ? __ldg(rp + j) : 0.f;
+            for (int j = 0; j < 5; ++j) vin[ci][ky][j] = (rok && ix0 + j >= 0 && ix0 + j < W) ? __ldg(rp + j) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const stem_f2_t v0 = stem_dup(v[kx]), v1 = stem_dup(v[kx + 2]);
+                const stem_f2_t v0 = stem_dup(vin[ci][ky][kx]), v1 = stem_dup(vin[ci][ky][kx + 2]);
                 const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_w + (ci * 9 + ky * 3 + kx) * COUT);
 #pragma unroll
                 for (int q = 0; q < COUT / 4; ++q) {
@@ -192,11 +199,18 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
             }
         }
     }
+    // Epilogue. A warp's 32 pixel pairs are 64 consecutive NHWC pixels = 8 KB of contiguous output when the row width is
+    // even (always for the 224 / 84 / 96 px pyramids): stage them in shared memory (XOR-swizzled, conflict-free both ways)
+    // and write 512 contiguous bytes per store instruction instead of 32 scattered 16-byte pieces.
+    __shared__ __align__(16) float4 s_out[4][64 * 8];
     const int64_t pix = ((int64_t)b * Ho + oy) * Wo + ox;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool staged = (Wo & 1) == 0 && (blockIdx.x + 1) * (int64_t)blockDim.x <= (int64_t)B * Ho * Wp;   // full block, no odd tail
 #pragma unroll
     for (int px = 0; px < 2; ++px) {
         if (px == 1 && !second) break;
         float4* yp = reinterpret_cast<float4*>(y + (pix + px) * COUT);
+        const int p = 2 * lane + px;
 #pragma unroll
         for (int q = 0; q < COUT / 4; ++q) {
             float a0, a1, a2, a3;
@@ -207,7 +221,17 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
             o.y = act_fast(fmaf(a1, s_sc[4 * q + 1], s_sh[4 * q + 1]), act);
             o.z = act_fast(fmaf(a2, s_sc[4 * q + 2], s_sh[4 * q + 2]), act);
             o.w = act_fast(fmaf(a3, s_sc[4 * q + 3], s_sh[4 * q + 3]), act);
-            yp[q] = o;
+            if (staged) s_out[warp][p * 8 + (q ^ ((p >> 1) & 7))] = o;
+            else yp[q] = o;
+        }
+    }
+    if (staged) {
+        __syncwarp();
+        float4* yw = reinterpret_cast<float4*>(y + (pix - 2 * lane) * COUT);   // the warp's first pixel (lane 0's pix)
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int i = it * 32 + lane, p = i >> 3, q = i & 7;
+            yw[i] = s_out[warp][p * 8 + (q ^ ((p >> 1) & 7))];
         }
     }
 }
