@@ -47,6 +47,7 @@ extern "C" int orbit_set_global_option(const char* key, int value) {
     if (!strcmp(key, "tc_debias_x1000")) { orbit::set_tcgen05_debias((float)value / 1000.0f); return ORBIT_OK; }
     if (!strcmp(key, "dw_variant")) { if (value < 1 || value > 3) return ORBIT_ERR_ARG; orbit::set_dw_variant(value); return ORBIT_OK; }
     if (!strcmp(key, "tc_a_in_tmem")) { orbit::set_tcgen05_atm(value != 0); return ORBIT_OK; }
+    if (!strcmp(key, "tc_merge")) { orbit::set_tcgen05_merge(value != 0); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 extern "C" int orbit_get_global_option(const char* key, int* value) {
@@ -54,6 +55,7 @@ extern "C" int orbit_get_global_option(const char* key, int* value) {
     if (!strcmp(key, "tc_debias_x1000")) { *value = (int)(orbit::get_tcgen05_debias() * 1000.0f + 0.5f); return ORBIT_OK; }
     if (!strcmp(key, "dw_variant")) { *value = orbit::get_dw_variant(); return ORBIT_OK; }
     if (!strcmp(key, "tc_a_in_tmem")) { *value = orbit::get_tcgen05_atm() ? 1 : 0; return ORBIT_OK; }
+    if (!strcmp(key, "tc_merge")) { *value = orbit::get_tcgen05_merge() ? 1 : 0; return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 

@@ -271,13 +271,20 @@ constexpr int SS_BYTES = 256;   // per epilogue warp: scale[32] | shift[32] of t
 //          MMAs take A from there: per k-block the shared-memory port then carries TMA 40 KB + one 16 KB read of A +
 //          12 x 3 KB of B instead of 172 KB (the per-role trace put the K-heavy layers on that port), and a ring slot
 //          shrinks from 56 to 40 KB (4 stages instead of 3). Costs the third main accumulator (TMEM is 512 columns).
-template <bool SPLIT, int GATED, int ACT, int RES, int XFW, bool ATM>
+//   MRG    merged products: every tcgen05.mma.kind::tf32 costs >= 93 clk whatever its N <= 96 (scripts/mma_rate.cu), so
+//          a_hi.b_hi and a_hi.b_lo are issued as ONE instruction against the stacked operand [B_hi ; B_lo] (N = 2 BN,
+//          the two tiles are adjacent in the ring slot): 8 instead of 12 instructions per k-block. The a_hi.b_lo term
+//          then lives next to the main accumulator and is promoted with it every k-block. Needs 6 BN (+128) TMEM columns.
+template <bool SPLIT, int GATED, int ACT, int RES, int XFW, bool ATM, bool MRG>
 __global__ void __launch_bounds__(num_threads(XFW), 1)
 pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ CUtensorMap map_res, const Params p) {
     constexpr int NUM_XF_WARPS = XFW, EPI_WARP0 = XF_WARP0 + XFW;
-    constexpr int NM = ATM ? 2 : NMAIN;            // main accumulators in flight
+    constexpr int NM = (ATM || MRG) ? 2 : NMAIN;   // main accumulators in flight
+    static_assert(!MRG || SPLIT, "merged products are a 3xTF32 feature");
+    const uint32_t MS = (MRG ? 2u : 1u) * (uint32_t)p.BN;          // TMEM columns per main buffer
+    const uint32_t CORR0 = NM * MS;                                // correction accumulators (x2), then A-in-TMEM (2 x 64)
     static_assert(!ATM || SPLIT, "A-in-TMEM is the 3xTF32 path");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -373,7 +380,8 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1;
                 if (SPLIT) mbar_wait(tmem_empty(acc), ((tcount >> 1) & 1) ^ 1);
-                const uint32_t d_corr = tmem_base + (NM + acc) * (uint32_t)p.BN;
+                const uint32_t d_corr = tmem_base + CORR0 + acc * (uint32_t)p.BN;
+                const uint32_t idesc2 = make_idesc_tf32(BM, 2 * p.BN);
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     mbar_wait(main_empty(mb), mph ^ 1);
                     trace_stamp(p.trace, it, 4);
@@ -381,31 +389,37 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     else mbar_wait(full(s), ph);
                     trace_stamp(p.trace, it, 6);
                     tc_fence_after();
-                    const uint32_t d_main = tmem_base + mb * (uint32_t)p.BN;
+                    const uint32_t d_main = tmem_base + mb * MS;
                     const uint32_t st = ring + s * stage_bytes;
                     const uint64_t a_hi = make_desc_sw128(st);
                     const uint64_t a_lo = make_desc_sw128(st + A_TILE_BYTES);
                     const uint64_t b_hi = make_desc_sw128(st + a_bytes);
                     const uint64_t b_lo = make_desc_sw128(st + a_bytes + p.b_tile_bytes);
                     if (ATM) {
-                        const uint32_t a_t = tmem_base + (NM + 2) * (uint32_t)p.BN + (it & 1) * 64;   // hi at +0, lo at +32 columns
+                        const uint32_t a_t = tmem_base + CORR0 + 2 * (uint32_t)p.BN + (it & 1) * 64;   // hi at +0, lo at +32 columns
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
                             umma_tf32_ts(d_corr, a_t + 32 + k * UMMA_K, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                            umma_tf32_ts(d_corr, a_t + k * UMMA_K, b_lo + adv, idesc, 1u);
-                            umma_tf32_ts(d_main, a_t + k * UMMA_K, b_hi + adv, idesc, k ? 1u : 0u);
+                            if (MRG) {
+                                umma_tf32_ts(d_main, a_t + k * UMMA_K, b_hi + adv, idesc2, k ? 1u : 0u);   // [main | a_hi.b_lo]
+                            } else {
+                                umma_tf32_ts(d_corr, a_t + k * UMMA_K, b_lo + adv, idesc, 1u);
+                                umma_tf32_ts(d_main, a_t + k * UMMA_K, b_hi + adv, idesc, k ? 1u : 0u);
+                            }
                         }
                         umma_commit(a_empty(it & 1));
                     } else {
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per k step inside the swizzle row
-                        if (SPLIT) {
-                            umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                            umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                        if (SPLIT) umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        if (MRG) {
+                            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc2, k ? 1u : 0u);                // [main | a_hi.b_lo]
+                        } else {
+                            if (SPLIT) umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, k ? 1u : 0u);
                         }
-                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, k ? 1u : 0u);
                     }
                     }
                     umma_commit(empty(s));           // ring slot reusable once these MMAs retire
@@ -428,7 +442,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             constexpr int HPT = 8 / XFW;                     // 16-column halves per thread: 2 (4 warps) or 1 (8 warps)
             const int t = threadIdx.x - XF_WARP0 * 32;
             const int r = t & 127, half0 = (t >> 7) * HPT;
-            const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (NM + 2) * (uint32_t)p.BN;
+            const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + CORR0 + 2 * (uint32_t)p.BN;
             uint32_t s = 0, ph = 0, xstep = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const float* grow = nullptr;
@@ -577,7 +591,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tc_fence_after();
                 if (have) {
                     float u[32];
-                    const uint32_t col = t_lane + mb * (uint32_t)p.BN + c0;
+                    const uint32_t col = t_lane + mb * MS + c0;
                     tmem_ld16_issue(col, u);
                     if (wide) tmem_ld16_issue(col + 16, u + 16);
                     else {
@@ -604,6 +618,13 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             sum[j] = f2_add(sum[j], f2_fma(pow2, debias2, up));
                         }
                     }
+                    if (MRG) {          // the a_hi.b_lo term of this k-block sits BN columns further
+                        tmem_ld16_issue(col + p.BN, u);
+                        if (wide) tmem_ld16_issue(col + p.BN + 16, u + 16);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sum[j] = f2_add(sum[j], f2_pack(u[2 * j], u[2 * j + 1]));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -614,7 +635,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (SPLIT) {   // tcgen05.commit covers ALL earlier MMAs: the last main_full also completed the correction terms
                 if (have) {
                     float u[32];
-                    const uint32_t col = t_lane + (NM + acc) * (uint32_t)p.BN + c0;
+                    const uint32_t col = t_lane + CORR0 + acc * (uint32_t)p.BN + c0;
                     tmem_ld16_issue(col, u);
                     if (wide) tmem_ld16_issue(col + 16, u + 16);
                     else {
@@ -717,6 +738,9 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 }  // namespace tc
 
 static float g_debias_kappa = 1.0f;   // one ulp of every promoted k-block partial (4 truncating MMAs: 0.5*(1+.75+.5+.25) ulp expected loss)
+static bool g_merge_enabled = false;   // measured: no gain (more n-tiles repeat the transform, two main buffers instead of three)
+void set_tcgen05_merge(bool on) { g_merge_enabled = on; }
+bool get_tcgen05_merge() { return g_merge_enabled; }
 static bool g_atm_enabled = true;
 void set_tcgen05_atm(bool on) { g_atm_enabled = on; }
 bool get_tcgen05_atm() { return g_atm_enabled; }
@@ -738,13 +762,17 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     p.trace = g_gemm_trace;
     // n-tiles of at most 96 columns (3 store slabs = one per epilogue warp of a lane group); with several n-tiles
     // BN must be a multiple of the 32-column store slab
-    p.n_tiles = ceil_div(N, 96);
+    // A-in-TMEM for the K-heavy gated 3xTF32 layers (>= 8 k-blocks per tile: the MBConv projections of the 14x14 / 7x7 stages;
+    // measured slower on the ungated conv_head, which prefers the third main accumulator). Merged products for every gated
+    // projection: TMEM then holds 6 BN (+128) columns, so BN <= 80 (64 with A in TMEM).
+    const bool mrg = passes == 3 && gate != nullptr && act == 0 && g_merge_enabled;
+    bool atm = passes == 3 && K >= 8 * BK && gate != nullptr && act == 0 && g_atm_enabled;
+    if (mrg && atm && N > 64 && N <= 80) atm = false;             // one 80-column tile beats two 64-column tiles
+    const int bn_max = mrg ? (atm ? 64 : 80) : 96;
+    p.n_tiles = ceil_div(N, bn_max);
     p.BN = p.n_tiles > 1 ? ceil_div(ceil_div(N, p.n_tiles), 32) * 32 : ceil_div(N, 16) * 16;
     p.m_tiles = ceil_div(M, BM);
     p.b_tile_bytes = p.BN * BK * 4;
-    // A-in-TMEM for the K-heavy gated 3xTF32 layers (>= 8 k-blocks per tile: the MBConv projections of the 14x14 / 7x7 stages;
-    // measured slower on the ungated conv_head, which prefers the third main accumulator)
-    const bool atm = passes == 3 && K >= 8 * BK && gate != nullptr && act == 0 && g_atm_enabled;
     const int stage_bytes = atm ? A_TILE_BYTES + 2 * p.b_tile_bytes : (A_TILE_BYTES + p.b_tile_bytes) * (passes == 3 ? 2 : 1);
     const int bar_bytes = (3 * MAX_STAGES + 10 + NUM_EPI_WARPS) * 8 + 16;
     const int budget = 227 * 1024 - 1024 /*alignment slack*/ - bar_bytes - NUM_EPI_WARPS * SS_BYTES;
@@ -773,21 +801,26 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     int xfw = 4;
     const bool g = gate != nullptr, r = residual != nullptr;
     if (passes == 3) {
-        if (atm && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, ATM_XFW, true>; xfw = ATM_XFW; }    // K-heavy MBConv project, A in TMEM
-        else if (atm && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, ATM_XFW, true>; xfw = ATM_XFW; } // ... + skip
-        else if (g && act == 0 && !r && K <= BK) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, false>;   // MBConv project, one k-block per tile
-        else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8, false>; xfw = 8; } // MBConv project
-        else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8, false>; xfw = 8; }  // MBConv project + skip
-        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, false>;    // MBConv expand / conv_head (SiLU)
-        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4, false>;    // Linear / downsample
-        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4, false>;     // Linear + residual (ViT), EdgeResidual project
-        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4, false>;    // conv + ReLU
-        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0, 4, false>;    // Linear + GELU
-        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4, false>;   // BasicBlock: relu(bn(conv) + identity)
-        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1, 4, false>;     // ConvBnAct + skip (EfficientNet-V2)
-        else fn = pw_tcgen05_kernel<true, -1, -1, -1, 4, false>;
+        if (mrg && atm && !r) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, true, true>;                    // K-heavy MBConv project: A in TMEM, merged
+        else if (mrg && atm && r) fn = pw_tcgen05_kernel<true, 1, 0, 1, 4, true, true>;                // ... + skip
+        else if (mrg && !r && K <= BK) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, false, true>;          // MBConv project, one k-block per tile, merged
+        else if (mrg && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8, false, true>; xfw = 8; }        // MBConv project, merged
+        else if (mrg && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8, false, true>; xfw = 8; }         // ... + skip
+        else if (atm && !r) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, true, false>;                     // (A/B) A in TMEM, three instructions per k-step
+        else if (atm && r) fn = pw_tcgen05_kernel<true, 1, 0, 1, 4, true, false>;
+        else if (g && act == 0 && !r && K <= BK) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, false, false>;
+        else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8, false, false>; xfw = 8; }
+        else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8, false, false>; xfw = 8; }
+        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, false, false>;    // MBConv expand / conv_head (SiLU)
+        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4, false, false>;    // Linear / downsample
+        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4, false, false>;     // Linear + residual (ViT), EdgeResidual project
+        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4, false, false>;    // conv + ReLU
+        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0, 4, false, false>;    // Linear + GELU
+        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4, false, false>;   // BasicBlock: relu(bn(conv) + identity)
+        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1, 4, false, false>;     // ConvBnAct + skip (EfficientNet-V2)
+        else fn = pw_tcgen05_kernel<true, -1, -1, -1, 4, false, false>;
     } else {
-        fn = pw_tcgen05_kernel<false, -1, -1, -1, 4, false>;
+        fn = pw_tcgen05_kernel<false, -1, -1, -1, 4, false, false>;
     }
     static int num_sms = 0;
     if (!num_sms) {

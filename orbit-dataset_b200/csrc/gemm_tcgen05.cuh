@@ -19,6 +19,9 @@ void set_tcgen05_debias(float kappa);
 // A-in-TMEM variant of the K-heavy 3xTF32 layers on/off (A/B switch; default on)
 void set_tcgen05_atm(bool on);
 bool get_tcgen05_atm();
+// merged a_hi.[b_hi;b_lo] products for the gated projections on/off (A/B switch; default OFF: measured slower)
+void set_tcgen05_merge(bool on);
+bool get_tcgen05_merge();
 // dev aid: device buffer of 256 x 16 uint32 that CTA 0 of every following GEMM launch fills with per-role clock stamps (null = off)
 void set_tcgen05_trace(unsigned* dev_buffer);
 float get_tcgen05_debias();

@@ -10,6 +10,8 @@ predict, per-task state and reset) follows the reference; every tensor operation
 hand-written CUDA kernel reached through the C ABI.  There is no CPU fallback: tensors that are not
 on an sm_100 device raise ``OrbitError``.
 """
+import time
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -43,11 +45,19 @@ class _HostStager:
         self.calls = 0
         self.bytes_copied = 0
         self.ramp = (96, 224, 480)
+        self.last_call = (-1.0, 0)              # (host time, frames) of the previous call
 
     def _plan(self, total):
+        # The ramp exists to start the backbone early on a call whose data is still on the host. A call issued right
+        # behind a larger one (predict() after personalise(): the host enqueues a pass in ~0.2 ms, the device needs
+        # ~18 us per frame, the copy engine ~11 us) finds its data already on the device: no ramp, full-size passes.
+        now = time.perf_counter()
+        behind = now - self.last_call[0] < 0.010 and self.last_call[1] >= total
+        self.last_call = (now, total)
+        ramp = () if behind else self.ramp
         sizes, pos, k = [], 0, 0
         while pos < total:
-            n = min(self.ramp[k], self.chunk_frames) if k < len(self.ramp) else self.chunk_frames
+            n = min(ramp[k], self.chunk_frames) if k < len(ramp) else self.chunk_frames
             n = min(n, total - pos)
             sizes.append(n)
             pos += n
