@@ -73,3 +73,38 @@ def test_pointwise_rejects_bad_arguments(cuda_device):
     assert lib.orbit_pointwise_conv(None, L.ptr(x), L.ptr(x), L.ptr(x), None, None, L.ptr(x), 8, 8, 8, 1, 0, 0, None, None) == -1
     assert lib.orbit_pointwise_conv(L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), None, None, L.ptr(x), 8, 8, 8, 1, 0, 1, None, None) == -1
     assert lib.orbit_pointwise_conv(L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), None, None, L.ptr(x), 8, 8, 8, 1, 7, 0, None, None) == -1
+
+
+@pytest.mark.parametrize("shape", [(7 * 14 * 14, 112, 672, 14 * 14, 0, True, True), (9 * 7 * 7, 192, 1152, 7 * 7, 0, True, False),
+                                   (3 * 28 * 28, 40, 240, 28 * 28, 0, True, True), (260, 80, 480, 65, 0, True, False)],
+                         ids=lambda s: f"M{s[0]}_N{s[1]}_K{s[2]}")
+def test_gated_projection_variants_agree(cuda_device, shape):
+    """The A/B variants of the gated-projection GEMM (A operand in shared vs tensor memory, three instructions per k-step vs
+    the merged [B_hi;B_lo] product) compute the same fp32-grade result: each within 2e-6 relative of fp64."""
+    from orbit_b200 import lib as L
+    lib = L.load()
+    M, N, K, rpf, act, gated, residual = shape
+    g = torch.Generator().manual_seed(M * 3 + N)
+    A = torch.randn(M, K, generator=g).to(cuda_device)
+    W = (torch.randn(N, K, generator=g) * K ** -0.5).to(cuda_device)
+    scale = (1 + 0.1 * torch.randn(N, generator=g)).to(cuda_device)
+    shift = (0.1 * torch.randn(N, generator=g)).to(cuda_device)
+    gate = torch.rand((M + rpf - 1) // rpf, K, generator=g).to(cuda_device)
+    res = torch.randn(M, N, generator=g).to(cuda_device) if residual else None
+    ref = (A.double() * gate.double().repeat_interleave(rpf, dim=0)[:M]) @ W.double().t() * scale.double() + shift.double()
+    if residual:
+        ref = ref + res.double()
+    outs = {}
+    try:
+        for atm in (0, 1):
+            for merge in (0, 1):
+                L.check(lib.orbit_set_global_option(b"tc_a_in_tmem", atm), "set tc_a_in_tmem")
+                L.check(lib.orbit_set_global_option(b"tc_merge", merge), "set tc_merge")
+                out = _run(1, A, W, scale, shift, gate, res, rpf, act)
+                err = ((out.double() - ref).abs().max() / ref.abs().max()).item()
+                outs[(atm, merge)] = err
+                assert err <= 2e-6, f"a_in_tmem={atm} merge={merge}: relative error {err:.2e}"
+    finally:
+        lib.orbit_set_global_option(b"tc_a_in_tmem", 1)
+        lib.orbit_set_global_option(b"tc_merge", 0)
+    print({k: f"{v:.1e}" for k, v in outs.items()})

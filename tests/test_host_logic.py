@@ -131,3 +131,23 @@ def test_ops_counter_interface_and_head_formulas():
     with pytest.raises(TypeError):
         oc.compute_macs(torch.nn.Linear(2, 2), torch.zeros(1, 2))
     assert clever_format([4007548, 1234, 12]) == ('4.01M', '1.23K', '12.00B')
+
+
+def test_host_stager_plan():
+    """_HostStager._plan: passes cover the call exactly, ramp first, no tiny tail, and no ramp for a call queued right
+    behind a larger one (predict() after personalise())."""
+    import time
+    from orbit_b200.few_shot_recognisers import _HostStager
+    st = _HostStager.__new__(_HostStager)
+    st.chunk_frames, st.ramp, st.copy_frames, st.last_call = 1600, (96, 224, 480), 160, (-1.0, 0)
+    assert st._plan(1600) == [96, 224, 480, 800]
+    assert st._plan(640) == [640]                      # issued right behind the 1600-frame call: data will be there
+    time.sleep(0.02)
+    assert st._plan(640) == [96, 224, 320]
+    time.sleep(0.02)
+    assert st._plan(830) == [96, 224, 510]             # a 30-frame tail is merged into the last pass
+    st.chunk_frames, st.ramp = 2, (4, 6)
+    for total in (1, 7, 30):
+        time.sleep(0.011)
+        plan = st._plan(total)
+        assert sum(plan) == total and all(n > 0 for n in plan)
