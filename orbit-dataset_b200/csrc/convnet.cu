@@ -549,7 +549,11 @@ template <> struct PairIO<2> {
 };
 
 // CT = compile-time channel count (0: use the runtime C): column offsets j*C become load/store immediates.
-template <int K, int S, int VEC, int MINB, int CT>
+// UNR (stride 1 only): the row loop is unrolled over the R phases of the accumulator ring, so that the ring never moves
+// (slot indices are compile-time): retires the 2 R TW NP rotation MOVs per row. MEASURED SLOWER on all four K=5 layers
+// (814 -> 892 us at 28x28x240, B=1600): the 5x larger loop body costs more instruction fetch than the MOVs it saves, as
+// the scalar version did in round 1. Not dispatched; kept as the record of the experiment.
+template <int K, int S, int VEC, int MINB, int CT, bool UNR = false>
 __global__ void __launch_bounds__(256, MINB)
 dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
            const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C_rt,
@@ -621,6 +625,58 @@ dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const floa
 #pragma unroll
                 for (int q = 0; q < NP; ++q) acc[r][t][q] = 0ull;
         load_row(row0 * S, v);
+        if constexpr (UNR) {
+            static_assert(!UNR || S == 1, "phase-unrolled ring: stride 1");
+            for (int m0 = row0; m0 < row1 + HALF; m0 += R) {
+#pragma unroll
+                for (int ph = 0; ph < R; ++ph) {
+                    const int m = m0 + ph;
+                    if (m < row1 + HALF) {
+                        load_row(m + 1, vn);
+#pragma unroll
+                        for (int ky = 0; ky < K; ++ky) {
+                            const int slot = (HALF - ky + ph) % R;        // compile time: logical slot HALF-ky, ring offset ph
+#pragma unroll
+                            for (int kx = 0; kx < K; ++kx) {
+                                f2_t w[NP];
+                                PairIO<NP>::load_shared(wlane + (ky * K + kx) * LXS * VEC, w);
+#pragma unroll
+                                for (int t = 0; t < TW; ++t)
+#pragma unroll
+                                    for (int q = 0; q < NP; ++q) acc[slot][t][q] = f2_fma(v[kx + t][q], w[q], acc[slot][t][q]);
+                            }
+                        }
+                        constexpr int dummy = 0; (void)dummy;
+                        const int o = ph % R;                              // the oldest pending output row lives here
+                        const int oy = m - HALF;
+                        if (oy >= row0) {
+                            float* yrow = yb + (int64_t)oy * Wo * C;
+#pragma unroll
+                            for (int t = 0; t < TW; ++t) {
+                                if (ox0 + t < Wo) {
+                                    float r[VEC];
+#pragma unroll
+                                    for (int q = 0; q < NP; ++q) {
+                                        f2_unpack(f2_fma(acc[o][t][q], sc[q], sh[q]), r[2 * q], r[2 * q + 1]);
+                                        r[2 * q] = act_fast(r[2 * q], act); r[2 * q + 1] = act_fast(r[2 * q + 1], act);
+                                        sum[2 * q] += r[2 * q]; sum[2 * q + 1] += r[2 * q + 1];
+                                    }
+                                    PairIO<NP>::store(yrow + t * C, r);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int t = 0; t < TW; ++t)
+#pragma unroll
+                            for (int q = 0; q < NP; ++q) acc[o][t][q] = 0ull;   // becomes the newest slot
+#pragma unroll
+                        for (int j = 0; j < SPAN; ++j)
+#pragma unroll
+                            for (int q = 0; q < NP; ++q) v[j][q] = vn[j][q];
+                    }
+                }
+            }
+        } else {
         // iteration m handles virtual rows m*S .. m*S+S-1; the oldest pending output row is m - HALF
         for (int m = row0; m < row1 + HALF; ++m) {
 #pragma unroll
@@ -675,6 +731,7 @@ dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const floa
 #pragma unroll
                 for (int q = 0; q < NP; ++q) acc[R - 1][t][q] = 0ull;
         }
+        }
     }
     if (partial) {
 #pragma unroll
@@ -714,7 +771,7 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
         const size_t smem2 = smem + sizeof(float) * (size_t)k * k * 32 * pl.VEC;
 #define ORBIT_DW2_LAUNCH(KK, SS, VV, MB, CC)                                                                           \
         {                                                                                                             \
-            dw2_kernel<KK, SS, VV, MB, CC><<<grid, block, smem2, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho,  \
+            dw2_kernel<KK, SS, VV, MB, CC, false><<<grid, block, smem2, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho,  \
                                                                        Wo, pad_t, pad_l, act, pl.LX, pl.LY,           \
                                                                        pl.rows_per_tile, pl.strip_blocks);            \
             ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                          \
