@@ -33,7 +33,7 @@ WORKLOAD = "S2: ProtoNet+efficientnet_b0, 224x224, 5-way, support 200 clips x 8 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='orbit_b200', choices=['orbit_b200', 'reference'])
     ap.add_argument('--gemm', type=int, default=int(os.environ.get('ORBIT_GEMM', '1')))
@@ -294,7 +294,7 @@ def main():
     # ---- end to end through the public API with pinned host clips -----------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e_steps = max(2, min(args.steps, 6))
+        e2e_steps = max(2, min(args.steps, 12))
         e_ms, _ = timed(step_host, e2e_steps, 2)
         ctx, _, tgt, _ = host_eps[0]
         e2e = {"value": world / (e_ms / e2e_steps / 1e3), "unit": "episodes/s",
