@@ -1073,17 +1073,48 @@ im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H
 // consecutive channel quads of one tap (contiguous in x and in col), one 64-bit division per thread. The scalar kernel
 // above ran 1 ms per launch on the ResNet-18 plan (40 of a 53 ms CNAPs episode); this one moves the same bytes at HBM speed.
 __global__ void __launch_bounds__(256)
-im2col_nhwc4_kernel(const float4* __restrict__ x, float4* __restrict__ col, int64_t total4, int H, int W, int C4, int k, int stride,
+im2col_nhwc4_kernel(const float4* __restrict__ x, float4* __restrict__ col, int64_t num_pix, int H, int W, int C4, int k, int stride,
                     int pad_t, int pad_l, int Ho, int Wo) {
-    const int kk = k * k, row4 = kk * C4;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = i / row4;
-        const int r = (int)(i - pix * row4), tap = r / C4, c4 = r - tap * C4;
-        const int hw = Ho * Wo, b = (int)(pix / hw), p = (int)(pix - (int64_t)b * hw), oy = p / Wo, ox = p - oy * Wo;
-        const int ky = tap / k, iy = oy * stride - pad_t + ky, ix = ox * stride - pad_l + (tap - ky * k);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((int64_t)b * H + iy) * W + ix) * C4 + c4);
-        col[i] = v;
+    // one block per output pixel (grid-stride): the pixel is decomposed once, a thread then owns elements r, r + 256, ... of
+    // the pixel's [k*k][C/4] row: one small 32-bit division per 128-bit element. (A variant that walks along an output row
+    // with the (ky, kx, c4) decomposition hoisted into registers measured slower.)
+    const int kk = k * k, row4 = kk * C4, hw = Ho * Wo;
+    for (int64_t pix = blockIdx.x; pix < num_pix; pix += gridDim.x) {
+        const int b = (int)(pix / hw), p = (int)(pix - (int64_t)b * hw), oy = p / Wo, ox = p - oy * Wo;
+        const int iy0 = oy * stride - pad_t, ix0 = ox * stride - pad_l;
+        const float4* xb = x + (int64_t)b * H * W * C4;
+        float4* crow = col + pix * row4;
+        for (int r = threadIdx.x; r < row4; r += blockDim.x) {
+            const int tap = r / C4, c4 = r - tap * C4, ky = tap / k, iy = iy0 + ky, ix = ix0 + (tap - ky * k);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xb + ((int64_t)iy * W + ix) * C4 + c4);
+            crow[r] = v;
+        }
+    }
+}
+
+// NCHW input (the first convolution of ResNet / EfficientNet-V2 / the set encoder): a thread copies the k contiguous
+// floats of one (channel, kernel row) of one output pixel; col index = c*k*k + ky*k + kx (torch weight order).
+__global__ void __launch_bounds__(256)
+im2col_nchw_rows_kernel(const float* __restrict__ x, float* __restrict__ col, int64_t num_pix, int H, int W, int C, int k, int stride,
+                        int pad_t, int pad_l, int Ho, int Wo, int Kpad) {
+    const int units = C * k, hw = Ho * Wo, per_block = blockDim.x / 32;       // one warp per pixel, lanes over (c, ky)
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int64_t pix = (int64_t)blockIdx.x * per_block + wib; pix < num_pix; pix += (int64_t)gridDim.x * per_block) {
+        const int b = (int)(pix / hw), p = (int)(pix - (int64_t)b * hw), oy = p / Wo, ox = p - oy * Wo;
+        const int iy0 = oy * stride - pad_t, ix0 = ox * stride - pad_l;
+        float* crow = col + pix * Kpad;
+        for (int u = lane; u < units; u += 32) {
+            const int c = u / k, ky = u - c * k, iy = iy0 + ky;
+            const float* xr = x + (((int64_t)b * C + c) * H + iy) * W;
+            float* dst = crow + u * k;
+            const bool rok = iy >= 0 && iy < H;
+            for (int kx = 0; kx < k; ++kx) {
+                const int ix = ix0 + kx;
+                dst[kx] = (rok && ix >= 0 && ix < W) ? __ldg(xr + ix) : 0.f;
+            }
+        }
+        for (int z = C * k * k + lane; z < Kpad; z += 32) crow[z] = 0.f;       // padding columns
     }
 }
 
@@ -1091,10 +1122,18 @@ int launch_im2col(const float* x, float* col, int B, int H, int W, int C, int k,
                   int Wo, int Kpad, int nchw, cudaStream_t st) {
     const int64_t total = (int64_t)B * Ho * Wo * Kpad;
     if (total == 0) return ORBIT_OK;
+    if (nchw) {
+        const int64_t num_pix = (int64_t)B * Ho * Wo;
+        im2col_nchw_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(num_pix, 8), 148 * 32), 256, 0, st>>>(
+            x, col, num_pix, H, W, C, k, stride, pad_t, pad_l, Ho, Wo, Kpad);
+        ORBIT_RETURN_IF_LAUNCH_FAILED();
+        return ORBIT_OK;
+    }
     if (!nchw && C % 4 == 0 && Kpad == k * k * C && aligned16(x) && aligned16(col)) {
-        const int64_t total4 = total / 4;
-        im2col_nhwc4_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total4, 256), 148 * 64), 256, 0, st>>>(
-            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(col), total4, H, W, C / 4, k, stride, pad_t, pad_l, Ho, Wo);
+        const int64_t num_pix = (int64_t)B * Ho * Wo;
+        const int row4 = k * k * C / 4, threads = std::min(256, (row4 + 31) / 32 * 32);
+        im2col_nhwc4_kernel<<<(unsigned)std::min<int64_t>(num_pix, 148 * 64), threads, 0, st>>>(
+            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(col), num_pix, H, W, C / 4, k, stride, pad_t, pad_l, Ho, Wo);
         ORBIT_RETURN_IF_LAUNCH_FAILED();
         return ORBIT_OK;
     }
