@@ -151,3 +151,24 @@ def test_host_stager_plan():
         time.sleep(0.011)
         plan = st._plan(total)
         assert sum(plan) == total and all(n > 0 for n in plan)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm: oracle port of the reference's PyTorch path) prints ONE JSON line with the
+    keys the driver reads; it needs no GPU and no liborbit_b200."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "episodes_per_sec" and d["unit"] == "episodes/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("S2")
