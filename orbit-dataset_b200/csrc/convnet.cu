@@ -749,6 +749,156 @@ dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const floa
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Third-generation depthwise kernel for stride 1 (the K=5 layers): same tiling, taps and rolling accumulators as
+// dw2_kernel, but the input rows arrive through a per-thread cp.async ring in shared memory, D rows deep, instead of a
+// one-row register prefetch. The K=5 stride-1 kernels ran at 0.18 instructions per clock per scheduler with 14 warps
+// per SM: each row waited for most of an HBM latency. Every thread copies and later reads only its own 8-byte slots, so
+// no block barrier is needed; out-of-image rows / columns are zero-filled by the copy itself (src-size 0).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ f2_t lds64(uint32_t addr) {
+    f2_t v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int K, int VEC, int CT, int D>
+__global__ void __launch_bounds__(256, 2)
+dw3_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
+           const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C_rt,
+           int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile, int strip_blocks) {
+    constexpr int TW = kDwTW, R = K, SPAN = TW - 1 + K, HALF = K - 1, NP = VEC / 2, LXS = 32;
+    const int C = CT ? CT : C_rt;
+    extern __shared__ __align__(16) float s_dyn[];
+    float* s_w = s_dyn;                                   // [K*K][LXS][VEC] taps of this block's channel chunk
+    float* s_red = s_dyn + K * K * LXS * VEC;             // [256][VEC] partial-sum reduction
+    const uint32_t s_ring = (uint32_t)__cvta_generic_to_shared(s_red + 256 * VEC);   // [D][SPAN][NP][blockDim] 8-byte slots
+    const int tile = blockIdx.x / strip_blocks, sb = blockIdx.x % strip_blocks, chunk = blockIdx.y, b = blockIdx.z;
+    const int groups = gridDim.x;
+    const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
+    const int Cv = C / VEC;
+    const int cv = chunk * LX + lx;
+    const int strip = sb * LY + ly;
+    const bool live = cv < Cv && strip * TW < Wo;
+    for (int i = threadIdx.x; i < K * K * LXS; i += blockDim.x) {
+        const int t = i / LXS, l = i % LXS, c = chunk * LX + l;
+        float wv[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) wv[e] = 0.f;
+        if (l < LX && c < Cv) VecIO<VEC>::load(wt + (int64_t)t * C + c * VEC, wv);
+        VecIO<VEC>::store(s_w + (size_t)i * VEC, wv);
+    }
+    __syncthreads();
+    float sum[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) sum[e] = 0.f;
+    const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
+    if (live && row0 < row1) {
+        f2_t sc[NP], sh[NP];
+        PairIO<NP>::load(scale + cv * VEC, sc);
+        PairIO<NP>::load(shift + cv * VEC, sh);
+        const int ox0 = strip * TW, ixb = ox0 - pad_l;
+        unsigned cmask = 0;                               // bit j: input column ixb + j exists
+#pragma unroll
+        for (int j = 0; j < SPAN; ++j) cmask |= (ixb + j >= 0 && ixb + j < W) ? (1u << j) : 0u;
+        const int64_t row_stride = (int64_t)W * C;
+        const float* xcol = x + (int64_t)b * H * row_stride + (int64_t)ixb * C + cv * VEC - pad_t * row_stride;
+        float* yb = y + ((int64_t)b * Ho * Wo + ox0) * C + cv * VEC;
+        const float* wlane = s_w + lx * VEC;
+        const int vy_lo = pad_t, vy_hi = min(H - 1 + pad_t, row1 - 1 + K - 1);   // virtual row = input row + pad_t
+        const uint32_t ring = s_ring + threadIdx.x * 8, estride = blockDim.x * 8;
+        auto issue_row = [&](int vy, int slot) {
+            const bool rok = vy >= vy_lo && vy <= vy_hi;
+            const float* rp = xcol + (int64_t)vy * row_stride;
+#pragma unroll
+            for (int j = 0; j < SPAN; ++j)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const bool ok = rok && ((cmask >> j) & 1u);
+                    cp_async8(ring + (uint32_t)((slot * SPAN + j) * NP + q) * estride, ok ? (const void*)(rp + j * C + 2 * q) : (const void*)x, ok);
+                }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        f2_t acc[R][TW][NP], v[SPAN][NP];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int t = 0; t < TW; ++t)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) acc[r][t][q] = 0ull;
+#pragma unroll
+        for (int d = 0; d < D; ++d) issue_row(row0 + d, d);
+        int slot = 0;
+        for (int m = row0; m < row1 + HALF; ++m) {       // virtual input row m; the oldest pending output row is m - HALF
+            asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+#pragma unroll
+            for (int j = 0; j < SPAN; ++j)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) v[j][q] = lds64(ring + (uint32_t)((slot * SPAN + j) * NP + q) * estride);
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const int s_ = HALF - ky;
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    f2_t w[NP];
+                    PairIO<NP>::load_shared(wlane + (ky * K + kx) * LXS * VEC, w);
+#pragma unroll
+                    for (int t = 0; t < TW; ++t)
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) acc[s_][t][q] = f2_fma(v[kx + t][q], w[q], acc[s_][t][q]);
+                }
+            }
+            const int oy = m - HALF;
+            if (oy >= row0) {
+                float* yrow = yb + (int64_t)oy * Wo * C;
+#pragma unroll
+                for (int t = 0; t < TW; ++t) {
+                    if (ox0 + t < Wo) {
+                        float r[VEC];
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            f2_unpack(f2_fma(acc[0][t][q], sc[q], sh[q]), r[2 * q], r[2 * q + 1]);
+                            r[2 * q] = act_fast(r[2 * q], act); r[2 * q + 1] = act_fast(r[2 * q + 1], act);
+                            sum[2 * q] += r[2 * q]; sum[2 * q + 1] += r[2 * q + 1];
+                        }
+                        PairIO<NP>::store(yrow + t * C, r);
+                    }
+                }
+            }
+            issue_row(m + D, slot);                       // refill the slot just consumed (its values are in registers)
+            slot = slot + 1 == D ? 0 : slot + 1;
+#pragma unroll
+            for (int r = 0; r + 1 < R; ++r)
+#pragma unroll
+                for (int t = 0; t < TW; ++t)
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) acc[r][t][q] = acc[r + 1][t][q];
+#pragma unroll
+            for (int t = 0; t < TW; ++t)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) acc[R - 1][t][q] = 0ull;
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    if (partial) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s_red[(ly * LX + lx) * VEC + e] = sum[e];
+        __syncthreads();
+        if (ly == 0 && cv < Cv) {
+            float t[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) t[e] = s_red[lx * VEC + e];
+            for (int r = 1; r < LY; ++r)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) t[e] += s_red[(r * LX + lx) * VEC + e];
+            VecIO<VEC>::store(partial + ((int64_t)b * groups + blockIdx.x) * C + cv * VEC, t);
+        }
+    }
+}
+
 static int g_dw_variant = 2;   // 1 = first-generation kernels (kept for A/B), 2 = packed-FMA kernels
 void set_dw_variant(int v) { g_dw_variant = v; }
 int get_dw_variant() { return g_dw_variant; }
@@ -766,6 +916,21 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
                                                         pad_l, act, pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks); \
         ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                              \
         return ORBIT_OK;                                                                                              \
+    }
+    if (g_dw_variant == 3 && k == 5 && stride == 1) {
+        constexpr int D = 3;
+        const size_t smem3 = sizeof(float) * ((size_t)k * k * 32 * pl.VEC + 256 * pl.VEC) + (size_t)D * (kDwTW - 1 + 5) * (pl.VEC / 2) * 8 * block.x;
+#define ORBIT_DW3_CT(CC)                                                                                              \
+        if (C == CC) {                                                                                                \
+            static bool attr_set = false;                                                                             \
+            if (!attr_set) { ORBIT_CUDA(cudaFuncSetAttribute(dw3_kernel<5, 2, CC, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = true; } \
+            dw3_kernel<5, 2, CC, D><<<grid, block, smem3, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t, pad_l, act, \
+                                                               pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks);      \
+            ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                          \
+            return ORBIT_OK;                                                                                          \
+        }
+        ORBIT_DW3_CT(240) ORBIT_DW3_CT(480) ORBIT_DW3_CT(672) ORBIT_DW3_CT(1152) ORBIT_DW3_CT(0)
+#undef ORBIT_DW3_CT
     }
     if (g_dw_variant >= 2) {
         const size_t smem2 = smem + sizeof(float) * (size_t)k * k * 32 * pl.VEC;
