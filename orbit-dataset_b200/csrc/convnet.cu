@@ -646,7 +646,6 @@ dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const floa
                                     for (int q = 0; q < NP; ++q) acc[slot][t][q] = f2_fma(v[kx + t][q], w[q], acc[slot][t][q]);
                             }
                         }
-                        constexpr int dummy = 0; (void)dummy;
                         const int o = ph % R;                              // the oldest pending output row lives here
                         const int oy = m - HALF;
                         if (oy >= row0) {
