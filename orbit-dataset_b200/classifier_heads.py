@@ -17,11 +17,34 @@ _METRICS = {'euclidean': 0, 'cosine': 1}
 
 def _class_index(labels: torch.Tensor):
     """Rank of each label among the sorted distinct labels (torch.unique order,
-    classifier_heads.py:96,246-248). Done on the host: labels are a few hundred int64s and are
-    needed there anyway to size the [C, D] outputs."""
+    classifier_heads.py:96,246-248). Done on the host: labels are a few hundred int64s and the class
+    COUNT is needed there anyway to size the [C, D] / [Nq, C] outputs."""
     lab = labels.detach().cpu().numpy().astype(np.int64).reshape(-1)
     classes, inverse = np.unique(lab, return_inverse=True)
     return classes, inverse.astype(np.int32)
+
+
+class ClassIndex:
+    """The label bookkeeping of one task, computed BEFORE the support set is enqueued.
+
+    Reading device labels back is a host sync (the reference has several per class: ``unique``, ``nonzero``,
+    classifier_heads.py:96-101). Done inside ``configure`` it would block the host until the whole support pass has
+    drained, and the query set's H2D copies could not be issued meanwhile; done first, it waits for nothing."""
+
+    def __init__(self, labels: torch.Tensor, device=None):
+        self.classes, self.index = _class_index(labels)
+        self.num_classes, self.num_clips = len(self.classes), len(self.index)
+        device = labels.device if device is None else device
+        self.index_dev = torch.from_numpy(self.index).to(device, non_blocking=True) if torch.device(device).type == 'cuda' else None
+
+    @staticmethod
+    def of(labels, class_index, device):
+        if class_index is None:
+            return ClassIndex(labels, device)
+        assert class_index.num_clips == labels.numel(), "class index was built for another label tensor"
+        if class_index.index_dev is None or class_index.index_dev.device != torch.device(device):
+            class_index.index_dev = torch.from_numpy(class_index.index).to(device, non_blocking=True)
+        return class_index
 
 
 class MeanPooler(nn.Module):
@@ -113,9 +136,10 @@ class PrototypicalClassifier(HeadClassifier):
             self.bias = None
         self.classes = None
 
-    def configure(self, context_features, context_labels, ops_counter=None, clip_length=1):
+    def configure(self, context_features, context_labels, ops_counter=None, clip_length=1, class_index=None):
         """``context_features``: clip features [N, D] (reference contract) or, with ``clip_length=L``,
-        the FRAME features [N*L, D] -- pooling is then fused into the same launch."""
+        the FRAME features [N*L, D] -- pooling is then fused into the same launch. ``class_index``: a ``ClassIndex``
+        of ``context_labels`` built earlier (keeps this call free of host syncs)."""
         if self.distance_fn not in _METRICS:
             raise ValueError(f"Distance function {self.distance_fn} not valid.")
         L.require_cuda(context_features, "context_features")
@@ -124,11 +148,11 @@ class PrototypicalClassifier(HeadClassifier):
         lib = L.load()
         feats = context_features.contiguous().float()
         dev = feats.device
-        classes, idx = _class_index(context_labels)
-        c, d, n = len(classes), feats.shape[1], len(idx)
+        ci = ClassIndex.of(context_labels, class_index, dev)
+        classes, idx_dev = ci.classes, ci.index_dev
+        c, d, n = ci.num_classes, feats.shape[1], ci.num_clips
         if c > 64:
             raise ValueError("orbit_b200 supports at most 64 classes per task")
-        idx_dev = torch.from_numpy(idx).to(dev, non_blocking=True)
         need = lib.orbit_proto_configure_scratch_bytes(64, d)
         if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
             self._scratch = torch.zeros(need, dtype=torch.uint8, device=dev)

@@ -4,7 +4,7 @@ import torch
 import torch.nn as nn
 
 from . import lib as L
-from .classifier_heads import HeadClassifier, _class_index, _head_predict
+from .classifier_heads import ClassIndex, HeadClassifier, _head_predict
 
 
 class DenseResidualBlock(nn.Module):
@@ -79,16 +79,16 @@ class VersaClassifier(HeadClassifier):
             raise AttributeError("Weight and/or bias not set - is model personalised?")
         return _head_predict(target_features, clip_length, self.weight, self.bias, 0, self.logit_scale, want_argmax)
 
-    def configure(self, context_features, context_labels, ops_counter=None, clip_length=1):
+    def configure(self, context_features, context_labels, ops_counter=None, clip_length=1, class_index=None):
         L.require_cuda(context_features, "context_features")
         assert context_features.size(0) == context_labels.size(0) * clip_length, \
             "context features and labels are different sizes!"
         lib = L.load()
         feats = context_features.contiguous().float()
         dev = feats.device
-        classes, idx = _class_index(context_labels)
-        c, d, n = len(classes), feats.shape[1], len(idx)
-        idx_dev = torch.from_numpy(idx).to(dev, non_blocking=True)
+        ci = ClassIndex.of(context_labels, class_index, dev)
+        idx_dev = ci.index_dev
+        c, d, n = ci.num_classes, feats.shape[1], ci.num_clips
         need = lib.orbit_proto_configure_scratch_bytes(64, d)
         if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
             self._scratch = torch.zeros(need, dtype=torch.uint8, device=dev)
@@ -132,7 +132,7 @@ class MahalanobisClassifier(HeadClassifier):
         L.count_launches(1)
         return out
 
-    def configure(self, context_features, context_labels, ops_counter=None, clip_length=1):
+    def configure(self, context_features, context_labels, ops_counter=None, clip_length=1, class_index=None):
         import ctypes as C
         import numpy as np
         L.require_cuda(context_features, "context_features")
@@ -141,8 +141,9 @@ class MahalanobisClassifier(HeadClassifier):
         lib = L.load()
         feats = self._pool(context_features, clip_length)
         dev = feats.device
-        classes, idx = _class_index(context_labels)
-        c, (n, d) = len(classes), feats.shape
+        ci = ClassIndex.of(context_labels, class_index, dev)
+        idx = ci.index
+        c, (n, d) = ci.num_classes, feats.shape
         order = np.argsort(idx, kind='stable').astype(np.int32)
         counts = np.bincount(idx, minlength=c).astype(np.int32)
         order_dev = torch.from_numpy(order).to(dev)

@@ -34,7 +34,7 @@ extern "C" int orbit_pointwise_conv(const float* A, const float* W, const float*
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) return launch_pointwise_ffma(A, W, scale, shift, gate, residual, out, M, N, K, rows_per_frame, act, st);
     if (!w_split || !aligned16(w_split)) return ORBIT_ERR_ARG;
-    const int rc = launch_tf32_split(W, (int64_t)N * K, w_split, st);
+    const int rc = launch_weight_split(W, N, K, w_split, st);
     if (rc) return rc;
     return launch_pointwise_tcgen05(A, w_split, scale, shift, gate, residual, out, M, N, K, rows_per_frame, act,
                                     mode == 1 ? 3 : 1, st);
@@ -46,16 +46,12 @@ extern "C" int orbit_set_global_option(const char* key, int value) {
     if (!key) return ORBIT_ERR_ARG;
     if (!strcmp(key, "tc_debias_x1000")) { orbit::set_tcgen05_debias((float)value / 1000.0f); return ORBIT_OK; }
     if (!strcmp(key, "dw_variant")) { if (value < 1 || value > 3) return ORBIT_ERR_ARG; orbit::set_dw_variant(value); return ORBIT_OK; }
-    if (!strcmp(key, "tc_a_in_tmem")) { orbit::set_tcgen05_atm(value != 0); return ORBIT_OK; }
-    if (!strcmp(key, "tc_merge")) { orbit::set_tcgen05_merge(value != 0); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 extern "C" int orbit_get_global_option(const char* key, int* value) {
     if (!key || !value) return ORBIT_ERR_ARG;
     if (!strcmp(key, "tc_debias_x1000")) { *value = (int)(orbit::get_tcgen05_debias() * 1000.0f + 0.5f); return ORBIT_OK; }
     if (!strcmp(key, "dw_variant")) { *value = orbit::get_dw_variant(); return ORBIT_OK; }
-    if (!strcmp(key, "tc_a_in_tmem")) { *value = orbit::get_tcgen05_atm() ? 1 : 0; return ORBIT_OK; }
-    if (!strcmp(key, "tc_merge")) { *value = orbit::get_tcgen05_merge() ? 1 : 0; return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 

@@ -35,7 +35,7 @@ struct Op {
     int64_t fold = -1;          // derived offset of scale[C], shift[C]
     int fold_idx = -1;          // index into orbit_engine::folds
     int64_t dw_wt = -1;         // derived offset of re-laid-out depthwise weights
-    int64_t w_split = -1;       // derived offset of tf32 hi/lo split weights (PW, tcgen05 path)
+    int64_t w_split = -1;       // derived offset of the fp16 hi/lo split weights (PW, tcgen05 path)
     int64_t w_gemm = -1;        // CONV3: derived offset of the weights re-laid-out to [cout, kpad] (im2col k-order)
     int kpad = 0;               // CONV3: im2col row length (k*k*cin rounded up to a multiple of 4)
     bool same_pad = false;      // CONV3: TF SAME geometry (asymmetric for stride 2) instead of the symmetric `pad`
@@ -584,12 +584,12 @@ extern "C" int orbit_engine_prepare(const orbit_engine* e, const float* params, 
             rc = launch_dw_relayout(params + op.w2, op.cin, op.se_reduce, derived + op.dw_wt, st);
             if (rc) return rc;
         } else if (op.kind == OP_PW && op.w_split >= 0) {
-            rc = launch_tf32_split(params + op.w, (int64_t)op.cout * op.cin, derived + op.w_split, st);
+            rc = launch_weight_split(params + op.w, op.cout, op.cin, derived + op.w_split, st);
             if (rc) return rc;
         } else if (op.kind == OP_CONV3) {
             rc = launch_conv_weight_relayout(params + op.w, derived + op.w_gemm, op.cout, op.cin, op.k * op.k, op.kpad, op.nchw_in, st);
             if (rc) return rc;
-            rc = launch_tf32_split(derived + op.w_gemm, (int64_t)op.cout * op.kpad, derived + op.w_split, st);
+            rc = launch_weight_split(derived + op.w_gemm, op.cout, op.kpad, derived + op.w_split, st);
             if (rc) return rc;
         }
     }

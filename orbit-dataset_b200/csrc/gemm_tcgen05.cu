@@ -4,43 +4,47 @@
 // model/few_shot_recognisers.py:114-117,143-146 (88% of EfficientNet-B0's MACs); the
 // FiLM gamma'/beta' (model/film.py, feature_adapters.py:66-78) arrive folded into `scale`/`shift`.
 //
-// Design (one persistent CTA per SM, warp-specialised, 768 threads):
+// Numerics: fp32-grade products from THREE fp16 tensor-core products ("FP16x3").  Every fp32 operand is split as
+//   x = hi + lo * 2^-11,  hi = fp16(x),  lo = fp16((x - hi) * 2^11)        (22-23 significant bits, like 3xTF32)
+// and  a.w ~= a_hi.w_hi + 2^-11 (a_hi.w_lo + a_lo.w_hi).  fp16 has the same 11-bit significand as tf32, and
+// tcgen05.mma.kind::f16 covers K = 16 per instruction where kind::tf32 covers 8 AT THE SAME COST PER INSTRUCTION
+// (scripts/mma_rate_f16.cu, profiles/r02_mma_rate_f16.txt: 93 clk for every N <= 96 for both kinds, the cost follows
+// the operand BYTES): half the tensor-core instructions and half the shared-memory operand traffic of round 1's
+// 3xTF32 kernel. The price is fp16's exponent range: |x| must stay below 65504 (conversions saturate); values
+// below 2^-14 lose nothing that matters because the scaled lo part carries the residual.
+//
+// Design (one persistent CTA per SM, warp-specialised):
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B, zero OOB fill) of the fp32 A tile
-//               [128 rows x 32 k] and the weight tiles [BN x 32 k] (tf32 hi and lo parts) into a
-//               multi-stage shared-memory ring, completion on mbarriers.
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) with the
-//               accumulator in TMEM (double buffered, 2 x BN columns); tcgen05.commit frees ring slots.
-//   warps 4-11  A transform: multiply the landed tile by the squeeze-excite gate (per frame, per input
-//               channel) and split it into tf32 hi / lo parts in shared memory (3xTF32: hi*hi + hi*lo + lo*hi
-//               gives fp32-grade products; the tensor core accumulates in fp32), then fence.proxy.async.
-//   warps 12-23 epilogue: tcgen05.ld the accumulator rows, apply folded BN/FiLM scale-shift, SiLU, residual,
-//               and store fp32 rows (16-byte vector stores).
-// The kernel is HBM-bound by design (A read once, out written once); the tensor pipe has the headroom
-// for the three passes.
+//               [128 rows x 64 k] (two 128-byte-wide boxes) and the fp16 weight tiles [BN x 64 k] (hi and lo
+//               parts, split once per task) into a multi-stage shared-memory ring, completion on mbarriers.
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16), accumulators in TMEM.
+//   warps 4..   A transform: multiply the landed fp32 tile by the squeeze-excite gate (per frame, per input
+//               channel), split it into fp16 hi / lo IN PLACE (32 KB of fp32 become 16 KB hi + 16 KB lo in the
+//               K-major SWIZZLE_128B layout the MMA reads), then fence.proxy.async.
+//   last 12     epilogue: per k-block promotion of the main accumulator into fp32 registers (see below), then
+//               folded BN/FiLM scale-shift, SiLU/ReLU/GELU, residual, swizzled staging slab, TMA store.
+// The kernel is HBM-bound by design (A read once, out written once).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "gemm_tcgen05.cuh"
 
 namespace orbit {
 
-// fp32 -> tf32 (10-bit mantissa) with round-to-nearest, returned in an fp32 container
-__device__ __forceinline__ float to_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
-
-__global__ void tf32_split_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ out) {
+// w [N,K] fp32 -> out: fp16 hi [N,Kp] | fp16 lo [N,Kp], Kp = K rounded up to 8 (16-byte rows for the TMA), zero padded
+__global__ void weight_split_kernel(const float* __restrict__ w, int N, int K, int Kp, __half* __restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float v = w[i];
-    const float hi = to_tf32(v);       // round-to-nearest tf32: |v - hi| <= 2^-12 |v|
+    if (i >= (int64_t)N * Kp) return;
+    const int n = (int)(i / Kp), k = (int)(i % Kp);
+    const float v = k < K ? w[(int64_t)n * K + k] : 0.f;
+    const __half hi = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
     out[i] = hi;
-    out[n + i] = to_tf32(v - hi);      // v - hi is exact in fp32; rounding it to tf32 leaves ~2^-23 |v|
+    out[(int64_t)N * Kp + i] = __float2half_rn(fminf(fmaxf((v - __half2float(hi)) * 2048.0f, -65504.f), 65504.f));   // v - hi is exact in fp32
 }
 
-int launch_tf32_split(const float* w, int64_t n, float* out, cudaStream_t st) {
-    tf32_split_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(w, n, out);
+int launch_weight_split(const float* w, int N, int K, float* out, cudaStream_t st) {
+    const int Kp = (K + 7) / 8 * 8;
+    weight_split_kernel<<<(unsigned)ceil_div64((int64_t)N * Kp, 256), 256, 0, st>>>(w, N, K, Kp, reinterpret_cast<__half*>(out));
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }
@@ -48,20 +52,20 @@ int launch_tf32_split(const float* w, int64_t n, float* out, cudaStream_t st) {
 namespace tc {
 
 constexpr int BM = 128;          // rows per tile (= UMMA M, one TMEM lane per row)
-constexpr int BK = 32;           // fp32 elements per k-block = 128 bytes = one swizzle-128B row
-constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction along K
-constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
+constexpr int BK = 64;           // k per ring stage = one 128-byte swizzle row of fp16 = two 128-byte rows of fp32
+constexpr int UMMA_K = 16;       // fp16: 32 bytes per instruction along K
+constexpr int A_BOX_BYTES = BM * 32 * 4;      // one fp32 TMA box [128 rows x 32 k] = 16 KB = one fp16 operand tile [128 x 64]
+constexpr int A_STAGE_BYTES = 2 * A_BOX_BYTES;
 // Warp roles. The hardware arbiter favours higher warp ids, so the epilogue (the role with real ALU work)
 // sits last; its first warp id must be a multiple of 4 (a warp reaches TMEM lanes 32*(warp%4)..+31).
-constexpr int XF_WARP0 = 4;       // transform warps: XFW = 4 (ungated: ~100 instructions per k-block) or 8 (gated K-heavy layers), template parameter
-constexpr int NUM_EPI_WARPS = 12, EPI_SPLIT = NUM_EPI_WARPS / 4;    // 4 lane groups x 3 column shares (first epilogue warp id: a multiple of 4)
+constexpr int XF_WARP0 = 4;       // transform warps: XFW = 4 (ungated) or 8 (gated), template parameter
+constexpr int NUM_EPI_WARPS = 12, EPI_SPLIT = NUM_EPI_WARPS / 4;    // 4 lane groups x 3 column shares
 constexpr int num_threads(int xfw) { return (XF_WARP0 + xfw + NUM_EPI_WARPS) * 32; }   // 640 (<= 102 registers) or 768 (<= 85)
 constexpr int MAX_STAGES = 8;
-constexpr int ATM_XFW = 4;        // transform warps of the A-in-TMEM variant
 constexpr int NMAIN = 3;          // main (per-k-block) accumulators in flight: the MMA issuer may run this far ahead of the epilogue
-constexpr int TMEM_COLS = 512;   // main accumulator x NMAIN + correction accumulator x2, BN (<= 96) fp32 columns each: 480
+constexpr int TMEM_COLS = 512;    // main accumulator x NMAIN + correction accumulator x2, BN (<= 96) fp32 columns each: 480
 constexpr int SLAB_BYTES = 32 * 128;       // epilogue staging slab: 32 rows x 32 fp32, SWIZZLE_128B (1 or 2 per warp)
-constexpr int L2_PREFETCH_DISTANCE = 12;   // k-blocks (16 KB of A each) requested into L2 ahead of the smem ring
+constexpr int L2_PREFETCH_DISTANCE = 6;    // k-blocks (32 KB of A each) requested into L2 ahead of the smem ring
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -90,22 +94,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (spin > 400000u) __trap();
     }
 }
-// Spinning wait (mbarrier.test_wait, no suspend) for the two waits on the per-k-block MMA <-> epilogue round trip.
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-#if defined(ORBIT_NO_SPIN)
-    mbar_wait(bar, parity);
-#else
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > 200000000u) __trap();
-    }
-#endif
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -131,8 +119,8 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ void sts128_u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds32u(uint32_t addr) {
@@ -168,36 +156,28 @@ __device__ __forceinline__ f2_t f2_silu(f2_t x) {
 }
 __device__ __forceinline__ f2_t f2_relu(f2_t x) { float a, b; f2_unpack(x, a, b); return f2_pack(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
 
-// fp32 -> tf32 with round-to-nearest (ties away), identical to cvt.rna.tf32.f32 on finite inputs: add half a
-// tf32 ulp to the magnitude and clear the 13 low mantissa bits. (The cvt instruction is emulated on sm_100 with
-// these two operations plus an inf/NaN guard per element; activations here are finite.)
-__device__ __forceinline__ float rna_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+// (x0, x1) fp32 -> packed fp16 pair hi (x0 in the low half = lower address = smaller k) and the scaled residual pair
+// lo = fp16((x - hi) * 2^11). x - hi is exact in fp32; saturating conversion keeps out-of-range inputs finite.
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    float h0, h1;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
+    const float r0 = (x0 - h0) * 2048.0f, r1 = (x1 - h1) * 2048.0f;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float x0, float x1) {
+    uint32_t hi;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    return hi;
+}
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// A operand from tensor memory (lanes = rows, one tf32 per 32-bit column), B from shared memory
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -213,10 +193,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b format TF32 [7,10)=[10,13)=2, K-major A and B,
+// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b format F16 [7,10)=[10,13)=0, K-major A and B,
 // n_dim [17,23) = N>>3, m_dim [24,29) = M>>4
-__device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {   // no wait: pair with tmem_ld_wait()
@@ -230,14 +210,6 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {   //
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// x * sigmoid(x) with the SFU approximations (ex2.approx, rcp.approx): ~3e-7 relative error, 2 MUFU ops.
-// The accurate expf + IEEE division cost ~30 issue slots per output and made the epilogue the bottleneck.
-#if defined(ORBIT_SILU_ACCURATE)
-__device__ __forceinline__ float silu_fast(float x) { return x / (1.0f + expf(-x)); }
-#else
-__device__ __forceinline__ float silu_fast(float x) { return silu_sfu(x); }
-#endif
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
@@ -264,36 +236,24 @@ __device__ __forceinline__ void trace_stamp(unsigned*, uint32_t, int) {}
 #endif
 constexpr int SS_BYTES = 256;   // per epilogue warp: scale[32] | shift[32] of the slab it is finishing
 
-// Template parameters fix at compile time what round 1 decided per element at run time (ncu: the epilogue ran
-// 1050 and the transform 530 instructions per warp per 128-row step, 2.5-4x the arithmetic actually needed):
-//   SPLIT  3xTF32 (hi/lo) or plain TF32;  GATED / RES  0, 1, or -1 = look at the arguments;  ACT  activation or -1.
-//   XFW    transform warps (4 or 8);  ATM  the transform warps write A's hi/lo parts to TENSOR MEMORY (tcgen05.st) and the
-//          MMAs take A from there: per k-block the shared-memory port then carries TMA 40 KB + one 16 KB read of A +
-//          12 x 3 KB of B instead of 172 KB (the per-role trace put the K-heavy layers on that port), and a ring slot
-//          shrinks from 56 to 40 KB (4 stages instead of 3). Costs the third main accumulator (TMEM is 512 columns).
-//   MRG    merged products: every tcgen05.mma.kind::tf32 costs >= 93 clk whatever its N <= 96 (scripts/mma_rate.cu), so
-//          a_hi.b_hi and a_hi.b_lo are issued as ONE instruction against the stacked operand [B_hi ; B_lo] (N = 2 BN,
-//          the two tiles are adjacent in the ring slot): 8 instead of 12 instructions per k-block. The a_hi.b_lo term
-//          then lives next to the main accumulator and is promoted with it every k-block. Needs 6 BN (+128) TMEM columns.
-template <bool SPLIT, int GATED, int ACT, int RES, int XFW, bool ATM, bool MRG>
+// Template parameters fix at compile time what would otherwise be decided per element at run time:
+//   SPLIT  FP16x3 (hi/lo, fp32-grade) or one plain fp16 product (the `fast` numerics mode, 2^-11 relative per product);
+//   GATED / RES  0, 1, or -1 = look at the arguments;  ACT  activation or -1;  XFW  transform warps (4 or 8).
+template <bool SPLIT, int GATED, int ACT, int RES, int XFW>
 __global__ void __launch_bounds__(num_threads(XFW), 1)
 pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ CUtensorMap map_res, const Params p) {
     constexpr int NUM_XF_WARPS = XFW, EPI_WARP0 = XF_WARP0 + XFW;
-    constexpr int NM = (ATM || MRG) ? 2 : NMAIN;   // main accumulators in flight
-    static_assert(!MRG || SPLIT, "merged products are a 3xTF32 feature");
-    const uint32_t MS = (MRG ? 2u : 1u) * (uint32_t)p.BN;          // TMEM columns per main buffer
-    const uint32_t CORR0 = NM * MS;                                // correction accumulators (x2), then A-in-TMEM (2 x 64)
-    static_assert(!ATM || SPLIT, "A-in-TMEM is the 3xTF32 path");
+    constexpr int NM = NMAIN;
+    const uint32_t MS = (uint32_t)p.BN;                            // TMEM columns per main buffer
+    const uint32_t CORR0 = NM * MS;                                // correction accumulators (x2)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const bool gated = GATED < 0 ? p.gate != nullptr : GATED != 0;
     const bool has_res = RES < 0 ? p.has_residual != 0 : RES != 0;
     const int act = ACT < 0 ? p.act : ACT;
-    const bool transform = SPLIT || gated;
-    const uint32_t a_bytes = A_TILE_BYTES * ((SPLIT && !ATM) ? 2 : 1);
-    const uint32_t stage_bytes = a_bytes + (uint32_t)p.b_tile_bytes * (SPLIT ? 2 : 1);
+    const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.b_tile_bytes * (SPLIT ? 2 : 1);
     const uint32_t staging = smem;                                   // [NUM_EPI_WARPS][slabs_per_warp][32 rows][128 B]
     const uint32_t sstab = staging + (uint32_t)(NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES);   // [NUM_EPI_WARPS][SS_BYTES]
     const uint32_t ring = sstab + NUM_EPI_WARPS * SS_BYTES;          // (3 KB: the ring stays 1024-byte aligned)
@@ -305,8 +265,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto main_full = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 2 + a); };  // [NMAIN] main accumulator of one k-block complete
     auto main_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 5 + a); }; // [NMAIN] ... added into the epilogue's registers
     auto res_bar = [&](uint32_t w) { return bars + 8u * (3 * MAX_STAGES + 8 + w); };    // residual slab landed
-    auto a_empty = [&](uint32_t a) { return bars + 8u * (3 * MAX_STAGES + 8 + NUM_EPI_WARPS + a); };   // [2] MMAs that read A-in-TMEM buffer a retired
-    const uint32_t tmem_base_slot = bars + 8u * (3 * MAX_STAGES + 10 + NUM_EPI_WARPS);
+    const uint32_t tmem_base_slot = bars + 8u * (3 * MAX_STAGES + 8 + NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = ceil_div(p.K, BK);
@@ -316,7 +275,6 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(ready(s), NUM_XF_WARPS); mbar_init(empty(s), 1); }
         for (int a = 0; a < 2; ++a) mbar_init(tmem_empty(a), NUM_EPI_WARPS);
         for (int a = 0; a < NM; ++a) { mbar_init(main_full(a), 1); mbar_init(main_empty(a), NUM_EPI_WARPS); }
-        for (int a = 0; a < 2; ++a) mbar_init(a_empty(a), 1);
         for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
@@ -329,29 +287,26 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = lds32u(tmem_base_slot);
-    // TMEM columns: main accumulators (hi*hi) at {0,1,2}*BN, correction accumulators (hi*lo + lo*hi) at {3,4}*BN.
-    // (Three main buffers, not two: the per-role clock trace showed the MMA issuer idle for ~3 k-blocks at every tile
-    // boundary while the epilogue warps finish the previous tile's activation + store phase.)
+    // TMEM columns: main accumulators (hi*hi) at {0,1,2}*BN, correction accumulators (hi*lo + lo*hi, scaled 2^11) at {3,4}*BN.
     // The tensor core adds into its fp32 accumulator with TRUNCATION (measured: -0.45 ulp per accumulation, a
     // systematic bias that grows with K and compounds over the network's ~33 GEMM layers). So the main accumulator
     // only ever holds ONE k-block (4 MMAs): the epilogue warps add it into fp32 registers with round-to-nearest
-    // every k-block (double-buffered against the MMAs), and the 2^-11-scaled correction terms -- whose truncation
+    // every k-block (triple-buffered against the MMAs), and the 2^-11-scaled correction terms -- whose truncation
     // error is negligible -- accumulate over the whole tile in their own accumulator.
 
-    // Register budget: 640 threads x 96 (ptxas) for every role. Round 1 ran 768 threads x 80 and moved registers
-    // between roles with setmaxnreg; the epilogue then spilled as soon as it grew, and a .inc can only claim what the
-    // CTA's own .dec freed (asking for more deadlocks). Halving the transform warps pays for 96 everywhere.
     if (warp < XF_WARP0) {
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            const uint32_t tx = A_TILE_BYTES + (uint32_t)p.BN * BK * 4 * (SPLIT ? 2 : 1);
+            const uint32_t b_bytes = (uint32_t)p.b_tile_bytes * (SPLIT ? 2 : 1);
             // L2 prefetch cursor: runs L2_PREFETCH_DISTANCE k-blocks ahead of the shared-memory ring, so that HBM
             // latency is covered by requests that cost no shared memory (the ring only has to cover L2 latency).
             int pf_tile = blockIdx.x, pf_kb = 0;
             auto prefetch_next = [&]() {
                 if (pf_tile >= num_tiles) return;
-                tma_prefetch_l2_2d(&map_a, pf_kb * BK, (pf_tile / p.n_tiles) * BM);
+                const int m0 = (pf_tile / p.n_tiles) * BM;
+                tma_prefetch_l2_2d(&map_a, pf_kb * BK, m0);
+                if (pf_kb * BK + 32 < p.K) tma_prefetch_l2_2d(&map_a, pf_kb * BK + 32, m0);
                 if (++pf_kb == num_k) { pf_kb = 0; pf_tile += gridDim.x; }
             };
             for (int i = 0; i < L2_PREFETCH_DISTANCE; ++i) prefetch_next();
@@ -360,13 +315,15 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
                 for (int kb = 0; kb < num_k; ++kb, ++step) {
                     prefetch_next();
+                    const bool two = kb * BK + 32 < p.K;          // the second 32-wide fp32 box holds real columns
                     mbar_wait(empty(s), ph ^ 1);
                     trace_stamp(p.trace, step, 0);
-                    mbar_expect_tx(full(s), tx);
+                    mbar_expect_tx(full(s), (two ? 2u : 1u) * A_BOX_BYTES + b_bytes);
                     const uint32_t st = ring + s * stage_bytes;
                     tma_load_2d(st, &map_a, full(s), kb * BK, m0);
-                    tma_load_2d(st + a_bytes, &map_bhi, full(s), kb * BK, n0);
-                    if (SPLIT) tma_load_2d(st + a_bytes + p.b_tile_bytes, &map_blo, full(s), kb * BK, n0);
+                    if (two) tma_load_2d(st + A_BOX_BYTES, &map_a, full(s), kb * BK + 32, m0);
+                    tma_load_2d(st + A_STAGE_BYTES, &map_bhi, full(s), kb * BK, n0);
+                    if (SPLIT) tma_load_2d(st + A_STAGE_BYTES + p.b_tile_bytes, &map_blo, full(s), kb * BK, n0);
                     trace_stamp(p.trace, step, 1);
                     if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
@@ -375,52 +332,35 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(BM, p.BN);
+            const uint32_t idesc = make_idesc_f16(BM, p.BN);
             uint32_t it = 0, tcount = 0, s = 0, ph = 0, mb = 0, mph = 0;   // it = global k-block counter; mb/mph = main buffer and its parity
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1;
                 if (SPLIT) mbar_wait(tmem_empty(acc), ((tcount >> 1) & 1) ^ 1);
                 const uint32_t d_corr = tmem_base + CORR0 + acc * (uint32_t)p.BN;
-                const uint32_t idesc2 = make_idesc_tf32(BM, 2 * p.BN);
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int ksteps = min(BK / UMMA_K, ceil_div(p.K - kb * BK, UMMA_K));
                     mbar_wait(main_empty(mb), mph ^ 1);
                     trace_stamp(p.trace, it, 4);
-                    if (transform) mbar_wait(ready(s), ph);   // the transform warps saw `full` (A and B landed) before they arrived
-                    else mbar_wait(full(s), ph);
+                    mbar_wait(ready(s), ph);   // the transform warps saw `full` (A and B landed) before they arrived
                     trace_stamp(p.trace, it, 6);
                     tc_fence_after();
                     const uint32_t d_main = tmem_base + mb * MS;
                     const uint32_t st = ring + s * stage_bytes;
                     const uint64_t a_hi = make_desc_sw128(st);
-                    const uint64_t a_lo = make_desc_sw128(st + A_TILE_BYTES);
-                    const uint64_t b_hi = make_desc_sw128(st + a_bytes);
-                    const uint64_t b_lo = make_desc_sw128(st + a_bytes + p.b_tile_bytes);
-                    if (ATM) {
-                        const uint32_t a_t = tmem_base + CORR0 + 2 * (uint32_t)p.BN + (it & 1) * 64;   // hi at +0, lo at +32 columns
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            umma_tf32_ts(d_corr, a_t + 32 + k * UMMA_K, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                            if (MRG) {
-                                umma_tf32_ts(d_main, a_t + k * UMMA_K, b_hi + adv, idesc2, k ? 1u : 0u);   // [main | a_hi.b_lo]
-                            } else {
-                                umma_tf32_ts(d_corr, a_t + k * UMMA_K, b_lo + adv, idesc, 1u);
-                                umma_tf32_ts(d_main, a_t + k * UMMA_K, b_hi + adv, idesc, k ? 1u : 0u);
-                            }
-                        }
-                        umma_commit(a_empty(it & 1));
-                    } else {
+                    const uint64_t a_lo = make_desc_sw128(st + A_BOX_BYTES);
+                    const uint64_t b_hi = make_desc_sw128(st + A_STAGE_BYTES);
+                    const uint64_t b_lo = make_desc_sw128(st + A_STAGE_BYTES + p.b_tile_bytes);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per k step inside the swizzle row
-                        if (SPLIT) umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                        if (MRG) {
-                            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc2, k ? 1u : 0u);                // [main | a_hi.b_lo]
-                        } else {
-                            if (SPLIT) umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-                            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, k ? 1u : 0u);
+                        if (k < ksteps) {
+                            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per k step inside the swizzle row
+                            if (SPLIT) {
+                                umma_f16(d_corr, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                                umma_f16(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                            }
+                            umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, k ? 1u : 0u);
                         }
-                    }
                     }
                     umma_commit(empty(s));           // ring slot reusable once these MMAs retire
                     umma_commit(main_full(mb));      // this k-block's main accumulator is complete (and, after the
@@ -434,111 +374,78 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     } else if (warp < EPI_WARP0) {
         // ================================ A transform ================================
-        // 128 threads; thread t owns the 16-byte chunk (t & 7) of rows (t >> 3) + 16 i: multiply by the squeeze-excite
-        // gate and split into tf32 hi / lo in place (3xTF32). Conflict-free: 8 consecutive threads cover one 128-byte row.
-        if (ATM) {
-            // XFW/4 threads per tile row (= TMEM lane; warps w and w+4 reach the same lane quarter): read 16 or 32 k-values
-            // of the row from the swizzled slot, gate, split, tcgen05.st the hi and lo parts
-            constexpr int HPT = 8 / XFW;                     // 16-column halves per thread: 2 (4 warps) or 1 (8 warps)
-            const int t = threadIdx.x - XF_WARP0 * 32;
-            const int r = t & 127, half0 = (t >> 7) * HPT;
-            const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + CORR0 + 2 * (uint32_t)p.BN;
-            uint32_t s = 0, ph = 0, xstep = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const float* grow = nullptr;
-                if (gated) grow = p.gate + (int64_t)(min((tile / p.n_tiles) * BM + r, p.M - 1) / p.rows_per_frame) * p.K + half0 * 16;
-                for (int kb = 0; kb < num_k; ++kb, ++xstep) {
-                    float4 g[4 * HPT];
-                    if (gated) {                                 // issue the gate loads before blocking on the TMA
+        // 8 threads per tile row; thread q converts k = 8q .. 8q+7 of the k-block: source = two 16-byte chunks of the
+        // fp32 box q/4 (TMA SWIZZLE_128B: chunk ^= row & 7), destination = the 16-byte chunk q of the fp16 hi tile
+        // (which overlays box 0) and of the lo tile (box 1). In place: a row is converted by 8 adjacent lanes of one
+        // warp, all loads of a batch of rows are issued before its stores.
+        constexpr int XR = BM / (NUM_XF_WARPS * 4);      // rows per thread (8 or 4)
+        constexpr int XS = NUM_XF_WARPS * 4;             // row stride between them (16 or 32: multiples of the 8-row swizzle period)
+        constexpr int RB = 2;                            // rows per load/convert/store batch
+        const int t = threadIdx.x - XF_WARP0 * 32;
+        const int q = t & 7;
+        const int rbase = t >> 3;                        // rows rbase + XS*i
+        const int sw = rbase & 7;
+        const uint32_t src_off = (uint32_t)((q >> 2) * A_BOX_BYTES + rbase * 128 + (((2 * (q & 3)) ^ sw) * 16));   // second chunk: ^ 16
+        const uint32_t dst_off = (uint32_t)(rbase * 128 + ((q ^ sw) * 16));
+        uint32_t s = 0, ph = 0, xstep = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const float* grow[XR];
+            if (gated) {
+                const int m0 = (tile / p.n_tiles) * BM;
 #pragma unroll
-                        for (int j = 0; j < 4 * HPT; ++j)
-                            g[j] = kb * BK + half0 * 16 + j * 4 < p.K ? ldg4(grow + kb * BK + j * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
-                    }
-                    const uint32_t ab = xstep & 1;
-                    mbar_wait(full(s), ph);
-                    if (t == 0) trace_stamp(p.trace, xstep, 2);
-                    const uint32_t rowaddr = ring + s * stage_bytes + (uint32_t)r * 128u;
-                    const uint32_t acol = t_row + ab * 64;
-#pragma unroll
-                    for (int hh = 0; hh < HPT; ++hh) {
-                        const int half = half0 + hh;
-                        float hi[16], lo[16];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int c = half * 4 + j;                                  // logical 16-byte chunk of the row
-                            float4 x = lds128(rowaddr + (uint32_t)((c ^ (r & 7)) * 16));
-                            if (gated) { const float4 gg = g[hh * 4 + j]; x.x *= gg.x; x.y *= gg.y; x.z *= gg.z; x.w *= gg.w; }
-                            hi[4 * j + 0] = rna_tf32(x.x); hi[4 * j + 1] = rna_tf32(x.y); hi[4 * j + 2] = rna_tf32(x.z); hi[4 * j + 3] = rna_tf32(x.w);
-                            lo[4 * j + 0] = x.x - hi[4 * j + 0]; lo[4 * j + 1] = x.y - hi[4 * j + 1];
-                            lo[4 * j + 2] = x.z - hi[4 * j + 2]; lo[4 * j + 3] = x.w - hi[4 * j + 3];
-                        }
-                        if (hh == 0) {           // the A buffer is free once the MMAs of two k-blocks ago retired
-                            mbar_wait(a_empty(ab), ((xstep >> 1) & 1) ^ 1);
-                            tc_fence_after();
-                        }
-                        tmem_st16(acol + half * 16, hi);
-                        tmem_st16(acol + 32 + half * 16, lo);
-                    }
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (t == 0) trace_stamp(p.trace, xstep, 3);
-                    if (lane == 0) mbar_arrive(ready(s));
-                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
-                }
+                for (int i = 0; i < XR; ++i)
+                    grow[i] = p.gate + (int64_t)(min(m0 + rbase + XS * i, p.M - 1) / p.rows_per_frame) * p.K + q * 8;
             }
-        } else if (transform) {
-            constexpr int XR = BM / (NUM_XF_WARPS * 4);      // rows per thread (8 or 4)
-            constexpr int XS = NUM_XF_WARPS * 4;             // row stride between them (16 or 32: multiples of the 8-row swizzle period)
-            const int t = threadIdx.x - XF_WARP0 * 32;       // 0..127
-            const int pchunk = t & 7;                        // physical 16-byte chunk inside the 128-byte row
-            const int rbase = t >> 3;                        // rows rbase + XS*i
-            const int jchunk = pchunk ^ (rbase & 7);         // logical chunk (SWIZZLE_128B: chunk ^= row & 7)
-            const uint32_t toff = (uint32_t)(rbase * 128 + pchunk * 16);
-            uint32_t s = 0, ph = 0, xstep = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const float* grow[XR];
-                if (gated) {
-                    const int m0 = (tile / p.n_tiles) * BM;
-#pragma unroll
-                    for (int i = 0; i < XR; ++i)
-                        grow[i] = p.gate + (int64_t)(min(m0 + rbase + XS * i, p.M - 1) / p.rows_per_frame) * p.K + jchunk * 4;
-                }
-                for (int kb = 0; kb < num_k; ++kb) {
-                    float4 g[XR];
-                    const bool g_on = gated && kb * BK + jchunk * 4 < p.K;
-                    if (g_on) {                                  // issue the gate loads before blocking on the TMA
-#pragma unroll
-                        for (int i = 0; i < XR; ++i) g[i] = ldg4(grow[i] + kb * BK);
-                    }
-                    mbar_wait(full(s), ph);
-                    if (t == 0) trace_stamp(p.trace, xstep, 2);
-                    const uint32_t a = ring + s * stage_bytes + toff;
-#if !defined(ORBIT_EXPERIMENT_NO_XF)   // timing experiment only (wrong results): how much of a k-block is the transform's smem traffic?
-                    float4 v[XR];
-#pragma unroll
-                    for (int i = 0; i < XR; ++i) v[i] = lds128(a + i * (XS * 128));
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int krem = p.K - kb * BK;                               // real columns left in this k-block
+                const bool active = q * 8 < ceil_div(min(krem, BK), UMMA_K) * UMMA_K;   // the MMAs read this 8-column group
+                const bool g0_on = gated && q * 8 < krem, g1_on = gated && q * 8 + 4 < krem;
+                float4 g0[XR], g1[XR];
+                if (gated) {                                 // issue the gate loads before blocking on the TMA
 #pragma unroll
                     for (int i = 0; i < XR; ++i) {
-                        if (g_on) { v[i].x *= g[i].x; v[i].y *= g[i].y; v[i].z *= g[i].z; v[i].w *= g[i].w; }
-                        if (SPLIT) {
-                            const float4 h = make_float4(rna_tf32(v[i].x), rna_tf32(v[i].y), rna_tf32(v[i].z), rna_tf32(v[i].w));
-                            sts128(a + i * (XS * 128), h);
-                            // lo = v - hi is exact in fp32 and has <= 13 significant bits; the tensor core reads its top 11
-                            // (at most half an fp32 ulp of v is dropped, with the sign of lo, i.e. unbiased w.r.t. v)
-                            sts128(a + A_TILE_BYTES + i * (XS * 128), make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w));
-                        } else {
-                            sts128(a + i * (XS * 128), v[i]);
+                        g0[i] = g0_on ? ldg4(grow[i] + kb * BK) : make_float4(1.f, 1.f, 1.f, 1.f);
+                        g1[i] = g1_on ? ldg4(grow[i] + kb * BK + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    }
+                }
+                mbar_wait(full(s), ph);
+                if (t == 0) trace_stamp(p.trace, xstep, 2);
+                const uint32_t a = ring + s * stage_bytes;
+                if (active) {
+#pragma unroll
+                    for (int b = 0; b < XR; b += RB) {
+                        float4 v0[RB], v1[RB];
+#pragma unroll
+                        for (int i = 0; i < RB; ++i) {
+                            v0[i] = lds128(a + src_off + (b + i) * (XS * 128));
+                            v1[i] = lds128(a + (src_off ^ 16u) + (b + i) * (XS * 128));
+                        }
+#pragma unroll
+                        for (int i = 0; i < RB; ++i) {
+                            if (gated) {
+                                const float4 ga = g0[b + i], gb = g1[b + i];
+                                v0[i].x *= ga.x; v0[i].y *= ga.y; v0[i].z *= ga.z; v0[i].w *= ga.w;
+                                v1[i].x *= gb.x; v1[i].y *= gb.y; v1[i].z *= gb.z; v1[i].w *= gb.w;
+                            }
+                            if (SPLIT) {
+                                uint32_t h[4], l[4];
+                                split_f16x2(v0[i].x, v0[i].y, h[0], l[0]); split_f16x2(v0[i].z, v0[i].w, h[1], l[1]);
+                                split_f16x2(v1[i].x, v1[i].y, h[2], l[2]); split_f16x2(v1[i].z, v1[i].w, h[3], l[3]);
+                                sts128_u(a + dst_off + (b + i) * (XS * 128), h[0], h[1], h[2], h[3]);
+                                sts128_u(a + A_BOX_BYTES + dst_off + (b + i) * (XS * 128), l[0], l[1], l[2], l[3]);
+                            } else {
+                                sts128_u(a + dst_off + (b + i) * (XS * 128), pack_f16x2(v0[i].x, v0[i].y), pack_f16x2(v0[i].z, v0[i].w),
+                                         pack_f16x2(v1[i].x, v1[i].y), pack_f16x2(v1[i].z, v1[i].w));
+                            }
                         }
                     }
-#endif
-                    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
-                    __syncwarp();
-                    if (t == 0) trace_stamp(p.trace, xstep, 3);
-                    if (lane == 0) mbar_arrive(ready(s));
-                    ++xstep;
-                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
+                fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (t == 0) trace_stamp(p.trace, xstep, 3);
+                if (lane == 0) mbar_arrive(ready(s));
+                ++xstep;
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else {
@@ -604,7 +511,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     // smaller magnitudes. Adding kappa * ulp(u) * sign(u) back removes the systematic part. For the
                     // default kappa = 1 that is "the next float away from zero", i.e. +1 on the bit pattern: one
                     // 64-bit integer add per column pair (no carry can cross the halves: the low word is never
-                    // 0xffffffff) instead of round 1's mask + FMA per element.
+                    // 0xffffffff) instead of a mask + FMA per element.
                     if (p.debias == 1.0f) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
@@ -617,13 +524,6 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             const f2_t pow2 = up & 0xff800000ff800000ull;            // sign * 2^exponent of each half
                             sum[j] = f2_add(sum[j], f2_fma(pow2, debias2, up));
                         }
-                    }
-                    if (MRG) {          // the a_hi.b_lo term of this k-block sits BN columns further
-                        tmem_ld16_issue(col + p.BN, u);
-                        if (wide) tmem_ld16_issue(col + p.BN + 16, u + 16);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) sum[j] = f2_add(sum[j], f2_pack(u[2 * j], u[2 * j + 1]));
                     }
                 }
                 tc_fence_before();
@@ -643,8 +543,9 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         for (int j = 16; j < 32; ++j) u[j] = 0.f;
                     }
                     tmem_ld_wait();
+                    const f2_t inv = f2_pack(4.8828125e-4f, 4.8828125e-4f);      // 2^-11: the lo parts were scaled by 2^11
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[j] = f2_add(sum[j], f2_pack(u[2 * j], u[2 * j + 1]));
+                    for (int j = 0; j < 16; ++j) sum[j] = f2_fma(f2_pack(u[2 * j], u[2 * j + 1]), inv, sum[j]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -721,29 +622,24 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, 32 cols] (128 bytes), SWIZZLE_128B, zero OOB fill
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows) {
+// 2-D row-major [rows, cols] tensor with a row pitch of `pitch` elements, box = [box_rows, 128 bytes], SWIZZLE_128B, zero OOB fill
+static int make_map(CUtensorMap* map, const void* base, bool f16, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return ORBIT_ERR_UNSUPPORTED;
+    const int esize = f16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * esize};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? ORBIT_OK : ORBIT_ERR_UNSUPPORTED;
 }
 
 }  // namespace tc
 
 static float g_debias_kappa = 1.0f;   // one ulp of every promoted k-block partial (4 truncating MMAs: 0.5*(1+.75+.5+.25) ulp expected loss)
-static bool g_merge_enabled = false;   // measured: no gain (more n-tiles repeat the transform, two main buffers instead of three)
-void set_tcgen05_merge(bool on) { g_merge_enabled = on; }
-bool get_tcgen05_merge() { return g_merge_enabled; }
-static bool g_atm_enabled = true;
-void set_tcgen05_atm(bool on) { g_atm_enabled = on; }
-bool get_tcgen05_atm() { return g_atm_enabled; }
 static unsigned* g_gemm_trace = nullptr;
 void set_tcgen05_trace(unsigned* dev_buffer) { g_gemm_trace = dev_buffer; }
 void set_tcgen05_debias(float kappa) { g_debias_kappa = kappa; }
@@ -762,37 +658,33 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     p.trace = g_gemm_trace;
     // n-tiles of at most 96 columns (3 store slabs = one per epilogue warp of a lane group); with several n-tiles
     // BN must be a multiple of the 32-column store slab
-    // A-in-TMEM for the K-heavy gated 3xTF32 layers (>= 8 k-blocks per tile: the MBConv projections of the 14x14 / 7x7 stages;
-    // measured slower on the ungated conv_head, which prefers the third main accumulator). Merged products for every gated
-    // projection: TMEM then holds 6 BN (+128) columns, so BN <= 80 (64 with A in TMEM).
-    const bool mrg = passes == 3 && gate != nullptr && act == 0 && g_merge_enabled;
-    bool atm = passes == 3 && K >= 8 * BK && gate != nullptr && act == 0 && g_atm_enabled;
-    if (mrg && atm && N > 64 && N <= 80) atm = false;             // one 80-column tile beats two 64-column tiles
-    const int bn_max = mrg ? (atm ? 64 : 80) : 96;
+    const int bn_max = 96;
     p.n_tiles = ceil_div(N, bn_max);
     p.BN = p.n_tiles > 1 ? ceil_div(ceil_div(N, p.n_tiles), 32) * 32 : ceil_div(N, 16) * 16;
     p.m_tiles = ceil_div(M, BM);
-    p.b_tile_bytes = p.BN * BK * 4;
-    const int stage_bytes = atm ? A_TILE_BYTES + 2 * p.b_tile_bytes : (A_TILE_BYTES + p.b_tile_bytes) * (passes == 3 ? 2 : 1);
-    const int bar_bytes = (3 * MAX_STAGES + 10 + NUM_EPI_WARPS) * 8 + 16;
+    p.b_tile_bytes = p.BN * BK * 2;
+    const int stage_bytes = A_STAGE_BYTES + p.b_tile_bytes * (passes == 3 ? 2 : 1);
+    const int bar_bytes = (3 * MAX_STAGES + 8 + NUM_EPI_WARPS) * 8 + 16;
     const int budget = 227 * 1024 - 1024 /*alignment slack*/ - bar_bytes - NUM_EPI_WARPS * SS_BYTES;
-    // double-buffered epilogue staging when that still leaves a 4-deep operand ring
-    p.slabs_per_warp = (budget - 2 * NUM_EPI_WARPS * SLAB_BYTES) / stage_bytes >= 4 ? 2 : 1;
+    // double-buffered epilogue staging when that still leaves a 3-deep operand ring
+    p.slabs_per_warp = (budget - 2 * NUM_EPI_WARPS * SLAB_BYTES) / stage_bytes >= 3 ? 2 : 1;
     const int staging_bytes = NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES;
     p.stages = std::min(MAX_STAGES, (budget - staging_bytes) / stage_bytes);
     if (p.stages < 2) return ORBIT_ERR_UNSUPPORTED;
     const size_t smem = (size_t)staging_bytes + NUM_EPI_WARPS * SS_BYTES + (size_t)p.stages * stage_bytes + bar_bytes + 1024;
 
+    const int Kp = (K + 7) / 8 * 8;                    // row pitch of the split weights (launch_weight_split)
+    const __half* w16 = reinterpret_cast<const __half*>(w_split);
     CUtensorMap map_a, map_bhi, map_blo, map_out, map_res;
-    int rc = make_map(&map_a, A, M, K, BM);
+    int rc = make_map(&map_a, A, false, M, K, K, BM);
     if (rc) return rc;
-    rc = make_map(&map_bhi, w_split, N, K, p.BN);
+    rc = make_map(&map_bhi, w16, true, N, K, Kp, p.BN);
     if (rc) return rc;
-    rc = make_map(&map_blo, w_split + (int64_t)N * K, N, K, p.BN);
+    rc = make_map(&map_blo, w16 + (int64_t)N * Kp, true, N, K, Kp, p.BN);
     if (rc) return rc;
-    rc = make_map(&map_out, out, M, N, 32);
+    rc = make_map(&map_out, out, false, M, N, N, 32);
     if (rc) return rc;
-    rc = make_map(&map_res, residual ? residual : out, M, N, 32);
+    rc = make_map(&map_res, residual ? residual : out, false, M, N, N, 32);
     if (rc) return rc;
 
     // specialisations for the shapes the backbones use; anything else runs the run-time-dispatch instance
@@ -801,26 +693,19 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     int xfw = 4;
     const bool g = gate != nullptr, r = residual != nullptr;
     if (passes == 3) {
-        if (mrg && atm && !r) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, true, true>;                    // K-heavy MBConv project: A in TMEM, merged
-        else if (mrg && atm && r) fn = pw_tcgen05_kernel<true, 1, 0, 1, 4, true, true>;                // ... + skip
-        else if (mrg && !r && K <= BK) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, false, true>;          // MBConv project, one k-block per tile, merged
-        else if (mrg && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8, false, true>; xfw = 8; }        // MBConv project, merged
-        else if (mrg && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8, false, true>; xfw = 8; }         // ... + skip
-        else if (atm && !r) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, true, false>;                     // (A/B) A in TMEM, three instructions per k-step
-        else if (atm && r) fn = pw_tcgen05_kernel<true, 1, 0, 1, 4, true, false>;
-        else if (g && act == 0 && !r && K <= BK) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, false, false>;
-        else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8, false, false>; xfw = 8; }
-        else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8, false, false>; xfw = 8; }
-        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, false, false>;    // MBConv expand / conv_head (SiLU)
-        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4, false, false>;    // Linear / downsample
-        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4, false, false>;     // Linear + residual (ViT), EdgeResidual project
-        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4, false, false>;    // conv + ReLU
-        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0, 4, false, false>;    // Linear + GELU
-        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4, false, false>;   // BasicBlock: relu(bn(conv) + identity)
-        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1, 4, false, false>;     // ConvBnAct + skip (EfficientNet-V2)
-        else fn = pw_tcgen05_kernel<true, -1, -1, -1, 4, false, false>;
+        if (g && act == 0 && !r && K <= 32) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4>;                // first MBConv project
+        else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8>; xfw = 8; }          // MBConv project
+        else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8>; xfw = 8; }           // ... + skip
+        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4>;    // MBConv expand / conv_head (SiLU)
+        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4>;    // Linear / downsample
+        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4>;     // Linear + residual (ViT), EdgeResidual project
+        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4>;    // conv + ReLU
+        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0, 4>;    // Linear + GELU
+        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4>;   // BasicBlock: relu(bn(conv) + identity)
+        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1, 4>;     // ConvBnAct + skip (EfficientNet-V2)
+        else fn = pw_tcgen05_kernel<true, -1, -1, -1, 4>;
     } else {
-        fn = pw_tcgen05_kernel<false, -1, -1, -1, 4, false, false>;
+        fn = pw_tcgen05_kernel<false, -1, -1, -1, 4>;
     }
     static int num_sms = 0;
     if (!num_sms) {

@@ -179,7 +179,7 @@ extern "C" int orbit_mahalanobis_configure(const float* clip_feats, const int32_
         rows_mean_kernel<<<ceil_div(D, 256), 256, 0, st>>>(clip_feats, rows, n, D, mean_out);
         center_transpose_kernel<<<(unsigned)ceil_div64((int64_t)D * n_pad, 256), 256, 0, st>>>(clip_feats, rows, n, n_pad, D, mean_out, tmat);
         fill_kernel<<<ceil_div(D, 256), 256, 0, st>>>(scale, D, 1.0f / (float)(n - 1));
-        int r = launch_tf32_split(tmat, (int64_t)D * n_pad, tsplit, st);
+        int r = launch_weight_split(tmat, D, n_pad, tsplit, st);
         if (r) return r;
         return launch_pointwise_tcgen05(tmat, tsplit, scale, shift, nullptr, nullptr, cov_out, D, D, n_pad, D, ACT_NONE, 3, st);
     };
@@ -252,7 +252,7 @@ extern "C" int orbit_mahalanobis_predict(const float* clip_feats, int num_clips,
     fill_kernel<<<ceil_div(D, 256), 256, 0, st>>>(shift, D, 0.f);
     for (int c = 0; c < num_classes; ++c) {
         diff_rows_kernel<<<(unsigned)ceil_div64((int64_t)Nq * D, 256), 256, 0, st>>>(means + (int64_t)c * D, clip_feats, Nq, D, diff);
-        int rc = launch_tf32_split(precisions + (int64_t)c * D * D, (int64_t)D * D, psplit, st);
+        int rc = launch_weight_split(precisions + (int64_t)c * D * D, D, D, psplit, st);
         if (rc) return rc;
         // tmp = diff . P_c^T  (= diff . P_c, P_c symmetric)
         rc = launch_pointwise_tcgen05(diff, psplit, scale, shift, nullptr, nullptr, tmp, Nq, D, D, Nq, ACT_NONE, 3, st);

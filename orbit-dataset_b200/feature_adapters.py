@@ -97,6 +97,8 @@ class FilmParameterGenerator(nn.Module):
         self.film_parameter_sizes = dict(film_parameter_sizes)
         self.hidden = hidden_size
         self.l2_term = 0.0
+        self._generation = 0
+        self._initial_key = None
         # flat parameter blob: every tensor 16-byte aligned; nn.Parameters are views (as in FeatureExtractor)
         layout, off = [], 0
 
@@ -177,10 +179,13 @@ class FilmParameterGenerator(nn.Module):
         dev = x.device
         z = x.reshape(-1).contiguous().float()
         assert z.numel() == self.hidden
-        # gamma0 / beta0 snapshot lives in the blob next to the generator weights
-        for i, name in enumerate(self.film_parameter_names):
-            row = self._rows[i]
-            self._blob[row['init']:row['init'] + row['size']].copy_(self.initial_film_parameters[name])
+        # gamma0 / beta0 snapshot lives in the blob next to the generator weights (re-copied only when the dict changed)
+        init_key = (self._blob.data_ptr(), tuple((id(v), v._version) for v in self.initial_film_parameters.values()))
+        if init_key != self._initial_key:
+            for i, name in enumerate(self.film_parameter_names):
+                row = self._rows[i]
+                self._blob[row['init']:row['init'] + row['size']].copy_(self.initial_film_parameters[name])
+            self._initial_key = init_key
         if self._table_dev is None:
             tab = np.zeros(len(self._rows), dtype=_TABLE_DTYPE)
             for i, (row, name) in enumerate(zip(self._rows, self.film_parameter_names)):
@@ -192,6 +197,8 @@ class FilmParameterGenerator(nn.Module):
         L.check(lib.orbit_film_generate(L.ptr(self._blob), L.ptr(self._table_dev), len(self._rows), self._max_size, L.ptr(z),
                                         self.hidden, L.ptr(film), L.stream_ptr(dev)), "orbit_film_generate")
         L.count_launches(1)
+        self._generation += 1
+        film._orbit_generation = (id(self), self._generation)   # the kernel wrote through a raw pointer: no version bump
         self._film_blob = film
         # l2 term of the regularisers (feature_adapters.py:76): depends on parameters only, not on the episode
         regs = [p for n, p in self.named_parameters() if n.startswith('regularizers.')]

@@ -63,6 +63,7 @@ class FeatureExtractor(nn.Module):
         self._derived = None
         self._workspace = None
         self._prepared_key = None
+        self._versioned = None
         self._build_tree()
         self.reset_parameters(seed)
 
@@ -104,7 +105,7 @@ class FeatureExtractor(nn.Module):
                 mod._buffers['num_batches_tracked'] = fn(mod._buffers['num_batches_tracked'])
         self._blob = new_blob
         self._rebind()
-        self._derived = self._workspace = self._prepared_key = None
+        self._derived = self._workspace = self._prepared_key = self._versioned = None
         return self
 
     @torch.no_grad()
@@ -222,7 +223,11 @@ class FeatureExtractor(nn.Module):
         if self._derived is None:
             self._derived = torch.empty(lib.orbit_engine_derived_floats(self._engine), dtype=torch.float32,
                                         device=self._blob.device)
-        key = (self._blob._version, None if film_blob is None else (film_blob.data_ptr(), film_blob._version))
+        # Parameters are views of the blob bound with `param.data = view`, which keeps each parameter's OWN version
+        # counter: load_state_dict / param.copy_ / optimiser steps bump those, not the blob's. The FiLM blob is written by
+        # a kernel through a raw pointer (no version bump at all): the generator stamps a generation id on it.
+        key = (self._state_version(), None if film_blob is None else
+               (film_blob.data_ptr(), film_blob._version, getattr(film_blob, '_orbit_generation', None)))
         if key == self._prepared_key:
             return
         if film_blob is not None:
@@ -232,6 +237,19 @@ class FeatureExtractor(nn.Module):
                                          L.stream_ptr(self._blob.device)), "orbit_engine_prepare")
         L.count_launches(2 + len(self._table) // 4)
         self._prepared_key = key
+
+    def _state_version(self):
+        if self._versioned is None:
+            self._versioned = [t for t in list(self.parameters()) + list(self.buffers())] + [self._blob]
+        return sum(t._version for t in self._versioned)
+
+    def mark_dirty(self):
+        """Call after writing parameters through an alias autograd cannot see (``param.data.copy_``, raw pointers)."""
+        self._prepared_key = None
+
+    def load_state_dict(self, *args, **kwargs):
+        self._prepared_key = None
+        return super().load_state_dict(*args, **kwargs)
 
     def forward(self, frames: torch.Tensor, film_blob=None) -> torch.Tensor:
         lib = L.load()

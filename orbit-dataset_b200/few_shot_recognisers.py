@@ -10,14 +10,12 @@ predict, per-task state and reset) follows the reference; every tensor operation
 hand-written CUDA kernel reached through the C ABI.  There is no CPU fallback: tensors that are not
 on an sm_100 device raise ``OrbitError``.
 """
-import time
-
 import numpy as np
 import torch
 import torch.nn as nn
 
 from . import lib as L
-from .classifier_heads import LinearClassifier, MeanPooler, PrototypicalClassifier
+from .classifier_heads import ClassIndex, LinearClassifier, MeanPooler, PrototypicalClassifier
 from .data_utils import get_batch_indices
 from .feature_extractors import (create_feature_extractor, get_film_parameter_sizes, get_film_parameters,
                                  unfreeze_film)
@@ -45,15 +43,15 @@ class _HostStager:
         self.calls = 0
         self.bytes_copied = 0
         self.ramp = (96, 224, 480)
-        self.last_call = (-1.0, 0)              # (host time, frames) of the previous call
+        self.last_done = None                   # completion event of the previous call's last backbone pass
+        self.last_buffer = None                 # (index, device view) of the most recent call's whole-call buffer
 
-    def _plan(self, total):
-        # The ramp exists to start the backbone early on a call whose data is still on the host. A call issued right
-        # behind a larger one (predict() after personalise(): the host enqueues a pass in ~0.2 ms, the device needs
-        # ~18 us per frame, the copy engine ~11 us) finds its data already on the device: no ramp, full-size passes.
-        now = time.perf_counter()
-        behind = now - self.last_call[0] < 0.010 and self.last_call[1] >= total
-        self.last_call = (now, total)
+    def _plan(self, total, behind):
+        # The ramp exists to start the backbone early on a call whose data is still on the host. A call issued while the
+        # device is still working through the previous call's passes (predict() right after personalise(): the host
+        # enqueues a pass in ~0.2 ms, the device needs ~18 us per frame, the copy engine ~11 us) finds its data
+        # already on the device when its first kernel starts: no ramp, full-size passes. `behind` comes from the
+        # previous call's completion EVENT (queued-work state), not from a timer, so the plan is reproducible.
         ramp = () if behind else self.ramp
         sizes, pos, k = [], 0, 0
         while pos < total:
@@ -62,9 +60,14 @@ class _HostStager:
             sizes.append(n)
             pos += n
             k += 1
-        if len(sizes) > 1 and sizes[-1] < 64:   # no tiny tail pass
-            tail = sizes.pop()
-            sizes[-1] += tail
+        if len(sizes) > 1 and sizes[-1] < 64:   # no tiny tail pass: fold it into the previous one, or rebalance the
+            tail = sizes.pop()                  # two when the engine would split the merged pass again
+            if sizes[-1] + tail <= self.chunk_frames:
+                sizes[-1] += tail
+            else:
+                both = sizes.pop() + tail
+                first = min((both // 2 + 7) // 8 * 8, both - 1)
+                sizes += [first, both - first]
         return sizes
 
     def stream(self, frames_cpu):
@@ -87,7 +90,9 @@ class _HostStager:
         elif self.done[i] is not None:
             self.copy_stream.wait_event(self.done[i])
         dst = self.dev[i][:need].view(frames_cpu.shape)
-        sizes = self._plan(total)
+        self.last_buffer = (i, dst)
+        behind = self.last_done is not None and not self.last_done.query()
+        sizes = self._plan(total, behind)
         pinned_src = frames_cpu.is_pinned()
         events, pos, j = [], 0, 0
         for n in sizes:
@@ -121,8 +126,14 @@ class _HostStager:
             compute.wait_event(ev)
             yield dst[pos:pos + n]
             pos += n
+        self.release(i)
+
+    def release(self, i):
+        """Marks buffer ``i`` as consumed up to this point of the compute stream (call again after enqueuing more work
+        that reads the buffer, e.g. a second traversal of the same staged clips)."""
         self.done[i] = torch.cuda.Event()
-        self.done[i].record(compute)
+        self.done[i].record(torch.cuda.current_stream(self.device))
+        self.last_done = self.done[i]
 
 
 class FewShotRecogniser(nn.Module):
@@ -158,6 +169,9 @@ class FewShotRecogniser(nn.Module):
             raise ValueError(f"Classifier {classifier} not valid.")
 
         self.frame_pooler = MeanPooler(T=self.clip_length)
+        # 'reference': OpsCounter totals equal the reference's (which re-runs the frozen extractor in every FineTuner
+        # grad step, few_shot_recognisers.py:231-246); 'actual': the MACs this library really executes
+        self.mac_accounting = 'reference'
         self.device = torch.device('cpu')
         self._stager = None
         self.stage_copy_frames = 160      # frames per async H2D copy for CPU-resident clips (97 MB at 224 px)
@@ -178,16 +192,19 @@ class FewShotRecogniser(nn.Module):
     def _film_blob(self, film_dict):
         return None  # overridden by SingleStepFewShotRecogniser
 
+    def _host_stager(self):
+        chunk = self.feature_extractor.get_option('chunk_frames')
+        if self._stager is None or self._stager.device != self.device or self._stager.chunk_frames != chunk:
+            self._stager = _HostStager(self.device, chunk)
+        self._stager.copy_frames, self._stager.ramp = self.stage_copy_frames, tuple(self.stage_ramp)
+        return self._stager
+
     def _run_extractor(self, frames, film_dict):
         """frames [F,3,H,W] on CPU or device -> [F, D] on device."""
         blob = self._film_blob(film_dict) if film_dict else None
         if frames.is_cuda:
             return self.feature_extractor(frames, blob)
-        chunk = self.feature_extractor.get_option('chunk_frames')
-        if self._stager is None or self._stager.device != self.device or self._stager.chunk_frames != chunk:
-            self._stager = _HostStager(self.device, chunk)
-        self._stager.copy_frames, self._stager.ramp = self.stage_copy_frames, tuple(self.stage_ramp)
-        outs = [self.feature_extractor(dev_frames, blob) for dev_frames in self._stager.stream(frames.float())]
+        outs = [self.feature_extractor(dev_frames, blob) for dev_frames in self._host_stager().stream(frames.float())]
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     def _get_features(self, clips, film_dict={}, ops_counter=None):
@@ -259,6 +276,14 @@ class FewShotRecogniser(nn.Module):
         if self.learn_extractor and not self.test_mode:
             raise NotImplementedError("training the extractor (train-mode BatchNorm + backward) is outside the "
                                       "B200 hot path implemented so far")
+        if self.adapt_features and not getattr(self, 'test_mode', True) and torch.is_grad_enabled() \
+                and isinstance(self, SingleStepFewShotRecogniser):
+            # CNAPs-style meta-training (single-step-learner.py:196-210): the loss must back-propagate through the
+            # frozen extractor into the FiLM generator / set encoder. The logits of this library carry no autograd graph,
+            # so refuse here instead of letting loss.backward() die later with torch's generic "does not require grad".
+            raise NotImplementedError("meta-training the FiLM generator / set encoder needs backbone backward kernels "
+                                      "(SURVEY.md 8f-3); call set_test_mode(True) and run under torch.no_grad() for "
+                                      "validation / testing")
 
 
 class SingleStepFewShotRecogniser(FewShotRecogniser):
@@ -282,6 +307,7 @@ class SingleStepFewShotRecogniser(FewShotRecogniser):
             self.set_encoder = NullSetEncoder()
             self.film_generator = NullGenerator()
         self.film_dict = None
+        self._staged_context = None
         self.test_mode = False
 
     def _reset(self):
@@ -298,13 +324,26 @@ class SingleStepFewShotRecogniser(FewShotRecogniser):
     def personalise(self, context_clips, context_labels, ops_counter=None):
         """few_shot_recognisers.py:313-326."""
         self._set_batch_norm_state()
+        self._require_device()
+        # the task's only host sync (label values -> class count), taken before anything is enqueued: see ClassIndex
+        class_index = ClassIndex(context_labels, self.device)
+        self._staged_context = None
         task_embedding = self._get_task_embedding_in_batches(context_clips, ops_counter)
         self.film_dict = self._generate_film_params(task_embedding, ops_counter)
-        context_features = self._get_features_in_batches(context_clips, self.film_dict, ops_counter)
+        if self._staged_context is not None:
+            # CPU-resident clips the set encoder has already pulled onto the device: the extractor reads that copy
+            # (the reference copies the support set H2D twice, few_shot_recognisers.py:322-324 / SURVEY Appendix B-6)
+            buffer_index, context_dev = self._staged_context
+            context_features = self._get_features_in_batches(context_dev, self.film_dict, ops_counter)
+            self._stager.release(buffer_index)
+            self._staged_context = None
+        else:
+            context_features = self._get_features_in_batches(context_clips, self.film_dict, ops_counter)
         # pooling (poolers.py:13-16) is fused into the head's configure kernel; its MACs are still the reference's
         if ops_counter:
             ops_counter.add_macs(context_features.size(0) * context_features.size(1))
-        self.classifier.configure(context_features, context_labels, ops_counter, clip_length=self.clip_length)
+        self.classifier.configure(context_features, context_labels, ops_counter, clip_length=self.clip_length,
+                                  class_index=class_index)
 
     def personalise_with_lite(self, context_clips, context_labels):
         """LITE (few_shot_recognisers.py:328-343) back-propagates through the extractor; the backward
@@ -319,10 +358,23 @@ class SingleStepFewShotRecogniser(FewShotRecogniser):
         self._require_device()
         reps = []
         num_clips = len(context_clips)
+        if not context_clips.is_cuda and num_clips:
+            # host clips: ONE staged H2D of the whole support set (pinned or pageable source, side stream); the set
+            # encoder consumes it pass by pass and personalise() hands the same device copy to the extractor. The
+            # per-frame embeddings do not depend on how frames are grouped into passes, so batch_size only matters
+            # for the MAC accounting below.
+            stager = self._host_stager()
+            frames = context_clips.flatten(end_dim=1) if context_clips.dim() == 5 else context_clips
+            reps = [self.set_encoder(dev_frames) for dev_frames in stager.stream(frames.float())]
+            buffer_index, staged = stager.last_buffer
+            self._staged_context = (buffer_index, staged.view(context_clips.shape))
+            if ops_counter:
+                ops_counter.compute_macs(self.set_encoder, context_clips)
+            return self.set_encoder.aggregate(reps, aggregation=aggregation)
         num_batches = int(np.ceil(float(num_clips) / float(self.batch_size)))
         for batch in range(num_batches):
             batch_start_index, batch_end_index = get_batch_indices(batch, num_clips, self.batch_size)
-            batch_clips = context_clips[batch_start_index:batch_end_index].to(self.device, non_blocking=True)
+            batch_clips = context_clips[batch_start_index:batch_end_index]
             reps.append(self.set_encoder(batch_clips))
             if ops_counter:
                 ops_counter.compute_macs(self.set_encoder, batch_clips)
@@ -384,10 +436,16 @@ class MultiStepFewShotRecogniser(FewShotRecogniser):
                                       "(SURVEY.md 8f-3)")
         num_classes = len(torch.unique(context_labels))
         self.init_classifier(num_classes)
+        macs_before = ops_counter.get_task_macs() if ops_counter else 0
         features = self._get_features_in_batches(context_clips, ops_counter=ops_counter)
         features = self._pool_features(features, ops_counter=ops_counter)
-        if ops_counter:   # the head's forward inside the loop (classifier_heads.py:72-73), once per clip per grad step;
-            # the extractor/pool MACs above are counted once because the frozen features are computed once
+        if ops_counter:
+            # The frozen features are computed ONCE here; the reference recomputes extractor + pooling in every grad
+            # step (few_shot_recognisers.py:231-246). "MACs to personalise" is a reported ORBIT metric, so by default
+            # the counter gets the reference's figure (x num_grad_steps); mac_accounting = 'actual' keeps what ran.
+            if self.mac_accounting == 'reference' and num_grad_steps > 1:
+                ops_counter.add_macs((num_grad_steps - 1) * (ops_counter.get_task_macs() - macs_before))
+            # the head's forward inside the loop (classifier_heads.py:72-73), once per clip per grad step
             ops_counter.add_macs(num_grad_steps * num_classes * features.size(0) * features.size(1))
         finetune_linear_head(self.classifier, features, context_labels, self.batch_size, num_grad_steps,
                              learning_rate, optimizer, dict(learning_args), self.logit_scale)

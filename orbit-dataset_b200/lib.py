@@ -59,6 +59,31 @@ _SIGNATURES = {
 }
 
 _lib = None
+_call_device = [None]   # device of the stream handed to the NEXT C call (set by stream_ptr, consumed by the call wrapper)
+
+
+def _guarded(fn):
+    """The kernels, cuTensorMapEncode and cudaFuncSetAttribute run in the CURRENT CUDA context, but the reference learners
+    pick `cuda:N` through `--gpu N` without ever calling torch.cuda.set_device. Every C call takes the stream of the
+    tensors' device (stream_ptr is evaluated as its last argument); the wrapper makes that device current for the call."""
+    def call(*args):
+        dev, _call_device[0] = _call_device[0], None
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args)
+        with torch.cuda.device(dev):
+            return fn(*args)
+    call.__name__ = getattr(fn, '__name__', 'orbit_call')
+    return call
+
+
+class _Lib:
+    """Attribute access returns the device-guarded ctypes functions."""
+
+    def __init__(self, cdll, names):
+        self._cdll = cdll
+        for name in names:
+            fn = getattr(cdll, name)
+            setattr(self, name, _guarded(fn) if _SIGNATURES[name][1] and _SIGNATURES[name][1][-1] is _p else fn)
 
 
 class OrbitError(RuntimeError):
@@ -78,7 +103,7 @@ def load():
             fn.restype, fn.argtypes = res, args
         if lib.orbit_abi_version() != 1:
             raise OrbitError("liborbit_b200.so ABI version mismatch; rebuild")
-        _lib = lib
+        _lib = _Lib(lib, list(_SIGNATURES))
     return _lib
 
 
@@ -94,6 +119,10 @@ def require_cuda(t: torch.Tensor, name: str):
 
 
 def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on ``device``; also tells the call wrapper which device to make current."""
+    if device is not None:
+        device = torch.device(device)
+        _call_device[0] = device if device.type == 'cuda' else None
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

@@ -6,7 +6,7 @@ import torch
 from orbit_b200 import lib as L
 B, hw, K, N, act, gated, resid = [int(a) for a in sys.argv[1:8]]
 lib = L.load(); dev = torch.device('cuda:0')
-if os.environ.get('ATM'): assert lib.orbit_set_global_option(b'tc_a_in_tmem', int(os.environ['ATM'])) == 0
+
 M = B * hw
 A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev) * K ** -0.5
 sc = torch.ones(N, device=dev); sh = torch.zeros(N, device=dev)
@@ -22,7 +22,7 @@ lib.orbit_debug_set_gemm_trace(L.ptr(trace)); run(); torch.cuda.synchronize(); l
 t = trace.cpu().numpy().astype('uint32').astype('int64')
 t0 = int(t[0, 0])
 names = ['P:empty_ok', 'P:tma_issued', 'X:full_ok', 'X:ready', 'M:main_empty_ok', '(unused)', 'M:ready_ok', 'M:committed', 'E:main_full_ok', 'E:arrived']
-num_k = (K + 31) // 32
+num_k = (K + 63) // 64
 print(f"M={M} K={K} N={N} num_k={num_k}; clocks relative to the first producer stamp; one row per k-block step of CTA 0")
 print('step ' + ' '.join(f'{n:>15s}' for n in names))
 for s in range(32, 32 + 3 * num_k + 4):

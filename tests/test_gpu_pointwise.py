@@ -1,6 +1,6 @@
 """GPU parity of the pointwise-conv GEMM kernels (C ABI orbit_pointwise_conv) against an fp64 reference:
-fp32 FFMA tiles (mode 0), tcgen05 3xTF32 (mode 1, must be fp32-grade) and tcgen05 1xTF32 (mode 2).
-Shapes are the EfficientNet-B0 layer shapes (expand / project / head) incl. ragged M, K<32, N not a multiple of 16."""
+fp32 FFMA tiles (mode 0), tcgen05 FP16x3 (mode 1, must be fp32-grade) and one plain fp16 product (mode 2, the `fast` mode).
+Shapes are the EfficientNet-B0 layer shapes (expand / project / head) incl. ragged M, K<64, K % 8 == 4, N not a multiple of 16."""
 import pytest
 import torch
 
@@ -17,6 +17,10 @@ SHAPES = [  # (M, N, K, rows_per_frame, act, gated, residual)
     (9 * 7 * 7, 1280, 320, 7 * 7, 1, False, False),        # conv_head
     (130, 16, 32, 65, 0, True, False),                     # blocks.0.0 project, tiny
     (1, 1280, 320, 1, 2, False, False),                    # single row, ReLU
+    (300, 64, 40, 100, 1, False, False),                   # K = 40: third k-step half empty
+    (300, 48, 36, 100, 0, True, True),                     # K % 8 == 4: padded weight pitch
+    (517, 40, 12, 517, 0, False, False),                   # K < 16
+    (1000, 200, 132, 250, 2, False, False),                # K = 2 k-blocks + 4
 ]
 
 
@@ -59,11 +63,11 @@ def test_pointwise_modes(cuda_device, shape):
     for mode in (0, 1, 2):
         out = _run(mode, A, W, scale, shift, gate, res, rpf, act)
         errs[mode] = (out.double() - ref).abs().max().item()
-    print(f"M={M} N={N} K={K}: max|err| ffma={errs[0]:.2e} 3xtf32={errs[1]:.2e} 1xtf32={errs[2]:.2e}")
+    print(f"M={M} N={N} K={K}: max|err| ffma={errs[0]:.2e} fp16x3={errs[1]:.2e} fp16x1={errs[2]:.2e}")
     mag = max(1.0, ref.abs().max().item())
     assert errs[0] <= 1e-5 * mag
-    assert errs[1] <= 1e-5 * mag          # 3xTF32 must be fp32-grade
-    assert errs[2] <= 5e-3 * mag          # plain TF32: 10-bit mantissa inputs
+    assert errs[1] <= 1e-5 * mag          # FP16x3 must be fp32-grade
+    assert errs[2] <= 5e-3 * mag          # one fp16 product: 11-bit significands
 
 
 def test_pointwise_rejects_bad_arguments(cuda_device):
@@ -75,36 +79,32 @@ def test_pointwise_rejects_bad_arguments(cuda_device):
     assert lib.orbit_pointwise_conv(L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), None, None, L.ptr(x), 8, 8, 8, 1, 7, 0, None, None) == -1
 
 
-@pytest.mark.parametrize("shape", [(7 * 14 * 14, 112, 672, 14 * 14, 0, True, True), (9 * 7 * 7, 192, 1152, 7 * 7, 0, True, False),
-                                   (3 * 28 * 28, 40, 240, 28 * 28, 0, True, True), (260, 80, 480, 65, 0, True, False)],
-                         ids=lambda s: f"M{s[0]}_N{s[1]}_K{s[2]}")
-def test_gated_projection_variants_agree(cuda_device, shape):
-    """The A/B variants of the gated-projection GEMM (A operand in shared vs tensor memory, three instructions per k-step vs
-    the merged [B_hi;B_lo] product) compute the same fp32-grade result: each within 2e-6 relative of fp64."""
-    from orbit_b200 import lib as L
-    lib = L.load()
-    M, N, K, rpf, act, gated, residual = shape
-    g = torch.Generator().manual_seed(M * 3 + N)
-    A = torch.randn(M, K, generator=g).to(cuda_device)
-    W = (torch.randn(N, K, generator=g) * K ** -0.5).to(cuda_device)
-    scale = (1 + 0.1 * torch.randn(N, generator=g)).to(cuda_device)
-    shift = (0.1 * torch.randn(N, generator=g)).to(cuda_device)
-    gate = torch.rand((M + rpf - 1) // rpf, K, generator=g).to(cuda_device)
-    res = torch.randn(M, N, generator=g).to(cuda_device) if residual else None
-    ref = (A.double() * gate.double().repeat_interleave(rpf, dim=0)[:M]) @ W.double().t() * scale.double() + shift.double()
-    if residual:
-        ref = ref + res.double()
-    outs = {}
-    try:
-        for atm in (0, 1):
-            for merge in (0, 1):
-                L.check(lib.orbit_set_global_option(b"tc_a_in_tmem", atm), "set tc_a_in_tmem")
-                L.check(lib.orbit_set_global_option(b"tc_merge", merge), "set tc_merge")
-                out = _run(1, A, W, scale, shift, gate, res, rpf, act)
-                err = ((out.double() - ref).abs().max() / ref.abs().max()).item()
-                outs[(atm, merge)] = err
-                assert err <= 2e-6, f"a_in_tmem={atm} merge={merge}: relative error {err:.2e}"
-    finally:
-        lib.orbit_set_global_option(b"tc_a_in_tmem", 1)
-        lib.orbit_set_global_option(b"tc_merge", 0)
-    print({k: f"{v:.1e}" for k, v in outs.items()})
+@pytest.mark.parametrize("a_scale,w_scale", [(1e-4, 1.0), (1.0, 1e-3), (300.0, 1.0), (1e-3, 30.0)])
+def test_fp16x3_dynamic_range(cuda_device, a_scale, w_scale):
+    """The fp16 split keeps fp32-grade RELATIVE accuracy over the magnitudes activations and weights take: small values
+    go through the 2^11-scaled lo part, so nothing is lost below fp16's normal range (2^-14)."""
+    M, N, K = 1024, 96, 672
+    g = torch.Generator().manual_seed(7)
+    A = (torch.randn(M, K, generator=g) * a_scale).to(cuda_device)
+    W = (torch.randn(N, K, generator=g) * K ** -0.5 * w_scale).to(cuda_device)
+    one, zero = torch.ones(N, device=cuda_device), torch.zeros(N, device=cuda_device)
+    ref = A.double() @ W.double().t()
+    out = _run(1, A, W, one, zero, None, None, M, 0)
+    rel = ((out.double() - ref).abs().max() / ref.abs().max()).item()
+    assert rel <= 2e-6, f"relative error {rel:.2e} at |a|~{a_scale}, |w|~{w_scale}"
+
+
+def test_fp16x3_is_unbiased(cuda_device):
+    """The tensor core truncates every accumulation; the per-k-block promotion + 1-ulp de-bias must leave no systematic
+    error (a bias compounds over the network's 33 GEMM layers: DESIGN.md section 4)."""
+    M, N, K = 4096, 96, 1152
+    g = torch.Generator().manual_seed(11)
+    A = torch.rand(M, K, generator=g).to(cuda_device)            # all-positive operands: worst case for truncation bias
+    W = (torch.rand(N, K, generator=g) / K).to(cuda_device)
+    one, zero = torch.ones(N, device=cuda_device), torch.zeros(N, device=cuda_device)
+    ref = A.double() @ W.double().t()
+    out = _run(1, A, W, one, zero, None, None, M, 0)
+    rel = (out.double() - ref) / ref
+    print(f"mean relative error {rel.mean().item():.2e}, rms {rel.pow(2).mean().sqrt().item():.2e}")
+    assert abs(rel.mean().item()) <= 3e-8
+    assert rel.pow(2).mean().sqrt().item() <= 1.5e-7

@@ -134,23 +134,79 @@ def test_ops_counter_interface_and_head_formulas():
 
 
 def test_host_stager_plan():
-    """_HostStager._plan: passes cover the call exactly, ramp first, no tiny tail, and no ramp for a call queued right
-    behind a larger one (predict() after personalise())."""
-    import time
+    """_HostStager._plan: passes cover the call exactly, ramp first, no tiny tail, and no ramp for a call queued while
+    the previous call is still running on the device (predict() after personalise()); deterministic (no timers)."""
     from orbit_b200.few_shot_recognisers import _HostStager
     st = _HostStager.__new__(_HostStager)
-    st.chunk_frames, st.ramp, st.copy_frames, st.last_call = 1600, (96, 224, 480), 160, (-1.0, 0)
-    assert st._plan(1600) == [96, 224, 480, 800]
-    assert st._plan(640) == [640]                      # issued right behind the 1600-frame call: data will be there
-    time.sleep(0.02)
-    assert st._plan(640) == [96, 224, 320]
-    time.sleep(0.02)
-    assert st._plan(830) == [96, 224, 510]             # a 30-frame tail is merged into the last pass
+    st.chunk_frames, st.ramp, st.copy_frames = 1600, (96, 224, 480), 160
+    assert st._plan(1600, behind=False) == [96, 224, 480, 800]
+    assert st._plan(640, behind=True) == [640]                 # data will be there before the device gets to it
+    assert st._plan(640, behind=False) == [96, 224, 320]
+    assert st._plan(830, behind=False) == [96, 224, 510]       # a 30-frame tail is merged into the last pass
+    assert st._plan(1630, behind=True) == [816, 814]           # ... or the last two passes are rebalanced when the
+    assert st._plan(3230, behind=True) == [1600, 816, 814]     # merged pass would exceed chunk_frames (engine would re-split)
     st.chunk_frames, st.ramp = 2, (4, 6)
     for total in (1, 7, 30):
-        time.sleep(0.011)
-        plan = st._plan(total)
-        assert sum(plan) == total and all(n > 0 for n in plan)
+        for behind in (False, True):
+            plan = st._plan(total, behind)
+            assert sum(plan) == total and all(n > 0 for n in plan)
+
+
+def test_training_paths_without_backward_kernels_are_refused():
+    """Every entry that needs gradients through the extractor refuses loudly instead of
+    returning graph-less logits that would fail later inside loss.backward()."""
+    m = orbit_b200.SingleStepFewShotRecogniser('efficientnet_b0', True, 'versa', 1, 4, False, 8)
+    clips, labels = torch.zeros(2, 1, 3, 64, 64), torch.tensor([0, 1])
+    with pytest.raises(NotImplementedError, match="LITE"):
+        m.personalise_with_lite(clips, labels)
+    m.set_test_mode(False)                                   # CNAPs meta-training: single-step-learner.py:196-210
+    with pytest.raises(NotImplementedError, match="meta-training"):
+        m.personalise(clips, labels)
+    with pytest.raises(NotImplementedError, match="meta-training"):
+        m.predict(clips)
+    m.set_test_mode(True)
+    with torch.no_grad(), pytest.raises(OrbitError):         # test mode passes the gate (then fails only for lack of a GPU)
+        m.personalise(clips, labels)
+    unfrozen = orbit_b200.SingleStepFewShotRecogniser('efficientnet_b0', False, 'proto', 1, 4, True, 8)
+    unfrozen.set_test_mode(False)
+    with pytest.raises(NotImplementedError, match="training the extractor"):
+        unfrozen.personalise(clips, labels)
+    ft = orbit_b200.MultiStepFewShotRecogniser('efficientnet_b0', True, 'linear', 1, 4, False)
+    args = {'num_grad_steps': 2, 'learning_rate': 0.1, 'optimizer': 'adam', 'loss_fn': None, 'extractor_lr_scale': 0.1}
+    with pytest.raises(NotImplementedError, match="fine-tuning FiLM"):
+        ft.personalise(clips, labels, args)
+    assert ft.personalise_with_lite(clips, labels) is None   # the reference's own no-op (few_shot_recognisers.py:260-261)
+
+
+def test_feature_extractor_reprepares_after_weight_updates():
+    """prepare() caches BN folds / weight splits; every way of changing weights must invalidate that cache
+    (parameters are views bound with .data, whose version counters are their own -- the blob's does not move)."""
+    from orbit_b200.feature_extractors import FeatureExtractor
+    fe = FeatureExtractor('efficientnet_b0')
+    v0 = fe._state_version()
+    other = FeatureExtractor('efficientnet_b0', seed=5)
+    fe._prepared_key = 'stale'
+    fe.load_state_dict(other.state_dict())
+    assert fe._prepared_key is None and fe._state_version() != v0
+    assert torch.equal(fe._blob, other._blob)                    # the parameters really are views of the blob
+    v1 = fe._state_version()
+    with torch.no_grad():
+        next(fe.parameters()).mul_(2.0)                          # what an optimiser step does
+    assert fe._state_version() != v1
+    v2 = fe._state_version()
+    fe.conv_stem.weight.data.copy_(other.conv_stem.weight)       # invisible alias write: needs mark_dirty()
+    assert fe._state_version() == v2
+    fe._prepared_key = 'stale'
+    fe.mark_dirty()
+    assert fe._prepared_key is None
+
+
+def test_class_index_is_built_without_touching_the_features():
+    from orbit_b200.classifier_heads import ClassIndex
+    ci = ClassIndex(torch.tensor([7, 3, 7, 9]), device='cpu')
+    assert ci.num_classes == 3 and ci.num_clips == 4 and ci.index.tolist() == [1, 0, 1, 2] and ci.index_dev is None
+    with pytest.raises(AssertionError, match="another label tensor"):
+        ClassIndex.of(torch.tensor([1, 2]), ci, 'cpu')
 
 
 def test_bench_reference_arm_contract():
