@@ -165,6 +165,18 @@ int orbit_depthwise_conv(const float* x, const float* weight, const float* scale
                          float* partial, float* weight_scratch, int B, int H, int W, int C, int k, int stride,
                          int act, void* stream);
 
+/* Fused front half of a timm InvertedResidual block with 16 or 24 input channels (EfficientNet-B0 blocks 1.0, 1.1, 2.0):
+ * conv_pw 1x1 + bn1 + SiLU -> conv_dw kxk (TF-SAME) + bn2 (FiLM site, model/film.py:43-44) + SiLU, one launch; the
+ * 6x-expanded tensor stays in shared memory. Same result as orbit_pointwise_conv (mode 0) followed by
+ * orbit_depthwise_conv up to fp32 summation order.
+ *   x [B,H,W,Cin] NHWC; w_expand [C,Cin]; scale1/shift1 [C] folded bn1; w_dw [C,1,k,k]; scale2/shift2 [C] folded bn2;
+ *   y [B,ceil(H/s),ceil(W/s),C]; partial: orbit_mbconv_partial_floats(...) floats (SE squeeze sums per block; nullable);
+ *   weight_scratch: k*k*C floats.                                                                                    */
+int64_t orbit_mbconv_partial_floats(int B, int H, int W, int C, int k, int stride);
+int orbit_mbconv_expand_dw(const float* x, const float* w_expand, const float* scale1, const float* shift1,
+                           const float* w_dw, const float* scale2, const float* shift2, float* y, float* partial,
+                           float* weight_scratch, int B, int H, int W, int Cin, int C, int k, int stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backbone engine: the feature extractor forward (reference: timm model called at
  * few_shot_recognisers.py:114-117,143-146, with FiLM by functional_call parameter substitution).

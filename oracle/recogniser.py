@@ -63,6 +63,22 @@ class OracleRecogniser:
             sd.update(('classifier.' + k, v.clone()) for k, v in self.versa_params.items())
         return sd
 
+    def load_state_dict(self, sd):
+        """Inverse of ``state_dict``: takes a reference-keyed checkpoint (e.g. the CUDA model's ``state_dict()``) so that
+        both sides of a parity check hold the same weights. The FiLM gamma0/beta0 snapshot is re-taken from the loaded
+        extractor, as the reference takes it at construction time (few_shot_recognisers.py:286)."""
+        def sub(prefix):
+            return OrderedDict((k[len(prefix):], v.detach().cpu().clone()) for k, v in sd.items() if k.startswith(prefix))
+        self.extractor.load_state_dict(sub('feature_extractor.'), strict=True)
+        if self.adapt_features:
+            self.set_encoder_params = sub('set_encoder.')
+            self.film_gen_params = sub('film_generator.')
+            ext = dict(self.extractor.named_parameters())
+            self.film_initial = {n: ext[n].detach().clone() for n in self.film_initial}
+        if self.classifier == 'versa':
+            self.versa_params = sub('classifier.')
+        self.reset()
+
     # -- features -------------------------------------------------------------------------
     @torch.no_grad()
     def _features(self, clips, film=None):

@@ -45,13 +45,13 @@ extern "C" int orbit_debug_set_gemm_trace(void* dev_buffer) { orbit::set_tcgen05
 extern "C" int orbit_set_global_option(const char* key, int value) {
     if (!key) return ORBIT_ERR_ARG;
     if (!strcmp(key, "tc_debias_x1000")) { orbit::set_tcgen05_debias((float)value / 1000.0f); return ORBIT_OK; }
-    if (!strcmp(key, "dw_variant")) { if (value < 1 || value > 3) return ORBIT_ERR_ARG; orbit::set_dw_variant(value); return ORBIT_OK; }
+    if (!strcmp(key, "tc_narrow")) { orbit::set_tcgen05_narrow(value != 0); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 extern "C" int orbit_get_global_option(const char* key, int* value) {
     if (!key || !value) return ORBIT_ERR_ARG;
     if (!strcmp(key, "tc_debias_x1000")) { *value = (int)(orbit::get_tcgen05_debias() * 1000.0f + 0.5f); return ORBIT_OK; }
-    if (!strcmp(key, "dw_variant")) { *value = orbit::get_dw_variant(); return ORBIT_OK; }
+    if (!strcmp(key, "tc_narrow")) { *value = orbit::get_tcgen05_narrow(); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 
@@ -65,6 +65,30 @@ extern "C" int64_t orbit_depthwise_partial_floats(int B, int H, int W, int C, in
     int ho, wo, p;
     same_geom(H, k, stride, &ho, &p); same_geom(W, k, stride, &wo, &p);
     return (int64_t)B * orbit::dw_partial_groups(C, ho, wo, k, stride) * C;
+}
+
+extern "C" int64_t orbit_mbconv_partial_floats(int B, int H, int W, int C, int k, int stride) {
+    int ho, wo, p;
+    same_geom(H, k, stride, &ho, &p); same_geom(W, k, stride, &wo, &p);
+    return (int64_t)B * orbit::mbx_partial_groups(C, ho, wo, k, stride) * C;
+}
+
+extern "C" int orbit_mbconv_expand_dw(const float* x, const float* w_expand, const float* scale1, const float* shift1,
+                                      const float* w_dw, const float* scale2, const float* shift2, float* y, float* partial,
+                                      float* weight_scratch, int B, int H, int W, int Cin, int C, int k, int stride, void* stream) {
+    using namespace orbit;
+    if (!x || !w_expand || !scale1 || !shift1 || !w_dw || !scale2 || !shift2 || !y || !weight_scratch) return ORBIT_ERR_ARG;
+    if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || C <= 0) return ORBIT_ERR_ARG;
+    if (C % 4 || !mbx_supported(Cin, k, stride)) return ORBIT_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(w_expand) || !aligned16(y) || !aligned16(weight_scratch)) return ORBIT_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    int ho, wo, pt, pl;
+    same_geom(H, k, stride, &ho, &pt); same_geom(W, k, stride, &wo, &pl);
+    int rc = launch_dw_relayout(w_dw, C, k * k, weight_scratch, st);
+    if (rc) return rc;
+    if (B == 0) return ORBIT_OK;
+    return launch_mbconv_expand_dw(x, w_expand, scale1, shift1, weight_scratch, scale2, shift2, y, partial, B, H, W, Cin, C, ho, wo,
+                                   k, stride, pt, pl, st);
 }
 
 extern "C" int orbit_depthwise_conv(const float* x, const float* weight, const float* scale, const float* shift, float* y,

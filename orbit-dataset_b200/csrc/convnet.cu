@@ -4,7 +4,7 @@
 // model/few_shot_recognisers.py:114-117,143-146 (timm==0.6.12 tf_efficientnet_b0, external), with
 // FiLM = substituted BatchNorm affine parameters (model/film.py:38-74).  Per layer:
 //   conv_stem+bn1+SiLU        -> stem_kernel            (direct conv, NCHW in / NHWC out)
-//   conv_dw+bn(+FiLM)+SiLU    -> dw_kernel              (HBM-bound stencil, fused SE squeeze partials)
+//   conv_dw+bn(+FiLM)+SiLU    -> dw2_kernel             (HBM-bound stencil, fused SE squeeze partials)
 //   SqueezeExcite FCs         -> se_gate_kernel
 //   conv_pw/conv_pwl/conv_head-> pw_ffma_kernel (this file, fp32 FFMA tiles) or the tcgen05 kernel
 //                                in gemm_tcgen05.cu; BN/FiLM scale-shift, SiLU, SE gate and residual fused
@@ -297,228 +297,8 @@ template <> struct VecIO<2> {
     static __device__ __forceinline__ void store(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
 };
 
-// Rolling accumulators, ONE iteration = S input rows = one finished output row (the ring is rotated through
-// registers instead of unrolling over its phases: 3-5x less code, the unrolled version stalled on instruction
-// fetch). Pending output rows o_old .. o_old+R-1 live in acc[0..R-1]; virtual input row vy (= input row + pad_t)
-// feeds output row (vy - ky)/S for every ky of matching parity.
-template <int K, int S, int VEC>
-__global__ void __launch_bounds__(256, 2)
-dw_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
-          const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C,
-          int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile, int strip_blocks) {
-    constexpr int TW = kDwTW, R = (K + S - 1) / S, SPAN = (TW - 1) * S + K, HALF = (K - 1) / S;
-    extern __shared__ __align__(16) float s_red[];  // [LY][LX][VEC] partial-sum reduction
-    const int tile = blockIdx.x / strip_blocks, sb = blockIdx.x % strip_blocks, chunk = blockIdx.y, b = blockIdx.z;
-    const int groups = gridDim.x;
-    const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
-    const int Cv = C / VEC;
-    const int cv = chunk * LX + lx;
-    const int strip = sb * LY + ly;
-    const bool live = cv < Cv && strip * TW < Wo;
-    float sum[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) sum[e] = 0.f;
-    const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
-    if (live && row0 < row1) {
-        float wreg[K * K][VEC], sc[VEC], sh[VEC];
-#pragma unroll
-        for (int t = 0; t < K * K; ++t) VecIO<VEC>::load(wt + (int64_t)t * C + cv * VEC, wreg[t]);
-        VecIO<VEC>::load(scale + cv * VEC, sc);
-        VecIO<VEC>::load(shift + cv * VEC, sh);
-        const float* xb = x + (int64_t)b * H * W * C + cv * VEC;
-        float* yb = y + (int64_t)b * Ho * Wo * C + cv * VEC;
-        const int ox0 = strip * TW, ixb = ox0 * S - pad_l;
-        float acc[R][TW][VEC];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int t = 0; t < TW; ++t)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[r][t][e] = 0.f;
-        // iteration m handles virtual rows m*S .. m*S+S-1; the oldest pending output row is o_old = m - HALF
-        // (HALF = (K-1)/S) and it is complete after the virtual row o_old*S + K-1, i.e. inside this iteration.
-        for (int m = row0; m < row1 + HALF; ++m) {
-#pragma unroll
-            for (int sub = 0; sub < S; ++sub) {
-                const int vy = m * S + sub;
-                const int iy = vy - pad_t;
-                if (iy >= 0 && iy < H) {
-                    const float* rowp = xb + (int64_t)iy * W * C;
-#pragma unroll
-                    for (int j = 0; j < SPAN; ++j) {
-                        const int ix = ixb + j;
-                        float v[VEC];
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) v[e] = 0.f;
-                        if (ix >= 0 && ix < W) VecIO<VEC>::load(rowp + (int64_t)ix * C, v);
-#pragma unroll
-                        for (int ky = sub; ky < K; ky += S) {          // ky with (vy - ky) divisible by S
-                            const int slot = HALF - (ky - sub) / S;    // output row m - (ky-sub)/S, relative to o_old
-#pragma unroll
-                            for (int t = 0; t < TW; ++t) {
-                                const int kx = j - t * S;
-                                if (kx >= 0 && kx < K) {
-#pragma unroll
-                                    for (int e = 0; e < VEC; ++e) acc[slot][t][e] = fmaf(v[e], wreg[ky * K + kx][e], acc[slot][t][e]);
-                                }
-                            }
-                        }
-                    }
-                }
-                if (sub == (K - 1) % S) {      // the oldest pending output row has now seen its last input row
-                    const int oy = m - HALF;
-                    if (oy >= row0 && oy < row1) {
-#pragma unroll
-                        for (int t = 0; t < TW; ++t) {
-                            if (ox0 + t < Wo) {
-                                float r[VEC];
-#pragma unroll
-                                for (int e = 0; e < VEC; ++e) { r[e] = act_fast(fmaf(acc[0][t][e], sc[e], sh[e]), act); sum[e] += r[e]; }
-                                VecIO<VEC>::store(yb + ((int64_t)oy * Wo + ox0 + t) * C, r);
-                            }
-                        }
-                    }
-                }
-            }
-            // rotate the ring: slot r <- slot r+1, newest slot cleared (rows above the tile accumulate garbage that is
-            // rotated out without ever being stored)
-#pragma unroll
-            for (int r = 0; r + 1 < R; ++r)
-#pragma unroll
-                for (int t = 0; t < TW; ++t)
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[r][t][e] = acc[r + 1][t][e];
-#pragma unroll
-            for (int t = 0; t < TW; ++t)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[R - 1][t][e] = 0.f;
-        }
-    }
-    if (partial) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) s_red[(ly * LX + lx) * VEC + e] = sum[e];
-        __syncthreads();
-        if (ly == 0 && cv < Cv) {
-            float t[VEC];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) t[e] = s_red[lx * VEC + e];
-            for (int r = 1; r < LY; ++r)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) t[e] += s_red[(r * LX + lx) * VEC + e];
-            VecIO<VEC>::store(partial + ((int64_t)b * groups + blockIdx.x) * C + cv * VEC, t);
-        }
-    }
-}
-
-// Variant that unrolls over the P = R*S phases of the accumulator ring instead of rotating it through registers;
-// faster for K=3, S=2 (measured), slower elsewhere (instruction-fetch bound).
-template <int K, int S, int VEC>
-__global__ void __launch_bounds__(256, 2)
-dw_kernel_unrolled(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
-          const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C,
-          int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile, int strip_blocks) {
-    constexpr int TW = kDwTW, R = (K + S - 1) / S, P = R * S, SPAN = (TW - 1) * S + K;
-    extern __shared__ __align__(16) float s_red[];  // [LY][LX][VEC] partial-sum reduction
-    const int tile = blockIdx.x / strip_blocks, sb = blockIdx.x % strip_blocks, chunk = blockIdx.y, b = blockIdx.z;
-    const int groups = gridDim.x;
-    const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
-    const int Cv = C / VEC;
-    const int cv = chunk * LX + lx;
-    const int strip = sb * LY + ly;
-    const bool live = cv < Cv && strip * TW < Wo;
-    float sum[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) sum[e] = 0.f;
-    const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
-    if (live && row0 < row1) {
-        float wreg[K * K][VEC], sc[VEC], sh[VEC];
-#pragma unroll
-        for (int t = 0; t < K * K; ++t) VecIO<VEC>::load(wt + (int64_t)t * C + cv * VEC, wreg[t]);
-        VecIO<VEC>::load(scale + cv * VEC, sc);
-        VecIO<VEC>::load(shift + cv * VEC, sh);
-        const float* xb = x + (int64_t)b * H * W * C + cv * VEC;
-        float* yb = y + (int64_t)b * Ho * Wo * C + cv * VEC;
-        const int ox0 = strip * TW, ixb = ox0 * S - pad_l;
-        float acc[R][TW][VEC];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int t = 0; t < TW; ++t)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[r][t][e] = 0.f;
-        const int vy_last = (row1 - 1) * S + K - 1;     // virtual row vy = input row + pad_t = oy*S + ky
-        for (int vyb = row0 * S; vyb <= vy_last; vyb += P) {
-#pragma unroll
-            for (int ph = 0; ph < P; ++ph) {
-                const int vy = vyb + ph;
-                if (vy > vy_last) break;
-                const int iy = vy - pad_t;
-                if (iy >= 0 && iy < H) {
-                    const float* rowp = xb + (int64_t)iy * W * C;
-#pragma unroll
-                    for (int j = 0; j < SPAN; ++j) {
-                        const int ix = ixb + j;
-                        float v[VEC];
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) v[e] = 0.f;
-                        if (ix >= 0 && ix < W) VecIO<VEC>::load(rowp + (int64_t)ix * C, v);
-#pragma unroll
-                        for (int ky = 0; ky < K; ++ky) {
-                            if (floor_mod(ph - ky, S) != 0) continue;                  // compile-time after unrolling
-                            const int slot = floor_mod(floor_div(ph - ky, S), R);     // compile-time
-#pragma unroll
-                            for (int t = 0; t < TW; ++t) {
-                                const int kx = j - t * S;
-                                if (kx >= 0 && kx < K) {
-#pragma unroll
-                                    for (int e = 0; e < VEC; ++e) acc[slot][t][e] = fmaf(v[e], wreg[ky * K + kx][e], acc[slot][t][e]);
-                                }
-                            }
-                        }
-                    }
-                }
-                if (floor_mod(ph - (K - 1), S) == 0) {   // an output row has now seen all K of its input rows
-                    const int rel = floor_div(ph - (K - 1), S);
-                    const int slot = floor_mod(rel, R);
-                    const int oy = vyb / S + rel;
-                    if (oy >= row0 && oy < row1) {
-#pragma unroll
-                        for (int t = 0; t < TW; ++t) {
-                            if (ox0 + t < Wo) {
-                                float r[VEC];
-#pragma unroll
-                                for (int e = 0; e < VEC; ++e) { r[e] = act_fast(fmaf(acc[slot][t][e], sc[e], sh[e]), act); sum[e] += r[e]; }
-                                VecIO<VEC>::store(yb + ((int64_t)oy * Wo + ox0 + t) * C, r);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < TW; ++t)
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[slot][t][e] = 0.f;
-                }
-            }
-        }
-    }
-    if (partial) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) s_red[(ly * LX + lx) * VEC + e] = sum[e];
-        __syncthreads();
-        if (ly == 0 && cv < Cv) {
-            float t[VEC];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) t[e] = s_red[lx * VEC + e];
-            for (int r = 1; r < LY; ++r)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) t[e] += s_red[(r * LX + lx) * VEC + e];
-            VecIO<VEC>::store(partial + ((int64_t)b * groups + blockIdx.x) * C + cv * VEC, t);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Second-generation depthwise kernel (same tiling and rolling accumulators as dw_kernel above). ncu of the first
-// version on the K=5 layers: 98 thread-instructions per output of which only 25 were FFMAs -- 64-bit address
+// The depthwise kernel. ncu of its first, scalar version on the K=5 layers: 98 thread-instructions per output of which only 25 were FFMAs -- 64-bit address
 // arithmetic (25 %), ring-rotation MOVs (13 %) and divergence bookkeeping made it ISSUE-bound at 1.3-1.7 TB/s.
 // Here: (i) channel PAIRS are processed with the Blackwell packed `fma.rn.f32x2` (two IEEE fp32 FMAs per issue
 // slot, bit-identical to two fmaf), (ii) column validity and column offsets are hoisted out of the row loop,
@@ -549,11 +329,9 @@ template <> struct PairIO<2> {
 };
 
 // CT = compile-time channel count (0: use the runtime C): column offsets j*C become load/store immediates.
-// UNR (stride 1 only): the row loop is unrolled over the R phases of the accumulator ring, so that the ring never moves
-// (slot indices are compile-time): retires the 2 R TW NP rotation MOVs per row. MEASURED SLOWER on all four K=5 layers
-// (814 -> 892 us at 28x28x240, B=1600): the 5x larger loop body costs more instruction fetch than the MOVs it saves, as
-// the scalar version did in round 1. Not dispatched; kept as the record of the experiment.
-template <int K, int S, int VEC, int MINB, int CT, bool UNR = false>
+// (Tried and removed, see DESIGN.md section 4: a row loop unrolled over the R phases of the accumulator ring -- 5x the code,
+// slower on instruction fetch -- and a per-thread cp.async input ring for K=5 stride 1 -- 4-10 % slower.)
+template <int K, int S, int VEC, int MINB, int CT>
 __global__ void __launch_bounds__(256, MINB)
 dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
            const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C_rt,
@@ -625,57 +403,6 @@ dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const floa
 #pragma unroll
                 for (int q = 0; q < NP; ++q) acc[r][t][q] = 0ull;
         load_row(row0 * S, v);
-        if constexpr (UNR) {
-            static_assert(!UNR || S == 1, "phase-unrolled ring: stride 1");
-            for (int m0 = row0; m0 < row1 + HALF; m0 += R) {
-#pragma unroll
-                for (int ph = 0; ph < R; ++ph) {
-                    const int m = m0 + ph;
-                    if (m < row1 + HALF) {
-                        load_row(m + 1, vn);
-#pragma unroll
-                        for (int ky = 0; ky < K; ++ky) {
-                            const int slot = (HALF - ky + ph) % R;        // compile time: logical slot HALF-ky, ring offset ph
-#pragma unroll
-                            for (int kx = 0; kx < K; ++kx) {
-                                f2_t w[NP];
-                                PairIO<NP>::load_shared(wlane + (ky * K + kx) * LXS * VEC, w);
-#pragma unroll
-                                for (int t = 0; t < TW; ++t)
-#pragma unroll
-                                    for (int q = 0; q < NP; ++q) acc[slot][t][q] = f2_fma(v[kx + t][q], w[q], acc[slot][t][q]);
-                            }
-                        }
-                        const int o = ph % R;                              // the oldest pending output row lives here
-                        const int oy = m - HALF;
-                        if (oy >= row0) {
-                            float* yrow = yb + (int64_t)oy * Wo * C;
-#pragma unroll
-                            for (int t = 0; t < TW; ++t) {
-                                if (ox0 + t < Wo) {
-                                    float r[VEC];
-#pragma unroll
-                                    for (int q = 0; q < NP; ++q) {
-                                        f2_unpack(f2_fma(acc[o][t][q], sc[q], sh[q]), r[2 * q], r[2 * q + 1]);
-                                        r[2 * q] = act_fast(r[2 * q], act); r[2 * q + 1] = act_fast(r[2 * q + 1], act);
-                                        sum[2 * q] += r[2 * q]; sum[2 * q + 1] += r[2 * q + 1];
-                                    }
-                                    PairIO<NP>::store(yrow + t * C, r);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int t = 0; t < TW; ++t)
-#pragma unroll
-                            for (int q = 0; q < NP; ++q) acc[o][t][q] = 0ull;   // becomes the newest slot
-#pragma unroll
-                        for (int j = 0; j < SPAN; ++j)
-#pragma unroll
-                            for (int q = 0; q < NP; ++q) v[j][q] = vn[j][q];
-                    }
-                }
-            }
-        } else {
         // iteration m handles virtual rows m*S .. m*S+S-1; the oldest pending output row is m - HALF
         for (int m = row0; m < row1 + HALF; ++m) {
 #pragma unroll
@@ -730,7 +457,6 @@ dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const floa
 #pragma unroll
                 for (int q = 0; q < NP; ++q) acc[R - 1][t][q] = 0ull;
         }
-        }
     }
     if (partial) {
 #pragma unroll
@@ -747,160 +473,6 @@ dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const floa
         }
     }
 }
-
-// ------------------------------------------------------------------------------------------------
-// Third-generation depthwise kernel for stride 1 (the K=5 layers): same tiling, taps and rolling accumulators as
-// dw2_kernel, but the input rows arrive through a per-thread cp.async ring in shared memory, D rows deep, instead of a
-// one-row register prefetch. The K=5 stride-1 kernels ran at 0.18 instructions per clock per scheduler with 14 warps
-// per SM: each row waited for most of an HBM latency. Every thread copies and later reads only its own 8-byte slots, so
-// no block barrier is needed; out-of-image rows / columns are zero-filled by the copy itself (src-size 0).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, bool valid) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(valid ? 8 : 0) : "memory");
-}
-__device__ __forceinline__ f2_t lds64(uint32_t addr) {
-    f2_t v;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
-    return v;
-}
-
-template <int K, int VEC, int CT, int D>
-__global__ void __launch_bounds__(256, 2)
-dw3_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
-           const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C_rt,
-           int Ho, int Wo, int pad_t, int pad_l, int act, int LX, int LY, int rows_per_tile, int strip_blocks) {
-    constexpr int TW = kDwTW, R = K, SPAN = TW - 1 + K, HALF = K - 1, NP = VEC / 2, LXS = 32;
-    const int C = CT ? CT : C_rt;
-    extern __shared__ __align__(16) float s_dyn[];
-    float* s_w = s_dyn;                                   // [K*K][LXS][VEC] taps of this block's channel chunk
-    float* s_red = s_dyn + K * K * LXS * VEC;             // [256][VEC] partial-sum reduction
-    const uint32_t s_ring = (uint32_t)__cvta_generic_to_shared(s_red + 256 * VEC);   // [D][SPAN][NP][blockDim] 8-byte slots
-    const int tile = blockIdx.x / strip_blocks, sb = blockIdx.x % strip_blocks, chunk = blockIdx.y, b = blockIdx.z;
-    const int groups = gridDim.x;
-    const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
-    const int Cv = C / VEC;
-    const int cv = chunk * LX + lx;
-    const int strip = sb * LY + ly;
-    const bool live = cv < Cv && strip * TW < Wo;
-    for (int i = threadIdx.x; i < K * K * LXS; i += blockDim.x) {
-        const int t = i / LXS, l = i % LXS, c = chunk * LX + l;
-        float wv[VEC];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) wv[e] = 0.f;
-        if (l < LX && c < Cv) VecIO<VEC>::load(wt + (int64_t)t * C + c * VEC, wv);
-        VecIO<VEC>::store(s_w + (size_t)i * VEC, wv);
-    }
-    __syncthreads();
-    float sum[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) sum[e] = 0.f;
-    const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
-    if (live && row0 < row1) {
-        f2_t sc[NP], sh[NP];
-        PairIO<NP>::load(scale + cv * VEC, sc);
-        PairIO<NP>::load(shift + cv * VEC, sh);
-        const int ox0 = strip * TW, ixb = ox0 - pad_l;
-        unsigned cmask = 0;                               // bit j: input column ixb + j exists
-#pragma unroll
-        for (int j = 0; j < SPAN; ++j) cmask |= (ixb + j >= 0 && ixb + j < W) ? (1u << j) : 0u;
-        const int64_t row_stride = (int64_t)W * C;
-        const float* xcol = x + (int64_t)b * H * row_stride + (int64_t)ixb * C + cv * VEC - pad_t * row_stride;
-        float* yb = y + ((int64_t)b * Ho * Wo + ox0) * C + cv * VEC;
-        const float* wlane = s_w + lx * VEC;
-        const int vy_lo = pad_t, vy_hi = min(H - 1 + pad_t, row1 - 1 + K - 1);   // virtual row = input row + pad_t
-        const uint32_t ring = s_ring + threadIdx.x * 8, estride = blockDim.x * 8;
-        auto issue_row = [&](int vy, int slot) {
-            const bool rok = vy >= vy_lo && vy <= vy_hi;
-            const float* rp = xcol + (int64_t)vy * row_stride;
-#pragma unroll
-            for (int j = 0; j < SPAN; ++j)
-#pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    const bool ok = rok && ((cmask >> j) & 1u);
-                    cp_async8(ring + (uint32_t)((slot * SPAN + j) * NP + q) * estride, ok ? (const void*)(rp + j * C + 2 * q) : (const void*)x, ok);
-                }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        f2_t acc[R][TW][NP], v[SPAN][NP];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int t = 0; t < TW; ++t)
-#pragma unroll
-                for (int q = 0; q < NP; ++q) acc[r][t][q] = 0ull;
-#pragma unroll
-        for (int d = 0; d < D; ++d) issue_row(row0 + d, d);
-        int slot = 0;
-        for (int m = row0; m < row1 + HALF; ++m) {       // virtual input row m; the oldest pending output row is m - HALF
-            asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
-#pragma unroll
-            for (int j = 0; j < SPAN; ++j)
-#pragma unroll
-                for (int q = 0; q < NP; ++q) v[j][q] = lds64(ring + (uint32_t)((slot * SPAN + j) * NP + q) * estride);
-#pragma unroll
-            for (int ky = 0; ky < K; ++ky) {
-                const int s_ = HALF - ky;
-#pragma unroll
-                for (int kx = 0; kx < K; ++kx) {
-                    f2_t w[NP];
-                    PairIO<NP>::load_shared(wlane + (ky * K + kx) * LXS * VEC, w);
-#pragma unroll
-                    for (int t = 0; t < TW; ++t)
-#pragma unroll
-                        for (int q = 0; q < NP; ++q) acc[s_][t][q] = f2_fma(v[kx + t][q], w[q], acc[s_][t][q]);
-                }
-            }
-            const int oy = m - HALF;
-            if (oy >= row0) {
-                float* yrow = yb + (int64_t)oy * Wo * C;
-#pragma unroll
-                for (int t = 0; t < TW; ++t) {
-                    if (ox0 + t < Wo) {
-                        float r[VEC];
-#pragma unroll
-                        for (int q = 0; q < NP; ++q) {
-                            f2_unpack(f2_fma(acc[0][t][q], sc[q], sh[q]), r[2 * q], r[2 * q + 1]);
-                            r[2 * q] = act_fast(r[2 * q], act); r[2 * q + 1] = act_fast(r[2 * q + 1], act);
-                            sum[2 * q] += r[2 * q]; sum[2 * q + 1] += r[2 * q + 1];
-                        }
-                        PairIO<NP>::store(yrow + t * C, r);
-                    }
-                }
-            }
-            issue_row(m + D, slot);                       // refill the slot just consumed (its values are in registers)
-            slot = slot + 1 == D ? 0 : slot + 1;
-#pragma unroll
-            for (int r = 0; r + 1 < R; ++r)
-#pragma unroll
-                for (int t = 0; t < TW; ++t)
-#pragma unroll
-                    for (int q = 0; q < NP; ++q) acc[r][t][q] = acc[r + 1][t][q];
-#pragma unroll
-            for (int t = 0; t < TW; ++t)
-#pragma unroll
-                for (int q = 0; q < NP; ++q) acc[R - 1][t][q] = 0ull;
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    }
-    if (partial) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) s_red[(ly * LX + lx) * VEC + e] = sum[e];
-        __syncthreads();
-        if (ly == 0 && cv < Cv) {
-            float t[VEC];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) t[e] = s_red[lx * VEC + e];
-            for (int r = 1; r < LY; ++r)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) t[e] += s_red[(r * LX + lx) * VEC + e];
-            VecIO<VEC>::store(partial + ((int64_t)b * groups + blockIdx.x) * C + cv * VEC, t);
-        }
-    }
-}
-
-static int g_dw_variant = 2;   // 1 = first-generation kernels (kept for A/B), 2 = packed-FMA kernels
-void set_dw_variant(int v) { g_dw_variant = v; }
-int get_dw_variant() { return g_dw_variant; }
 
 int launch_depthwise(const float* x, const float* wt, const float* scale, const float* shift, float* y, float* partial,
                      int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, int act,
@@ -908,57 +480,245 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
     if (C % 4) return ORBIT_ERR_UNSUPPORTED;
     const DwPlan pl = dw_plan(C, Ho, Wo, k, stride);
     dim3 grid(pl.groups, pl.nchunks, B), block(pl.LX * pl.LY);
-    const size_t smem = sizeof(float) * (size_t)pl.LY * pl.LX * pl.VEC;
-#define ORBIT_DW_CASE(KK, SS, VV)                                                                                     \
-    if (k == KK && stride == SS) {                                                                                    \
-        dw_kernel<KK, SS, VV><<<grid, block, smem, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t,     \
-                                                        pad_l, act, pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks); \
+    const size_t smem = sizeof(float) * ((size_t)pl.LY * pl.LX * pl.VEC + (size_t)k * k * 32 * pl.VEC);
+#define ORBIT_DW2_LAUNCH(KK, SS, VV, MB, CC)                                                                          \
+    {                                                                                                                 \
+        dw2_kernel<KK, SS, VV, MB, CC><<<grid, block, smem, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t,   \
+                                                                 pad_l, act, pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks); \
         ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                              \
         return ORBIT_OK;                                                                                              \
     }
-    if (g_dw_variant == 3 && k == 5 && stride == 1) {
-        constexpr int D = 3;
-        const size_t smem3 = sizeof(float) * ((size_t)k * k * 32 * pl.VEC + 256 * pl.VEC) + (size_t)D * (kDwTW - 1 + 5) * (pl.VEC / 2) * 8 * block.x;
-#define ORBIT_DW3_CT(CC)                                                                                              \
-        if (C == CC) {                                                                                                \
-            static bool attr_set = false;                                                                             \
-            if (!attr_set) { ORBIT_CUDA(cudaFuncSetAttribute(dw3_kernel<5, 2, CC, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = true; } \
-            dw3_kernel<5, 2, CC, D><<<grid, block, smem3, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t, pad_l, act, \
-                                                               pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks);      \
-            ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                          \
-            return ORBIT_OK;                                                                                          \
-        }
-        ORBIT_DW3_CT(240) ORBIT_DW3_CT(480) ORBIT_DW3_CT(672) ORBIT_DW3_CT(1152) ORBIT_DW3_CT(0)
-#undef ORBIT_DW3_CT
-    }
-    if (g_dw_variant >= 2) {
-        const size_t smem2 = smem + sizeof(float) * (size_t)k * k * 32 * pl.VEC;
-#define ORBIT_DW2_LAUNCH(KK, SS, VV, MB, CC)                                                                           \
-        {                                                                                                             \
-            dw2_kernel<KK, SS, VV, MB, CC, false><<<grid, block, smem2, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho,  \
-                                                                       Wo, pad_t, pad_l, act, pl.LX, pl.LY,           \
-                                                                       pl.rows_per_tile, pl.strip_blocks);            \
-            ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                          \
-            return ORBIT_OK;                                                                                          \
-        }
 #define ORBIT_DW2_CT(KK, SS, VV, CC) if (k == KK && stride == SS && C == CC) ORBIT_DW2_LAUNCH(KK, SS, VV, 2, CC)
 #define ORBIT_DW2_ANY(KK, SS, VV) if (k == KK && stride == SS) ORBIT_DW2_LAUNCH(KK, SS, VV, 2, 0)
-        // the EfficientNet-B0 depthwise shapes get compile-time channel counts; everything else the generic kernels
-        ORBIT_DW2_CT(5, 2, 2, 144) ORBIT_DW2_CT(5, 2, 2, 672)
-        ORBIT_DW2_CT(5, 1, 2, 240) ORBIT_DW2_CT(5, 1, 2, 480) ORBIT_DW2_CT(5, 1, 2, 672) ORBIT_DW2_CT(5, 1, 2, 1152)
-        ORBIT_DW2_ANY(3, 1, 4) ORBIT_DW2_ANY(3, 2, 4) ORBIT_DW2_ANY(5, 1, 2) ORBIT_DW2_ANY(5, 2, 2)
+    // the EfficientNet-B0 depthwise shapes get compile-time channel counts; everything else the generic kernels
+    ORBIT_DW2_CT(5, 2, 2, 144) ORBIT_DW2_CT(5, 2, 2, 672)
+    ORBIT_DW2_CT(5, 1, 2, 240) ORBIT_DW2_CT(5, 1, 2, 480) ORBIT_DW2_CT(5, 1, 2, 672) ORBIT_DW2_CT(5, 1, 2, 1152)
+    ORBIT_DW2_ANY(3, 1, 4) ORBIT_DW2_ANY(3, 2, 4) ORBIT_DW2_ANY(5, 1, 2) ORBIT_DW2_ANY(5, 2, 2)
 #undef ORBIT_DW2_CT
 #undef ORBIT_DW2_ANY
 #undef ORBIT_DW2_LAUNCH
+    return ORBIT_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused MBConv front half:  expand 1x1 + bn1 + SiLU  ->  depthwise KxK + bn2(+FiLM) + SiLU (+ SE squeeze partials).
+//
+// Reference op sites: timm InvertedResidual conv_pw/bn1 -> conv_dw/bn2 (FiLM site, model/film.py:43-44) inside the
+// extractor invoked at model/few_shot_recognisers.py:114-117,143-146. At the 112x112 and 56x56 stages the 6x-expanded
+// tensor is 27 % of ALL layer-boundary traffic of the network (written by the expand GEMM, read back by the depthwise
+// kernel): here it never reaches HBM. The block input has only 16 / 24 channels, so the expansion is cheap enough for the
+// CUDA cores (exact fp32 FMA chains: no operand split needed) and is computed exactly ONCE per (pixel, channel):
+//   per virtual input row, all threads of the block expand the row segment the block's strips need
+//   ([pixels][channel pairs] -> shared memory, double buffered, one __syncthreads per row), then every thread feeds
+//   its strip's SPAN pixels from shared memory into the same rolling accumulators as dw2_kernel.
+// Zero padding applies to the EXPANDED tensor: out-of-image pixels are stored as zeros, not as expand(0).
+// Thread (lx, ly): channel pair lx of this block's chunk for both phases (its 2 x CIN expand weights live in registers),
+// pixels ly, ly + LY, ... in the expand phase, strip ly in the depthwise phase.
+// ------------------------------------------------------------------------------------------------
+template <int K, int S, int CIN, int CT>
+__global__ void __launch_bounds__(256, 2)
+mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const float* __restrict__ scale1,
+           const float* __restrict__ shift1, const float* __restrict__ wt, const float* __restrict__ scale,
+           const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C_rt,
+           int Ho, int Wo, int pad_t, int pad_l, int LX, int LY, int rows_per_tile, int strip_blocks) {
+    constexpr int TW = kDwTW, R = (K + S - 1) / S, SPAN = (TW - 1) * S + K, HALF = (K - 1) / S, VEC = 2;
+    const int C = CT ? CT : C_rt;
+    extern __shared__ __align__(16) float s_dyn[];
+    constexpr int LXS = 32;
+    const int P = (LY * TW - 1) * S + K;                  // input columns the block's strips touch
+    float* s_w = s_dyn;                                   // [K*K][LXS][2] depthwise taps of this block's channel chunk
+    float* s_red = s_w + K * K * LXS * VEC;               // [LY][LX][2] partial-sum reduction
+    float* s_e = s_red + LY * LX * VEC;                   // [2][P][LX][2] expanded rows (double buffered)
+    const int tile = blockIdx.x / strip_blocks, sb = blockIdx.x % strip_blocks, chunk = blockIdx.y, b = blockIdx.z;
+    const int groups = gridDim.x;
+    const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
+    const int Cv = C / VEC;
+    const int cv = chunk * LX + lx;
+    const bool chan = cv < Cv;
+    const int strip = sb * LY + ly;
+    const bool live = chan && strip * TW < Wo;
+    for (int i = threadIdx.x; i < K * K * LXS; i += blockDim.x) {
+        const int t = i / LXS, l = i % LXS, c = chunk * LX + l;
+        float wv[VEC] = {0.f, 0.f};
+        if (l < LX && c < Cv) VecIO<VEC>::load(wt + (int64_t)t * C + c * VEC, wv);
+        VecIO<VEC>::store(s_w + (size_t)i * VEC, wv);
     }
-    if (k == 3 && stride == 2) {
-        dw_kernel_unrolled<3, 2, 4><<<grid, block, smem, st>>>(x, wt, scale, shift, y, partial, H, W, C, Ho, Wo, pad_t, pad_l, act,
-                                                              pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks);
-        ORBIT_RETURN_IF_LAUNCH_FAILED();
-        return ORBIT_OK;
+    // this thread's two rows of the expand weight matrix [C][CIN] and the folded bn1 of its channels
+    float w0[CIN], w1[CIN];
+    float s1a = 0.f, s1b = 0.f, h1a = 0.f, h1b = 0.f;
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) { w0[k] = 0.f; w1[k] = 0.f; }
+    if (chan) {
+#pragma unroll
+        for (int k4 = 0; k4 < CIN / 4; ++k4) {
+            const float4 a = ldg4(we + (int64_t)(cv * VEC) * CIN + 4 * k4), c4 = ldg4(we + (int64_t)(cv * VEC + 1) * CIN + 4 * k4);
+            w0[4 * k4] = a.x; w0[4 * k4 + 1] = a.y; w0[4 * k4 + 2] = a.z; w0[4 * k4 + 3] = a.w;
+            w1[4 * k4] = c4.x; w1[4 * k4 + 1] = c4.y; w1[4 * k4 + 2] = c4.z; w1[4 * k4 + 3] = c4.w;
+        }
+        s1a = __ldg(scale1 + cv * VEC); s1b = __ldg(scale1 + cv * VEC + 1);
+        h1a = __ldg(shift1 + cv * VEC); h1b = __ldg(shift1 + cv * VEC + 1);
     }
-    ORBIT_DW_CASE(3, 1, 4) ORBIT_DW_CASE(5, 1, 2) ORBIT_DW_CASE(5, 2, 2)
-#undef ORBIT_DW_CASE
+    float sum[VEC] = {0.f, 0.f};
+    const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
+    const int bx0 = sb * LY * TW * S - pad_l;             // input column of expanded-row slot 0
+    // virtual row vy = input row + pad_t; rows that exist and that this tile needs: [vy_lo, vy_hi]
+    const int vy_lo = pad_t, vy_hi = min(H - 1 + pad_t, (row1 - 1) * S + K - 1);
+    const float* xfr = xin + (int64_t)b * H * W * CIN;
+    const uint32_t e_base = (uint32_t)__cvta_generic_to_shared(s_e);
+    const uint32_t e_row_bytes = (uint32_t)(P * LX * VEC * 4);
+
+    // ---- expand phase: virtual row vy -> buffer eb -------------------------------------------------------------
+    auto expand_row = [&](int vy, int eb) {
+        const bool row_ok = vy >= vy_lo && vy <= vy_hi;
+        const float* xrow = xfr + (int64_t)(vy - pad_t) * W * CIN;
+        const uint32_t dst0 = e_base + (uint32_t)eb * e_row_bytes + (uint32_t)(lx * VEC * 4);
+#pragma unroll 2
+        for (int p = ly; p < P; p += LY) {
+            const int col = bx0 + p;
+            float e0 = 0.f, e1 = 0.f;
+            if (row_ok && chan && col >= 0 && col < W) {
+                const float* xp = xrow + (int64_t)col * CIN;
+                float4 xv[CIN / 4];
+#pragma unroll
+                for (int k4 = 0; k4 < CIN / 4; ++k4) xv[k4] = ldg4(xp + 4 * k4);   // same address for all lx lanes: one broadcast request
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < CIN / 4; ++k4) {
+                    a0 = fmaf(xv[k4].x, w0[4 * k4], a0); a1 = fmaf(xv[k4].x, w1[4 * k4], a1);
+                    a0 = fmaf(xv[k4].y, w0[4 * k4 + 1], a0); a1 = fmaf(xv[k4].y, w1[4 * k4 + 1], a1);
+                    a0 = fmaf(xv[k4].z, w0[4 * k4 + 2], a0); a1 = fmaf(xv[k4].z, w1[4 * k4 + 2], a1);
+                    a0 = fmaf(xv[k4].w, w0[4 * k4 + 3], a0); a1 = fmaf(xv[k4].w, w1[4 * k4 + 3], a1);
+                }
+                e0 = silu_sfu(fmaf(a0, s1a, h1a));
+                e1 = silu_sfu(fmaf(a1, s1b, h1b));
+            }
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst0 + (uint32_t)(p * LX * VEC * 4)), "f"(e0), "f"(e1) : "memory");
+        }
+    };
+
+    f2_t sc[1], sh[1];
+    sc[0] = sh[0] = 0ull;
+    if (live) { PairIO<1>::load(scale + cv * VEC, sc); PairIO<1>::load(shift + cv * VEC, sh); }
+    const int ox0 = strip * TW;
+    float* yb = y + ((int64_t)b * Ho * Wo + ox0) * C + cv * VEC;
+    const float* wlane = s_w + lx * VEC;
+    const uint32_t e_mine = e_base + (uint32_t)((ly * TW * S * LX + lx) * VEC * 4);   // slot of this strip's first input column
+    f2_t acc[R][TW], v[SPAN];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int t = 0; t < TW; ++t) acc[r][t] = 0ull;
+
+    if (row0 < row1) {          // block-uniform
+        expand_row(row0 * S, 0);
+        __syncthreads();        // also covers the tap table
+        int eb = 0;
+        // iteration m handles virtual rows m*S .. m*S+S-1; the oldest pending output row is m - HALF
+        for (int m = row0; m < row1 + HALF; ++m) {
+#pragma unroll
+            for (int sub = 0; sub < S; ++sub) {
+                expand_row(m * S + sub + 1, eb ^ 1);          // next row, other buffer
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < SPAN; ++j)
+                        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[j]) : "r"(e_mine + (uint32_t)eb * e_row_bytes + (uint32_t)(j * LX * VEC * 4)) : "memory");
+#pragma unroll
+                    for (int ky = sub; ky < K; ky += S) {      // ky with (vy - ky) divisible by S
+                        const int slot = HALF - (ky - sub) / S;
+#pragma unroll
+                        for (int kx = 0; kx < K; ++kx) {
+                            f2_t w[1];
+                            PairIO<1>::load_shared(wlane + (ky * K + kx) * LXS * VEC, w);
+#pragma unroll
+                            for (int t = 0; t < TW; ++t) acc[slot][t] = f2_fma(v[kx + t * S], w[0], acc[slot][t]);
+                        }
+                    }
+                    if (sub == (K - 1) % S) {      // the oldest pending output row has now seen its last input row
+                        const int oy = m - HALF;
+                        if (oy >= row0) {          // (oy < row1 by the loop bound)
+                            float* yrow = yb + (int64_t)oy * Wo * C;
+#pragma unroll
+                            for (int t = 0; t < TW; ++t) {
+                                if (ox0 + t < Wo) {
+                                    float r[VEC];
+                                    f2_unpack(f2_fma(acc[0][t], sc[0], sh[0]), r[0], r[1]);
+                                    r[0] = silu_sfu(r[0]); r[1] = silu_sfu(r[1]);
+                                    sum[0] += r[0]; sum[1] += r[1];
+                                    PairIO<1>::store(yrow + t * C, r);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncthreads();      // row eb consumed by everyone, row eb^1 complete
+                eb ^= 1;
+            }
+            // rotate the ring: slot r <- slot r+1, newest slot cleared
+#pragma unroll
+            for (int r = 0; r + 1 < R; ++r)
+#pragma unroll
+                for (int t = 0; t < TW; ++t) acc[r][t] = acc[r + 1][t];
+#pragma unroll
+            for (int t = 0; t < TW; ++t) acc[R - 1][t] = 0ull;
+        }
+    } else {
+        __syncthreads();
+    }
+    if (partial) {
+        s_red[(ly * LX + lx) * VEC] = sum[0];
+        s_red[(ly * LX + lx) * VEC + 1] = sum[1];
+        __syncthreads();
+        if (ly == 0 && chan) {
+            float t[VEC] = {s_red[lx * VEC], s_red[lx * VEC + 1]};
+            for (int r = 1; r < LY; ++r) { t[0] += s_red[(r * LX + lx) * VEC]; t[1] += s_red[(r * LX + lx) * VEC + 1]; }
+            VecIO<VEC>::store(partial + ((int64_t)b * groups + blockIdx.x) * C + cv * VEC, t);
+        }
+    }
+}
+
+struct MbxPlan { int LX, LY, nchunks, tiles, rows_per_tile, strip_blocks, groups; };
+static MbxPlan mbx_plan(int C, int Ho, int Wo, int k, int stride) {
+    MbxPlan p;
+    const int Cv = C / 2;
+    p.nchunks = ceil_div(Cv, 32);
+    p.LX = ceil_div(Cv, p.nchunks);
+    const int strips = ceil_div(Wo, kDwTW);
+    const int ly_max = std::max(1, 256 / p.LX);
+    p.strip_blocks = ceil_div(strips, ly_max);
+    p.LY = ceil_div(strips, p.strip_blocks);              // balanced strip blocks (14 strips -> 7 + 7, not 10 + 4)
+    const int R = ceil_div(k, stride);
+    const int want_tiles = std::min(ceil_div(Ho, R), Ho >= 112 ? 4 : (Ho >= 56 ? 2 : 1));
+    p.rows_per_tile = ceil_div(ceil_div(Ho, want_tiles), R) * R;
+    p.tiles = ceil_div(Ho, p.rows_per_tile);
+    p.groups = p.tiles * p.strip_blocks;
+    return p;
+}
+
+bool mbx_supported(int cin, int k, int stride) { return (cin == 16 || cin == 24) && (k == 3 || k == 5) && (stride == 1 || stride == 2); }
+int mbx_partial_groups(int C, int Ho, int Wo, int k, int stride) { return mbx_plan(C, Ho, Wo, k, stride).groups; }
+
+int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scale1, const float* shift1, const float* wt,
+                            const float* scale, const float* shift, float* y, float* partial, int B, int H, int W, int Cin,
+                            int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, cudaStream_t st) {
+    if (C % 2 || !mbx_supported(Cin, k, stride)) return ORBIT_ERR_UNSUPPORTED;
+    const MbxPlan pl = mbx_plan(C, Ho, Wo, k, stride);
+    dim3 grid(pl.groups, pl.nchunks, B), block(pl.LX * pl.LY);
+    const int P = (pl.LY * kDwTW - 1) * stride + k;
+    const size_t smem = sizeof(float) * ((size_t)k * k * 32 * 2 + (size_t)pl.LY * pl.LX * 2 + (size_t)2 * P * pl.LX * 2);
+    if (smem > 200 * 1024) return ORBIT_ERR_UNSUPPORTED;
+#define ORBIT_MBX(KK, SS, CI, CC)                                                                                     \
+    if (k == KK && stride == SS && Cin == CI && (CC == 0 || C == CC)) {                                              \
+        if (smem > 48 * 1024) ORBIT_CUDA(cudaFuncSetAttribute(mbx_kernel<KK, SS, CI, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        mbx_kernel<KK, SS, CI, CC><<<grid, block, smem, st>>>(xin, we, scale1, shift1, wt, scale, shift, y, partial, H, W, C, Ho, Wo, \
+                                                             pad_t, pad_l, pl.LX, pl.LY, pl.rows_per_tile, pl.strip_blocks); \
+        ORBIT_RETURN_IF_LAUNCH_FAILED();                                                                              \
+        return ORBIT_OK;                                                                                              \
+    }
+    // the three EfficientNet-B0 blocks with 16 / 24 input channels get compile-time channel counts
+    ORBIT_MBX(3, 2, 16, 96) ORBIT_MBX(3, 1, 24, 144) ORBIT_MBX(5, 2, 24, 144)
+    ORBIT_MBX(3, 1, 16, 0) ORBIT_MBX(3, 2, 16, 0) ORBIT_MBX(5, 1, 16, 0) ORBIT_MBX(5, 2, 16, 0)
+    ORBIT_MBX(3, 1, 24, 0) ORBIT_MBX(3, 2, 24, 0) ORBIT_MBX(5, 1, 24, 0) ORBIT_MBX(5, 2, 24, 0)
+#undef ORBIT_MBX
     return ORBIT_ERR_UNSUPPORTED;
 }
 

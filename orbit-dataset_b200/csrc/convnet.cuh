@@ -42,9 +42,15 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
                      int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, int act,
                      cudaStream_t st);
 
-// depthwise kernel generation: 1 = first kernels (A/B only), 2 = packed fma.rn.f32x2 kernels (default)
-void set_dw_variant(int v);
-int get_dw_variant();
+
+// Fused expand 1x1 (+bn1+SiLU) -> depthwise kxk (+bn2/FiLM+SiLU, SE squeeze partials) for MBConv blocks with 16 / 24 input
+// channels: xin [B,H,W,Cin] -> y [B,Ho,Wo,C]; we = expand weights [C][Cin] (torch layout), scale1/shift1 = folded bn1,
+// wt = depthwise taps [k*k][C], scale/shift = folded bn2. partial as launch_depthwise with mbx_partial_groups(...).
+bool mbx_supported(int cin, int k, int stride);
+int mbx_partial_groups(int C, int Ho, int Wo, int k, int stride);
+int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scale1, const float* shift1, const float* wt,
+                            const float* scale, const float* shift, float* y, float* partial, int B, int H, int W, int Cin,
+                            int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, cudaStream_t st);
 
 // squeeze-excite gate: partial [B][tiles][C] -> gate [B][C] = sigmoid(W2 silu(W1 mean + b1) + b2);
 // w2t = the expand weight [C][R] transposed to [R][C] (launch_dw_relayout(w2, C, R, w2t))

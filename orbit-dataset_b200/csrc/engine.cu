@@ -66,7 +66,8 @@ struct orbit_engine {
     int tokens = 0;             // ViT: tokens per frame (patches + class token)
     std::vector<Op> ops;
     int chunk_frames = 256;   // frames per pass through the layer plan (workspace ~10 MB per 224-px frame)
-    int gemm_mode = 1;        // tcgen05 3xTF32
+    int gemm_mode = 1;        // tcgen05 FP16x3
+    int fuse_mbconv = 1;      // expand 1x1 -> depthwise in one kernel where the block input has 16 / 24 channels
     mutable std::atomic<int64_t> last_launches{0};
     // optional per-launch CUDA-event timing (option "profile"): one event before every launch + one at the end
     int profile = 0;
@@ -462,7 +463,11 @@ static int plan_buffers(const orbit_engine* e, int H, int W, BufSizes* bs) {
                 h = ho; w = wo;
                 if (h < 1 || w < 1) return ORBIT_ERR_UNSUPPORTED;
                 need(op.out, (int64_t)h * w * op.cout);
-                if (op.kind == OP_DW) need(BUF_PARTIAL, (int64_t)dw_partial_groups(op.cout, h, w, op.k, op.stride) * op.cout);
+                if (op.kind == OP_DW) {
+                    need(BUF_PARTIAL, (int64_t)dw_partial_groups(op.cout, h, w, op.k, op.stride) * op.cout);
+                    if (op.cout % 2 == 0 && (op.k == 3 || op.k == 5))     // the fused expand + depthwise kernel tiles differently
+                        need(BUF_PARTIAL, (int64_t)mbx_partial_groups(op.cout, h, w, op.k, op.stride) * op.cout);
+                }
                 break;
             }
             case OP_SE: need(BUF_GATE, op.cout); break;
@@ -552,6 +557,7 @@ extern "C" int orbit_engine_set_option(orbit_engine* e, const char* key, int val
     if (!std::strcmp(key, "chunk_frames")) { if (value < 1 || value > 4096) return ORBIT_ERR_ARG; e->chunk_frames = value; return ORBIT_OK; }
     if (!std::strcmp(key, "gemm")) { if (value < 0 || value > 2) return ORBIT_ERR_ARG; e->gemm_mode = value; return ORBIT_OK; }
     if (!std::strcmp(key, "profile")) { e->profile = value != 0; return ORBIT_OK; }
+    if (!std::strcmp(key, "fuse_mbconv")) { e->fuse_mbconv = value != 0; return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 extern "C" int orbit_engine_get_option(const orbit_engine* e, const char* key, int* value) {
@@ -559,6 +565,7 @@ extern "C" int orbit_engine_get_option(const orbit_engine* e, const char* key, i
     if (!std::strcmp(key, "chunk_frames")) { *value = e->chunk_frames; return ORBIT_OK; }
     if (!std::strcmp(key, "gemm")) { *value = e->gemm_mode; return ORBIT_OK; }
     if (!std::strcmp(key, "profile")) { *value = e->profile; return ORBIT_OK; }
+    if (!std::strcmp(key, "fuse_mbconv")) { *value = e->fuse_mbconv; return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 
@@ -710,9 +717,33 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
             return b >= 0 ? buf[b] : nullptr;
         };
         int h = height, w = width, se_tiles = 0, se_hw = 0;
-        for (const Op& op : e->ops) {
+        for (size_t oi = 0; oi < e->ops.size(); ++oi) {
+            const Op& op = e->ops[oi];
             const int passes = (calib && op.fold_idx >= 0) ? 2 : 1;
             int ho = h, wo = w;
+            // MBConv front half in one kernel (expand 1x1 + bn1 + SiLU -> depthwise + bn2/FiLM + SiLU + SE partials): the
+            // 6x-expanded tensor never reaches HBM. Not during BatchNorm calibration (needs the expand output's statistics).
+            if (!calib && e->fuse_mbconv && e->gemm_mode != 0 && op.kind == OP_PW && !op.gated && op.act == ACT_SILU && op.res == BUF_NONE &&
+                oi + 1 < e->ops.size() && e->ops[oi + 1].kind == OP_DW && e->ops[oi + 1].in == op.out &&
+                e->ops[oi + 1].act == ACT_SILU && mbx_supported(op.cin, e->ops[oi + 1].k, e->ops[oi + 1].stride) && !e->tokens) {
+                const Op& dw = e->ops[oi + 1];
+                int pt, pl;
+                same_geometry(h, dw.k, dw.stride, &ho, &pt);
+                same_geometry(w, dw.k, dw.stride, &wo, &pl);
+                if (e->profile) { rc = prof_mark(e, st); if (rc) return rc; }
+                rc = launch_mbconv_expand_dw(ptr(op.in), params + op.w, derived + op.fold, derived + op.fold + op.cout,
+                                             derived + dw.dw_wt, derived + dw.fold, derived + dw.fold + dw.cout, ptr(dw.out),
+                                             buf[BUF_PARTIAL], B, h, w, op.cin, op.cout, ho, wo, dw.k, dw.stride, pt, pl, st);
+                if (rc) return rc;
+                ++launches;
+                se_tiles = mbx_partial_groups(op.cout, ho, wo, dw.k, dw.stride); se_hw = ho * wo;
+                if (e->profile)
+                    e->prof_recs.push_back({(int)OP_DW, 4.0 * B * ((double)h * w * op.cin + (double)ho * wo * dw.cout + (double)se_tiles * dw.cout),
+                                            2.0 * B * ((double)h * w * op.cin * op.cout + (double)dw.k * dw.k * dw.cout * ho * wo)});
+                h = ho; w = wo;
+                ++oi;            // the depthwise op is done too
+                continue;
+            }
             for (int pass = 0; pass < passes; ++pass) {
                 const bool raw = passes == 2 && pass == 0;
                 const float* scale = (raw || op.bias_only) ? derived + e->ident : derived + op.fold;

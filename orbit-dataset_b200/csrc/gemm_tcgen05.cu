@@ -157,12 +157,15 @@ __device__ __forceinline__ f2_t f2_silu(f2_t x) {
 __device__ __forceinline__ f2_t f2_relu(f2_t x) { float a, b; f2_unpack(x, a, b); return f2_pack(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
 
 // (x0, x1) fp32 -> packed fp16 pair hi (x0 in the low half = lower address = smaller k) and the scaled residual pair
-// lo = fp16((x - hi) * 2^11). x - hi is exact in fp32; saturating conversion keeps out-of-range inputs finite.
-__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+// lo = fp16((x - hi) * 2^11). x - hi is exact in fp32, and so are the 2^11 scalings, so the residual is formed with two
+// packed fp32x2 operations (x * 2^11, then hi * -2^11 + that); saturating conversions keep out-of-range inputs finite.
+__device__ __forceinline__ void split_f16x2(f2_t x, uint32_t& hi, uint32_t& lo) {
+    float x0, x1, h0, h1, r0, r1;
+    f2_unpack(x, x0, x1);
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-    float h0, h1;
     asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
-    const float r0 = (x0 - h0) * 2048.0f, r1 = (x1 - h1) * 2048.0f;
+    const f2_t r = f2_fma(f2_pack(h0, h1), f2_pack(-2048.0f, -2048.0f), f2_mul(x, f2_pack(2048.0f, 2048.0f)));
+    f2_unpack(r, r0, r1);
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 __device__ __forceinline__ uint32_t pack_f16x2(float x0, float x1) {
@@ -239,7 +242,8 @@ constexpr int SS_BYTES = 256;   // per epilogue warp: scale[32] | shift[32] of t
 // Template parameters fix at compile time what would otherwise be decided per element at run time:
 //   SPLIT  FP16x3 (hi/lo, fp32-grade) or one plain fp16 product (the `fast` numerics mode, 2^-11 relative per product);
 //   GATED / RES  0, 1, or -1 = look at the arguments;  ACT  activation or -1;  XFW  transform warps (4 or 8).
-template <bool SPLIT, int GATED, int ACT, int RES, int XFW>
+//   NARROW the transform's lane mapping for K <= 32 (one k-block, fp32 box 0 only), see the transform role.
+template <bool SPLIT, int GATED, int ACT, int RES, int XFW, bool NARROW>
 __global__ void __launch_bounds__(num_threads(XFW), 1)
 pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
@@ -374,19 +378,37 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     } else if (warp < EPI_WARP0) {
         // ================================ A transform ================================
-        // 8 threads per tile row; thread q converts k = 8q .. 8q+7 of the k-block: source = two 16-byte chunks of the
-        // fp32 box q/4 (TMA SWIZZLE_128B: chunk ^= row & 7), destination = the 16-byte chunk q of the fp16 hi tile
-        // (which overlays box 0) and of the lo tile (box 1). In place: a row is converted by 8 adjacent lanes of one
-        // warp, all loads of a batch of rows are issued before its stores.
-        constexpr int XR = BM / (NUM_XF_WARPS * 4);      // rows per thread (8 or 4)
+        // fp32 [128 x 64] (two TMA boxes, SWIZZLE_128B: 16-byte chunk ^= row & 7) -> fp16 hi tile (overlays box 0) and
+        // lo tile (overlays box 1), in place. A thread converts 8 consecutive k of one row: two 16-byte source chunks,
+        // one 16-byte destination chunk per tile. All lanes that touch a row sit in ONE warp and a batch's loads are
+        // issued before its stores, which is what makes the in-place overwrite safe.
+        //   K > 32: 8 lanes per row (lane q <-> k = 8q..8q+7: box q/4, source chunks 2(q&3), 2(q&3)+1). The lanes of box 1
+        //           fetch their ODD chunk first: a quarter-warp then reads 8 distinct bank groups per LDS.128 (it was a
+        //           2-way conflict when both boxes fetched the even chunk: ncu r02a, 48 % of the shared wavefronts).
+        //   K <= 32 (one k-block, box 0 only: the 112x112 / 56x56 layers): 4 lanes per row, 8 rows per warp step instead of
+        //           leaving half (K = 24, 32) or three quarters (K = 16) of the lanes idle; a quarter-warp holds rows m and
+        //           m ^ 5, whose swizzles differ in bits 0 and 2 = conflict-free loads AND stores.
+        constexpr int XR = BM / (NUM_XF_WARPS * 4);      // rows per thread in the wide mapping (8 or 4)
         constexpr int XS = NUM_XF_WARPS * 4;             // row stride between them (16 or 32: multiples of the 8-row swizzle period)
         constexpr int RB = 2;                            // rows per load/convert/store batch
         const int t = threadIdx.x - XF_WARP0 * 32;
-        const int q = t & 7;
-        const int rbase = t >> 3;                        // rows rbase + XS*i
-        const int sw = rbase & 7;
-        const uint32_t src_off = (uint32_t)((q >> 2) * A_BOX_BYTES + rbase * 128 + (((2 * (q & 3)) ^ sw) * 16));   // second chunk: ^ 16
-        const uint32_t dst_off = (uint32_t)(rbase * 128 + ((q ^ sw) * 16));
+        constexpr bool narrow = NARROW;
+        int q, row0, box;
+        if (narrow) {
+            const int j = lane >> 2, m = j >> 1;
+            q = lane & 3; box = 0;
+            row0 = (t >> 5) * 8 + ((j & 1) ? (m ^ 5) : m);
+        } else {
+            q = t & 7; box = q >> 2;
+            row0 = t >> 3;
+        }
+        constexpr int nrows = narrow ? XR / 2 : XR;      // rows row0 + rstride * i
+        constexpr uint32_t rstride = (narrow ? 2u : 1u) * XS * 128u;      // bytes
+        const int sw = row0 & 7;
+        const bool swap = box != 0;                       // this lane loaded its odd chunk first
+        const int ka = 8 * q + 4 * box, kb4 = 8 * q + 4 * (1 - box);      // k (inside the k-block) of the first / second chunk loaded
+        const uint32_t src_off = (uint32_t)(box * A_BOX_BYTES + row0 * 128 + (((2 * (q & 3) + box) ^ sw) * 16));   // second chunk: ^ 16
+        const uint32_t dst_off = (uint32_t)(row0 * 128 + ((q ^ sw) * 16));
         uint32_t s = 0, ph = 0, xstep = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const float* grow[XR];
@@ -394,18 +416,18 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int m0 = (tile / p.n_tiles) * BM;
 #pragma unroll
                 for (int i = 0; i < XR; ++i)
-                    grow[i] = p.gate + (int64_t)(min(m0 + rbase + XS * i, p.M - 1) / p.rows_per_frame) * p.K + q * 8;
+                    grow[i] = p.gate + (int64_t)(min(m0 + row0 + (int)(rstride >> 7) * i, p.M - 1) / p.rows_per_frame) * p.K;
             }
             for (int kb = 0; kb < num_k; ++kb) {
                 const int krem = p.K - kb * BK;                               // real columns left in this k-block
                 const bool active = q * 8 < ceil_div(min(krem, BK), UMMA_K) * UMMA_K;   // the MMAs read this 8-column group
-                const bool g0_on = gated && q * 8 < krem, g1_on = gated && q * 8 + 4 < krem;
-                float4 g0[XR], g1[XR];
+                const bool ga_on = gated && ka < krem, gb_on = gated && kb4 < krem;
+                float4 ga[XR], gb[XR];
                 if (gated) {                                 // issue the gate loads before blocking on the TMA
 #pragma unroll
                     for (int i = 0; i < XR; ++i) {
-                        g0[i] = g0_on ? ldg4(grow[i] + kb * BK) : make_float4(1.f, 1.f, 1.f, 1.f);
-                        g1[i] = g1_on ? ldg4(grow[i] + kb * BK + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                        ga[i] = (ga_on && i < nrows) ? ldg4(grow[i] + kb * BK + ka) : make_float4(1.f, 1.f, 1.f, 1.f);
+                        gb[i] = (gb_on && i < nrows) ? ldg4(grow[i] + kb * BK + kb4) : make_float4(1.f, 1.f, 1.f, 1.f);
                     }
                 }
                 mbar_wait(full(s), ph);
@@ -414,28 +436,36 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (active) {
 #pragma unroll
                     for (int b = 0; b < XR; b += RB) {
-                        float4 v0[RB], v1[RB];
+                        if (b < nrows) {
+                            float4 va[RB], vb[RB];
 #pragma unroll
-                        for (int i = 0; i < RB; ++i) {
-                            v0[i] = lds128(a + src_off + (b + i) * (XS * 128));
-                            v1[i] = lds128(a + (src_off ^ 16u) + (b + i) * (XS * 128));
-                        }
-#pragma unroll
-                        for (int i = 0; i < RB; ++i) {
-                            if (gated) {
-                                const float4 ga = g0[b + i], gb = g1[b + i];
-                                v0[i].x *= ga.x; v0[i].y *= ga.y; v0[i].z *= ga.z; v0[i].w *= ga.w;
-                                v1[i].x *= gb.x; v1[i].y *= gb.y; v1[i].z *= gb.z; v1[i].w *= gb.w;
+                            for (int i = 0; i < RB; ++i) {
+                                va[i] = lds128(a + src_off + (b + i) * rstride);
+                                vb[i] = lds128(a + (src_off ^ 16u) + (b + i) * rstride);
                             }
-                            if (SPLIT) {
-                                uint32_t h[4], l[4];
-                                split_f16x2(v0[i].x, v0[i].y, h[0], l[0]); split_f16x2(v0[i].z, v0[i].w, h[1], l[1]);
-                                split_f16x2(v1[i].x, v1[i].y, h[2], l[2]); split_f16x2(v1[i].z, v1[i].w, h[3], l[3]);
-                                sts128_u(a + dst_off + (b + i) * (XS * 128), h[0], h[1], h[2], h[3]);
-                                sts128_u(a + A_BOX_BYTES + dst_off + (b + i) * (XS * 128), l[0], l[1], l[2], l[3]);
-                            } else {
-                                sts128_u(a + dst_off + (b + i) * (XS * 128), pack_f16x2(v0[i].x, v0[i].y), pack_f16x2(v0[i].z, v0[i].w),
-                                         pack_f16x2(v1[i].x, v1[i].y), pack_f16x2(v1[i].z, v1[i].w));
+#pragma unroll
+                            for (int i = 0; i < RB; ++i) {
+                                f2_t xa[2] = {f2_pack(va[i].x, va[i].y), f2_pack(va[i].z, va[i].w)};
+                                f2_t xb[2] = {f2_pack(vb[i].x, vb[i].y), f2_pack(vb[i].z, vb[i].w)};
+                                if (gated) {
+                                    const float4 g0 = ga[b + i], g1 = gb[b + i];
+                                    xa[0] = f2_mul(xa[0], f2_pack(g0.x, g0.y)); xa[1] = f2_mul(xa[1], f2_pack(g0.z, g0.w));
+                                    xb[0] = f2_mul(xb[0], f2_pack(g1.x, g1.y)); xb[1] = f2_mul(xb[1], f2_pack(g1.z, g1.w));
+                                    f2_unpack(xa[0], va[i].x, va[i].y); f2_unpack(xa[1], va[i].z, va[i].w);
+                                    f2_unpack(xb[0], vb[i].x, vb[i].y); f2_unpack(xb[1], vb[i].z, vb[i].w);
+                                }
+                                const uint32_t d = a + dst_off + (b + i) * rstride;
+                                if (SPLIT) {
+                                    uint32_t ha[2], la[2], hb[2], lb[2];
+                                    split_f16x2(xa[0], ha[0], la[0]); split_f16x2(xa[1], ha[1], la[1]);
+                                    split_f16x2(xb[0], hb[0], lb[0]); split_f16x2(xb[1], hb[1], lb[1]);
+                                    sts128_u(d, swap ? hb[0] : ha[0], swap ? hb[1] : ha[1], swap ? ha[0] : hb[0], swap ? ha[1] : hb[1]);
+                                    sts128_u(d + A_BOX_BYTES, swap ? lb[0] : la[0], swap ? lb[1] : la[1], swap ? la[0] : lb[0], swap ? la[1] : lb[1]);
+                                } else {
+                                    const uint32_t ha0 = pack_f16x2(va[i].x, va[i].y), ha1 = pack_f16x2(va[i].z, va[i].w);
+                                    const uint32_t hb0 = pack_f16x2(vb[i].x, vb[i].y), hb1 = pack_f16x2(vb[i].z, vb[i].w);
+                                    sts128_u(d, swap ? hb0 : ha0, swap ? hb1 : ha1, swap ? ha0 : hb0, swap ? ha1 : hb1);
+                                }
                             }
                         }
                     }
@@ -471,7 +501,20 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int sl = (share + EPI_SPLIT - (int)(tcount % EPI_SPLIT)) % EPI_SPLIT;
             const int c0 = sl * 32;
             const bool have = sl < n_slabs;                                  // this warp holds a slab of the tile
-            const bool live = have && row0 < p.M && n0 + c0 < p.N;           // ... that has rows / columns to store
+            if (!have) {
+                // Narrow layers (N <= 64) leave one or two of a lane group's three warps without a slab. They still take part
+                // in every accumulator hand-off (wait + arrive, nothing else): every waiter must observe every phase of an
+                // mbarrier -- a warp that skipped tiles could fall two phases behind and mistake an older completion of the
+                // same parity for its own (tried in round 2: deadlocks under load).
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    mbar_wait(main_full(mb), mph);
+                    if (lane == 0) mbar_arrive(main_empty(mb));
+                    if (++mb == NM) { mb = 0; mph ^= 1; }
+                }
+                if (SPLIT && lane == 0) mbar_arrive(tmem_empty(acc));
+                continue;
+            }
+            const bool live = row0 < p.M && n0 + c0 < p.N;                   // ... that has rows / columns to store
             const bool wide = p.BN - c0 > 16;                                // the slab's second 16 columns exist in TMEM
             const uint32_t stage = my_staging + (slab_count % nbuf) * SLAB_BYTES;
             auto wait_staging_free = [&]() { if (nbuf == 2) tma_store_wait_read1(); else tma_store_wait_read0(); };
@@ -496,7 +539,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 mbar_wait(main_full(mb), mph);
                 if (ew == 0 && lane == 0) trace_stamp(p.trace, it, 8);
                 tc_fence_after();
-                if (have) {
+                {
                     float u[32];
                     const uint32_t col = t_lane + mb * MS + c0;
                     tmem_ld16_issue(col, u);
@@ -533,7 +576,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++mb == NM) { mb = 0; mph ^= 1; }
             }
             if (SPLIT) {   // tcgen05.commit covers ALL earlier MMAs: the last main_full also completed the correction terms
-                if (have) {
+                {
                     float u[32];
                     const uint32_t col = t_lane + CORR0 + acc * (uint32_t)p.BN + c0;
                     tmem_ld16_issue(col, u);
@@ -641,6 +684,9 @@ static int make_map(CUtensorMap* map, const void* base, bool f16, int64_t rows, 
 
 static float g_debias_kappa = 1.0f;   // one ulp of every promoted k-block partial (4 truncating MMAs: 0.5*(1+.75+.5+.25) ulp expected loss)
 static unsigned* g_gemm_trace = nullptr;
+static int g_narrow = 1;
+void set_tcgen05_narrow(int on) { g_narrow = on; }
+int get_tcgen05_narrow() { return g_narrow; }
 void set_tcgen05_trace(unsigned* dev_buffer) { g_gemm_trace = dev_buffer; }
 void set_tcgen05_debias(float kappa) { g_debias_kappa = kappa; }
 float get_tcgen05_debias() { return g_debias_kappa; }
@@ -692,20 +738,22 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     KernelFn fn = nullptr;
     int xfw = 4;
     const bool g = gate != nullptr, r = residual != nullptr;
+    const bool narrow = K <= 32 && g_narrow;
     if (passes == 3) {
-        if (g && act == 0 && !r && K <= 32) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4>;                // first MBConv project
-        else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8>; xfw = 8; }          // MBConv project
-        else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8>; xfw = 8; }           // ... + skip
-        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4>;    // MBConv expand / conv_head (SiLU)
-        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4>;    // Linear / downsample
-        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4>;     // Linear + residual (ViT), EdgeResidual project
-        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4>;    // conv + ReLU
-        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0, 4>;    // Linear + GELU
-        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4>;   // BasicBlock: relu(bn(conv) + identity)
-        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1, 4>;     // ConvBnAct + skip (EfficientNet-V2)
-        else fn = pw_tcgen05_kernel<true, -1, -1, -1, 4>;
+        if (g && act == 0 && !r && narrow) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, true>;           // first MBConv project (K = 32)
+        else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8, false>; xfw = 8; }   // MBConv project
+        else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8, false>; xfw = 8; }    // ... + skip
+        else if (!g && act == 1 && !r && narrow) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, true>;    // MBConv expand at 112x112 / 56x56 (K = 16, 24)
+        else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, false>;    // MBConv expand / conv_head (SiLU)
+        else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4, false>;    // Linear / downsample
+        else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4, false>;     // Linear + residual (ViT), EdgeResidual project
+        else if (!g && act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4, false>;    // conv + ReLU
+        else if (!g && act == 4 && !r) fn = pw_tcgen05_kernel<true, 0, 4, 0, 4, false>;    // Linear + GELU
+        else if (!g && act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4, false>;   // BasicBlock: relu(bn(conv) + identity)
+        else if (!g && act == 1 && r) fn = pw_tcgen05_kernel<true, 0, 1, 1, 4, false>;     // ConvBnAct + skip (EfficientNet-V2)
+        else fn = pw_tcgen05_kernel<true, -1, -1, -1, 4, false>;
     } else {
-        fn = pw_tcgen05_kernel<false, -1, -1, -1, 4>;
+        fn = pw_tcgen05_kernel<false, -1, -1, -1, 4, false>;
     }
     static int num_sms = 0;
     if (!num_sms) {

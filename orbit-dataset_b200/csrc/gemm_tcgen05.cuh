@@ -20,5 +20,8 @@ void set_tcgen05_debias(float kappa);
 // dev aid: device buffer of 256 x 16 uint32 that CTA 0 of every following GEMM launch fills with per-role clock stamps (null = off)
 void set_tcgen05_trace(unsigned* dev_buffer);
 float get_tcgen05_debias();
+// dev A/B switch: 4-lanes-per-row transform mapping for K <= 32 (default on)
+void set_tcgen05_narrow(int on);
+int get_tcgen05_narrow();
 
 }  // namespace orbit

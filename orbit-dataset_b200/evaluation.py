@@ -31,6 +31,15 @@ class ShardedFrameAccuracy:
         self.counts += torch.stack((correct, torch.tensor(n, device=correct.device)))
         self.sums += torch.stack((acc, acc * acc, torch.ones((), dtype=torch.float64, device=acc.device)))
 
+    def append_videos(self, predictions: torch.Tensor, labels: torch.Tensor):
+        """``predictions`` [videos, frames] arg-max class indices of equally long videos, ``labels`` [videos]: the same
+        sums as calling append_video per row, in four device operations and without a host sync."""
+        hit = predictions.long() == labels.long().unsqueeze(1)
+        correct = hit.sum(dim=1)
+        acc = correct.double() / predictions.shape[1]
+        self.counts += torch.stack((correct.sum(), torch.tensor(predictions.numel(), device=correct.device)))
+        self.sums += torch.stack((acc.sum(), (acc * acc).sum(), torch.tensor(float(len(acc)), dtype=torch.float64, device=acc.device)))
+
     def reduce(self, group=None):
         """All-reduce over the ranks (NCCL on GPUs, gloo on CPU) and return the run's statistics."""
         import torch.distributed as dist

@@ -70,6 +70,27 @@ def make_episode(spec: EpisodeSpec, index: int = 0, seed: int = 1991, pin: bool 
     return ctx, ctx_labels, tgt, tgt_labels
 
 
+def make_episode_on_device(spec: EpisodeSpec, index: int, device, seed: int = 1991):
+    """Same construction as ``make_episode`` with the frame noise drawn by the DEVICE generator (Philox, seeded by the
+    episode index only): a fixed list of episodes can be materialised on whichever GPU an episode is dealt to, and is
+    bit-identical there -- what the sharded evaluation's exactness check needs. Labels / object choice
+    come from the CPU generator (a few hundred integers)."""
+    g = torch.Generator(device=device).manual_seed(seed + index)
+    cg = torch.Generator().manual_seed(seed + index)
+    ns, nq = spec.way * spec.support_clips_per_class, spec.way * spec.query_clips_per_class
+    shape = (spec.clip_length, 3, spec.frame_size, spec.frame_size)
+    ctx = torch.randn((ns,) + shape, generator=g, device=device)
+    tgt = torch.randn((nq,) + shape, generator=g, device=device)
+    objects = torch.randperm(NUM_OBJECTS, generator=cg)[:spec.way]
+    ctx_labels = torch.arange(spec.way).repeat_interleave(spec.support_clips_per_class)[torch.randperm(ns, generator=cg)]
+    tgt_labels = torch.arange(spec.way).repeat_interleave(spec.query_clips_per_class)[torch.randperm(nq, generator=cg)]
+    bank = object_bank(spec.frame_size)[objects].to(device)
+    ctx_labels, tgt_labels = ctx_labels.to(device), tgt_labels.to(device)
+    ctx += bank[ctx_labels][:, None]
+    tgt += bank[tgt_labels][:, None]
+    return ctx, ctx_labels, tgt, tgt_labels
+
+
 def load_synthetic_checkpoint(model, frame_size: int = 224, seed: int = 1991):
     """Gives a recogniser that is already on its CUDA device a synthetic 'pretrained' extractor: seeded
     isometric weights (FeatureExtractor.reset_parameters) + BatchNorm statistics calibrated on device over

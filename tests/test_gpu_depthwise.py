@@ -6,8 +6,6 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-DEFAULT_VARIANT = 2   # keep in step with g_dw_variant in csrc/convnet.cu
-
 CASES = [  # (B, H, C, k, stride)
     (2, 112, 32, 3, 1), (2, 112, 96, 3, 2), (3, 56, 144, 5, 2), (3, 28, 240, 5, 1), (2, 28, 240, 3, 2),
     (4, 14, 480, 3, 1), (3, 14, 672, 5, 1), (5, 14, 672, 5, 2), (7, 7, 1152, 5, 1), (3, 7, 1152, 3, 1),
@@ -15,17 +13,11 @@ CASES = [  # (B, H, C, k, stride)
 ]
 
 
-@pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("B,H,C,k,stride", CASES)
-def test_depthwise_matches_torch(cuda_device, B, H, C, k, stride, variant):
-    """variant 2 = packed-FMA kernels with a one-row register prefetch; 3 = the cp.async-ring kernel (K=5, stride 1 only;
-    other shapes fall through to variant 2)."""
+def test_depthwise_matches_torch(cuda_device, B, H, C, k, stride):
     from orbit_b200 import lib as L
     from oracle.backbones import tf_same_pad
     lib = L.load()
-    if variant == 3 and not (k == 5 and stride == 1):
-        pytest.skip("variant 3 only replaces the K=5 stride-1 kernels")
-    L.check(lib.orbit_set_global_option(b"dw_variant", variant), "dw_variant")
     g = torch.Generator().manual_seed(H * C + k)
     x = torch.randn(B, C, H, H, generator=g)
     w = torch.randn(C, 1, k, k, generator=g) * 0.3
@@ -48,7 +40,6 @@ def test_depthwise_matches_torch(cuda_device, B, H, C, k, stride, variant):
                                      L.ptr(y), L.ptr(partial), L.ptr(scratch), B, H, H, C, k, stride, 1, L.stream_ptr(cuda_device)),
             "orbit_depthwise_conv")
     torch.cuda.synchronize()
-    lib.orbit_set_global_option(b"dw_variant", DEFAULT_VARIANT)
     got = y.permute(0, 3, 1, 2).cpu()
     assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
     sums = partial.view(B, -1, C).sum(1).cpu()

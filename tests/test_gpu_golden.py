@@ -1,0 +1,182 @@
+"""The CUDA path against the REFERENCE's own outputs, in one hop.
+
+tests/golden/{recogniser,parts}.npz were written by oracle/make_golden.py running the UNMODIFIED reference modules
+(model/few_shot_recognisers.py, classifier_heads.py, set_encoders.py, feature_adapters.py, poolers.py) in the build
+container. Here the same seeded inputs and weights go through liborbit_b200 and are compared with those arrays
+directly -- not with the oracle restatement (tests/test_oracle_golden.py pins the oracle to the same arrays on the CPU).
+Reference sites: few_shot_recognisers.py:313-326,453-473 (single step), :207-258 (FineTuner),
+classifier_heads.py:94-105,202-263 (prototypes), :121-180 (versa), :265-368 (mahalanobis)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_logits_match
+from oracle import parts
+from oracle.recogniser import OracleRecogniser
+from orbit_b200.synthetic import EpisodeSpec, calibration_frames, make_episode
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+CASES = {   # tag -> (extractor, adapt_features, classifier): the six recogniser configurations make_golden.py ran
+    'proto_b0': ('efficientnet_b0', False, 'proto'),
+    'cosine_b0': ('efficientnet_b0', False, 'proto_cosine'),
+    'cnaps_b0': ('efficientnet_b0', True, 'versa'),
+    'protofilm_b0': ('efficientnet_b0', True, 'proto'),
+    'simplecnaps_b0': ('efficientnet_b0', True, 'mahalanobis'),
+    'proto_vit': ('vit_b_32', False, 'proto'),
+}
+
+
+def checksum(*tensors):
+    return float(sum(t.double().abs().sum().item() for t in tensors))
+
+
+@pytest.fixture(scope='module')
+def gr():
+    return np.load(os.path.join(GOLD, 'recogniser.npz'))
+
+
+@pytest.fixture(scope='module')
+def gp():
+    return np.load(os.path.join(GOLD, 'parts.npz'))
+
+
+def head_case(seed, ns, nq, L, D, C, offset=0, stride=1):
+    g = torch.Generator().manual_seed(seed)
+    sf = torch.randn(ns * L, D, generator=g) * 0.7 + 0.3
+    qf = torch.randn(nq * L, D, generator=g) * 0.7 + 0.3
+    labels = ((torch.arange(ns) % C) * stride + offset)[torch.randperm(ns, generator=g)]
+    return sf, qf, labels
+
+
+@pytest.mark.parametrize('tag', list(CASES))
+@pytest.mark.parametrize('on_device', [True, False], ids=['device_clips', 'host_clips'])
+def test_recogniser_matches_reference_output(cuda_device, gr, tag, on_device):
+    import orbit_b200
+    extractor, adapt, head = CASES[tag]
+    way, sup, qry, L, size = gr[tag + '_spec'].tolist()
+    # the checkpoint the reference run loaded (make_golden.py: ref.load_state_dict(oracle.state_dict()))
+    weights = OracleRecogniser(extractor, adapt, head, L, 4, 1.0, 1991, calibration_frames(size)).state_dict()
+    m = orbit_b200.SingleStepFewShotRecogniser(extractor, adapt, head, L, 4, False, 16, 1.0)
+    m.load_state_dict(weights, strict=True)
+    m._set_device(cuda_device)
+    m._send_to_device()
+    m.set_test_mode(True)
+    if adapt:   # gamma0/beta0 = the norm weights at construction time (few_shot_recognisers.py:286)
+        from orbit_b200.feature_extractors import get_film_parameters
+        m.film_generator.initial_film_parameters = get_film_parameters(m.film_parameter_names, m.feature_extractor)
+    ctx, ctx_y, tgt, _ = make_episode(EpisodeSpec(way, sup, qry, L, size), index=1)
+    assert checksum(ctx, tgt, ctx_y) == pytest.approx(float(gr[tag + '_checksum']), rel=1e-12)
+    c, t = (ctx.to(cuda_device), tgt.to(cuda_device)) if on_device else (ctx, tgt)
+    with torch.no_grad():
+        m.personalise(c, ctx_y.to(cuda_device))
+        logits = m.predict(t)
+    assert_logits_match(logits, gr[tag + '_logits'], f"{tag} vs reference")
+    if adapt:
+        ref_film = torch.as_tensor(gr[tag + '_film_bn1_weight'])
+        assert (m.film_dict['bn1.weight'].cpu() - ref_film).abs().max().item() <= 1e-5
+    # predict_a_batch (few_shot_recognisers.py:464-473) is the same computation on one un-batched call
+    with torch.no_grad():
+        one = m.predict_a_batch(t[:3])
+    assert torch.equal(one, logits[:3]) or (one - logits[:3]).abs().max().item() <= 1e-6 * max(1.0, float(logits.abs().max()))
+    m._reset()
+
+
+def test_finetuner_matches_reference_output(cuda_device, gr):
+    """MultiStepFewShotRecogniser, 5 Adam steps, vs the reference's learned head and logits (few_shot_recognisers.py:207-258)."""
+    import orbit_b200
+    weights = OracleRecogniser('efficientnet_b0', False, 'linear', 1, 5, 1.0, 1991, calibration_frames(64)).state_dict()
+    m = orbit_b200.MultiStepFewShotRecogniser('efficientnet_b0', False, 'linear', 1, 5, False, 1.0)
+    m.load_state_dict(weights, strict=True)
+    m._set_device(cuda_device)
+    m._send_to_device()
+    m.set_test_mode(True)
+    ctx, ctx_y, tgt, _ = make_episode(EpisodeSpec(4, 3, 2, 1, 64), index=2)
+    assert checksum(ctx, tgt, ctx_y) == pytest.approx(float(gr['finetune_checksum']), rel=1e-12)
+    args = {'num_grad_steps': 5, 'learning_rate': 0.1, 'optimizer': 'adam', 'loss_fn': None, 'extractor_lr_scale': 0.1,
+            'epsilon': 1e-8, 'weight_decay': 0.0, 'betas': (0.9, 0.999), 'momentum': 0.0}
+    m.personalise(ctx, ctx_y, dict(args))
+    assert (m.classifier.weight.detach().cpu() - torch.as_tensor(gr['finetune_weight'])).abs().max().item() <= 1e-4
+    assert (m.classifier.bias.detach().cpu() - torch.as_tensor(gr['finetune_bias'])).abs().max().item() <= 1e-4
+    assert_logits_match(m.predict(tgt), gr['finetune_logits'], "FineTuner vs reference")
+
+
+@pytest.mark.parametrize('i', range(4))
+@pytest.mark.parametrize('name,metric', [('proto', 'euclidean'), ('proto_cosine', 'cosine')])
+def test_proto_head_matches_reference_output(cuda_device, gp, i, name, metric):
+    from orbit_b200 import PrototypicalClassifier
+    seed, ns, nq, L, D, C, off, st = gp[f'{name}{i}_args'].tolist()
+    sf, qf, labels = head_case(seed, ns, nq, L, D, C, off, st)
+    assert checksum(sf, qf, labels) == pytest.approx(float(gp[f'{name}{i}_checksum']), rel=1e-12)
+    head = PrototypicalClassifier(1.7, metric)
+    head.configure(sf.to(cuda_device), labels.to(cuda_device), clip_length=L)
+    logits, am = head.predict(qf.to(cuda_device), clip_length=L, want_argmax=True)
+    ref = torch.as_tensor(gp[f'{name}{i}_logits'])
+    assert (head.weight.detach().cpu() - torch.as_tensor(gp[f'{name}{i}_weight'])).abs().max().item() <= 1e-5
+    if metric == 'euclidean':
+        b_ref = torch.as_tensor(gp[f'{name}{i}_bias'])
+        assert (head.bias.detach().cpu() - b_ref).abs().max().item() <= 1e-5 * max(1.0, b_ref.abs().max().item())
+    assert (logits.cpu() - ref).abs().max().item() <= 4e-6 * max(1.0, ref.abs().max().item())
+    assert torch.equal(am.cpu().long(), ref.argmax(1))            # every row
+    assert torch.equal(head.classes, torch.unique(labels))
+
+
+def test_versa_mahalanobis_linear_heads_match_reference_output(cuda_device, gp):
+    from orbit_b200.classifier_heads import LinearClassifier
+    from orbit_b200.classifier_heads_ext import MahalanobisClassifier, VersaClassifier
+    sf, qf, labels = head_case(200, 40, 16, 1, 128, 5)
+    versa = VersaClassifier(128, 0.5)
+    versa.load_state_dict(parts.init_versa_params(128, seed=7), strict=True)
+    versa.to(cuda_device)
+    versa.configure(sf.to(cuda_device), labels.to(cuda_device))
+    assert (versa.weight.detach().cpu() - torch.as_tensor(gp['versa_weight'])).abs().max().item() <= 2e-6
+    assert (versa.bias.detach().cpu() - torch.as_tensor(gp['versa_bias'])).abs().max().item() <= 2e-6
+    assert_logits_match(versa.predict(qf.to(cuda_device)), gp['versa_logits'], "versa head vs reference")
+    sf, qf, labels = head_case(201, 40, 16, 1, 32, 4)
+    maha = MahalanobisClassifier(2.0)
+    maha.configure(sf.to(cuda_device), labels.to(cuda_device))
+    assert (maha.means.detach().cpu() - torch.as_tensor(gp['maha_means'])).abs().max().item() <= 1e-5
+    ref = torch.as_tensor(gp['maha_logits'])
+    got = maha.predict(qf.to(cuda_device)).cpu()
+    assert (got - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+    assert torch.equal(got.argmax(1), ref.argmax(1))
+    g = torch.Generator().manual_seed(202)
+    lin = LinearClassifier(64, 3.0)
+    lin.init(6)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(6, 64, generator=g))
+        lin.bias.copy_(torch.randn(6, generator=g))
+    lin.to(cuda_device)
+    x = torch.randn(10, 64, generator=g)
+    assert_logits_match(lin.predict(x.to(cuda_device)), gp['linear_logits'], "linear head vs reference")
+
+
+def test_set_encoder_and_film_generator_match_reference_output(cuda_device, gp):
+    from orbit_b200.feature_adapters import FilmParameterGenerator, SetEncoder
+    enc = SetEncoder()
+    enc.load_state_dict(parts.init_set_encoder_params(seed=11), strict=True)
+    enc.to(cuda_device)
+    g = torch.Generator().manual_seed(203)
+    for size in (84, 224):
+        clips = torch.randn(3, 2, 3, size, size, generator=g)
+        assert checksum(clips) == pytest.approx(float(gp[f'setenc{size}_checksum']), rel=1e-12)
+        reps = enc(clips.to(cuda_device))
+        ref = torch.as_tensor(gp[f'setenc{size}_reps'])
+        assert (reps.cpu() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+        agg = enc.aggregate([reps[:2], reps[2:]]).cpu()
+        assert (agg - torch.as_tensor(gp[f'setenc{size}_agg'])).abs().max().item() <= 2e-5
+    names = ['blocks.1.0.bn2.bias', 'blocks.1.0.bn2.weight', 'bn1.bias', 'bn1.weight']
+    sizes = {'blocks.1.0.bn2.bias': 96, 'blocks.1.0.bn2.weight': 96, 'bn1.bias': 32, 'bn1.weight': 32}
+    g = torch.Generator().manual_seed(204)
+    initial = {n: torch.randn(sizes[n], generator=g) for n in names}
+    gen = FilmParameterGenerator(sizes, {k: v.clone() for k, v in initial.items()}, 64, 64)
+    gen.load_state_dict(parts.init_film_generator_params([sizes[n] for n in sorted(names)], seed=13), strict=True)
+    gen.to(cuda_device)
+    z = torch.randn(1, 64, generator=g)
+    film = gen(z.to(cuda_device))
+    for n in names:
+        assert (film[n].cpu() - torch.as_tensor(gp['film_' + n])).abs().max().item() <= 2e-6, n
+    assert float(gen.regularization_term()) == pytest.approx(float(gp['film_l2']), rel=1e-4)
