@@ -307,6 +307,7 @@ template <> struct VecIO<2> {
 // ------------------------------------------------------------------------------------------------
 typedef unsigned long long f2_t;   // two packed fp32
 __device__ __forceinline__ void f2_unpack(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_pack(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
     f2_t d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -506,15 +507,36 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
 // Reference op sites: timm InvertedResidual conv_pw/bn1 -> conv_dw/bn2 (FiLM site, model/film.py:43-44) inside the
 // extractor invoked at model/few_shot_recognisers.py:114-117,143-146. At the 112x112 and 56x56 stages the 6x-expanded
 // tensor is 27 % of ALL layer-boundary traffic of the network (written by the expand GEMM, read back by the depthwise
-// kernel): here it never reaches HBM. The block input has only 16 / 24 channels, so the expansion is cheap enough for the
-// CUDA cores (exact fp32 FMA chains: no operand split needed) and is computed exactly ONCE per (pixel, channel):
-//   per virtual input row, all threads of the block expand the row segment the block's strips need
-//   ([pixels][channel pairs] -> shared memory, double buffered, one __syncthreads per row), then every thread feeds
-//   its strip's SPAN pixels from shared memory into the same rolling accumulators as dw2_kernel.
-// Zero padding applies to the EXPANDED tensor: out-of-image pixels are stored as zeros, not as expand(0).
-// Thread (lx, ly): channel pair lx of this block's chunk for both phases (its 2 x CIN expand weights live in registers),
-// pixels ly, ly + LY, ... in the expand phase, strip ly in the depthwise phase.
+// kernel): here it never reaches HBM. Per virtual input row of a block (= a set of adjacent 4-column strips x a chunk of
+// 2 LX channels of one frame):
+//   1. staging   the row segment of the 16/24-channel block input arrives in shared memory two rows ahead (coalesced
+//                float4 loads, one __syncthreads per row covers everything);
+//   2. expand    warp w owns the 8-channel group w (its weight fragments live in registers) and runs 16-pixel x 8-channel
+//                warp-level tensor-core tiles (mma.sync m16n8k8 tf32) over the segment: every (pixel, channel) is computed
+//                exactly ONCE, fp32-grade through the 3xTF32 split (hi.hi + lo.hi + hi.lo; each hi.hi product tile is
+//                added in fp32 registers with round-to-nearest, because tensor-core accumulation truncates), then
+//                bn1 + SiLU on packed fp32x2, zeroed outside the image (the zero padding applies to the EXPANDED
+//                tensor), stored [pixel][channel pair] to shared memory (double buffered);
+//   3. depthwise thread (lx, ly) feeds the SPAN pixels of strip ly for channel pair lx from shared memory into the same
+//                rolling accumulators as dw2_kernel and emits bn2/FiLM + SiLU outputs and the SE squeeze partial sums.
+// (Round-2 history, see DESIGN.md: a CUDA-core expand -- 2 x CIN scalar FMAs per value -- was correct but ALU-bound and
+// 20 % SLOWER than the unfused pair; loading the input inside the expand loop exposed an L2 round trip per pixel.)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2], const float (&c)[4]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+// fp32 -> tf32 hi (round to nearest, ties away: add half a tf32 ulp, clear 13 bits) and the exact residual lo = v - hi
+// (<= 13 significant bits; the tensor core reads its top 11)
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+
+constexpr int kMbxXPad = 4;      // floats of padding per staged input pixel: conflict-free A-fragment loads
+constexpr int kMbxEPad = 4;      // channel pairs of padding per expanded pixel: conflict-free C-fragment stores
+
 template <int K, int S, int CIN, int CT>
 __global__ void __launch_bounds__(256, 2)
 mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const float* __restrict__ scale1,
@@ -522,42 +544,57 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
            const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C_rt,
            int Ho, int Wo, int pad_t, int pad_l, int LX, int LY, int rows_per_tile, int strip_blocks) {
     constexpr int TW = kDwTW, R = (K + S - 1) / S, SPAN = (TW - 1) * S + K, HALF = (K - 1) / S, VEC = 2;
+    constexpr int KS = CIN / 8;                           // k-steps of the expand MMA
+    constexpr int XS = CIN + kMbxXPad;                    // staged pixel stride (floats)
     const int C = CT ? CT : C_rt;
     extern __shared__ __align__(16) float s_dyn[];
     constexpr int LXS = 32;
     const int P = (LY * TW - 1) * S + K;                  // input columns the block's strips touch
+    const int PM = (P + 15) / 16 * 16;                    // ... rounded up to whole 16-pixel MMA tiles
+    const int ES = LX + kMbxEPad;                         // expanded pixel stride (channel pairs)
     float* s_w = s_dyn;                                   // [K*K][LXS][2] depthwise taps of this block's channel chunk
     float* s_red = s_w + K * K * LXS * VEC;               // [LY][LX][2] partial-sum reduction
-    float* s_e = s_red + LY * LX * VEC;                   // [2][P][LX][2] expanded rows (double buffered)
+    float* s_e = s_red + LY * LX * VEC;                   // [2][PM][ES][2] expanded rows (double buffered)
+    float* s_x = s_e + 2 * PM * ES * VEC;                 // [2][PM][XS] block-input row segments (double buffered)
     const int tile = blockIdx.x / strip_blocks, sb = blockIdx.x % strip_blocks, chunk = blockIdx.y, b = blockIdx.z;
     const int groups = gridDim.x;
-    const int lx = threadIdx.x % LX, ly = threadIdx.x / LX;
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int lx = tid % LX, ly = tid / LX;               // depthwise role (threads beyond LX*LY only stage and expand)
     const int Cv = C / VEC;
     const int cv = chunk * LX + lx;
-    const bool chan = cv < Cv;
     const int strip = sb * LY + ly;
-    const bool live = chan && strip * TW < Wo;
-    for (int i = threadIdx.x; i < K * K * LXS; i += blockDim.x) {
+    const bool live = ly < LY && cv < Cv && strip * TW < Wo;
+    for (int i = tid; i < K * K * LXS; i += nthreads) {
         const int t = i / LXS, l = i % LXS, c = chunk * LX + l;
         float wv[VEC] = {0.f, 0.f};
         if (l < LX && c < Cv) VecIO<VEC>::load(wt + (int64_t)t * C + c * VEC, wv);
         VecIO<VEC>::store(s_w + (size_t)i * VEC, wv);
     }
-    // this thread's two rows of the expand weight matrix [C][CIN] and the folded bn1 of its channels
-    float w0[CIN], w1[CIN];
-    float s1a = 0.f, s1b = 0.f, h1a = 0.f, h1b = 0.f;
+    // zero both staging buffers once: padding floats and pixels beyond P are read by the MMA fragments
+    for (int i = tid; i < 2 * PM * XS; i += nthreads) s_x[i] = 0.f;
+
+    // ---- expand role: warp -> 8-channel groups warp, warp + nwarps, ... (LX / 4 groups); fragments of m16n8k8:
+    //      g = lane / 4, t = lane % 4;  A: (pixel g | g+8, k t | t+4);  B: (k t | t+4, channel g);  C: (pixel g | g+8, channel 2t, 2t+1)
+    const int g = lane >> 2, t4 = lane & 3;
+    const int ngroups = LX / 4;
+    constexpr int kMaxGroups = 1;                          // groups per warp: the launcher gives every group its own warp
+    uint32_t bh[kMaxGroups][KS][2], bl[kMaxGroups][KS][2];
+    f2_t s1p[kMaxGroups], h1p[kMaxGroups];
 #pragma unroll
-    for (int k = 0; k < CIN; ++k) { w0[k] = 0.f; w1[k] = 0.f; }
-    if (chan) {
+    for (int gi = 0; gi < kMaxGroups; ++gi) {
+        const int grp = warp + gi * nwarps;
+        const int cb = (chunk * LX + grp * 4) * VEC + g;            // channel of this lane's B column
+        const int cc = (chunk * LX + grp * 4 + t4) * VEC;           // first channel of this lane's C pair
+        const bool bok = grp < ngroups && cb < C, cok = grp < ngroups && cc < C;
 #pragma unroll
-        for (int k4 = 0; k4 < CIN / 4; ++k4) {
-            const float4 a = ldg4(we + (int64_t)(cv * VEC) * CIN + 4 * k4), c4 = ldg4(we + (int64_t)(cv * VEC + 1) * CIN + 4 * k4);
-            w0[4 * k4] = a.x; w0[4 * k4 + 1] = a.y; w0[4 * k4 + 2] = a.z; w0[4 * k4 + 3] = a.w;
-            w1[4 * k4] = c4.x; w1[4 * k4 + 1] = c4.y; w1[4 * k4 + 2] = c4.z; w1[4 * k4 + 3] = c4.w;
+        for (int ks = 0; ks < KS; ++ks) {
+            split_tf32(bok ? __ldg(we + (int64_t)cb * CIN + ks * 8 + t4) : 0.f, bh[gi][ks][0], bl[gi][ks][0]);
+            split_tf32(bok ? __ldg(we + (int64_t)cb * CIN + ks * 8 + t4 + 4) : 0.f, bh[gi][ks][1], bl[gi][ks][1]);
         }
-        s1a = __ldg(scale1 + cv * VEC); s1b = __ldg(scale1 + cv * VEC + 1);
-        h1a = __ldg(shift1 + cv * VEC); h1b = __ldg(shift1 + cv * VEC + 1);
+        s1p[gi] = cok ? __ldg(reinterpret_cast<const f2_t*>(scale1 + cc)) : 0ull;
+        h1p[gi] = cok ? __ldg(reinterpret_cast<const f2_t*>(shift1 + cc)) : 0ull;
     }
+
     float sum[VEC] = {0.f, 0.f};
     const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
     const int bx0 = sb * LY * TW * S - pad_l;             // input column of expanded-row slot 0
@@ -565,34 +602,84 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
     const int vy_lo = pad_t, vy_hi = min(H - 1 + pad_t, (row1 - 1) * S + K - 1);
     const float* xfr = xin + (int64_t)b * H * W * CIN;
     const uint32_t e_base = (uint32_t)__cvta_generic_to_shared(s_e);
-    const uint32_t e_row_bytes = (uint32_t)(P * LX * VEC * 4);
+    const uint32_t e_row_bytes = (uint32_t)(PM * ES * VEC * 4);
+    const uint32_t x_base = (uint32_t)__cvta_generic_to_shared(s_x);
+    const uint32_t x_row_bytes = (uint32_t)(PM * XS * 4);
 
-    // ---- expand phase: virtual row vy -> buffer eb -------------------------------------------------------------
-    auto expand_row = [&](int vy, int eb) {
+    // ---- input staging: the row segment [bx0, bx0 + P) x CIN of virtual row vy is one contiguous byte range of the NHWC
+    // tensor: every thread fetches at most kXLoads float4 of it (coalesced), two rows ahead of its use, so the L2 / HBM
+    // latency hides behind a whole row of expand + depthwise work.
+    constexpr int kXLoads = 3;
+    const int nf4 = P * CIN / 4;
+    auto fetch_row = [&](int vy, float4 (&xr)[kXLoads]) {
         const bool row_ok = vy >= vy_lo && vy <= vy_hi;
-        const float* xrow = xfr + (int64_t)(vy - pad_t) * W * CIN;
-        const uint32_t dst0 = e_base + (uint32_t)eb * e_row_bytes + (uint32_t)(lx * VEC * 4);
-#pragma unroll 2
-        for (int p = ly; p < P; p += LY) {
-            const int col = bx0 + p;
-            float e0 = 0.f, e1 = 0.f;
-            if (row_ok && chan && col >= 0 && col < W) {
-                const float* xp = xrow + (int64_t)col * CIN;
-                float4 xv[CIN / 4];
+        const float* xrow = xfr + ((int64_t)(vy - pad_t) * W + bx0) * CIN;
 #pragma unroll
-                for (int k4 = 0; k4 < CIN / 4; ++k4) xv[k4] = ldg4(xp + 4 * k4);   // same address for all lx lanes: one broadcast request
-                float a0 = 0.f, a1 = 0.f;
+        for (int j = 0; j < kXLoads; ++j) {
+            const int f = tid + j * nthreads;
+            const int col = bx0 + (4 * f) / CIN;
+            xr[j] = (row_ok && f < nf4 && col >= 0 && col < W) ? ldg4(xrow + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto stash_row = [&](int xb, const float4 (&xr)[kXLoads]) {
 #pragma unroll
-                for (int k4 = 0; k4 < CIN / 4; ++k4) {
-                    a0 = fmaf(xv[k4].x, w0[4 * k4], a0); a1 = fmaf(xv[k4].x, w1[4 * k4], a1);
-                    a0 = fmaf(xv[k4].y, w0[4 * k4 + 1], a0); a1 = fmaf(xv[k4].y, w1[4 * k4 + 1], a1);
-                    a0 = fmaf(xv[k4].z, w0[4 * k4 + 2], a0); a1 = fmaf(xv[k4].z, w1[4 * k4 + 2], a1);
-                    a0 = fmaf(xv[k4].w, w0[4 * k4 + 3], a0); a1 = fmaf(xv[k4].w, w1[4 * k4 + 3], a1);
-                }
-                e0 = silu_sfu(fmaf(a0, s1a, h1a));
-                e1 = silu_sfu(fmaf(a1, s1b, h1b));
+        for (int j = 0; j < kXLoads; ++j) {
+            const int f = tid + j * nthreads;
+            if (f < nf4) {
+                const int pix = (4 * f) / CIN, k = (4 * f) % CIN;
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(x_base + (uint32_t)xb * x_row_bytes + (uint32_t)((pix * XS + k) * 4)),
+                             "f"(xr[j].x), "f"(xr[j].y), "f"(xr[j].z), "f"(xr[j].w) : "memory");
             }
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst0 + (uint32_t)(p * LX * VEC * 4)), "f"(e0), "f"(e1) : "memory");
+        }
+    };
+    // ---- expand phase: virtual row vy (staged in s_x[xb]) -> s_e[eb] ----------------------------------------------
+    auto expand_row = [&](int vy, int xb, int eb) {
+        const bool row_ok = vy >= vy_lo && vy <= vy_hi;
+        const uint32_t src0 = x_base + (uint32_t)xb * x_row_bytes + (uint32_t)((g * XS + t4) * 4);
+        const uint32_t dst0 = e_base + (uint32_t)eb * e_row_bytes + (uint32_t)((g * ES + t4) * VEC * 4);
+        const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int mt = 0; mt < PM / 16; ++mt) {
+            // image-validity of this lane's two pixels (rows g and g + 8 of the tile)
+            const int c_lo = bx0 + mt * 16 + g, c_hi = c_lo + 8;
+            const bool ok_lo = row_ok && c_lo >= 0 && c_lo < W, ok_hi = row_ok && c_hi >= 0 && c_hi < W;
+            uint32_t ah[KS][4], al[KS][4];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const uint32_t ad = src0 + (uint32_t)((mt * 16 * XS + ks * 8) * 4);
+                float a0, a1, a2, a3;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a0) : "r"(ad) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(ad + (uint32_t)(8 * XS * 4)) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(ad + 16u) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a3) : "r"(ad + (uint32_t)(8 * XS * 4) + 16u) : "memory");
+                split_tf32(a0, ah[ks][0], al[ks][0]); split_tf32(a1, ah[ks][1], al[ks][1]);
+                split_tf32(a2, ah[ks][2], al[ks][2]); split_tf32(a3, ah[ks][3], al[ks][3]);
+            }
+#pragma unroll
+            for (int gi = 0; gi < kMaxGroups; ++gi) {
+                const int grp = warp + gi * nwarps;
+                if (grp < ngroups) {            // warp-uniform
+                    float acc4[4] = {0.f, 0.f, 0.f, 0.f}, corr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        float m4[4];
+                        mma_tf32_16x8x8(m4, ah[ks], bh[gi][ks], zero4);          // hi.hi of one k-step, added below with RN
+                        mma_tf32_16x8x8(corr, al[ks], bh[gi][ks], corr);
+                        mma_tf32_16x8x8(corr, ah[ks], bl[gi][ks], corr);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc4[i] += m4[i];
+                    }
+                    f2_t lo2 = f2_pack(acc4[0] + corr[0], acc4[1] + corr[1]), hi2 = f2_pack(acc4[2] + corr[2], acc4[3] + corr[3]);
+                    lo2 = f2_fma(lo2, s1p[gi], h1p[gi]);
+                    hi2 = f2_fma(hi2, s1p[gi], h1p[gi]);
+                    float e0, e1, e2, e3;
+                    f2_unpack(lo2, e0, e1); f2_unpack(hi2, e2, e3);
+                    e0 = ok_lo ? silu_sfu(e0) : 0.f; e1 = ok_lo ? silu_sfu(e1) : 0.f;
+                    e2 = ok_hi ? silu_sfu(e2) : 0.f; e3 = ok_hi ? silu_sfu(e3) : 0.f;
+                    const uint32_t d = dst0 + (uint32_t)((mt * 16 * ES + grp * 4) * VEC * 4);
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(d), "f"(e0), "f"(e1) : "memory");
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(d + (uint32_t)(8 * ES * VEC * 4)), "f"(e2), "f"(e3) : "memory");
+                }
+            }
         }
     };
 
@@ -602,7 +689,7 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
     const int ox0 = strip * TW;
     float* yb = y + ((int64_t)b * Ho * Wo + ox0) * C + cv * VEC;
     const float* wlane = s_w + lx * VEC;
-    const uint32_t e_mine = e_base + (uint32_t)((ly * TW * S * LX + lx) * VEC * 4);   // slot of this strip's first input column
+    const uint32_t e_mine = e_base + (uint32_t)((ly * TW * S * ES + lx) * VEC * 4);   // slot of this strip's first input column
     f2_t acc[R][TW], v[SPAN];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -610,18 +697,29 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
         for (int t = 0; t < TW; ++t) acc[r][t] = 0ull;
 
     if (row0 < row1) {          // block-uniform
-        expand_row(row0 * S, 0);
-        __syncthreads();        // also covers the tap table
-        int eb = 0;
+        // pipeline: s_x holds the block input of virtual rows v+1 (being expanded) and v+2 (arriving); s_e holds the expanded
+        // rows v (being consumed) and v+1 (being produced). One __syncthreads per row.
+        float4 xr[kXLoads];
+        const int v0 = row0 * S;
+        fetch_row(v0, xr);
+        __syncthreads();                                  // tap table + zeroed staging buffers
+        stash_row(v0 & 1, xr);
+        fetch_row(v0 + 1, xr);
+        __syncthreads();
+        expand_row(v0, v0 & 1, v0 & 1);
+        stash_row((v0 + 1) & 1, xr);
+        __syncthreads();
         // iteration m handles virtual rows m*S .. m*S+S-1; the oldest pending output row is m - HALF
         for (int m = row0; m < row1 + HALF; ++m) {
 #pragma unroll
             for (int sub = 0; sub < S; ++sub) {
-                expand_row(m * S + sub + 1, eb ^ 1);          // next row, other buffer
+                const int vy = m * S + sub, eb = vy & 1;
+                fetch_row(vy + 2, xr);                        // in flight during this row's work
+                expand_row(vy + 1, eb ^ 1, eb ^ 1);           // next row: s_x[eb^1] -> s_e[eb^1]
                 if (live) {
 #pragma unroll
                     for (int j = 0; j < SPAN; ++j)
-                        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[j]) : "r"(e_mine + (uint32_t)eb * e_row_bytes + (uint32_t)(j * LX * VEC * 4)) : "memory");
+                        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[j]) : "r"(e_mine + (uint32_t)eb * e_row_bytes + (uint32_t)(j * ES * VEC * 4)) : "memory");
 #pragma unroll
                     for (int ky = sub; ky < K; ky += S) {      // ky with (vy - ky) divisible by S
                         const int slot = HALF - (ky - sub) / S;
@@ -650,8 +748,8 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
                         }
                     }
                 }
-                __syncthreads();      // row eb consumed by everyone, row eb^1 complete
-                eb ^= 1;
+                stash_row(eb, xr);    // s_x[eb] (row vy) was last read by the previous iteration's expand: free
+                __syncthreads();      // s_e[eb] consumed by everyone; s_e[eb^1] and s_x[eb] complete
             }
             // rotate the ring: slot r <- slot r+1, newest slot cleared
 #pragma unroll
@@ -665,10 +763,12 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
         __syncthreads();
     }
     if (partial) {
-        s_red[(ly * LX + lx) * VEC] = sum[0];
-        s_red[(ly * LX + lx) * VEC + 1] = sum[1];
+        if (ly < LY) {
+            s_red[(ly * LX + lx) * VEC] = sum[0];
+            s_red[(ly * LX + lx) * VEC + 1] = sum[1];
+        }
         __syncthreads();
-        if (ly == 0 && chan) {
+        if (ly == 0 && cv < Cv) {
             float t[VEC] = {s_red[lx * VEC], s_red[lx * VEC + 1]};
             for (int r = 1; r < LY; ++r) { t[0] += s_red[(r * LX + lx) * VEC]; t[1] += s_red[(r * LX + lx) * VEC + 1]; }
             VecIO<VEC>::store(partial + ((int64_t)b * groups + blockIdx.x) * C + cv * VEC, t);
@@ -676,12 +776,12 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
     }
 }
 
-struct MbxPlan { int LX, LY, nchunks, tiles, rows_per_tile, strip_blocks, groups; };
-static MbxPlan mbx_plan(int C, int Ho, int Wo, int k, int stride) {
+struct MbxPlan { int LX, LY, nchunks, tiles, rows_per_tile, strip_blocks, groups, threads, P, PM; size_t smem; };
+static MbxPlan mbx_plan(int Cin, int C, int Ho, int Wo, int k, int stride) {
     MbxPlan p;
     const int Cv = C / 2;
     p.nchunks = ceil_div(Cv, 32);
-    p.LX = ceil_div(Cv, p.nchunks);
+    p.LX = ceil_div(ceil_div(Cv, p.nchunks), 4) * 4;      // channel pairs per block: whole 8-channel MMA groups
     const int strips = ceil_div(Wo, kDwTW);
     const int ly_max = std::max(1, 256 / p.LX);
     p.strip_blocks = ceil_div(strips, ly_max);
@@ -691,21 +791,30 @@ static MbxPlan mbx_plan(int C, int Ho, int Wo, int k, int stride) {
     p.rows_per_tile = ceil_div(ceil_div(Ho, want_tiles), R) * R;
     p.tiles = ceil_div(Ho, p.rows_per_tile);
     p.groups = p.tiles * p.strip_blocks;
+    p.threads = std::max(32 * (p.LX / 4), ceil_div(p.LX * p.LY, 32) * 32);    // one warp per 8-channel group at least (<= 256)
+    p.P = (p.LY * kDwTW - 1) * stride + k;
+    p.PM = ceil_div(p.P, 16) * 16;
+    p.smem = sizeof(float) * ((size_t)k * k * 32 * 2 + (size_t)p.LY * p.LX * 2 + (size_t)2 * p.PM * (p.LX + kMbxEPad) * 2 +
+                              (size_t)2 * p.PM * (Cin + kMbxXPad));
     return p;
 }
 
 bool mbx_supported(int cin, int k, int stride) { return (cin == 16 || cin == 24) && (k == 3 || k == 5) && (stride == 1 || stride == 2); }
-int mbx_partial_groups(int C, int Ho, int Wo, int k, int stride) { return mbx_plan(C, Ho, Wo, k, stride).groups; }
+// whether the fused kernel's shared-memory footprint and its 3-loads-per-thread input staging cover this geometry
+bool mbx_fits(int Cin, int C, int Ho, int Wo, int k, int stride) {
+    if (C % 8 || !mbx_supported(Cin, k, stride)) return false;
+    const MbxPlan pl = mbx_plan(Cin, C, Ho, Wo, k, stride);
+    return pl.smem <= 100 * 1024 && (size_t)pl.P * Cin / 4 <= (size_t)3 * pl.threads && pl.LX / 4 <= pl.threads / 32 && pl.threads <= 256;
+}
+int mbx_partial_groups(int C, int Ho, int Wo, int k, int stride) { return mbx_plan(16, C, Ho, Wo, k, stride).groups; }
 
 int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scale1, const float* shift1, const float* wt,
                             const float* scale, const float* shift, float* y, float* partial, int B, int H, int W, int Cin,
                             int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, cudaStream_t st) {
-    if (C % 2 || !mbx_supported(Cin, k, stride)) return ORBIT_ERR_UNSUPPORTED;
-    const MbxPlan pl = mbx_plan(C, Ho, Wo, k, stride);
-    dim3 grid(pl.groups, pl.nchunks, B), block(pl.LX * pl.LY);
-    const int P = (pl.LY * kDwTW - 1) * stride + k;
-    const size_t smem = sizeof(float) * ((size_t)k * k * 32 * 2 + (size_t)pl.LY * pl.LX * 2 + (size_t)2 * P * pl.LX * 2);
-    if (smem > 200 * 1024) return ORBIT_ERR_UNSUPPORTED;
+    if (!mbx_fits(Cin, C, Ho, Wo, k, stride)) return ORBIT_ERR_UNSUPPORTED;
+    const MbxPlan pl = mbx_plan(Cin, C, Ho, Wo, k, stride);
+    dim3 grid(pl.groups, pl.nchunks, B), block(pl.threads);
+    const size_t smem = pl.smem;
 #define ORBIT_MBX(KK, SS, CI, CC)                                                                                     \
     if (k == KK && stride == SS && Cin == CI && (CC == 0 || C == CC)) {                                              \
         if (smem > 48 * 1024) ORBIT_CUDA(cudaFuncSetAttribute(mbx_kernel<KK, SS, CI, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -47,6 +47,7 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
 // channels: xin [B,H,W,Cin] -> y [B,Ho,Wo,C]; we = expand weights [C][Cin] (torch layout), scale1/shift1 = folded bn1,
 // wt = depthwise taps [k*k][C], scale/shift = folded bn2. partial as launch_depthwise with mbx_partial_groups(...).
 bool mbx_supported(int cin, int k, int stride);
+bool mbx_fits(int Cin, int C, int Ho, int Wo, int k, int stride);
 int mbx_partial_groups(int C, int Ho, int Wo, int k, int stride);
 int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scale1, const float* shift1, const float* wt,
                             const float* scale, const float* shift, float* y, float* partial, int B, int H, int W, int Cin,

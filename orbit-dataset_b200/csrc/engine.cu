@@ -725,7 +725,9 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
             // 6x-expanded tensor never reaches HBM. Not during BatchNorm calibration (needs the expand output's statistics).
             if (!calib && e->fuse_mbconv && e->gemm_mode != 0 && op.kind == OP_PW && !op.gated && op.act == ACT_SILU && op.res == BUF_NONE &&
                 oi + 1 < e->ops.size() && e->ops[oi + 1].kind == OP_DW && e->ops[oi + 1].in == op.out &&
-                e->ops[oi + 1].act == ACT_SILU && mbx_supported(op.cin, e->ops[oi + 1].k, e->ops[oi + 1].stride) && !e->tokens) {
+                e->ops[oi + 1].act == ACT_SILU && mbx_supported(op.cin, e->ops[oi + 1].k, e->ops[oi + 1].stride) && !e->tokens &&
+                mbx_fits(op.cin, op.cout, (h + e->ops[oi + 1].stride - 1) / e->ops[oi + 1].stride,
+                         (w + e->ops[oi + 1].stride - 1) / e->ops[oi + 1].stride, e->ops[oi + 1].k, e->ops[oi + 1].stride)) {
                 const Op& dw = e->ops[oi + 1];
                 int pt, pl;
                 same_geometry(h, dw.k, dw.stride, &ho, &pt);

@@ -86,7 +86,11 @@ def test_recogniser_matches_reference_output(cuda_device, gr, tag, on_device):
 
 
 def test_finetuner_matches_reference_output(cuda_device, gr):
-    """MultiStepFewShotRecogniser, 5 Adam steps, vs the reference's learned head and logits (few_shot_recognisers.py:207-258)."""
+    """MultiStepFewShotRecogniser, 5 Adam steps, vs the reference's learned head and logits (few_shot_recognisers.py:207-258).
+    Case `finetune2` (class counts 3,3,3,2): in the balanced case `finetune` the first bias gradient of the zero-initialised
+    head is exactly 0 in exact arithmetic and Adam's g/(|g|+eps) amplifies whatever rounding noise the summation order of
+    the implementation leaves (+-0.04 on the bias) -- that case can only pin an implementation that shares torch's CPU
+    summation order (the oracle, tests/test_oracle_golden.py); it is still checked here for its class indices."""
     import orbit_b200
     weights = OracleRecogniser('efficientnet_b0', False, 'linear', 1, 5, 1.0, 1991, calibration_frames(64)).state_dict()
     m = orbit_b200.MultiStepFewShotRecogniser('efficientnet_b0', False, 'linear', 1, 5, False, 1.0)
@@ -98,10 +102,14 @@ def test_finetuner_matches_reference_output(cuda_device, gr):
     assert checksum(ctx, tgt, ctx_y) == pytest.approx(float(gr['finetune_checksum']), rel=1e-12)
     args = {'num_grad_steps': 5, 'learning_rate': 0.1, 'optimizer': 'adam', 'loss_fn': None, 'extractor_lr_scale': 0.1,
             'epsilon': 1e-8, 'weight_decay': 0.0, 'betas': (0.9, 0.999), 'momentum': 0.0}
+    m.personalise(ctx[:-1], ctx_y[:-1], dict(args))
+    assert (m.classifier.weight.detach().cpu() - torch.as_tensor(gr['finetune2_weight'])).abs().max().item() <= 1e-4
+    assert (m.classifier.bias.detach().cpu() - torch.as_tensor(gr['finetune2_bias'])).abs().max().item() <= 1e-4
+    assert_logits_match(m.predict(tgt), gr['finetune2_logits'], "FineTuner vs reference")
+    m._reset()
     m.personalise(ctx, ctx_y, dict(args))
-    assert (m.classifier.weight.detach().cpu() - torch.as_tensor(gr['finetune_weight'])).abs().max().item() <= 1e-4
-    assert (m.classifier.bias.detach().cpu() - torch.as_tensor(gr['finetune_bias'])).abs().max().item() <= 1e-4
-    assert_logits_match(m.predict(tgt), gr['finetune_logits'], "FineTuner vs reference")
+    balanced = m.predict(tgt).cpu()
+    assert torch.equal(balanced.argmax(1), torch.as_tensor(gr['finetune_logits']).argmax(1))
 
 
 @pytest.mark.parametrize('i', range(4))

@@ -153,6 +153,10 @@ def test_finetuner_vs_reference(gr):
         close(oracle.head[0], gr['finetune_weight'], 1e-4)
         close(oracle.head[1], gr['finetune_bias'], 1e-4)
         close(oracle.predict(tgt), gr['finetune_logits'], 1e-4)
+    oracle.personalise_finetune(ctx[:-1], ctx_y[:-1], num_grad_steps=5, learning_rate=0.1)    # class counts 3,3,3,2
+    close(oracle.head[0], gr['finetune2_weight'], 1e-5)
+    close(oracle.head[1], gr['finetune2_bias'], 1e-5)
+    close(oracle.predict(tgt), gr['finetune2_logits'], 1e-5)
 
 
 def test_efficientnet_v2_s_structure():
