@@ -313,6 +313,21 @@ __device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+// x * sigmoid(x) on a channel pair: the four MUFU ops stay scalar, the three fp32 ops around them are packed
+__device__ __forceinline__ f2_t f2_silu_pair(f2_t x) {
+    f2_t t, r;
+    float t0, t1, e0, e1, r0, r1;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(f2_pack(-1.4426950408889634f, -1.4426950408889634f)));
+    f2_unpack(t, t0, t1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(f2_pack(e0, e1)), "l"(f2_pack(1.0f, 1.0f)));
+    f2_unpack(t, t0, t1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(f2_pack(r0, r1)));
+    return r;
+}
 template <int NP> struct PairIO;
 template <> struct PairIO<1> {
     static __device__ __forceinline__ void load(const float* p, f2_t* v) { v[0] = __ldg(reinterpret_cast<const f2_t*>(p)); }
@@ -537,8 +552,11 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 constexpr int kMbxXPad = 4;      // floats of padding per staged input pixel: conflict-free A-fragment loads
 constexpr int kMbxEPad = 4;      // channel pairs of padding per expanded pixel: conflict-free C-fragment stores
 
+#ifndef ORBIT_MBX_MINB
+#define ORBIT_MBX_MINB 2      // 128 registers: 3 blocks per SM (96 registers) spills the fragment registers and measured 15-25 % slower
+#endif
 template <int K, int S, int CIN, int CT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(192, ORBIT_MBX_MINB)
 mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const float* __restrict__ scale1,
            const float* __restrict__ shift1, const float* __restrict__ wt, const float* __restrict__ scale,
            const float* __restrict__ shift, float* __restrict__ y, float* __restrict__ partial, int H, int W, int C_rt,
@@ -576,13 +594,17 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
     // ---- expand role: warp -> 8-channel groups warp, warp + nwarps, ... (LX / 4 groups); fragments of m16n8k8:
     //      g = lane / 4, t = lane % 4;  A: (pixel g | g+8, k t | t+4);  B: (k t | t+4, channel g);  C: (pixel g | g+8, channel 2t, 2t+1)
     const int g = lane >> 2, t4 = lane & 3;
-    const int ngroups = LX / 4;
-    constexpr int kMaxGroups = 1;                          // groups per warp: the launcher gives every group its own warp
+    // warp -> a PAIR of 8-channel groups (2 pair, 2 pair + 1) and a class of 16-pixel tiles (mt = mclass, mclass + mclasses, ..):
+    // the tf32 split of an A fragment is shared by the two groups (a first version gave every warp one group and all tiles:
+    // every warp then re-split every fragment).
+    const int ngroups = LX / 4, npairs = (ngroups + 1) / 2, mclasses = max(1, nwarps / npairs);
+    const int pair = warp % npairs, mclass = warp / npairs;
+    constexpr int kMaxGroups = 2;
     uint32_t bh[kMaxGroups][KS][2], bl[kMaxGroups][KS][2];
     f2_t s1p[kMaxGroups], h1p[kMaxGroups];
 #pragma unroll
     for (int gi = 0; gi < kMaxGroups; ++gi) {
-        const int grp = warp + gi * nwarps;
+        const int grp = 2 * pair + gi;
         const int cb = (chunk * LX + grp * 4) * VEC + g;            // channel of this lane's B column
         const int cc = (chunk * LX + grp * 4 + t4) * VEC;           // first channel of this lane's C pair
         const bool bok = grp < ngroups && cb < C, cok = grp < ngroups && cc < C;
@@ -594,6 +616,7 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
         s1p[gi] = cok ? __ldg(reinterpret_cast<const f2_t*>(scale1 + cc)) : 0ull;
         h1p[gi] = cok ? __ldg(reinterpret_cast<const f2_t*>(shift1 + cc)) : 0ull;
     }
+    const bool second = 2 * pair + 1 < ngroups;          // warp-uniform: the pair's second group exists
 
     float sum[VEC] = {0.f, 0.f};
     const int row0 = tile * rows_per_tile, row1 = min(Ho, row0 + rows_per_tile);
@@ -606,79 +629,94 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
     const uint32_t x_base = (uint32_t)__cvta_generic_to_shared(s_x);
     const uint32_t x_row_bytes = (uint32_t)(PM * XS * 4);
 
-    // ---- input staging: the row segment [bx0, bx0 + P) x CIN of virtual row vy is one contiguous byte range of the NHWC
+    // Everything below that does not depend on the row is computed ONCE (ncu of the first tensor-core version: 45 % of
+    // the 618 instructions per warp per row were address / predicate arithmetic re-derived every row).
+    // ---- input staging: the row segment [bx0, bx0 + P) x CIN of a virtual row is one contiguous byte range of the NHWC
     // tensor: every thread fetches at most kXLoads float4 of it (coalesced), two rows ahead of its use, so the L2 / HBM
     // latency hides behind a whole row of expand + depthwise work.
     constexpr int kXLoads = 3;
     const int nf4 = P * CIN / 4;
-    auto fetch_row = [&](int vy, float4 (&xr)[kXLoads]) {
-        const bool row_ok = vy >= vy_lo && vy <= vy_hi;
-        const float* xrow = xfr + ((int64_t)(vy - pad_t) * W + bx0) * CIN;
+    int x_goff[kXLoads];          // float offset of this thread's j-th float4 inside the row segment (or -1: nothing to fetch)
+    uint32_t x_soff[kXLoads];     // its byte offset inside a staging buffer
 #pragma unroll
-        for (int j = 0; j < kXLoads; ++j) {
-            const int f = tid + j * nthreads;
-            const int col = bx0 + (4 * f) / CIN;
-            xr[j] = (row_ok && f < nf4 && col >= 0 && col < W) ? ldg4(xrow + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int j = 0; j < kXLoads; ++j) {
+        const int f = tid + j * nthreads;
+        const int pix = (4 * f) / CIN, kk = (4 * f) % CIN, col = bx0 + pix;
+        x_goff[j] = (f < nf4 && col >= 0 && col < W) ? 4 * f : -1;
+        x_soff[j] = (uint32_t)((pix * XS + kk) * 4);
+    }
+    const int64_t x_row_stride = (int64_t)W * CIN;
+    // ---- expand: image-validity of this lane's pixels per 16-pixel tile (bit 2 mt: row g, bit 2 mt + 1: row g + 8)
+    uint32_t okbits = 0;
+    for (int mt = 0; mt < PM / 16; ++mt) {
+        const int c_lo = bx0 + mt * 16 + g, c_hi = c_lo + 8;
+        okbits |= ((c_lo >= 0 && c_lo < W) ? 1u : 0u) << (2 * mt);
+        okbits |= ((c_hi >= 0 && c_hi < W) ? 1u : 0u) << (2 * mt + 1);
+    }
+    const uint32_t a_off = (uint32_t)(((mclass * 16 + g) * XS + t4) * 4);                        // A fragment base inside a staging buffer
+    const uint32_t c_off = (uint32_t)((((mclass * 16 + g) * ES + t4) + pair * 8) * VEC * 4);     // C fragment base inside an expanded-row buffer
+    const bool expander = mclass < mclasses;       // warp-uniform
+    const int n_mt = PM / 16;
+
+    auto fetch_row = [&](const float* xrow, bool row_ok, float4 (&xr)[kXLoads]) {
+#pragma unroll
+        for (int j = 0; j < kXLoads; ++j)
+            xr[j] = (row_ok && x_goff[j] >= 0) ? ldg4(xrow + x_goff[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    auto stash_row = [&](int xb, const float4 (&xr)[kXLoads]) {
+    auto stash_row = [&](uint32_t xbuf, const float4 (&xr)[kXLoads]) {
 #pragma unroll
-        for (int j = 0; j < kXLoads; ++j) {
-            const int f = tid + j * nthreads;
-            if (f < nf4) {
-                const int pix = (4 * f) / CIN, k = (4 * f) % CIN;
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(x_base + (uint32_t)xb * x_row_bytes + (uint32_t)((pix * XS + k) * 4)),
+        for (int j = 0; j < kXLoads; ++j)
+            if (tid + j * nthreads < nf4)
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(xbuf + x_soff[j]),
                              "f"(xr[j].x), "f"(xr[j].y), "f"(xr[j].z), "f"(xr[j].w) : "memory");
-            }
-        }
     };
-    // ---- expand phase: virtual row vy (staged in s_x[xb]) -> s_e[eb] ----------------------------------------------
-    auto expand_row = [&](int vy, int xb, int eb) {
-        const bool row_ok = vy >= vy_lo && vy <= vy_hi;
-        const uint32_t src0 = x_base + (uint32_t)xb * x_row_bytes + (uint32_t)((g * XS + t4) * 4);
-        const uint32_t dst0 = e_base + (uint32_t)eb * e_row_bytes + (uint32_t)((g * ES + t4) * VEC * 4);
+    // ---- expand phase: staged row at xbuf -> expanded row at ebuf ---------------------------------------------------
+    auto expand_row = [&](uint32_t xbuf, uint32_t ebuf, bool row_ok) {
+        if (!expander) return;
         const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int mt = 0; mt < PM / 16; ++mt) {
-            // image-validity of this lane's two pixels (rows g and g + 8 of the tile)
-            const int c_lo = bx0 + mt * 16 + g, c_hi = c_lo + 8;
-            const bool ok_lo = row_ok && c_lo >= 0 && c_lo < W, ok_hi = row_ok && c_hi >= 0 && c_hi < W;
-            uint32_t ah[KS][4], al[KS][4];
+        uint32_t ad = xbuf + a_off, d = ebuf + c_off, ok = (row_ok ? okbits : 0u) >> (2 * mclass);
+        for (int mt = mclass; mt < n_mt; mt += mclasses, ad += (uint32_t)(mclasses * 16 * XS * 4),
+                 d += (uint32_t)(mclasses * 16 * ES * VEC * 4), ok >>= 2 * mclasses) {
+            float acc0[4] = {0.f, 0.f, 0.f, 0.f}, cor0[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc1[4] = {0.f, 0.f, 0.f, 0.f}, cor1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                const uint32_t ad = src0 + (uint32_t)((mt * 16 * XS + ks * 8) * 4);
                 float a0, a1, a2, a3;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a0) : "r"(ad) : "memory");
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(ad + (uint32_t)(8 * XS * 4)) : "memory");
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(ad + 16u) : "memory");
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a3) : "r"(ad + (uint32_t)(8 * XS * 4) + 16u) : "memory");
-                split_tf32(a0, ah[ks][0], al[ks][0]); split_tf32(a1, ah[ks][1], al[ks][1]);
-                split_tf32(a2, ah[ks][2], al[ks][2]); split_tf32(a3, ah[ks][3], al[ks][3]);
-            }
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a0) : "r"(ad + (uint32_t)(ks * 32)) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(ad + (uint32_t)(ks * 32 + 8 * XS * 4)) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(ad + (uint32_t)(ks * 32 + 16)) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a3) : "r"(ad + (uint32_t)(ks * 32 + 8 * XS * 4 + 16)) : "memory");
+                uint32_t ah[4], al[4];
+                split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
+                split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+                float m4[4];
+                mma_tf32_16x8x8(m4, ah, bh[0][ks], zero4);              // hi.hi of one k-step, added below with RN
+                mma_tf32_16x8x8(cor0, al, bh[0][ks], cor0);
+                mma_tf32_16x8x8(cor0, ah, bl[0][ks], cor0);
 #pragma unroll
-            for (int gi = 0; gi < kMaxGroups; ++gi) {
-                const int grp = warp + gi * nwarps;
-                if (grp < ngroups) {            // warp-uniform
-                    float acc4[4] = {0.f, 0.f, 0.f, 0.f}, corr[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int i = 0; i < 4; ++i) acc0[i] += m4[i];
+                if (second) {
+                    mma_tf32_16x8x8(m4, ah, bh[1][ks], zero4);
+                    mma_tf32_16x8x8(cor1, al, bh[1][ks], cor1);
+                    mma_tf32_16x8x8(cor1, ah, bl[1][ks], cor1);
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        float m4[4];
-                        mma_tf32_16x8x8(m4, ah[ks], bh[gi][ks], zero4);          // hi.hi of one k-step, added below with RN
-                        mma_tf32_16x8x8(corr, al[ks], bh[gi][ks], corr);
-                        mma_tf32_16x8x8(corr, ah[ks], bl[gi][ks], corr);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc4[i] += m4[i];
-                    }
-                    f2_t lo2 = f2_pack(acc4[0] + corr[0], acc4[1] + corr[1]), hi2 = f2_pack(acc4[2] + corr[2], acc4[3] + corr[3]);
-                    lo2 = f2_fma(lo2, s1p[gi], h1p[gi]);
-                    hi2 = f2_fma(hi2, s1p[gi], h1p[gi]);
-                    float e0, e1, e2, e3;
-                    f2_unpack(lo2, e0, e1); f2_unpack(hi2, e2, e3);
-                    e0 = ok_lo ? silu_sfu(e0) : 0.f; e1 = ok_lo ? silu_sfu(e1) : 0.f;
-                    e2 = ok_hi ? silu_sfu(e2) : 0.f; e3 = ok_hi ? silu_sfu(e3) : 0.f;
-                    const uint32_t d = dst0 + (uint32_t)((mt * 16 * ES + grp * 4) * VEC * 4);
-                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(d), "f"(e0), "f"(e1) : "memory");
-                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(d + (uint32_t)(8 * ES * VEC * 4)), "f"(e2), "f"(e3) : "memory");
+                    for (int i = 0; i < 4; ++i) acc1[i] += m4[i];
                 }
+            }
+            // bn1 + SiLU on channel pairs (packed fp32x2 around the four MUFU ops), zero outside the image
+            f2_t lo2 = f2_fma(f2_pack(acc0[0] + cor0[0], acc0[1] + cor0[1]), s1p[0], h1p[0]);
+            f2_t hi2 = f2_fma(f2_pack(acc0[2] + cor0[2], acc0[3] + cor0[3]), s1p[0], h1p[0]);
+            lo2 = (ok & 1u) ? f2_silu_pair(lo2) : 0ull;
+            hi2 = (ok & 2u) ? f2_silu_pair(hi2) : 0ull;
+            asm volatile("st.shared.b64 [%0], %1;" ::"r"(d), "l"(lo2) : "memory");
+            asm volatile("st.shared.b64 [%0], %1;" ::"r"(d + (uint32_t)(8 * ES * VEC * 4)), "l"(hi2) : "memory");
+            if (second) {
+                lo2 = f2_fma(f2_pack(acc1[0] + cor1[0], acc1[1] + cor1[1]), s1p[1], h1p[1]);
+                hi2 = f2_fma(f2_pack(acc1[2] + cor1[2], acc1[3] + cor1[3]), s1p[1], h1p[1]);
+                lo2 = (ok & 1u) ? f2_silu_pair(lo2) : 0ull;
+                hi2 = (ok & 2u) ? f2_silu_pair(hi2) : 0ull;
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(d + (uint32_t)(4 * VEC * 4)), "l"(lo2) : "memory");
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(d + (uint32_t)((8 * ES + 4) * VEC * 4)), "l"(hi2) : "memory");
             }
         }
     };
@@ -687,9 +725,11 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
     sc[0] = sh[0] = 0ull;
     if (live) { PairIO<1>::load(scale + cv * VEC, sc); PairIO<1>::load(shift + cv * VEC, sh); }
     const int ox0 = strip * TW;
-    float* yb = y + ((int64_t)b * Ho * Wo + ox0) * C + cv * VEC;
     const float* wlane = s_w + lx * VEC;
-    const uint32_t e_mine = e_base + (uint32_t)((ly * TW * S * ES + lx) * VEC * 4);   // slot of this strip's first input column
+    const uint32_t e_mine = (uint32_t)((ly * TW * S * ES + lx) * VEC * 4);   // slot of this strip's first input column
+    uint32_t colmask = 0;                              // bit t: output column ox0 + t exists
+#pragma unroll
+    for (int t = 0; t < TW; ++t) colmask |= (ox0 + t < Wo) ? (1u << t) : 0u;
     f2_t acc[R][TW], v[SPAN];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -701,25 +741,33 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
         // rows v (being consumed) and v+1 (being produced). One __syncthreads per row.
         float4 xr[kXLoads];
         const int v0 = row0 * S;
-        fetch_row(v0, xr);
+        const float* xrow = xfr + ((int64_t)(v0 - pad_t) * W + bx0) * CIN;      // segment start of virtual row v0 (may point outside: guarded)
+        const uint32_t xbuf[2] = {x_base, x_base + x_row_bytes}, ebuf[2] = {e_base, e_base + e_row_bytes};
+        auto row_ok = [&](int vy) { return vy >= vy_lo && vy <= vy_hi; };
+        fetch_row(xrow, row_ok(v0), xr);
         __syncthreads();                                  // tap table + zeroed staging buffers
-        stash_row(v0 & 1, xr);
-        fetch_row(v0 + 1, xr);
+        stash_row(xbuf[v0 & 1], xr);
+        fetch_row(xrow + x_row_stride, row_ok(v0 + 1), xr);
         __syncthreads();
-        expand_row(v0, v0 & 1, v0 & 1);
-        stash_row((v0 + 1) & 1, xr);
+        expand_row(xbuf[v0 & 1], ebuf[v0 & 1], row_ok(v0));
+        stash_row(xbuf[(v0 + 1) & 1], xr);
         __syncthreads();
+        xrow += 2 * x_row_stride;                         // -> virtual row v0 + 2
+        float* yrow = y + (((int64_t)b * Ho + row0) * Wo + ox0) * C + cv * VEC;   // output row row0 of this strip / channel pair
+        const int64_t y_row_stride = (int64_t)Wo * C;
+        int vy = v0;
         // iteration m handles virtual rows m*S .. m*S+S-1; the oldest pending output row is m - HALF
         for (int m = row0; m < row1 + HALF; ++m) {
 #pragma unroll
-            for (int sub = 0; sub < S; ++sub) {
-                const int vy = m * S + sub, eb = vy & 1;
-                fetch_row(vy + 2, xr);                        // in flight during this row's work
-                expand_row(vy + 1, eb ^ 1, eb ^ 1);           // next row: s_x[eb^1] -> s_e[eb^1]
+            for (int sub = 0; sub < S; ++sub, ++vy, xrow += x_row_stride) {
+                const int eb = vy & 1;
+                fetch_row(xrow, row_ok(vy + 2), xr);                        // in flight during this row's work
+                expand_row(xbuf[eb ^ 1], ebuf[eb ^ 1], row_ok(vy + 1));     // next row
                 if (live) {
+                    const uint32_t er = ebuf[eb] + e_mine;
 #pragma unroll
                     for (int j = 0; j < SPAN; ++j)
-                        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[j]) : "r"(e_mine + (uint32_t)eb * e_row_bytes + (uint32_t)(j * ES * VEC * 4)) : "memory");
+                        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[j]) : "r"(er + (uint32_t)(j * ES * VEC * 4)) : "memory");
 #pragma unroll
                     for (int ky = sub; ky < K; ky += S) {      // ky with (vy - ky) divisible by S
                         const int slot = HALF - (ky - sub) / S;
@@ -732,24 +780,23 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
                         }
                     }
                     if (sub == (K - 1) % S) {      // the oldest pending output row has now seen its last input row
-                        const int oy = m - HALF;
-                        if (oy >= row0) {          // (oy < row1 by the loop bound)
-                            float* yrow = yb + (int64_t)oy * Wo * C;
+                        if (m - HALF >= row0) {    // (m - HALF < row1 by the loop bound)
 #pragma unroll
                             for (int t = 0; t < TW; ++t) {
-                                if (ox0 + t < Wo) {
-                                    float r[VEC];
-                                    f2_unpack(f2_fma(acc[0][t], sc[0], sh[0]), r[0], r[1]);
-                                    r[0] = silu_sfu(r[0]); r[1] = silu_sfu(r[1]);
-                                    sum[0] += r[0]; sum[1] += r[1];
-                                    PairIO<1>::store(yrow + t * C, r);
+                                if (colmask & (1u << t)) {
+                                    const f2_t o = f2_silu_pair(f2_fma(acc[0][t], sc[0], sh[0]));
+                                    float r0, r1;
+                                    f2_unpack(o, r0, r1);
+                                    sum[0] += r0; sum[1] += r1;
+                                    *reinterpret_cast<f2_t*>(yrow + t * C) = o;
                                 }
                             }
+                            yrow += y_row_stride;
                         }
                     }
                 }
-                stash_row(eb, xr);    // s_x[eb] (row vy) was last read by the previous iteration's expand: free
-                __syncthreads();      // s_e[eb] consumed by everyone; s_e[eb^1] and s_x[eb] complete
+                stash_row(xbuf[eb], xr);   // s_x[eb] (row vy) was last read by the previous iteration's expand: free
+                __syncthreads();           // s_e[eb] consumed by everyone; s_e[eb^1] and s_x[eb] complete
             }
             // rotate the ring: slot r <- slot r+1, newest slot cleared
 #pragma unroll
@@ -780,10 +827,10 @@ struct MbxPlan { int LX, LY, nchunks, tiles, rows_per_tile, strip_blocks, groups
 static MbxPlan mbx_plan(int Cin, int C, int Ho, int Wo, int k, int stride) {
     MbxPlan p;
     const int Cv = C / 2;
-    p.nchunks = ceil_div(Cv, 32);
+    p.nchunks = ceil_div(Cv, 24);                         // <= 24 channel pairs = 6 eight-channel MMA groups = 6 warps per block
     p.LX = ceil_div(ceil_div(Cv, p.nchunks), 4) * 4;      // channel pairs per block: whole 8-channel MMA groups
     const int strips = ceil_div(Wo, kDwTW);
-    const int ly_max = std::max(1, 256 / p.LX);
+    const int ly_max = std::max(1, 192 / p.LX);
     p.strip_blocks = ceil_div(strips, ly_max);
     p.LY = ceil_div(strips, p.strip_blocks);              // balanced strip blocks (14 strips -> 7 + 7, not 10 + 4)
     const int R = ceil_div(k, stride);
@@ -791,7 +838,7 @@ static MbxPlan mbx_plan(int Cin, int C, int Ho, int Wo, int k, int stride) {
     p.rows_per_tile = ceil_div(ceil_div(Ho, want_tiles), R) * R;
     p.tiles = ceil_div(Ho, p.rows_per_tile);
     p.groups = p.tiles * p.strip_blocks;
-    p.threads = std::max(32 * (p.LX / 4), ceil_div(p.LX * p.LY, 32) * 32);    // one warp per 8-channel group at least (<= 256)
+    p.threads = std::max(32 * ((p.LX / 4 + 1) / 2), ceil_div(p.LX * p.LY, 32) * 32);    // one warp per pair of 8-channel groups at least (<= 192)
     p.P = (p.LY * kDwTW - 1) * stride + k;
     p.PM = ceil_div(p.P, 16) * 16;
     p.smem = sizeof(float) * ((size_t)k * k * 32 * 2 + (size_t)p.LY * p.LX * 2 + (size_t)2 * p.PM * (p.LX + kMbxEPad) * 2 +
@@ -804,7 +851,7 @@ bool mbx_supported(int cin, int k, int stride) { return (cin == 16 || cin == 24)
 bool mbx_fits(int Cin, int C, int Ho, int Wo, int k, int stride) {
     if (C % 8 || !mbx_supported(Cin, k, stride)) return false;
     const MbxPlan pl = mbx_plan(Cin, C, Ho, Wo, k, stride);
-    return pl.smem <= 100 * 1024 && (size_t)pl.P * Cin / 4 <= (size_t)3 * pl.threads && pl.LX / 4 <= pl.threads / 32 && pl.threads <= 256;
+    return pl.smem <= 100 * 1024 && (size_t)pl.P * Cin / 4 <= (size_t)3 * pl.threads && (pl.LX / 4 + 1) / 2 <= pl.threads / 32 && pl.threads <= 192;
 }
 int mbx_partial_groups(int C, int Ho, int Wo, int k, int stride) { return mbx_plan(16, C, Ho, Wo, k, stride).groups; }
 
