@@ -443,6 +443,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                 va[i] = lds128(a + src_off + (b + i) * rstride);
                                 vb[i] = lds128(a + (src_off ^ 16u) + (b + i) * rstride);
                             }
+                            __syncwarp(__activemask());      // in-place: every lane of the row has read before any lane writes
 #pragma unroll
                             for (int i = 0; i < RB; ++i) {
                                 f2_t xa[2] = {f2_pack(va[i].x, va[i].y), f2_pack(va[i].z, va[i].w)};

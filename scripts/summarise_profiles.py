@@ -30,16 +30,25 @@ with open(f'{ROOT}/profiles/{tag}_launches_summary.csv', 'w') as f:
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['us']):
         f.write(f"\"{k}\",{a['launches']},{a['us']:.1f},{100*a['us']/tot:.2f},{a['us']/a['launches']:.1f},{a['rd']/1e9:.3f},{a['wr']/1e9:.3f},"
                 f"{(a['rd']+a['wr'])/max(a['us'],1e-9)/1e3:.0f}\n")
-fam = {'pointwise_gemm': 'pw_tcgen05', 'depthwise_conv': 'dw2_kernel|dw_kernel', 'stem_conv': 'stem_kernel', 'se_gate': 'se_gate', 'spatial_mean': 'spatial_mean'}
+fam = {'pointwise_gemm': 'pw_tcgen05', 'depthwise_conv': 'dw2_kernel|mbx_kernel', 'stem_conv': 'stem_kernel', 'se_gate': 'se_gate', 'spatial_mean': 'spatial_mean'}
+# the TIMED episode only: the bench command runs calibration, 3 warm-up episodes, then ONE timed episode = the launches
+# from the second-to-last stem_kernel (support pass; the last one is the query pass) to the end of the process
+order = list(launch.values())
+stems = [i for i, d in enumerate(order) if 'stem_kernel' in d['name']]
+episode = order[stems[-2]:] if len(stems) >= 2 else order
+ep_tot = sum(d.get('gpu__time_duration.sum', 0) for d in episode)
 traffic = {}
 for fname, pat in fam.items():
-    sel = [a for k, a in agg.items() if re.match(pat, k)]
-    n = sum(a['launches'] for a in sel)
-    if n:
-        traffic[fname] = {'launches': n, 'dram_bytes_per_launch': sum(a['rd'] + a['wr'] for a in sel) / n,
-                          'share_of_gpu_time_pct': 100 * sum(a['us'] for a in sel) / tot}
-json.dump({'command': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --profile-steps 0',
-           'note': 'all launches of the process incl. BatchNorm calibration and warm-up episodes; per-launch averages', 'families': traffic},
+    sel = [d for d in episode if re.match(pat, short(d['name']))]
+    if sel:
+        traffic[fname] = {'launches': len(sel),
+                          'dram_bytes_per_launch': sum(d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0) for d in sel) / len(sel),
+                          'dram_bytes_per_episode': sum(d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0) for d in sel),
+                          'share_of_episode_gpu_time_pct': 100 * sum(d.get('gpu__time_duration.sum', 0) for d in sel) / ep_tot}
+json.dump({'command': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --profile-steps 0 --episodes 0',
+           'note': 'launches of the ONE timed episode only (2,240 frames: a 1,600-frame support pass and a 640-frame query pass); per-launch averages',
+           'episode_launches': len(episode), 'episode_dram_bytes': sum(d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0) for d in episode),
+           'families': traffic},
           open(f'{ROOT}/profiles/{tag}_traffic.json', 'w'), indent=1)
 print(open(f'{ROOT}/profiles/{tag}_launches_summary.csv').read())
 print(json.dumps(traffic, indent=1))
@@ -50,7 +59,7 @@ keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum']
 with open(f'{ROOT}/profiles/{tag}_ncu_full.csv', 'w') as f:
     first = True
-    for rep in (f'{tag}_gemm_full', f'{tag}_dw_full'):
+    for rep in (f'{tag}_gemm_full', f'{tag}_dw_full', f'{tag}_mbx_full'):
         path = f'{ROOT}/gpurun_out/{rep}.ncu-rep'
         if not os.path.exists(path): continue
         raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
