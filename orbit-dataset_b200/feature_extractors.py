@@ -62,7 +62,6 @@ class FeatureExtractor(nn.Module):
         self._shapes = {}
         self._derived = None
         self._workspace = None
-        self._workspaces = {}
         self._prepared_key = None
         self._versioned = None
         self._build_tree()
@@ -107,7 +106,6 @@ class FeatureExtractor(nn.Module):
         self._blob = new_blob
         self._rebind()
         self._derived = self._workspace = self._prepared_key = self._versioned = None
-        self._workspaces = {}
         return self
 
     @torch.no_grad()
@@ -192,7 +190,6 @@ class FeatureExtractor(nn.Module):
     def set_option(self, key: str, value: int):
         L.check(L.load().orbit_engine_set_option(self._engine, key.encode(), int(value)), f"set_option({key})")
         self._workspace = None
-        self._workspaces = {}
 
     def get_option(self, key: str) -> int:
         v = C.c_int()
@@ -254,8 +251,7 @@ class FeatureExtractor(nn.Module):
         self._prepared_key = None
         return super().load_state_dict(*args, **kwargs)
 
-    def forward(self, frames: torch.Tensor, film_blob=None, slot: int = 0) -> torch.Tensor:
-        """``slot`` selects the workspace: passes that run concurrently on different streams need different slots."""
+    def forward(self, frames: torch.Tensor, film_blob=None) -> torch.Tensor:
         lib = L.load()
         L.require_cuda(frames, "frames")
         if frames.dim() != 4 or frames.shape[1] != 3:
@@ -266,10 +262,9 @@ class FeatureExtractor(nn.Module):
         ws_bytes = lib.orbit_engine_workspace_bytes(self._engine, h, w)
         if ws_bytes < 0:
             L.check(int(ws_bytes), "orbit_engine_workspace_bytes")
-        ws = self._workspaces.get(slot)
-        if ws is None or ws.numel() < ws_bytes or ws.device != frames.device:
-            ws = self._workspaces[slot] = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
-        self._workspace = ws
+        if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != frames.device:
+            self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
+        ws = self._workspace
         feats = torch.empty(n, self.output_size, dtype=torch.float32, device=frames.device)
         L.check(lib.orbit_engine_forward(self._engine, L.ptr(self._blob), L.ptr(self._derived), L.ptr(frames), n, h, w,
                                          L.ptr(feats), L.ptr(ws), ws.numel(),

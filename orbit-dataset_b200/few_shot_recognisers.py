@@ -70,11 +70,9 @@ class _HostStager:
                 sizes += [first, both - first]
         return sizes
 
-    def stream(self, frames_cpu, yield_events=False):
+    def stream(self, frames_cpu):
         """Yields device views of consecutive chunks of ``frames_cpu`` [F,3,H,W]; a view stays valid until the
-        call after next. Default: the current stream is made to wait for each chunk's copy and the buffer is released when
-        the generator ends. ``yield_events=True`` yields ``(view, copy_done_event)`` instead and leaves both the waiting
-        and the final ``release(last_buffer[0])`` to the caller (who may consume chunks on several streams)."""
+        call after next."""
         compute = torch.cuda.current_stream(self.device)
         total = frames_cpu.shape[0]
         if total == 0:
@@ -125,14 +123,10 @@ class _HostStager:
         self.bytes_copied += need * 4
         pos = 0
         for n, ev in zip(sizes, events):
-            if yield_events:
-                yield dst[pos:pos + n], ev
-            else:
-                compute.wait_event(ev)
-                yield dst[pos:pos + n]
+            compute.wait_event(ev)
+            yield dst[pos:pos + n]
             pos += n
-        if not yield_events:
-            self.release(i)
+        self.release(i)
 
     def release(self, i):
         """Marks buffer ``i`` as consumed up to this point of the compute stream (call again after enqueuing more work
@@ -180,8 +174,6 @@ class FewShotRecogniser(nn.Module):
         self.mac_accounting = 'reference'
         self.device = torch.device('cpu')
         self._stager = None
-        self._side_stream = None
-        self.overlap_passes = True        # consecutive passes of a host-clip call on two streams (see _run_extractor)
         self.stage_copy_frames = 160      # frames per async H2D copy for CPU-resident clips (97 MB at 224 px)
         self.stage_ramp = (96, 224, 480)  # sizes of the first backbone passes of a call (frames)
 
@@ -212,36 +204,12 @@ class FewShotRecogniser(nn.Module):
         blob = self._film_blob(film_dict) if film_dict else None
         if frames.is_cuda:
             return self.feature_extractor(frames, blob)
-        # Host clips arrive in passes (a short ramp, then chunk_frames). Consecutive passes alternate between the current
-        # stream and one side stream, each with its own workspace: the tail of pass k (7x7 layers: a few dozen tiles, a chain
-        # of ~70 short launches) overlaps the head of pass k+1 instead of idling most SMs for ~1 ms per pass.
-        fe, stager = self.feature_extractor, self._host_stager()
-        fe.prepare(blob)
-        main = torch.cuda.current_stream(self.device)
-        if self._side_stream is None or self._side_stream.device != self.device:
-            self._side_stream = torch.cuda.Stream(self.device)
-        side = self._side_stream
-        entry = torch.cuda.Event()
-        entry.record(main)
-        side.wait_event(entry)               # parameters / FiLM folds prepared on the current stream
-        outs, used_side = [], False
-        for k, (dev_frames, copied) in enumerate(stager.stream(frames.float(), yield_events=True)):
-            lane = side if (k % 2 and self.overlap_passes) else main
-            lane.wait_event(copied)
-            with torch.cuda.stream(lane):
-                out = fe(dev_frames, blob, slot=1 if lane is side else 0)
-            if lane is side:
-                used_side = True
-                out.record_stream(main)
-            outs.append(out)
-        if used_side:
-            joined = torch.cuda.Event()
-            joined.record(side)
-            main.wait_event(joined)
-        if stager.last_buffer is not None and outs:
-            stager.release(stager.last_buffer[0])
+        # Host clips arrive in passes (a short ramp, then chunk_frames), each waiting only for its own bytes. (Tried in round 2
+        # and removed: alternating consecutive passes between two streams / workspaces so that the tail of one pass overlaps
+        # the head of the next -- no gain, the persistent GEMM kernels own every SM's shared memory)
+        outs = [self.feature_extractor(dev_frames, blob) for dev_frames in self._host_stager().stream(frames.float())]
         if not outs:
-            return torch.empty(0, fe.output_size, device=self.device)
+            return torch.empty(0, self.feature_extractor.output_size, device=self.device)
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     def _get_features(self, clips, film_dict={}, ops_counter=None):
