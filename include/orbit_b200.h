@@ -262,6 +262,35 @@ int orbit_video_stats(const float* logits, const int32_t* predictions, int num_c
                       const int32_t* video_offsets, const int32_t* video_labels, int num_videos, int32_t* stats,
                       int32_t* pred_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training through the frozen extractor (first slice of SURVEY.md 8f-3): FineTuner + FiLM, i.e.
+ * MultiStepFewShotRecogniser.personalise with adapt_features=True (model/few_shot_recognisers.py:196-198,207-246).
+ * MBConv networks (ORBIT_ARCH_EFFICIENTNET_B0) only; other architectures return ORBIT_ERR_UNSUPPORTED.
+ *   orbit_engine_train_saved_floats   floats PER FRAME of the activation arena forward_train fills
+ *   orbit_engine_train_derived_floats floats of the transposed / split 1x1 weights (prepare_train; weights are frozen)
+ *   orbit_engine_forward_train        same result as orbit_engine_forward (layer at a time, BatchNorm in eval mode) for
+ *                                     num_frames <= chunk_frames, keeping the pre-activations in `saved`
+ *   orbit_engine_backward_train       dfeats [num_frames, feat_dim] -> ACCUMULATES d loss / d (BatchNorm weight, bias) of
+ *                                     every FiLM site into grad_params, a blob with the layout of `params`
+ *   orbit_linear_ce_backward          linear head + cross entropy (utils/optim.py:8-9; mean over the batch times
+ *                                     loss_scale = batch_len / context_size, few_shot_recognisers.py:241-243): accumulates
+ *                                     grad_weight [C,D] and grad_bias [C], writes grad_frame_feats [num_clips*L, D];
+ *                                     labels int32 in [0,C); scratch: orbit_linear_ce_scratch_floats(...) floats          */
+int64_t orbit_engine_train_saved_floats(const orbit_engine* engine, int height, int width);
+int64_t orbit_engine_train_derived_floats(const orbit_engine* engine);
+int orbit_engine_prepare_train(const orbit_engine* engine, const float* params, float* tderived, void* stream);
+int orbit_engine_forward_train(const orbit_engine* engine, const float* params, const float* derived, const float* frames,
+                               int num_frames, int height, int width, float* feats, float* saved, int64_t saved_floats,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+int orbit_engine_backward_train(const orbit_engine* engine, const float* params, const float* derived, const float* tderived,
+                                const float* saved, const float* dfeats, int num_frames, int height, int width,
+                                float* grad_params, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t orbit_linear_ce_scratch_floats(int num_clips, int feat_dim, int num_classes);
+int orbit_linear_ce_backward(const float* frame_feats, const int32_t* labels, const float* weight, const float* bias,
+                             int num_clips, int clip_length, int feat_dim, int num_classes, float logit_scale,
+                             float loss_scale, float* grad_weight, float* grad_bias, float* grad_frame_feats,
+                             float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

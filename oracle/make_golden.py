@@ -191,6 +191,21 @@ def golden_recogniser():
         out['finetune2_logits'] = ref2.predict(tgt).numpy()
     out['finetune2_weight'] = ref2.classifier.weight.detach().numpy()
     out['finetune2_bias'] = ref2.classifier.bias.detach().numpy()
+    # FineTuner + FiLM (--adapt_features in the multi-step learner): the FiLM-tagged BatchNorm weight / bias and the head are
+    # trained THROUGH the frozen extractor (few_shot_recognisers.py:196-198,207-246); 3 Adam steps, batches of 5 clips
+    ref3 = MultiStepFewShotRecogniser('efficientnet_b0', True, 'linear', 1, 5, False, 1.0)
+    ref3.load_state_dict(oracle.state_dict(), strict=True)
+    ref3._set_device(torch.device('cpu'))
+    ref3.set_test_mode(True)
+    ref3.personalise(ctx[:-1], ctx_y[:-1], dict(args, num_grad_steps=3, learning_rate=0.01))
+    with torch.no_grad():
+        out['finetune_film_logits'] = ref3.predict(tgt).numpy()
+    out['finetune_film_weight'] = ref3.classifier.weight.detach().numpy()
+    out['finetune_film_bias'] = ref3.classifier.bias.detach().numpy()
+    sd3 = ref3.state_dict()
+    for k in ('bn1.weight', 'bn1.bias', 'blocks.1.0.bn2.weight', 'blocks.3.1.bn2.bias', 'blocks.6.0.bn2.weight', 'bn2.weight', 'bn2.bias'):
+        out['finetune_film_' + k] = sd3['feature_extractor.' + k].detach().numpy()
+        out['finetune_film_init_' + k] = oracle.state_dict()['feature_extractor.' + k].numpy()
     np.savez_compressed(os.path.join(OUT, 'recogniser.npz'), **out)
     print('recogniser.npz', len(out), 'arrays')
 

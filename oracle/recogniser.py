@@ -170,3 +170,43 @@ class OracleRecogniser:
             opt.zero_grad()
         self.film_dict = {}
         self.head = (w.detach(), b.detach())
+
+    def personalise_finetune_film(self, context_clips, context_labels, num_grad_steps=5, learning_rate=1e-3,
+                                  optimizer='adam', betas=(0.9, 0.999), epsilon=1e-8, weight_decay=0.0, momentum=0.0):
+        """FineTuner + FiLM: few_shot_recognisers.py:196-198 (the FiLM-tagged norm layers' weight / bias are unfrozen) and
+        :207-246 (per grad step, per support batch: extractor forward in eval mode WITH autograd, pool, linear head,
+        CE(mean) * batch_len / N, backward; then ONE optimiser step over the head and -- second parameter group, same
+        learning rate: torch.optim ignores the 'lr_scale' key of utils/optim.py:27-30 -- the extractor's trainable
+        parameters). Returns nothing; the extractor's FiLM parameters are updated in place, the head is stored."""
+        labels = context_labels.cpu().long()
+        n = len(labels)
+        num_classes = len(torch.unique(labels))
+        names = set(parts.film_parameter_names(self.name, self.extractor))
+        film = []
+        for pname, p in self.extractor.named_parameters():
+            p.requires_grad_(pname in names)
+            if pname in names:
+                film.append(p)
+        w = torch.zeros(num_classes, self.feat_dim, requires_grad=True)
+        b = torch.zeros(num_classes, requires_grad=True)
+        groups = [{'params': [w, b]}, {'params': film}]
+        if optimizer == 'adam':
+            opt = torch.optim.Adam(groups, lr=learning_rate, betas=betas, eps=epsilon, weight_decay=weight_decay)
+        else:
+            opt = torch.optim.SGD(groups, lr=learning_rate, momentum=momentum, weight_decay=weight_decay)
+        opt.zero_grad()
+        self.extractor.eval()
+        for _ in range(num_grad_steps):
+            for s in range(0, n, self.batch_size):
+                clips = context_clips[s:s + self.batch_size]
+                frames = clips.flatten(end_dim=1) if clips.dim() == 5 else clips
+                x = parts.pool_clips(self.extractor(frames), self.clip_length)
+                y = labels[s:s + self.batch_size]
+                loss = F.cross_entropy(parts.linear_predict(x, w, b, self.logit_scale), y)
+                (loss * (len(y) / n)).backward()
+            opt.step()
+            opt.zero_grad()
+        for p in self.extractor.parameters():
+            p.requires_grad_(False)
+        self.film_dict = {}
+        self.head = (w.detach(), b.detach())

@@ -77,4 +77,20 @@ int launch_maxpool(const float* x, float* y, int B, int H, int W, int C, int k, 
 // spatial mean: x [B,HW,C] -> y [B,C]
 int launch_spatial_mean(const float* x, float* y, int B, int HW, int C, cudaStream_t st);
 
+// ---- training (csrc/train.cu): forward pieces that keep pre-activations, and the backward kernels --------------------
+// y = act(scale x + shift), act in {ACT_NONE, ACT_SILU}
+int launch_bn_act_forward(const float* x, const float* scale, const float* shift, float* y, int64_t M, int C, int act, cudaStream_t st);
+// backward of the above; see train.cu for `mode`. grad_gamma / grad_beta (nullable) are ACCUMULATED; partial needs
+// bn_act_backward_partial_floats(M, C) floats when they are requested.
+int64_t bn_act_backward_partial_floats(int64_t M, int C);
+int launch_bn_act_backward(const float* c, const float* dy, const float* aux0, const float* aux1, const float* scale,
+                           const float* shift, const float* mean, const float* var, float eps, float* dc, float* partial,
+                           float* grad_gamma, float* grad_beta, int64_t M, int C, int act, int mode, int rows_per_frame,
+                           cudaStream_t st);
+int launch_dw_dgrad(const float* dy, const float* wt, float* dx, int B, int H, int W, int C, int Ho, int Wo, int k, int stride,
+                    int pad_t, int pad_l, cudaStream_t st);
+int launch_se_backward(const float* dga, const float* a, const float* m, const float* w1, const float* b1, const float* w2,
+                       const float* b2, float* dgate, float* dmean, int B, int HW, int C, int R, cudaStream_t st);
+int launch_transpose(const float* w, float* out, int rows, int cols, cudaStream_t st);
+
 }  // namespace orbit

@@ -915,3 +915,301 @@ extern "C" int orbit_engine_calibrate(const orbit_engine* e, float* params, floa
     return run_plan(e, params, params, derived, frames, num_frames, height, width, feats, workspace, workspace_bytes,
                     (cudaStream_t)stream);
 }
+
+// =================================================================================================
+// Training through the frozen extractor (first slice: MBConv networks = EfficientNet-B0).
+// Reference: MultiStepFewShotRecogniser.personalise with adapt_features=True (model/few_shot_recognisers.py:196-198,
+// 207-246): gradient steps on the FiLM parameters (affine weight/bias of the tagged BatchNorms, model/film.py:38-79)
+// and a new linear head, BatchNorm in eval mode. forward_train keeps what the backward needs (raw conv outputs `c` of
+// every BatchNorm'd layer that is followed by an activation or is a FiLM site, the activated depthwise outputs, the
+// squeeze-excite means and gates); backward_train walks the plan in reverse. Gradients live in the workspace buffer with
+// the same id as the activation they belong to.
+// =================================================================================================
+namespace {
+
+struct TrainGeom {
+    std::vector<int> in_h, in_w, out_h, out_w;
+    std::vector<int64_t> c_off, a_off, m_off, g_off, wt_off;     // per-op offsets: saved arena (floats per FRAME), transposed weights
+    int64_t saved_per_frame = 0, tderived_floats = 0;
+    bool ok = true;
+};
+
+TrainGeom train_geometry(const orbit_engine* e, int H, int W) {
+    TrainGeom t;
+    const size_t n = e->ops.size();
+    t.in_h.assign(n, 0); t.in_w.assign(n, 0); t.out_h.assign(n, 0); t.out_w.assign(n, 0);
+    t.c_off.assign(n, -1); t.a_off.assign(n, -1); t.m_off.assign(n, -1); t.g_off.assign(n, -1); t.wt_off.assign(n, -1);
+    if (e->tokens) { t.ok = false; return t; }
+    int h = H, w = W;
+    for (size_t i = 0; i < n; ++i) {
+        const Op& op = e->ops[i];
+        t.in_h[i] = h; t.in_w[i] = w;
+        int ho = h, wo = w, p;
+        switch (op.kind) {
+            case OP_STEM: case OP_DW:
+                same_geometry(h, op.k, op.stride, &ho, &p);
+                same_geometry(w, op.k, op.stride, &wo, &p);
+                t.c_off[i] = t.saved_per_frame; t.saved_per_frame += (int64_t)ho * wo * op.cout;
+                if (op.kind == OP_DW) {
+                    t.a_off[i] = t.saved_per_frame; t.saved_per_frame += (int64_t)ho * wo * op.cout;
+                    t.m_off[i] = t.saved_per_frame; t.saved_per_frame += op.cout;
+                }
+                break;
+            case OP_SE: t.g_off[i] = t.saved_per_frame; t.saved_per_frame += op.cout; break;
+            case OP_PW:
+                if (op.bias_only || op.patch) { t.ok = false; return t; }
+                if (op.act == ACT_SILU) { t.c_off[i] = t.saved_per_frame; t.saved_per_frame += (int64_t)h * w * op.cout; }
+                else if (op.act != ACT_NONE) { t.ok = false; return t; }
+                t.wt_off[i] = t.tderived_floats; t.tderived_floats += 3 * (int64_t)op.cin * op.cout + 8;
+                break;
+            case OP_SPATIAL_MEAN: break;
+            default: t.ok = false; return t;
+        }
+        t.out_h[i] = ho; t.out_w[i] = wo;
+        h = ho; w = wo;
+        t.saved_per_frame = (t.saved_per_frame + 3) / 4 * 4;
+        t.tderived_floats = (t.tderived_floats + 3) / 4 * 4;
+    }
+    return t;
+}
+
+void workspace_buffers(const orbit_engine* e, const BufSizes& bs, void* workspace, float** buf) {
+    char* p = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 1024));
+    for (int i = 0; i < BUF_COUNT; ++i) {
+        buf[i] = reinterpret_cast<float*>(p);
+        p += align_up(bs.per_frame[i] * e->chunk_frames * (int64_t)sizeof(float), 1024);
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t orbit_engine_train_saved_floats(const orbit_engine* e, int height, int width) {
+    if (!e || height <= 0 || width <= 0) return ORBIT_ERR_ARG;
+    const TrainGeom t = train_geometry(e, height, width);
+    return t.ok ? t.saved_per_frame : (int64_t)ORBIT_ERR_UNSUPPORTED;
+}
+
+extern "C" int64_t orbit_engine_train_derived_floats(const orbit_engine* e) {
+    if (!e) return ORBIT_ERR_ARG;
+    const TrainGeom t = train_geometry(e, 224, 224);
+    return t.ok ? t.tderived_floats : (int64_t)ORBIT_ERR_UNSUPPORTED;
+}
+
+// transposed (+ fp16 hi/lo split) 1x1 weights for the data-gradient GEMMs; the weights are frozen: once per model
+extern "C" int orbit_engine_prepare_train(const orbit_engine* e, const float* params, float* tderived, void* stream) {
+    if (!e || !params || !tderived) return ORBIT_ERR_ARG;
+    const TrainGeom t = train_geometry(e, 224, 224);
+    if (!t.ok) return ORBIT_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const Op& op = e->ops[i];
+        if (op.kind != OP_PW) continue;
+        float* wt = tderived + t.wt_off[i];                       // [cin][cout]
+        int rc = launch_transpose(params + op.w, wt, op.cout, op.cin, st);
+        if (rc) return rc;
+        rc = launch_weight_split(wt, op.cin, op.cout, wt + (int64_t)op.cin * op.cout, st);
+        if (rc) return rc;
+    }
+    return ORBIT_OK;
+}
+
+extern "C" int orbit_engine_forward_train(const orbit_engine* e, const float* params, const float* derived, const float* frames,
+                                          int num_frames, int height, int width, float* feats, float* saved, int64_t saved_floats,
+                                          void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_forward_args(e, params, derived, frames, num_frames, height, width, feats, workspace);
+    if (rc) return rc;
+    if (!saved || !aligned16(saved)) return ORBIT_ERR_ARG;
+    const TrainGeom t = train_geometry(e, height, width);
+    if (!t.ok) return ORBIT_ERR_UNSUPPORTED;
+    const int B = num_frames;
+    if (B > e->chunk_frames) return ORBIT_ERR_UNSUPPORTED;        // one pass: the arena is indexed by frame
+    if (saved_floats < t.saved_per_frame * B) return ORBIT_ERR_WORKSPACE;
+    BufSizes bs;
+    if ((rc = plan_buffers(e, height, width, &bs))) return rc;
+    if (workspace_bytes < orbit_engine_workspace_bytes(e, height, width)) return ORBIT_ERR_WORKSPACE;
+    float* buf[BUF_COUNT];
+    workspace_buffers(e, bs, workspace, buf);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto ptr = [&](int b) -> float* {
+        if (b == BUF_INPUT) return const_cast<float*>(frames);
+        if (b == BUF_OUTPUT) return feats;
+        return b >= 0 ? buf[b] : nullptr;
+    };
+    const float* ones = derived + e->ident;
+    const float* zeros = derived + e->ident + e->max_c;
+    int64_t launches = 0;
+    const float* gate = nullptr;
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const Op& op = e->ops[i];
+        const int h = t.in_h[i], w = t.in_w[i], ho = t.out_h[i], wo = t.out_w[i];
+        const float* scale = derived + op.fold;
+        const float* shift = derived + op.fold + op.cout;
+        float* c = t.c_off[i] >= 0 ? saved + t.c_off[i] * B : nullptr;
+        switch (op.kind) {
+            case OP_STEM: {
+                int pt, pl, d;
+                same_geometry(h, op.k, op.stride, &d, &pt);
+                same_geometry(w, op.k, op.stride, &d, &pl);
+                rc = launch_stem(ptr(op.in), params + op.w, ones, zeros, c, B, h, w, ho, wo, pt, pl, op.cout, ACT_NONE, st);
+                if (rc) return rc;
+                rc = launch_bn_act_forward(c, scale, shift, ptr(op.out), (int64_t)B * ho * wo, op.cout, op.act, st);
+                launches += 2;
+                break;
+            }
+            case OP_DW: {
+                int pt, pl, d;
+                same_geometry(h, op.k, op.stride, &d, &pt);
+                same_geometry(w, op.k, op.stride, &d, &pl);
+                rc = launch_depthwise(ptr(op.in), derived + op.dw_wt, ones, zeros, c, nullptr, B, h, w, op.cin, ho, wo, op.k, op.stride,
+                                      pt, pl, ACT_NONE, st);
+                if (rc) return rc;
+                float* a = saved + t.a_off[i] * B;
+                rc = launch_bn_act_forward(c, scale, shift, a, (int64_t)B * ho * wo, op.cout, op.act, st);
+                if (rc) return rc;
+                rc = launch_spatial_mean(a, saved + t.m_off[i] * B, B, ho * wo, op.cout, st);
+                if (rc) return rc;
+                rc = cudaMemcpyAsync(ptr(op.out), a, sizeof(float) * (size_t)B * ho * wo * op.cout, cudaMemcpyDeviceToDevice, st);
+                launches += 4;
+                break;
+            }
+            case OP_SE: {
+                float* g = saved + t.g_off[i] * B;
+                // the depthwise op right before this one holds the squeeze means
+                rc = launch_se_gate(saved + t.m_off[i - 1] * B, 1, 1, params + op.w, params + op.b, derived + op.dw_wt, params + op.b2, g,
+                                    B, op.cin, op.se_reduce, st);
+                gate = g;
+                ++launches;
+                break;
+            }
+            case OP_PW: {
+                const int M = B * h * w;
+                if (op.act == ACT_SILU) {
+                    rc = launch_pointwise_tcgen05(ptr(op.in), derived + op.w_split, ones, zeros, nullptr, nullptr, c, M, op.cout, op.cin,
+                                                  h * w, ACT_NONE, 3, st);
+                    if (rc) return rc;
+                    rc = launch_bn_act_forward(c, scale, shift, ptr(op.out), M, op.cout, op.act, st);
+                    launches += 2;
+                } else {
+                    rc = launch_pointwise_tcgen05(ptr(op.in), derived + op.w_split, scale, shift, op.gated ? gate : nullptr, ptr(op.res),
+                                                  ptr(op.out), M, op.cout, op.cin, h * w, ACT_NONE, 3, st);
+                    ++launches;
+                }
+                break;
+            }
+            case OP_SPATIAL_MEAN:
+                rc = launch_spatial_mean(ptr(op.in), ptr(op.out), B, h * w, op.cin, st);
+                ++launches;
+                break;
+            default: return ORBIT_ERR_UNSUPPORTED;
+        }
+        if (rc) return rc;
+    }
+    e->last_launches.store(launches);
+    return ORBIT_OK;
+}
+
+// grad_params: a blob with the layout of `params`; the gradients of the FiLM-site BatchNorm weight / bias are ACCUMULATED
+// at the offsets of those parameters (everything else is left untouched). dfeats [num_frames, feat_dim].
+extern "C" int orbit_engine_backward_train(const orbit_engine* e, const float* params, const float* derived, const float* tderived,
+                                           const float* saved, const float* dfeats, int num_frames, int height, int width,
+                                           float* grad_params, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!e || !params || !derived || !tderived || !saved || !dfeats || !grad_params || !workspace) return ORBIT_ERR_ARG;
+    if (num_frames <= 0 || height <= 0 || width <= 0) return ORBIT_ERR_ARG;
+    const TrainGeom t = train_geometry(e, height, width);
+    if (!t.ok) return ORBIT_ERR_UNSUPPORTED;
+    const int B = num_frames;
+    if (B > e->chunk_frames) return ORBIT_ERR_UNSUPPORTED;
+    BufSizes bs;
+    int rc = plan_buffers(e, height, width, &bs);
+    if (rc) return rc;
+    if (workspace_bytes < orbit_engine_workspace_bytes(e, height, width)) return ORBIT_ERR_WORKSPACE;
+    float* buf[BUF_COUNT];
+    workspace_buffers(e, bs, workspace, buf);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* ones = derived + e->ident;
+    const float* zeros = derived + e->ident + e->max_c;
+    int64_t launches = 0;
+    bool from_pool = false;              // the gradient of the current tensor is dfeats / HW (global average pool)
+    const float* skip = nullptr;         // gradient flowing around the block through the residual connection
+    float* scratch = buf[BUF_E];         // per-channel partial sums of the FiLM-site reductions (free whenever a site is processed)
+    auto film_grads = [&](const Op& op, float** gg, float** gb) {
+        const FoldEntry& f = e->folds[op.fold_idx];
+        const bool site = f.film_gamma >= 0;
+        *gg = site ? grad_params + f.gamma : nullptr;
+        *gb = site ? grad_params + f.beta : nullptr;
+        return site;
+    };
+    for (int i = (int)e->ops.size() - 1; i >= 0; --i) {
+        const Op& op = e->ops[i];
+        const int h = t.in_h[i], w = t.in_w[i], ho = t.out_h[i], wo = t.out_w[i];
+        const float* scale = op.fold >= 0 ? derived + op.fold : nullptr;
+        const float* shift = op.fold >= 0 ? derived + op.fold + op.cout : nullptr;
+        const FoldEntry* f = op.fold_idx >= 0 ? &e->folds[op.fold_idx] : nullptr;
+        const float* c = t.c_off[i] >= 0 ? saved + t.c_off[i] * B : nullptr;
+        switch (op.kind) {
+            case OP_SPATIAL_MEAN: from_pool = true; break;
+            case OP_PW: {
+                const int M = B * h * w;
+                const float* wt_split = tderived + t.wt_off[i] + (int64_t)op.cin * op.cout;
+                if (op.act == ACT_SILU) {          // expand / conv_head: bn + SiLU backward, then dx = dc W
+                    float *gg, *gb;
+                    film_grads(op, &gg, &gb);
+                    float* dc = buf[op.out];       // in place for the expand (its output gradient lives there), fresh for conv_head
+                    rc = launch_bn_act_backward(c, from_pool ? dfeats : buf[op.out], nullptr, nullptr, scale, shift, params + f->mean,
+                                                params + f->var, f->eps, dc, scratch == dc ? buf[BUF_D] : scratch, gg, gb, M, op.cout,
+                                                ACT_SILU, from_pool ? 1 : 0, h * w, st);
+                    if (rc) return rc;
+                    from_pool = false;
+                    rc = launch_pointwise_tcgen05(dc, wt_split, ones, zeros, nullptr, skip, buf[op.in], M, op.cin, op.cout, h * w, ACT_NONE, 3, st);
+                    skip = nullptr;
+                    launches += 2;
+                } else {                           // gated project (no activation): dga = (dy scale3) W
+                    const int other = op.out == BUF_X0 ? BUF_X1 : BUF_X0;          // the block-input buffer: free until dx is written
+                    rc = launch_bn_act_backward(buf[op.out], buf[op.out], nullptr, nullptr, scale, shift, nullptr, nullptr, 0.f, buf[other],
+                                                nullptr, nullptr, nullptr, M, op.cout, ACT_NONE, 0, h * w, st);
+                    if (rc) return rc;
+                    rc = launch_pointwise_tcgen05(buf[other], wt_split, ones, zeros, nullptr, nullptr, buf[op.in], M, op.cin, op.cout, h * w,
+                                                  ACT_NONE, 3, st);
+                    skip = op.res != BUF_NONE ? buf[op.out] : nullptr;
+                    launches += 2;
+                }
+                break;
+            }
+            case OP_SE: {
+                // dga lives in BUF_D (the project's input gradient); the depthwise op before holds a and the squeeze means
+                rc = launch_se_backward(buf[BUF_D], saved + t.a_off[i - 1] * B, saved + t.m_off[i - 1] * B, params + op.w, params + op.b,
+                                        params + op.w2, params + op.b2, buf[BUF_GATE], buf[BUF_PARTIAL], B, h * w, op.cin, op.se_reduce, st);
+                launches += 2;
+                break;
+            }
+            case OP_DW: {
+                int pt, pl, d;
+                same_geometry(h, op.k, op.stride, &d, &pt);
+                same_geometry(w, op.k, op.stride, &d, &pl);
+                float *gg, *gb;
+                film_grads(op, &gg, &gb);
+                // da = dga gate + dmean / HW (the SE op right after this one), then bn2 + SiLU backward, in place in BUF_D
+                const float* gate = saved + t.g_off[i + 1] * B;
+                rc = launch_bn_act_backward(c, buf[BUF_D], gate, buf[BUF_PARTIAL], scale, shift, params + f->mean, params + f->var, f->eps,
+                                            buf[BUF_D], op.in == BUF_E ? buf[BUF_E] : buf[BUF_H], gg, gb, (int64_t)B * ho * wo, op.cout,
+                                            ACT_SILU, 2, ho * wo, st);
+                if (rc) return rc;
+                rc = launch_dw_dgrad(buf[BUF_D], derived + op.dw_wt, buf[op.in], B, h, w, op.cin, ho, wo, op.k, op.stride, pt, pl, st);
+                launches += 3;
+                break;
+            }
+            case OP_STEM: {
+                float *gg, *gb;
+                if (film_grads(op, &gg, &gb))
+                    rc = launch_bn_act_backward(c, buf[op.out], nullptr, nullptr, scale, shift, params + f->mean, params + f->var, f->eps,
+                                                nullptr, scratch, gg, gb, (int64_t)B * ho * wo, op.cout, ACT_SILU, 0, ho * wo, st);
+                launches += 2;
+                break;
+            }
+            default: return ORBIT_ERR_UNSUPPORTED;
+        }
+        if (rc) return rc;
+    }
+    e->last_launches.store(launches);
+    return ORBIT_OK;
+}

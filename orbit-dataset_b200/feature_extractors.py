@@ -64,6 +64,7 @@ class FeatureExtractor(nn.Module):
         self._workspace = None
         self._prepared_key = None
         self._versioned = None
+        self._train_derived = self._saved = self._grad_blob = self._train_shape = None
         self._build_tree()
         self.reset_parameters(seed)
 
@@ -106,6 +107,7 @@ class FeatureExtractor(nn.Module):
         self._blob = new_blob
         self._rebind()
         self._derived = self._workspace = self._prepared_key = self._versioned = None
+        self._train_derived = self._saved = self._grad_blob = self._train_shape = None
         return self
 
     @torch.no_grad()
@@ -271,6 +273,63 @@ class FeatureExtractor(nn.Module):
                                          L.stream_ptr(frames.device)), "orbit_engine_forward")
         L.count_launches(lib.orbit_engine_last_launches(self._engine))
         return feats
+
+    # ---- training through the frozen extractor (FineTuner + FiLM) -----------------------------------
+    def forward_train(self, frames: torch.Tensor) -> torch.Tensor:
+        """Forward pass that keeps the pre-activations the backward needs (BatchNorm in eval mode, layer at a time);
+        same features as ``forward``. One pass: ``len(frames) <= chunk_frames``. Follow with ``backward_train``."""
+        lib = L.load()
+        L.require_cuda(frames, "frames")
+        if frames.dim() != 4 or frames.shape[1] != 3:
+            raise ValueError(f"frames must be [B,3,H,W], got {tuple(frames.shape)}")
+        frames = frames.contiguous().float()
+        self.prepare(None)
+        n, _, h, w = frames.shape
+        per_frame = lib.orbit_engine_train_saved_floats(self._engine, h, w)
+        if per_frame < 0:
+            raise NotImplementedError(f"training through '{self.extractor_name}' needs backward kernels that do not exist yet "
+                                      "(SURVEY.md 8f-3: only the MBConv networks are covered)")
+        if n > self.get_option('chunk_frames'):
+            self.set_option('chunk_frames', n)
+        if self._train_derived is None:
+            self._train_derived = torch.empty(lib.orbit_engine_train_derived_floats(self._engine), dtype=torch.float32, device=frames.device)
+            L.check(lib.orbit_engine_prepare_train(self._engine, L.ptr(self._blob), L.ptr(self._train_derived), L.stream_ptr(frames.device)),
+                    "orbit_engine_prepare_train")
+        if self._saved is None or self._saved.numel() < per_frame * n:
+            self._saved = torch.empty(per_frame * n, dtype=torch.float32, device=frames.device)
+        ws_bytes = lib.orbit_engine_workspace_bytes(self._engine, h, w)
+        if self._workspace is None or self._workspace.numel() < ws_bytes:
+            self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
+        feats = torch.empty(n, self.output_size, dtype=torch.float32, device=frames.device)
+        L.check(lib.orbit_engine_forward_train(self._engine, L.ptr(self._blob), L.ptr(self._derived), L.ptr(frames), n, h, w, L.ptr(feats),
+                                               L.ptr(self._saved), self._saved.numel(), L.ptr(self._workspace), self._workspace.numel(),
+                                               L.stream_ptr(frames.device)), "orbit_engine_forward_train")
+        L.count_launches(lib.orbit_engine_last_launches(self._engine))
+        self._train_shape = (n, h, w)
+        return feats
+
+    def backward_train(self, dfeats: torch.Tensor):
+        """Back-propagates ``dfeats`` [B, output_size] of the last ``forward_train`` and ACCUMULATES the gradients of the
+        FiLM parameters into ``param.grad`` (views of one gradient blob laid out like the parameters)."""
+        lib = L.load()
+        n, h, w = self._train_shape
+        dfeats = dfeats.contiguous().float()
+        assert dfeats.shape == (n, self.output_size)
+        if self._grad_blob is None:
+            self._grad_blob = torch.zeros(self._n_floats, dtype=torch.float32, device=dfeats.device)
+            tagged = {name for name, _, _ in self._film_table}
+            params = dict(self.named_parameters())
+            for name, numel, offset in self._table:
+                if name in tagged:
+                    params[name].grad = self._grad_blob[offset:offset + numel].view(self._shapes[name])
+        L.check(lib.orbit_engine_backward_train(self._engine, L.ptr(self._blob), L.ptr(self._derived), L.ptr(self._train_derived),
+                                                L.ptr(self._saved), L.ptr(dfeats), n, h, w, L.ptr(self._grad_blob), L.ptr(self._workspace),
+                                                self._workspace.numel(), L.stream_ptr(dfeats.device)), "orbit_engine_backward_train")
+        L.count_launches(lib.orbit_engine_last_launches(self._engine))
+
+    def zero_film_grads(self):
+        if self._grad_blob is not None:
+            self._grad_blob.zero_()
 
     def __del__(self):
         try:

@@ -436,11 +436,13 @@ class MultiStepFewShotRecogniser(FewShotRecogniser):
         optimizer = learning_args.pop('optimizer')
         learning_args.pop('loss_fn')
         learning_args.pop('extractor_lr_scale')
-        if self.adapt_features or self.learn_extractor:
-            raise NotImplementedError("fine-tuning FiLM layers / the extractor needs backbone backward kernels "
-                                      "(SURVEY.md 8f-3)")
+        if self.learn_extractor:
+            raise NotImplementedError("fine-tuning the extractor's weights needs weight-gradient kernels (SURVEY.md 8f-3)")
         num_classes = len(torch.unique(context_labels))
         self.init_classifier(num_classes)
+        if self.adapt_features:
+            return self._personalise_film(context_clips, context_labels, num_grad_steps, learning_rate, optimizer,
+                                          dict(learning_args), ops_counter)
         macs_before = ops_counter.get_task_macs() if ops_counter else 0
         features = self._get_features_in_batches(context_clips, ops_counter=ops_counter)
         features = self._pool_features(features, ops_counter=ops_counter)
@@ -454,6 +456,59 @@ class MultiStepFewShotRecogniser(FewShotRecogniser):
             ops_counter.add_macs(num_grad_steps * num_classes * features.size(0) * features.size(1))
         finetune_linear_head(self.classifier, features, context_labels, self.batch_size, num_grad_steps,
                              learning_rate, optimizer, dict(learning_args), self.logit_scale)
+
+    def _personalise_film(self, context_clips, context_labels, num_grad_steps, learning_rate, optimizer, opt_args, ops_counter):
+        """FineTuner + FiLM (few_shot_recognisers.py:196-198,225-246): gradient steps on the linear head AND on the affine
+        weight / bias of the FiLM-tagged BatchNorms, through the frozen extractor (BatchNorm in eval mode). Per batch: a
+        forward that keeps pre-activations, the head + cross-entropy backward, the extractor backward (native kernels,
+        csrc/train.cu + the tcgen05 GEMM on transposed weights); per grad step: one optimiser step (utils/optim.py:11-32;
+        torch.optim over the ~20 k trainable values, exactly the reference's optimiser)."""
+        import ctypes as C
+        from .classifier_heads import _class_index
+        lib = L.load()
+        self._require_device()
+        fe, dev = self.feature_extractor, self.device
+        classes, idx = _class_index(context_labels)
+        labels_dev = torch.from_numpy(idx).to(dev)
+        film_params = [p for n, p in fe.named_parameters() if n in set(self.film_parameter_names)]
+        head_params = [self.classifier.weight, self.classifier.bias]
+        if optimizer == 'adam':
+            opt = torch.optim.Adam([{'params': head_params}, {'params': film_params}], lr=learning_rate,
+                                   eps=opt_args.get('epsilon', 1e-8), weight_decay=opt_args.get('weight_decay', 0.0),
+                                   betas=tuple(opt_args.get('betas', (0.9, 0.999))))
+        elif optimizer == 'sgd':
+            opt = torch.optim.SGD([{'params': head_params}, {'params': film_params}], lr=learning_rate,
+                                  momentum=opt_args.get('momentum', 0.0), weight_decay=opt_args.get('weight_decay', 0.0))
+        else:
+            raise ValueError(f"Optimizer {optimizer} not valid.")
+        n_ctx, Lc, d, c = len(context_labels), self.clip_length, fe.output_size, len(classes)
+        num_batches = int(np.ceil(float(n_ctx) / float(self.batch_size)))
+        gw, gb = torch.zeros_like(self.classifier.weight), torch.zeros_like(self.classifier.bias)
+        self.classifier.weight.grad, self.classifier.bias.grad = gw, gb
+        scratch = torch.empty(lib.orbit_linear_ce_scratch_floats(self.batch_size, d, c), dtype=torch.float32, device=dev)
+        for _ in range(num_grad_steps):
+            for batch in range(num_batches):
+                b0, b1 = get_batch_indices(batch, n_ctx, self.batch_size)
+                clips = context_clips[b0:b1]
+                frames = clips.flatten(end_dim=1) if clips.dim() == 5 else clips
+                feats = fe.forward_train(frames.to(dev, non_blocking=True).float())
+                if ops_counter:
+                    ops_counter.compute_macs(fe, frames)
+                    ops_counter.add_macs(feats.size(0) * feats.size(1))
+                    ops_counter.add_macs(c * (b1 - b0) * d)
+                dfeats = torch.empty_like(feats)
+                L.check(lib.orbit_linear_ce_backward(L.ptr(feats), L.ptr(labels_dev[b0:b1].contiguous()), L.ptr(self.classifier.weight.detach()),
+                                                     L.ptr(self.classifier.bias.detach()), b1 - b0, Lc, d, c, float(self.logit_scale),
+                                                     float(b1 - b0) / float(n_ctx), L.ptr(gw), L.ptr(gb), L.ptr(dfeats), L.ptr(scratch),
+                                                     L.stream_ptr(dev)), "orbit_linear_ce_backward")
+                L.count_launches(2)
+                fe.backward_train(dfeats)
+            opt.step()
+            gw.zero_(); gb.zero_()
+            fe.zero_film_grads()
+        for p in film_params + head_params:
+            p.grad = None
+        fe._grad_blob = None
 
     def predict(self, clips, ops_counter=None):
         """few_shot_recognisers.py:248-258."""

@@ -55,6 +55,13 @@ _SIGNATURES = {
     "orbit_video_stats": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _p, _p]),
     "orbit_engine_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p]),
     "orbit_engine_calibrate": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p]),
+    "orbit_engine_train_saved_floats": (_i64, [_p, _i, _i]),
+    "orbit_engine_train_derived_floats": (_i64, [_p]),
+    "orbit_engine_prepare_train": (_i, [_p, _p, _p, _p]),
+    "orbit_engine_forward_train": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p, _i64, _p]),
+    "orbit_engine_backward_train": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p]),
+    "orbit_linear_ce_scratch_floats": (_i64, [_i, _i, _i]),
+    "orbit_linear_ce_backward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p]),
     "orbit_engine_profile_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]),
     "orbit_engine_last_launches": (_i64, [_p]),

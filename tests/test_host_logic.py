@@ -171,10 +171,14 @@ def test_training_paths_without_backward_kernels_are_refused():
     unfrozen.set_test_mode(False)
     with pytest.raises(NotImplementedError, match="training the extractor"):
         unfrozen.personalise(clips, labels)
-    ft = orbit_b200.MultiStepFewShotRecogniser('efficientnet_b0', True, 'linear', 1, 4, False)
     args = {'num_grad_steps': 2, 'learning_rate': 0.1, 'optimizer': 'adam', 'loss_fn': None, 'extractor_lr_scale': 0.1}
-    with pytest.raises(NotImplementedError, match="fine-tuning FiLM"):
-        ft.personalise(clips, labels, args)
+    ft = orbit_b200.MultiStepFewShotRecogniser('efficientnet_b0', True, 'linear', 1, 4, False)
+    with pytest.raises(OrbitError):                          # FineTuner + FiLM IS implemented (tests/test_gpu_train.py): only the GPU is missing here
+        ft.personalise(clips, labels, dict(args))
+    assert any(p.requires_grad for p in ft.feature_extractor.parameters())      # unfreeze_film (film.py:76-79)
+    unfrozen_ft = orbit_b200.MultiStepFewShotRecogniser('efficientnet_b0', False, 'linear', 1, 4, True)
+    with pytest.raises(NotImplementedError, match="weight-gradient"):
+        unfrozen_ft.personalise(clips, labels, dict(args))
     assert ft.personalise_with_lite(clips, labels) is None   # the reference's own no-op (few_shot_recognisers.py:260-261)
 
 

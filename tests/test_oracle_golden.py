@@ -159,6 +159,19 @@ def test_finetuner_vs_reference(gr):
     close(oracle.predict(tgt), gr['finetune2_logits'], 1e-5)
 
 
+def test_finetuner_film_vs_reference(gr):
+    """FineTuner + FiLM (few_shot_recognisers.py:196-198,207-246): the oracle restatement vs the unmodified reference."""
+    oracle = OracleRecogniser('efficientnet_b0', False, 'linear', 1, 5, 1.0, 1991, calibration_frames(64))
+    ctx, ctx_y, tgt, _ = make_episode(EpisodeSpec(4, 3, 2, 1, 64), index=2)
+    oracle.personalise_finetune_film(ctx[:-1], ctx_y[:-1], num_grad_steps=3, learning_rate=0.01)
+    close(oracle.head[0], gr['finetune_film_weight'], 1e-5)
+    close(oracle.head[1], gr['finetune_film_bias'], 1e-5)
+    sd = oracle.extractor.state_dict()
+    for k in ('bn1.weight', 'blocks.1.0.bn2.weight', 'blocks.3.1.bn2.bias', 'bn2.bias'):
+        close(sd[k], gr['finetune_film_' + k], 1e-5)
+    close(oracle.predict(tgt), gr['finetune_film_logits'], 1e-4)
+
+
 def test_efficientnet_v2_s_structure():
     """tf_efficientnetv2_s with num_classes=0: 20,177,488 parameters (timm's published 21.46 M minus the 1280x1000+1000
     classifier), 84 FiLM tensors (2 root + 2 ConvBnAct + 8 EdgeResidual + 30 InvertedResidual sites, weight + bias)."""
