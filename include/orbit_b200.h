@@ -263,9 +263,12 @@ int orbit_video_stats(const float* logits, const int32_t* predictions, int num_c
                       int32_t* pred_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Training through the frozen extractor (first slice of SURVEY.md 8f-3): FineTuner + FiLM, i.e.
- * MultiStepFewShotRecogniser.personalise with adapt_features=True (model/few_shot_recognisers.py:196-198,207-246).
- * MBConv networks (ORBIT_ARCH_EFFICIENTNET_B0) only; other architectures return ORBIT_ERR_UNSUPPORTED.
+ * Training through the frozen extractor: FineTuner + FiLM, i.e. MultiStepFewShotRecogniser.personalise
+ * with adapt_features=True (model/few_shot_recognisers.py:196-198,207-246), and CNAPs-style meta-training of the set
+ * encoder + FiLM generator (single-step-learner.py:196-243, few_shot_recognisers.py:313-343,388-437).
+ * ORBIT_ARCH_EFFICIENTNET_B0 (gradients of the FiLM-site BatchNorm weight / bias) and ORBIT_ARCH_SET_ENCODER (gradients
+ * of every parameter; `frames` = the input of the forward pass, needed for the first conv's weight gradient; `tderived`
+ * is rewritten from the current weights on every call); other architectures return ORBIT_ERR_UNSUPPORTED.
  *   orbit_engine_train_saved_floats   floats PER FRAME of the activation arena forward_train fills
  *   orbit_engine_train_derived_floats floats of the transposed / split 1x1 weights (prepare_train; weights are frozen)
  *   orbit_engine_forward_train        same result as orbit_engine_forward (layer at a time, BatchNorm in eval mode) for
@@ -282,9 +285,23 @@ int orbit_engine_prepare_train(const orbit_engine* engine, const float* params, 
 int orbit_engine_forward_train(const orbit_engine* engine, const float* params, const float* derived, const float* frames,
                                int num_frames, int height, int width, float* feats, float* saved, int64_t saved_floats,
                                void* workspace, int64_t workspace_bytes, void* stream);
-int orbit_engine_backward_train(const orbit_engine* engine, const float* params, const float* derived, const float* tderived,
-                                const float* saved, const float* dfeats, int num_frames, int height, int width,
+int orbit_engine_backward_train(const orbit_engine* engine, const float* params, const float* derived, float* tderived,
+                                const float* saved, const float* frames, const float* dfeats, int num_frames, int height, int width,
                                 float* grad_params, void* workspace, int64_t workspace_bytes, void* stream);
+/* copies the FiLM-site gradients out of a grad_params blob into the film-blob layout (orbit_engine_film_info order):
+ * d loss / d (generated gamma', beta') for the generator backward                                                     */
+int orbit_engine_film_grad(const orbit_engine* engine, const float* grad_params, float* grad_film, void* stream);
+/* FilmParameterGenerator backward (model/feature_adapters.py:66-78): grad_film [film floats] -> grad_gen_params (layout of
+ * gen_params, WRITTEN for every trainable tensor of the table) and grad_embedding [hidden]; scratch: num_tensors * hidden */
+int orbit_film_generate_backward(const float* gen_params, const void* table, int num_tensors, const float* task_embedding,
+                                 int hidden, const float* grad_film, float* grad_gen_params, float* grad_embedding,
+                                 float* scratch, void* stream);
+/* query path of the linear-form heads (linear / versa / proto: metric EUCLIDEAN -> logits = s (q W^T + b); proto_cosine:
+ * metric COSINE), classifier_heads.py:60-79,161-180,202-230: grad_logits [num_clips, C] -> grad_frame_feats [num_clips*L, D]
+ * through the clip mean-pool (poolers.py:13-16)                                                                        */
+int orbit_head_predict_backward(const float* frame_feats, const float* weight, const float* grad_logits, int num_clips,
+                                int clip_length, int feat_dim, int num_classes, int metric, float logit_scale,
+                                float* grad_frame_feats, void* stream);
 int64_t orbit_linear_ce_scratch_floats(int num_clips, int feat_dim, int num_classes);
 int orbit_linear_ce_backward(const float* frame_feats, const int32_t* labels, const float* weight, const float* bias,
                              int num_clips, int clip_length, int feat_dim, int num_classes, float logit_scale,

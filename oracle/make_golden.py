@@ -210,6 +210,71 @@ def golden_recogniser():
     print('recogniser.npz', len(out), 'arrays')
 
 
+TRAIN_CASES = [
+    # tag, classifier, EpisodeSpec args (way, support/class, query/class, clip length, size), batch size, lite samples (0: no LITE)
+    ('cnaps', 'versa', (4, 3, 2, 2, 64), 4, 0),
+    ('protofilm_cosine', 'proto_cosine', (3, 2, 3, 1, 64), 4, 0),
+    ('cnaps_lite', 'versa', (4, 3, 2, 1, 64), 5, 4),
+]
+TRAIN_FULL_GENERATORS = (0, 9, 33)      # generators whose full gradients are stored (the others: sums and norms)
+
+
+def golden_training():
+    """Meta-training gradients of the UNMODIFIED reference (single-step-learner.py:196-243 train_task / train_task_with_lite):
+    frozen extractor, adapt_features=True; loss = CE / tasks_per_batch + 0.001 l2 (or the LITE scaling), one backward."""
+    import timm.models.efficientnet as shim_cfg
+    from model.few_shot_recognisers import SingleStepFewShotRecogniser
+    from utils.optim import cross_entropy
+    from oracle.recogniser import OracleRecogniser
+    from orbit_b200.synthetic import EpisodeSpec, make_episode, calibration_frames
+    out = {}
+    tasks_per_batch = 4
+    for tag, head, spec_args, batch, lite in TRAIN_CASES:
+        spec = EpisodeSpec(*spec_args)
+        calib = calibration_frames(spec.frame_size)
+        shim_cfg._SEED_ARGS = (1991, calib)
+        oracle = OracleRecogniser('efficientnet_b0', True, head, spec.clip_length, batch, 1.0, 1991, calib)
+        ref = SingleStepFewShotRecogniser('efficientnet_b0', True, head, spec.clip_length, batch, False, max(lite, 1), 1.0)
+        ref.load_state_dict(oracle.state_dict(), strict=True)
+        ref._set_device(torch.device('cpu'))
+        ref.set_test_mode(False)
+        ctx, ctx_y, tgt, tgt_y = make_episode(spec, index=3)
+        if lite:
+            ref._clear_caches()
+            np.random.seed(11)
+            ref.personalise_with_lite(ctx, ctx_y)
+            tgt, tgt_y = tgt[:batch], tgt_y[:batch]
+            logits = ref.predict_a_batch(tgt)
+            loss = len(ctx_y) / (lite * tasks_per_batch) * cross_entropy(logits, tgt_y)
+        else:
+            ref.personalise(ctx, ctx_y)
+            logits = ref.predict(tgt)
+            loss = cross_entropy(logits, tgt_y) / tasks_per_batch
+        loss = loss + 0.001 * ref.film_generator.regularization_term()
+        loss.backward()
+        out[tag + '_logits'] = logits.detach().numpy()
+        out[tag + '_loss'] = np.array(loss.item())
+        out[tag + '_checksum'] = np.array(checksum(ctx, tgt, ctx_y))
+        for name, p in ref.set_encoder.named_parameters():
+            out[f'{tag}_grad_set_encoder.{name}'] = p.grad.numpy()
+        names, sums, norms = [], [], []
+        for name, p in ref.film_generator.named_parameters():
+            names.append(name); sums.append(p.grad.double().sum().item()); norms.append(p.grad.double().norm().item())
+            idx = int(name.split('.')[1])
+            if idx in TRAIN_FULL_GENERATORS:
+                out[f'{tag}_grad_film_generator.{name}'] = p.grad.numpy()
+        out[tag + '_gen_names'] = np.array(names)
+        out[tag + '_gen_grad_sums'] = np.array(sums)
+        out[tag + '_gen_grad_norms'] = np.array(norms)
+        for name, p in ref.feature_extractor.named_parameters():
+            assert p.grad is None, name          # the extractor is frozen
+        print(tag, 'loss %.5f' % loss.item(), 'max|logit| %.2f' % float(logits.abs().max()),
+              'set-encoder grad norm %.3e' % float(torch.cat([p.grad.flatten() for p in ref.set_encoder.parameters()]).norm()),
+              'generator grad norm %.3e' % float(np.sqrt(np.sum(np.square(norms)))))
+    np.savez_compressed(os.path.join(OUT, 'training.npz'), **out)
+    print('training.npz', len(out), 'arrays')
+
+
 def evaluator_case(seed=1991):
     """Seeded evaluator workload shared by make_golden and the tests: users -> tasks -> videos of (label, logits, paths).
     Every video is padded to a multiple of 4 frames by repeating its last frame (as the reference's clip loader does),
@@ -277,6 +342,10 @@ if __name__ == '__main__':
     if 'evaluator' in sys.argv[1:]:
         golden_evaluator()
         sys.exit(0)
+    if 'training' in sys.argv[1:]:
+        golden_training()
+        sys.exit(0)
     golden_parts()
     golden_recogniser()
     golden_evaluator()
+    golden_training()

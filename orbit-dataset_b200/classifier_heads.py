@@ -66,8 +66,17 @@ class MeanPooler(nn.Module):
 
 
 def _head_predict(features, clip_length, weight, bias, metric, logit_scale, want_argmax=False):
+    if features.requires_grad and torch.is_grad_enabled() and not want_argmax:
+        # meta-training: logits with a graph back to the query features (the head's weights are leaf Parameters)
+        from .training import HeadPredictFn
+        return HeadPredictFn.apply(features, clip_length, weight.detach(), bias.detach() if bias is not None else None, metric,
+                                   logit_scale)
+    return _head_predict_raw(features, clip_length, weight, bias, metric, logit_scale, want_argmax)
+
+
+def _head_predict_raw(features, clip_length, weight, bias, metric, logit_scale, want_argmax=False):
     L.require_cuda(features, "features")
-    features = features.contiguous().float()
+    features = features.detach().contiguous().float()
     n = features.shape[0] // clip_length
     c, d = weight.shape
     if features.shape[1] != d:

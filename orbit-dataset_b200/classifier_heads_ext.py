@@ -170,6 +170,9 @@ class MahalanobisClassifier(HeadClassifier):
     def predict(self, target_features, ops_counter=None, clip_length=1, want_argmax=False):
         if self.means is None or self.precisions is None:
             raise AttributeError("Means and/or precisions not set - is model personalised?")
+        if target_features.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("meta-training through the Mahalanobis head (Simple CNAPs) needs its backward kernel "
+                                      "(SURVEY.md 8f-3); the linear-form heads (versa / proto / proto_cosine) are covered")
         L.require_cuda(target_features, "target_features")
         lib = L.load()
         q = self._pool(target_features, clip_length)

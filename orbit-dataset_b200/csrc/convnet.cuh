@@ -93,4 +93,24 @@ int launch_se_backward(const float* dga, const float* a, const float* m, const f
                        const float* b2, float* dgate, float* dmean, int B, int HW, int C, int R, cudaStream_t st);
 int launch_transpose(const float* w, float* out, int rows, int cols, cudaStream_t st);
 
+// ---- set-encoder training (csrc/train_setenc.cu) -----------------------------------------------------------------------
+// p = maxpool2x2(relu(scale c + shift)), floor mode
+int launch_bn_relu_pool2_forward(const float* c, const float* scale, const float* shift, float* p, int B, int H, int W, int C,
+                                 cudaStream_t st);
+// backward of the above (mode 0: dp [B,H/2,W/2,C]; mode 1: dp = dfeat [B,C] / (H/2 * W/2)); dc [B,H,W,C]; the BatchNorm weight /
+// bias and conv-bias gradients are ACCUMULATED; partial: pool_bn_relu_backward_partial_floats(...) floats
+int64_t pool_bn_relu_backward_partial_floats(int B, int H, int W, int C);
+int launch_pool_bn_relu_backward(const float* c, const float* dp, const float* scale, const float* shift, const float* conv_bias,
+                                 const float* mean, const float* var, float eps, float* dc, float* partial, float* grad_gamma,
+                                 float* grad_beta, float* grad_conv_bias, int B, int H, int W, int C, int mode, cudaStream_t st);
+// conv3x3 (pad 1, stride 1) weight gradient, NHWC input: grad_w [Cout,Cin,3,3] += ...; partial: scratch of `partial_capacity`
+// floats (at least 9 Cin Cout; more lets more blocks work in parallel)
+int launch_conv3_wgrad(const float* dc, const float* in, float* partial, int64_t partial_capacity, float* grad_w, int B, int H, int W,
+                       int Cin, int Cout, cudaStream_t st);
+// weight gradient from an im2col matrix col [M,Kpad]: grad_w [64,K] += dc^T col; partial: at most 56 M floats
+int launch_col_wgrad(const float* dc, const float* col, float* partial, float* grad_w, int64_t M, int Cout, int K, int Kpad,
+                     cudaStream_t st);
+// conv weight [Cout,Cin,3,3] -> [Cin][9*Cout] for the data-gradient GEMM over im2col(dc)
+int launch_conv3_dgrad_weight(const float* w, float* out, int Cin, int Cout, cudaStream_t st);
+
 }  // namespace orbit

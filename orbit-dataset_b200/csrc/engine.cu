@@ -963,6 +963,18 @@ TrainGeom train_geometry(const orbit_engine* e, int H, int W) {
                 t.wt_off[i] = t.tderived_floats; t.tderived_floats += 3 * (int64_t)op.cin * op.cout + 8;
                 break;
             case OP_SPATIAL_MEAN: break;
+            case OP_CONV3:       // set encoder: conv3x3 (pad 1, stride 1, bias) + BatchNorm + ReLU, followed by maxpool 2x2
+                if (e->arch != ORBIT_ARCH_SET_ENCODER || op.k != 3 || op.stride != 1 || op.pad != 1 || op.act != ACT_RELU || op.cout != 64 ||
+                    i + 1 >= n || e->ops[i + 1].kind != OP_MAXPOOL) { t.ok = false; return t; }
+                t.c_off[i] = t.saved_per_frame; t.saved_per_frame += (int64_t)h * w * op.cout;
+                if (!op.nchw_in) { t.wt_off[i] = t.tderived_floats; t.tderived_floats += 2 * (int64_t)op.cin * 9 * op.cout + 8; }
+                break;
+            case OP_MAXPOOL:
+                if (e->arch != ORBIT_ARCH_SET_ENCODER || op.k != 2 || op.stride != 2 || op.pad != 0) { t.ok = false; return t; }
+                ho = h / 2; wo = w / 2;
+                if (ho < 1 || wo < 1) { t.ok = false; return t; }
+                t.a_off[i] = t.saved_per_frame; t.saved_per_frame += (int64_t)ho * wo * op.cout;      // pooled output = next conv's input
+                break;
             default: t.ok = false; return t;
         }
         t.out_h[i] = ho; t.out_w[i] = wo;
@@ -1096,10 +1108,31 @@ extern "C" int orbit_engine_forward_train(const orbit_engine* e, const float* pa
                 }
                 break;
             }
-            case OP_SPATIAL_MEAN:
-                rc = launch_spatial_mean(ptr(op.in), ptr(op.out), B, h * w, op.cin, st);
+            case OP_SPATIAL_MEAN: {
+                // set encoder: the pooled output of the last block lives in the saved arena
+                const float* in = (i > 0 && e->ops[i - 1].kind == OP_MAXPOOL) ? saved + t.a_off[i - 1] * B : ptr(op.in);
+                rc = launch_spatial_mean(in, ptr(op.out), B, h * w, op.cin, st);
                 ++launches;
                 break;
+            }
+            case OP_CONV3: {
+                // raw convolution (no bias: it is folded into shift) into the arena; im2col + the tcgen05 GEMM as in run_plan
+                const float* in = op.nchw_in ? ptr(op.in) : saved + t.a_off[i - 1] * B;
+                const int M = B * h * w;
+                rc = launch_im2col(in, buf[BUF_COL], B, h, w, op.cin, 3, 1, 1, 1, h, w, op.kpad, op.nchw_in, st);
+                if (rc) return rc;
+                rc = launch_pointwise_tcgen05(buf[BUF_COL], derived + op.w_split, ones, zeros, nullptr, nullptr, c, M, op.cout, op.kpad, h * w,
+                                              ACT_NONE, 3, st);
+                launches += 2;
+                break;
+            }
+            case OP_MAXPOOL: {
+                const Op& conv = e->ops[i - 1];
+                rc = launch_bn_relu_pool2_forward(saved + t.c_off[i - 1] * B, derived + conv.fold, derived + conv.fold + conv.cout,
+                                                  saved + t.a_off[i] * B, B, h, w, op.cin, st);
+                ++launches;
+                break;
+            }
             default: return ORBIT_ERR_UNSUPPORTED;
         }
         if (rc) return rc;
@@ -1108,11 +1141,83 @@ extern "C" int orbit_engine_forward_train(const orbit_engine* e, const float* pa
     return ORBIT_OK;
 }
 
+extern "C" int orbit_engine_film_grad(const orbit_engine* e, const float* grad_params, float* grad_film, void* stream) {
+    if (!e || !grad_params || !grad_film) return ORBIT_ERR_ARG;
+    for (const FoldEntry& f : e->folds) {
+        if (f.film_gamma >= 0)
+            ORBIT_CUDA(cudaMemcpyAsync(grad_film + f.film_gamma, grad_params + f.gamma, sizeof(float) * f.channels, cudaMemcpyDeviceToDevice,
+                                       (cudaStream_t)stream));
+        if (f.film_beta >= 0)
+            ORBIT_CUDA(cudaMemcpyAsync(grad_film + f.film_beta, grad_params + f.beta, sizeof(float) * f.channels, cudaMemcpyDeviceToDevice,
+                                       (cudaStream_t)stream));
+    }
+    return e->lns.empty() ? ORBIT_OK : ORBIT_ERR_UNSUPPORTED;
+}
+
+// Set-encoder backward (model/set_encoders.py:81-120; every parameter is trainable: conv weight / bias, BatchNorm weight / bias;
+// BatchNorm in eval mode, few_shot_recognisers.py:176-183). Gradients are ACCUMULATED into grad_params (layout of `params`).
+static int set_encoder_backward(const orbit_engine* e, const TrainGeom& t, const float* params, const float* derived, float* tderived,
+                                const float* saved, const float* frames, const float* dfeats, int B, float* grad_params, float** buf,
+                                int64_t col_capacity, cudaStream_t st) {
+    const float* ones = derived + e->ident;
+    const float* zeros = derived + e->ident + e->max_c;
+    int64_t launches = 0;
+    int rc = ORBIT_OK;
+    const float* dp = dfeats;          // gradient of the current pooled tensor (mode 1 for the first step: dfeats / HW)
+    int mode = 1;
+    for (int i = (int)e->ops.size() - 1; i >= 0; --i) {
+        const Op& op = e->ops[i];
+        if (op.kind != OP_CONV3) continue;
+        const int h = t.in_h[i], w = t.in_w[i];
+        const FoldEntry& f = e->folds[op.fold_idx];
+        const float* c = saved + t.c_off[i] * B;
+        float* dc = buf[BUF_E];
+        // maxpool + ReLU + BatchNorm backward; partial sums at the head of the (idle) im2col buffer
+        rc = launch_pool_bn_relu_backward(c, dp, derived + op.fold, derived + op.fold + op.cout, params + op.b, params + f.mean,
+                                          params + f.var, f.eps, dc, buf[BUF_COL], grad_params + f.gamma, grad_params + f.beta,
+                                          grad_params + op.b, B, h, w, op.cout, mode, st);
+        if (rc) return rc;
+        launches += 2;
+        if (op.nchw_in) {
+            // first conv (3 input channels): explicit im2col of the frames, weight gradient from the col matrix
+            if (!frames) return ORBIT_ERR_ARG;
+            rc = launch_im2col(frames, buf[BUF_COL], B, h, w, op.cin, 3, 1, 1, 1, h, w, op.kpad, 1, st);
+            if (rc) return rc;
+            // partial sums behind the col matrix: at most 56 M floats against the 116 M the buffer has left (M = B h w)
+            rc = launch_col_wgrad(dc, buf[BUF_COL], buf[BUF_COL] + (int64_t)B * h * w * op.kpad, grad_params + op.w, (int64_t)B * h * w,
+                                  op.cout, 9 * op.cin, op.kpad, st);
+            if (rc) return rc;
+            launches += 3;
+        } else {
+            const float* in = saved + t.a_off[i - 1] * B;       // pooled output of the previous block
+            rc = launch_conv3_wgrad(dc, in, buf[BUF_COL], col_capacity, grad_params + op.w, B, h, w, op.cin, op.cout, st);
+            if (rc) return rc;
+            // data gradient: im2col(dc) x flipped / transposed weights -> gradient of the previous pooled tensor
+            float* wd = tderived + t.wt_off[i];
+            rc = launch_conv3_dgrad_weight(params + op.w, wd, op.cin, op.cout, st);
+            if (rc) return rc;
+            rc = launch_weight_split(wd, op.cin, 9 * op.cout, wd + (int64_t)op.cin * 9 * op.cout, st);
+            if (rc) return rc;
+            rc = launch_im2col(dc, buf[BUF_COL], B, h, w, op.cout, 3, 1, 1, 1, h, w, 9 * op.cout, 0, st);
+            if (rc) return rc;
+            float* dprev = buf[e->ops[i - 1].out];               // the previous maxpool's output buffer
+            rc = launch_pointwise_tcgen05(buf[BUF_COL], wd + (int64_t)op.cin * 9 * op.cout, ones, zeros, nullptr, nullptr, dprev, B * h * w,
+                                          op.cin, 9 * op.cout, h * w, ACT_NONE, 3, st);
+            if (rc) return rc;
+            launches += 6;
+            dp = dprev;
+            mode = 0;
+        }
+    }
+    e->last_launches.store(launches);
+    return ORBIT_OK;
+}
+
 // grad_params: a blob with the layout of `params`; the gradients of the FiLM-site BatchNorm weight / bias are ACCUMULATED
 // at the offsets of those parameters (everything else is left untouched). dfeats [num_frames, feat_dim].
-extern "C" int orbit_engine_backward_train(const orbit_engine* e, const float* params, const float* derived, const float* tderived,
-                                           const float* saved, const float* dfeats, int num_frames, int height, int width,
-                                           float* grad_params, void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int orbit_engine_backward_train(const orbit_engine* e, const float* params, const float* derived, float* tderived,
+                                           const float* saved, const float* frames, const float* dfeats, int num_frames, int height,
+                                           int width, float* grad_params, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!e || !params || !derived || !tderived || !saved || !dfeats || !grad_params || !workspace) return ORBIT_ERR_ARG;
     if (num_frames <= 0 || height <= 0 || width <= 0) return ORBIT_ERR_ARG;
     const TrainGeom t = train_geometry(e, height, width);
@@ -1126,6 +1231,9 @@ extern "C" int orbit_engine_backward_train(const orbit_engine* e, const float* p
     float* buf[BUF_COUNT];
     workspace_buffers(e, bs, workspace, buf);
     cudaStream_t st = (cudaStream_t)stream;
+    if (e->arch == ORBIT_ARCH_SET_ENCODER)
+        return set_encoder_backward(e, t, params, derived, tderived, saved, frames, dfeats, B, grad_params, buf,
+                                    bs.per_frame[BUF_COL] * e->chunk_frames, st);
     const float* ones = derived + e->ident;
     const float* zeros = derived + e->ident + e->max_c;
     int64_t launches = 0;

@@ -56,12 +56,22 @@ class SetEncoder(FeatureExtractor):
     def forward(self, x):
         if x.dim() == 5:
             x = x.flatten(end_dim=1)
+        if torch.is_grad_enabled() and self.train_graph:
+            # meta-training (single-step-learner.py:196-243): the embeddings carry a graph back to every parameter
+            from .training import SetEncoderFn
+            params = tuple(p for p in self.parameters() if p.requires_grad)
+            if params:
+                return SetEncoderFn.apply(self, x, *params)
         return super().forward(x)
     # count_macs: inherited from FeatureExtractor (the set encoder runs through the same engine)
+
+    train_graph = False      # set by the recogniser: True while meta-training (not test mode, autograd on)
 
     def aggregate(self, x, aggregation='mean'):
         if not isinstance(x, torch.Tensor):
             x = torch.cat(x, dim=0)
+        if aggregation == 'mean' and x.requires_grad and torch.is_grad_enabled():
+            return x.mean(dim=0, keepdim=True)      # meta-training: autograd routes the mean (set_encoders.py:68-71)
         if aggregation == 'mean':
             out = torch.empty(1, x.shape[1], dtype=torch.float32, device=x.device)
             x = x.contiguous()
@@ -173,7 +183,30 @@ class FilmParameterGenerator(nn.Module):
         """The film blob behind a dict returned by forward() (None for an empty dict)."""
         return self._film_blob if film_dict else None
 
+    def _param_slots(self):
+        params = dict(self.named_parameters())
+        return {id(params[name]): (o, n, shape) for name, shape, o, n in self._layout if name in params}
+
     def forward(self, x):
+        if x.requires_grad and torch.is_grad_enabled():
+            # meta-training: film blob with a graph back to the generator's parameters and the task embedding
+            from .training import FilmGeneratorFn
+            params = tuple(p for p in self.parameters() if p.requires_grad)
+            film = FilmGeneratorFn.apply(self, x, *params)
+            film._orbit_generation = (id(self), self._generation)
+            self._film_blob = film
+            regs = [p for n, p in self.named_parameters() if n.startswith('regularizers.')]
+            self.l2_term = sum((r ** 2).sum() for r in regs)        # feature_adapters.py:76, differentiable
+        else:
+            film = self._generate(x)
+            self._film_blob = film
+            # l2 term of the regularisers (feature_adapters.py:76): depends on parameters only, not on the episode
+            regs = [p for n, p in self.named_parameters() if n.startswith('regularizers.')]
+            self.l2_term = sum((r.detach() ** 2).sum() for r in regs)
+        return {name: film[self._out_offsets[name]:self._out_offsets[name] + self.film_parameter_sizes[name]]
+                for name in self.film_parameter_names}
+
+    def _generate(self, x):
         lib = L.load()
         L.require_cuda(x, "task embedding")
         dev = x.device
@@ -199,9 +232,4 @@ class FilmParameterGenerator(nn.Module):
         L.count_launches(1)
         self._generation += 1
         film._orbit_generation = (id(self), self._generation)   # the kernel wrote through a raw pointer: no version bump
-        self._film_blob = film
-        # l2 term of the regularisers (feature_adapters.py:76): depends on parameters only, not on the episode
-        regs = [p for n, p in self.named_parameters() if n.startswith('regularizers.')]
-        self.l2_term = sum((r.detach() ** 2).sum() for r in regs)
-        return {name: film[self._out_offsets[name]:self._out_offsets[name] + self.film_parameter_sizes[name]]
-                for name in self.film_parameter_names}
+        return film

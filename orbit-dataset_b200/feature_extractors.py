@@ -64,7 +64,7 @@ class FeatureExtractor(nn.Module):
         self._workspace = None
         self._prepared_key = None
         self._versioned = None
-        self._train_derived = self._saved = self._grad_blob = self._train_shape = None
+        self._train_derived = self._saved = self._grad_blob = self._train_state = None
         self._build_tree()
         self.reset_parameters(seed)
 
@@ -107,7 +107,7 @@ class FeatureExtractor(nn.Module):
         self._blob = new_blob
         self._rebind()
         self._derived = self._workspace = self._prepared_key = self._versioned = None
-        self._train_derived = self._saved = self._grad_blob = self._train_shape = None
+        self._train_derived = self._saved = self._grad_blob = self._train_state = None
         return self
 
     @torch.no_grad()
@@ -254,6 +254,10 @@ class FeatureExtractor(nn.Module):
         return super().load_state_dict(*args, **kwargs)
 
     def forward(self, frames: torch.Tensor, film_blob=None) -> torch.Tensor:
+        if film_blob is not None and film_blob.requires_grad and torch.is_grad_enabled():
+            # meta-training: the loss back-propagates through the frozen extractor into the FiLM generator
+            from .training import ExtractorFilmFn
+            return ExtractorFilmFn.apply(self, frames, film_blob, getattr(film_blob, '_orbit_generation', None))
         lib = L.load()
         L.require_cuda(frames, "frames")
         if frames.dim() != 4 or frames.shape[1] != 3:
@@ -274,47 +278,76 @@ class FeatureExtractor(nn.Module):
         L.count_launches(lib.orbit_engine_last_launches(self._engine))
         return feats
 
-    # ---- training through the frozen extractor (FineTuner + FiLM) -----------------------------------
-    def forward_train(self, frames: torch.Tensor) -> torch.Tensor:
-        """Forward pass that keeps the pre-activations the backward needs (BatchNorm in eval mode, layer at a time);
-        same features as ``forward``. One pass: ``len(frames) <= chunk_frames``. Follow with ``backward_train``."""
+    # ---- training through the frozen extractor (FineTuner + FiLM, CNAPs meta-training) ---------------------
+    def _param_slots(self):
+        """{id(parameter): (blob offset, numel, shape)} for the autograd bridges of training.py"""
+        params = dict(self.named_parameters())
+        return {id(params[name]): (offset, numel, self._shapes[name]) for name, numel, offset in self._table if name in params}
+
+    def _forward_train_impl(self, frames, film_blob, fresh_arena):
+        """One training-mode pass (BatchNorm in eval mode, layer at a time, pre-activations kept): returns the features and
+        the state the backward needs. ``fresh_arena``: allocate a new activation arena (several passes may be alive before the
+        backward runs, as under autograd) instead of reusing the module's."""
         lib = L.load()
         L.require_cuda(frames, "frames")
         if frames.dim() != 4 or frames.shape[1] != 3:
             raise ValueError(f"frames must be [B,3,H,W], got {tuple(frames.shape)}")
         frames = frames.contiguous().float()
-        self.prepare(None)
+        self.prepare(film_blob)
         n, _, h, w = frames.shape
         per_frame = lib.orbit_engine_train_saved_floats(self._engine, h, w)
         if per_frame < 0:
             raise NotImplementedError(f"training through '{self.extractor_name}' needs backward kernels that do not exist yet "
-                                      "(SURVEY.md 8f-3: only the MBConv networks are covered)")
+                                      "(SURVEY.md 8f-3: the MBConv networks and the set encoder are covered)")
         if n > self.get_option('chunk_frames'):
             self.set_option('chunk_frames', n)
         if self._train_derived is None:
-            self._train_derived = torch.empty(lib.orbit_engine_train_derived_floats(self._engine), dtype=torch.float32, device=frames.device)
+            self._train_derived = torch.empty(max(4, lib.orbit_engine_train_derived_floats(self._engine)), dtype=torch.float32,
+                                              device=frames.device)
             L.check(lib.orbit_engine_prepare_train(self._engine, L.ptr(self._blob), L.ptr(self._train_derived), L.stream_ptr(frames.device)),
                     "orbit_engine_prepare_train")
-        if self._saved is None or self._saved.numel() < per_frame * n:
-            self._saved = torch.empty(per_frame * n, dtype=torch.float32, device=frames.device)
+        if fresh_arena:
+            saved = torch.empty(per_frame * n, dtype=torch.float32, device=frames.device)
+        else:
+            if self._saved is None or self._saved.numel() < per_frame * n:
+                self._saved = torch.empty(per_frame * n, dtype=torch.float32, device=frames.device)
+            saved = self._saved
         ws_bytes = lib.orbit_engine_workspace_bytes(self._engine, h, w)
         if self._workspace is None or self._workspace.numel() < ws_bytes:
             self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
         feats = torch.empty(n, self.output_size, dtype=torch.float32, device=frames.device)
         L.check(lib.orbit_engine_forward_train(self._engine, L.ptr(self._blob), L.ptr(self._derived), L.ptr(frames), n, h, w, L.ptr(feats),
-                                               L.ptr(self._saved), self._saved.numel(), L.ptr(self._workspace), self._workspace.numel(),
+                                               L.ptr(saved), saved.numel(), L.ptr(self._workspace), self._workspace.numel(),
                                                L.stream_ptr(frames.device)), "orbit_engine_forward_train")
         L.count_launches(lib.orbit_engine_last_launches(self._engine))
-        self._train_shape = (n, h, w)
+        return feats, (saved, frames, (n, h, w))
+
+    def _backward_train_impl(self, dfeats, state, film_blob, grad_blob):
+        """ACCUMULATES into ``grad_blob`` (layout of the parameter blob): the FiLM-site BatchNorm weight / bias gradients of
+        an MBConv extractor, every parameter's gradient of the set encoder."""
+        lib = L.load()
+        saved, frames, (n, h, w) = state
+        dfeats = dfeats.contiguous().float()
+        assert dfeats.shape == (n, self.output_size)
+        self.prepare(film_blob)            # no-op unless another task's FiLM parameters were folded in between
+        ws_bytes = lib.orbit_engine_workspace_bytes(self._engine, h, w)
+        if self._workspace is None or self._workspace.numel() < ws_bytes:
+            self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dfeats.device)
+        L.check(lib.orbit_engine_backward_train(self._engine, L.ptr(self._blob), L.ptr(self._derived), L.ptr(self._train_derived),
+                                                L.ptr(saved), L.ptr(frames), L.ptr(dfeats), n, h, w, L.ptr(grad_blob),
+                                                L.ptr(self._workspace), self._workspace.numel(), L.stream_ptr(dfeats.device)),
+                "orbit_engine_backward_train")
+        L.count_launches(lib.orbit_engine_last_launches(self._engine))
+
+    def forward_train(self, frames: torch.Tensor) -> torch.Tensor:
+        """Forward pass that keeps the pre-activations the backward needs (BatchNorm in eval mode, layer at a time);
+        same features as ``forward``. One pass: ``len(frames) <= chunk_frames``. Follow with ``backward_train``."""
+        feats, self._train_state = self._forward_train_impl(frames, None, fresh_arena=False)
         return feats
 
     def backward_train(self, dfeats: torch.Tensor):
         """Back-propagates ``dfeats`` [B, output_size] of the last ``forward_train`` and ACCUMULATES the gradients of the
         FiLM parameters into ``param.grad`` (views of one gradient blob laid out like the parameters)."""
-        lib = L.load()
-        n, h, w = self._train_shape
-        dfeats = dfeats.contiguous().float()
-        assert dfeats.shape == (n, self.output_size)
         if self._grad_blob is None:
             self._grad_blob = torch.zeros(self._n_floats, dtype=torch.float32, device=dfeats.device)
             tagged = {name for name, _, _ in self._film_table}
@@ -322,10 +355,7 @@ class FeatureExtractor(nn.Module):
             for name, numel, offset in self._table:
                 if name in tagged:
                     params[name].grad = self._grad_blob[offset:offset + numel].view(self._shapes[name])
-        L.check(lib.orbit_engine_backward_train(self._engine, L.ptr(self._blob), L.ptr(self._derived), L.ptr(self._train_derived),
-                                                L.ptr(self._saved), L.ptr(dfeats), n, h, w, L.ptr(self._grad_blob), L.ptr(self._workspace),
-                                                self._workspace.numel(), L.stream_ptr(dfeats.device)), "orbit_engine_backward_train")
-        L.count_launches(lib.orbit_engine_last_launches(self._engine))
+        self._backward_train_impl(dfeats, self._train_state, None, self._grad_blob)
 
     def zero_film_grads(self):
         if self._grad_blob is not None:

@@ -202,6 +202,10 @@ class FewShotRecogniser(nn.Module):
     def _run_extractor(self, frames, film_dict):
         """frames [F,3,H,W] on CPU or device -> [F, D] on device."""
         blob = self._film_blob(film_dict) if film_dict else None
+        if not frames.is_cuda and blob is not None and blob.requires_grad and torch.is_grad_enabled():
+            # meta-training: the frames are kept for the backward pass, so they get their own device copy (the stager's
+            # buffers are recycled by the next call)
+            frames = frames.to(self.device, non_blocking=True).float()
         if frames.is_cuda:
             return self.feature_extractor(frames, blob)
         # Host clips arrive in passes (a short ramp, then chunk_frames), each waiting only for its own bytes. (Tried in round 2
@@ -279,16 +283,15 @@ class FewShotRecogniser(nn.Module):
         implemented and is refused rather than silently approximated."""
         self.eval()
         if self.learn_extractor and not self.test_mode:
-            raise NotImplementedError("training the extractor (train-mode BatchNorm + backward) is outside the "
-                                      "B200 hot path implemented so far")
-        if self.adapt_features and not getattr(self, 'test_mode', True) and torch.is_grad_enabled() \
-                and isinstance(self, SingleStepFewShotRecogniser):
-            # CNAPs-style meta-training (single-step-learner.py:196-210): the loss must back-propagate through the
-            # frozen extractor into the FiLM generator / set encoder. The logits of this library carry no autograd graph,
-            # so refuse here instead of letting loss.backward() die later with torch's generic "does not require grad".
-            raise NotImplementedError("meta-training the FiLM generator / set encoder needs backbone backward kernels "
-                                      "(SURVEY.md 8f-3); call set_test_mode(True) and run under torch.no_grad() for "
-                                      "validation / testing")
+            raise NotImplementedError("training the extractor's own weights (train-mode BatchNorm + weight gradients) is "
+                                      "outside the B200 hot path implemented so far (SURVEY.md 8f-3)")
+        if isinstance(self, SingleStepFewShotRecogniser) and self.adapt_features:
+            # CNAPs-style meta-training (single-step-learner.py:196-243): outside test mode and with autograd on, the set
+            # encoder / FiLM generator / extractor / head calls build a graph of native backward kernels (training.py)
+            self.set_encoder.train_graph = self._meta_training()
+
+    def _meta_training(self):
+        return bool(self.adapt_features and not getattr(self, 'test_mode', True) and torch.is_grad_enabled())
 
 
 class SingleStepFewShotRecogniser(FewShotRecogniser):
@@ -335,7 +338,11 @@ class SingleStepFewShotRecogniser(FewShotRecogniser):
         self._staged_context = None
         task_embedding = self._get_task_embedding_in_batches(context_clips, ops_counter)
         self.film_dict = self._generate_film_params(task_embedding, ops_counter)
-        if self._staged_context is not None:
+        if self._meta_training():
+            # the support -> head path carries no gradient (configure() makes leaf Parameters): inference kernels
+            with torch.no_grad():
+                context_features = self._get_features_in_batches(context_clips, self.film_dict, ops_counter)
+        elif self._staged_context is not None:
             # CPU-resident clips the set encoder has already pulled onto the device: the extractor reads that copy
             # (the reference copies the support set H2D twice, few_shot_recognisers.py:322-324 / SURVEY Appendix B-6)
             buffer_index, context_dev = self._staged_context
@@ -351,9 +358,61 @@ class SingleStepFewShotRecogniser(FewShotRecogniser):
                                   class_index=class_index)
 
     def personalise_with_lite(self, context_clips, context_labels):
-        """LITE (few_shot_recognisers.py:328-343) back-propagates through the extractor; the backward
-        kernels are not part of the B200 hot path yet."""
-        raise NotImplementedError("LITE training needs backbone backward kernels (SURVEY.md 8f-3)")
+        """LITE (few_shot_recognisers.py:328-343): a random subset of ``num_lite_samples`` context clips is processed with
+        back-propagation enabled, the remainder comes from a no-grad cache. ``np.random.permutation`` is unseeded here as in
+        the reference."""
+        self._set_batch_norm_state()
+        self._require_device()
+        shuffled_idxs = np.random.permutation(len(context_clips))
+        grad_idxs = shuffled_idxs[0:self.num_lite_samples]
+        no_grad_idxs = shuffled_idxs[self.num_lite_samples:]
+        self._staged_context = None
+        task_embedding = self._get_task_embedding_with_split_batch(context_clips, grad_idxs, no_grad_idxs)
+        self.film_dict = self._generate_film_params(task_embedding)
+        context_features = self._get_features_with_split_batch(context_clips, self.film_dict, grad_idxs, no_grad_idxs)
+        shuffled_labels = context_labels[torch.as_tensor(shuffled_idxs, device=context_labels.device)]
+        self.classifier.configure(context_features, shuffled_labels, clip_length=self.clip_length)
+
+    def _get_task_embedding(self, context_clips, ops_counter=None, aggregation='mean'):
+        """few_shot_recognisers.py:345-359."""
+        context_clips = context_clips.to(self.device, non_blocking=True)
+        reps = self.set_encoder(context_clips)
+        if ops_counter:
+            ops_counter.compute_macs(self.set_encoder, context_clips)
+        return self.set_encoder.aggregate(reps, aggregation=aggregation)
+
+    def _get_task_embedding_with_split_batch(self, context_clips, grad_idxs, no_grad_idxs):
+        """few_shot_recognisers.py:388-413. The cache holds PER-FRAME embeddings and is indexed with CLIP indices, exactly as
+        the reference does (identical for clip_length 1, its LITE training setting)."""
+        from .feature_adapters import NullSetEncoder
+        if isinstance(self.set_encoder, NullSetEncoder):
+            return None
+        self._set_batch_norm_state()
+        if getattr(self, 'reps_cache', None) is None:
+            with torch.set_grad_enabled(False):
+                self.reps_cache = self._get_task_embedding_in_batches(context_clips, aggregation='none')
+        with torch.set_grad_enabled(True):
+            reps_with_grads = self._get_task_embedding(context_clips[grad_idxs], aggregation='none')
+        reps_without_grads = self.reps_cache[torch.as_tensor(no_grad_idxs, device=self.reps_cache.device)]
+        return torch.cat((reps_with_grads, reps_without_grads)).mean(dim=0)
+
+    def _get_features_with_split_batch(self, context_clips, film_dict, grad_idxs, no_grad_idxs):
+        """few_shot_recognisers.py:415-437. With a frozen extractor no gradient flows from the head back into the context
+        features (the head's weights are leaf Parameters): the ``with grads`` part is computed by the same
+        inference kernels (equal values), and the returned rows are ordered [grad_idxs, no_grad_idxs] as in the reference."""
+        self._set_batch_norm_state()
+        with torch.no_grad():
+            if getattr(self, 'features_cache', None) is None:
+                if self._staged_context is not None:      # the set-encoder cache pass already staged the host clips
+                    buffer_index, context_dev = self._staged_context
+                    self.features_cache = self._get_features_in_batches(context_dev, film_dict)
+                    self._stager.release(buffer_index)
+                else:
+                    self.features_cache = self._get_features_in_batches(context_clips, film_dict)
+            self._staged_context = None
+            features_with_grads = self._get_features(context_clips[grad_idxs], film_dict)
+            features_without_grads = self.features_cache[torch.as_tensor(no_grad_idxs, device=self.features_cache.device)]
+            return torch.cat((features_with_grads, features_without_grads))
 
     def _get_task_embedding_in_batches(self, context_clips, ops_counter=None, aggregation='mean'):
         """few_shot_recognisers.py:361-386."""
@@ -363,7 +422,7 @@ class SingleStepFewShotRecogniser(FewShotRecogniser):
         self._require_device()
         reps = []
         num_clips = len(context_clips)
-        if not context_clips.is_cuda and num_clips:
+        if not context_clips.is_cuda and num_clips and not (self.set_encoder.train_graph and torch.is_grad_enabled()):
             # host clips: ONE staged H2D of the whole support set (pinned or pageable source, side stream); the set
             # encoder consumes it pass by pass and personalise() hands the same device copy to the extractor. The
             # per-frame embeddings do not depend on how frames are grouped into passes, so batch_size only matters
@@ -379,7 +438,7 @@ class SingleStepFewShotRecogniser(FewShotRecogniser):
         num_batches = int(np.ceil(float(num_clips) / float(self.batch_size)))
         for batch in range(num_batches):
             batch_start_index, batch_end_index = get_batch_indices(batch, num_clips, self.batch_size)
-            batch_clips = context_clips[batch_start_index:batch_end_index]
+            batch_clips = context_clips[batch_start_index:batch_end_index].to(self.device, non_blocking=True)
             reps.append(self.set_encoder(batch_clips))
             if ops_counter:
                 ops_counter.compute_macs(self.set_encoder, batch_clips)
