@@ -302,6 +302,10 @@ int orbit_film_generate_backward(const float* gen_params, const void* table, int
 int orbit_head_predict_backward(const float* frame_feats, const float* weight, const float* grad_logits, int num_clips,
                                 int clip_length, int feat_dim, int num_classes, int metric, float logit_scale,
                                 float* grad_frame_feats, void* stream);
+/* the same for the Mahalanobis head (classifier_heads.py:328-350): logits = -s (q - mu_c)^T P_c (q - mu_c)              */
+int orbit_mahalanobis_predict_backward(const float* frame_feats, const float* means, const float* precisions,
+                                       const float* grad_logits, int num_clips, int clip_length, int feat_dim,
+                                       int num_classes, float logit_scale, float* grad_frame_feats, void* stream);
 int64_t orbit_linear_ce_scratch_floats(int num_clips, int feat_dim, int num_classes);
 int orbit_linear_ce_backward(const float* frame_feats, const int32_t* labels, const float* weight, const float* bias,
                              int num_clips, int clip_length, int feat_dim, int num_classes, float logit_scale,

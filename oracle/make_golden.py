@@ -215,6 +215,7 @@ TRAIN_CASES = [
     ('cnaps', 'versa', (4, 3, 2, 2, 64), 4, 0),
     ('protofilm_cosine', 'proto_cosine', (3, 2, 3, 1, 64), 4, 0),
     ('cnaps_lite', 'versa', (4, 3, 2, 1, 64), 5, 4),
+    ('simplecnaps', 'mahalanobis', (3, 3, 2, 1, 64), 4, 0),
 ]
 TRAIN_FULL_GENERATORS = (0, 9, 33)      # generators whose full gradients are stored (the others: sums and norms)
 

@@ -170,12 +170,18 @@ class MahalanobisClassifier(HeadClassifier):
     def predict(self, target_features, ops_counter=None, clip_length=1, want_argmax=False):
         if self.means is None or self.precisions is None:
             raise AttributeError("Means and/or precisions not set - is model personalised?")
-        if target_features.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("meta-training through the Mahalanobis head (Simple CNAPs) needs its backward kernel "
-                                      "(SURVEY.md 8f-3); the linear-form heads (versa / proto / proto_cosine) are covered")
+        if target_features.requires_grad and torch.is_grad_enabled() and not want_argmax:
+            from .training import MahalanobisPredictFn      # meta-training (Simple CNAPs): logits with a graph to the query features
+            return MahalanobisPredictFn.apply(self, target_features, clip_length)
+        logits = self._predict_raw(target_features, clip_length)
+        if want_argmax:
+            return logits, logits.argmax(dim=1).int()
+        return logits
+
+    def _predict_raw(self, target_features, clip_length):
         L.require_cuda(target_features, "target_features")
         lib = L.load()
-        q = self._pool(target_features, clip_length)
+        q = self._pool(target_features.detach(), clip_length)
         nq, d = q.shape
         c = self.means.shape[0]
         logits = torch.empty(nq, c, dtype=torch.float32, device=q.device)
@@ -184,6 +190,4 @@ class MahalanobisClassifier(HeadClassifier):
                                               float(self.logit_scale), L.ptr(logits), L.ptr(ws), L.stream_ptr(q.device)),
                 "orbit_mahalanobis_predict")
         L.count_launches(4 * c + 2)
-        if want_argmax:
-            return logits, logits.argmax(dim=1).int()
         return logits

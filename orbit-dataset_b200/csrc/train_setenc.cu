@@ -480,9 +480,69 @@ head_predict_backward_kernel(const float* __restrict__ feats, const float* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mahalanobis head query path backward (classifier_heads.py:328-350): logits[n,c] = -s (q_n - mu_c)^T P_c (q_n - mu_c), so
+//   dq[n,:] = -s sum_c dlogits[n,c] (P_c + P_c^T) (q_n - mu_c),   dfeat[(n L + l),:] = dq[n,:] / L   (mean-pooled clips)
+// (P_c + P_c^T, not 2 P_c: the computed inverse is symmetric only up to rounding and autograd differentiates what is there).
+// One block per query clip; P_c is read twice per clip, row-wise (a warp per row) and column-wise (a thread per column).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mahalanobis_predict_backward_kernel(const float* __restrict__ feats, const float* __restrict__ means, const float* __restrict__ precisions,
+                                    const float* __restrict__ dlogits, int L, int D, int C, float logit_scale, float* __restrict__ dfeat) {
+    extern __shared__ float s_mb[];      // q[D], diff[D], acc[D]
+    float* s_q = s_mb; float* s_diff = s_q + D; float* s_acc = s_diff + D;
+    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) s += feats[((int64_t)n * L + l) * D + d];
+        s_q[d] = s / (float)L;
+        s_acc[d] = 0.f;
+    }
+    __syncthreads();
+    for (int c = 0; c < C; ++c) {
+        const float coef = -logit_scale * dlogits[(int64_t)n * C + c];
+        const float* P = precisions + (int64_t)c * D * D;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) s_diff[d] = s_q[d] - means[(int64_t)c * D + d];
+        __syncthreads();
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {       // (P^T diff)[d] = sum_e P[e,d] diff[e]: coalesced over d
+            float s = 0.f;
+            for (int e = 0; e < D; ++e) s = fmaf(__ldg(P + (int64_t)e * D + d), s_diff[e], s);
+            s_acc[d] = fmaf(coef, s, s_acc[d]);
+        }
+        __syncthreads();
+        for (int d = warp; d < D; d += nw) {                      // (P diff)[d]: a warp per row
+            float s = 0.f;
+            for (int e = lane; e < D; e += 32) s = fmaf(__ldg(P + (int64_t)d * D + e), s_diff[e], s);
+            s = warp_sum(s);
+            if (lane == 0) s_acc[d] = fmaf(coef, s, s_acc[d]);
+        }
+        __syncthreads();
+    }
+    const float invL = 1.0f / (float)L;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float v = s_acc[d] * invL;
+        for (int l = 0; l < L; ++l) dfeat[((int64_t)n * L + l) * D + d] = v;
+    }
+}
+
 }  // namespace orbit
 
 using namespace orbit;
+
+extern "C" int orbit_mahalanobis_predict_backward(const float* frame_feats, const float* means, const float* precisions,
+                                                  const float* grad_logits, int num_clips, int clip_length, int feat_dim,
+                                                  int num_classes, float logit_scale, float* grad_frame_feats, void* stream) {
+    if (!frame_feats || !means || !precisions || !grad_logits || !grad_frame_feats) return ORBIT_ERR_ARG;
+    if (num_clips < 0 || clip_length <= 0 || feat_dim <= 0 || num_classes <= 0) return ORBIT_ERR_ARG;
+    if (num_clips == 0) return ORBIT_OK;
+    const size_t smem = sizeof(float) * 3 * (size_t)feat_dim;
+    if (smem > 200 * 1024) return ORBIT_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) ORBIT_CUDA(cudaFuncSetAttribute(mahalanobis_predict_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mahalanobis_predict_backward_kernel<<<num_clips, 256, smem, (cudaStream_t)stream>>>(frame_feats, means, precisions, grad_logits, clip_length,
+                                                                                       feat_dim, num_classes, logit_scale, grad_frame_feats);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
 
 extern "C" int orbit_film_generate_backward(const float* gen_params, const void* table, int num_tensors, const float* task_embedding,
                                             int hidden, const float* grad_film, float* grad_gen_params, float* grad_embedding,

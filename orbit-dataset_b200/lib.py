@@ -63,6 +63,7 @@ _SIGNATURES = {
     "orbit_engine_film_grad": (_i, [_p, _p, _p, _p]),
     "orbit_film_generate_backward": (_i, [_p, _p, _i, _p, _i, _p, _p, _p, _p, _p]),
     "orbit_head_predict_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p]),
+    "orbit_mahalanobis_predict_backward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p]),
     "orbit_linear_ce_scratch_floats": (_i64, [_i, _i, _i]),
     "orbit_linear_ce_backward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p]),
     "orbit_engine_profile_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double),

@@ -117,3 +117,54 @@ class HeadPredictFn(torch.autograd.Function):
                 "orbit_head_predict_backward")
         L.count_launches(1)
         return dfeat, None, None, None, None, None
+
+
+class MahalanobisPredictFn(torch.autograd.Function):
+    """frame features -> Mahalanobis logits (classifier_heads.py:328-350); backward: d loss / d frame features. The class
+    means / precisions are leaf Parameters created by configure() (classifier_heads.py:323-326): no gradient, as in the reference."""
+
+    @staticmethod
+    def forward(ctx, head, features, clip_length):
+        features = features.detach().contiguous().float()
+        ctx.save_for_backward(features, head.means.detach(), head.precisions.detach())
+        ctx.args = (clip_length, head.logit_scale)
+        return head._predict_raw(features, clip_length)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        features, means, precisions = ctx.saved_tensors
+        clip_length, logit_scale = ctx.args
+        n = features.shape[0] // clip_length
+        c, d = means.shape
+        dfeat = torch.empty_like(features)
+        L.check(L.load().orbit_mahalanobis_predict_backward(L.ptr(features), L.ptr(means), L.ptr(precisions.contiguous()),
+                                                            L.ptr(dlogits.contiguous().float()), n, clip_length, d, c, float(logit_scale),
+                                                            L.ptr(dfeat), L.stream_ptr(features.device)), "orbit_mahalanobis_predict_backward")
+        L.count_launches(1)
+        return None, dfeat, None
+
+
+def allreduce_gradients(parameters, group=None):
+    """Data-parallel meta-training (training variant): the ``tasks_per_batch`` tasks of one optimiser step
+    (single-step-learner.py:150-166) are dealt round-robin to the ranks (``evaluation.shard_episodes``), every rank
+    accumulates the gradients of its own tasks -- each task's loss is already divided by ``tasks_per_batch``
+    (single-step-learner.py:203), so the per-rank gradients simply ADD -- and this sums them over the ranks with ONE
+    all-reduce (NCCL over NVLink on the GPU box, gloo on CPU) of one flat buffer before ``optimizer.step()``.
+    Parameters without a gradient on this rank (no task dealt to it) contribute zeros. Returns the number of values reduced."""
+    import torch.distributed as dist
+    params = [p for p in parameters if p.requires_grad]
+    if not params:
+        return 0
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    offset = 0
+    for p in params:
+        n = p.numel()
+        g = flat[offset:offset + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        offset += n
+    return offset

@@ -46,6 +46,27 @@ def test_head_predict_backward_matches_autograd(cuda_device):
         assert rel_err(fd.grad, f.grad) <= 2e-5, name
 
 
+def test_mahalanobis_predict_backward_matches_autograd(cuda_device):
+    from orbit_b200.classifier_heads_ext import MahalanobisClassifier
+    g = torch.Generator().manual_seed(6)
+    n, Lc, d, c = 7, 2, 256, 4
+    feats = torch.randn(n * Lc, d, generator=g)
+    means = torch.randn(c, d, generator=g)
+    a = torch.randn(c, d, d, generator=g) * 0.1
+    precs = a @ a.transpose(1, 2) + torch.eye(d) + 0.01 * torch.randn(c, d, d, generator=g)     # not exactly symmetric
+    dl = torch.randn(n, c, generator=g)
+    f = feats.clone().requires_grad_(True)
+    ref = parts.mahalanobis_predict(parts.pool_clips(f, Lc), means, precs, 1.3)
+    ref.backward(dl)
+    head = MahalanobisClassifier(1.3)
+    head.means, head.precisions = torch.nn.Parameter(means.to(cuda_device)), torch.nn.Parameter(precs.to(cuda_device))
+    fd = feats.to(cuda_device).requires_grad_(True)
+    out = head.predict(fd, clip_length=Lc)
+    assert (out.detach().cpu() - ref.detach()).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    out.backward(dl.to(cuda_device))
+    assert rel_err(fd.grad, f.grad) <= 2e-5
+
+
 def test_set_encoder_gradients_match_autograd(cuda_device):
     """every parameter gradient of the set encoder (conv weight / bias, BatchNorm weight / bias) at 64 and 84 px (84: odd
     sizes in the pooling chain) for a random upstream gradient"""
@@ -122,7 +143,7 @@ def _recogniser(tag_head, spec, batch, lite, cuda_device):
 
 
 TRAIN_CASES = [('cnaps', 'versa', (4, 3, 2, 2, 64), 4, 0), ('protofilm_cosine', 'proto_cosine', (3, 2, 3, 1, 64), 4, 0),
-               ('cnaps_lite', 'versa', (4, 3, 2, 1, 64), 5, 4)]
+               ('cnaps_lite', 'versa', (4, 3, 2, 1, 64), 5, 4), ('simplecnaps', 'mahalanobis', (3, 3, 2, 1, 64), 4, 0)]
 
 
 @pytest.mark.parametrize("tag,head,spec_args,batch,lite", TRAIN_CASES)
