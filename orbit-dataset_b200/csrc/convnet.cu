@@ -328,6 +328,21 @@ __device__ __forceinline__ f2_t f2_silu_pair(f2_t x) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(f2_pack(r0, r1)));
     return r;
 }
+// Fraction of the fused kernel's expand-phase SiLUs that take the SFU-free path (common.cuh silu2_fma): ncu (r02) shows the
+// XU pipe (MUFU + conversions) as the busiest pipe of mbx_kernel. 0 = none, 1 = half (the row-g+8 pair), 2 = all.
+#ifndef ORBIT_MBX_SILU_FMA
+#define ORBIT_MBX_SILU_FMA 0
+#endif
+#if ORBIT_MBX_SILU_FMA == 0
+#define MBX_SILU_LO(x) f2_silu_pair(x)
+#define MBX_SILU_HI(x) f2_silu_pair(x)
+#elif ORBIT_MBX_SILU_FMA == 1
+#define MBX_SILU_LO(x) f2_silu_pair(x)
+#define MBX_SILU_HI(x) silu2_fma(x)
+#else
+#define MBX_SILU_LO(x) silu2_fma(x)
+#define MBX_SILU_HI(x) silu2_fma(x)
+#endif
 template <int NP> struct PairIO;
 template <> struct PairIO<1> {
     static __device__ __forceinline__ void load(const float* p, f2_t* v) { v[0] = __ldg(reinterpret_cast<const f2_t*>(p)); }
@@ -706,15 +721,15 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
             // bn1 + SiLU on channel pairs (packed fp32x2 around the four MUFU ops), zero outside the image
             f2_t lo2 = f2_fma(f2_pack(acc0[0] + cor0[0], acc0[1] + cor0[1]), s1p[0], h1p[0]);
             f2_t hi2 = f2_fma(f2_pack(acc0[2] + cor0[2], acc0[3] + cor0[3]), s1p[0], h1p[0]);
-            lo2 = (ok & 1u) ? f2_silu_pair(lo2) : 0ull;
-            hi2 = (ok & 2u) ? f2_silu_pair(hi2) : 0ull;
+            lo2 = (ok & 1u) ? MBX_SILU_LO(lo2) : 0ull;
+            hi2 = (ok & 2u) ? MBX_SILU_HI(hi2) : 0ull;
             asm volatile("st.shared.b64 [%0], %1;" ::"r"(d), "l"(lo2) : "memory");
             asm volatile("st.shared.b64 [%0], %1;" ::"r"(d + (uint32_t)(8 * ES * VEC * 4)), "l"(hi2) : "memory");
             if (second) {
                 lo2 = f2_fma(f2_pack(acc1[0] + cor1[0], acc1[1] + cor1[1]), s1p[1], h1p[1]);
                 hi2 = f2_fma(f2_pack(acc1[2] + cor1[2], acc1[3] + cor1[3]), s1p[1], h1p[1]);
-                lo2 = (ok & 1u) ? f2_silu_pair(lo2) : 0ull;
-                hi2 = (ok & 2u) ? f2_silu_pair(hi2) : 0ull;
+                lo2 = (ok & 1u) ? MBX_SILU_LO(lo2) : 0ull;
+                hi2 = (ok & 2u) ? MBX_SILU_HI(hi2) : 0ull;
                 asm volatile("st.shared.b64 [%0], %1;" ::"r"(d + (uint32_t)(4 * VEC * 4)), "l"(lo2) : "memory");
                 asm volatile("st.shared.b64 [%0], %1;" ::"r"(d + (uint32_t)((8 * ES + 4) * VEC * 4)), "l"(hi2) : "memory");
             }

@@ -68,6 +68,9 @@ struct orbit_engine {
     int chunk_frames = 256;   // frames per pass through the layer plan (workspace ~10 MB per 224-px frame)
     int gemm_mode = 1;        // tcgen05 FP16x3
     int fuse_mbconv = 1;      // expand 1x1 -> depthwise in one kernel where the block input has 16 / 24 channels: 0 = never,
+                              // 1 = the stride-2 block with 16 input channels (B0 block 1.0: measured faster than the
+                              // streaming expand GEMM + depthwise pair), 3 = every stride-2 block (also B0 block 2.0, which the
+                              // unfused pair now beats), 2 = every supported block;   [the two comment lines below are older]
                               // 1 = stride-2 blocks (measured faster: B0 blocks 1.0 and 2.0), 2 = every supported block
     mutable std::atomic<int64_t> last_launches{0};
     // optional per-launch CUDA-event timing (option "profile"): one event before every launch + one at the end
@@ -558,7 +561,7 @@ extern "C" int orbit_engine_set_option(orbit_engine* e, const char* key, int val
     if (!std::strcmp(key, "chunk_frames")) { if (value < 1 || value > 4096) return ORBIT_ERR_ARG; e->chunk_frames = value; return ORBIT_OK; }
     if (!std::strcmp(key, "gemm")) { if (value < 0 || value > 2) return ORBIT_ERR_ARG; e->gemm_mode = value; return ORBIT_OK; }
     if (!std::strcmp(key, "profile")) { e->profile = value != 0; return ORBIT_OK; }
-    if (!std::strcmp(key, "fuse_mbconv")) { if (value < 0 || value > 2) return ORBIT_ERR_ARG; e->fuse_mbconv = value; return ORBIT_OK; }
+    if (!std::strcmp(key, "fuse_mbconv")) { if (value < 0 || value > 3) return ORBIT_ERR_ARG; e->fuse_mbconv = value; return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 extern "C" int orbit_engine_get_option(const orbit_engine* e, const char* key, int* value) {
@@ -727,7 +730,7 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
             if (!calib && e->fuse_mbconv && e->gemm_mode != 0 && op.kind == OP_PW && !op.gated && op.act == ACT_SILU && op.res == BUF_NONE &&
                 oi + 1 < e->ops.size() && e->ops[oi + 1].kind == OP_DW && e->ops[oi + 1].in == op.out &&
                 e->ops[oi + 1].act == ACT_SILU && mbx_supported(op.cin, e->ops[oi + 1].k, e->ops[oi + 1].stride) && !e->tokens &&
-                (e->fuse_mbconv == 2 || e->ops[oi + 1].stride == 2) &&
+                (e->fuse_mbconv == 2 || (e->ops[oi + 1].stride == 2 && (e->fuse_mbconv == 3 || op.cin == 16))) &&
                 mbx_fits(op.cin, op.cout, (h + e->ops[oi + 1].stride - 1) / e->ops[oi + 1].stride,
                          (w + e->ops[oi + 1].stride - 1) / e->ops[oi + 1].stride, e->ops[oi + 1].k, e->ops[oi + 1].stride)) {
                 const Op& dw = e->ops[oi + 1];

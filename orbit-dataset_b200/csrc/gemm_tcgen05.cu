@@ -49,6 +49,12 @@ int launch_weight_split(const float* w, int N, int K, float* out, cudaStream_t s
     return ORBIT_OK;
 }
 
+// which of a slab's 16 column pairs (bit 2q + h) take the SFU-free SiLU (common.cuh silu2_fma) instead of ex2 + rcp:
+// balances the MUFU port against the issue slots of the epilogue warps
+#ifndef ORBIT_SILU_FMA_MASK
+#define ORBIT_SILU_FMA_MASK 0x0
+#endif
+
 namespace tc {
 
 constexpr int BM = 128;          // rows per tile (= UMMA M, one TMEM lane per row)
@@ -222,11 +228,30 @@ struct Params {
     const float* gate;       // [frames, K] or null
     int has_residual;
     int M, N, K, rows_per_frame, act;
+    uint32_t rpf_mul, rpf_shift;   // row / rows_per_frame = __umulhi(row, rpf_mul) >> rpf_shift for row < 2^31 (host: fast_div)
     int BN, n_tiles, m_tiles, stages;
     int b_tile_bytes;        // BN * 128 (multiple of 2048)
     int slabs_per_warp;      // 1 or 2 staging slabs per epilogue warp
+    int staging_warps;       // epilogue warps that own staging slabs: 12, or 4 * slabs-per-tile with the fixed mapping
+    int fixed_slabs;         // tiles of < 3 slabs: slab sl always belongs to column share sl (no rotation): the other shares' staging
+                             // memory goes to the operand ring (one or two more stages in flight for the small-N projections)
     float debias;            // kappa: expected truncation loss of a promoted k-block partial, in ulps of that partial
     unsigned* trace;         // dev aid (orbit_debug_set_gemm_trace): per-role clock stamps of CTA 0, [kTraceSteps][16]; else null
+};
+
+// Tile -> (m tile, n tile) without a division per tile: the SASS of the straightforward `tile / n_tiles`, `tile % n_tiles`,
+// `row / rows_per_frame` had an I2F + MUFU.RCP + fix-up sequence (~150 dependent clocks) for EACH of them at the top of every
+// tile in every role (in-kernel trace, round 2: 800 clocks between a slab's TMA store and the next tile's first wait).
+struct TileIter {
+    int mt, nt, step_m, step_n, n_tiles;
+    __device__ __forceinline__ TileIter(int tile0, int stride, int n_tiles_) : n_tiles(n_tiles_) {
+        mt = tile0 / n_tiles; nt = tile0 - mt * n_tiles;
+        step_m = stride / n_tiles; step_n = stride - step_m * n_tiles;
+    }
+    __device__ __forceinline__ void next() {
+        mt += step_m; nt += step_n;
+        if (nt >= n_tiles) { nt -= n_tiles; ++mt; }
+    }
 };
 
 constexpr int kTraceSteps = 256;   // k-block steps of CTA 0 recorded when Params::trace is set
@@ -259,7 +284,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int act = ACT < 0 ? p.act : ACT;
     const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.b_tile_bytes * (SPLIT ? 2 : 1);
     const uint32_t staging = smem;                                   // [NUM_EPI_WARPS][slabs_per_warp][32 rows][128 B]
-    const uint32_t sstab = staging + (uint32_t)(NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES);   // [NUM_EPI_WARPS][SS_BYTES]
+    const uint32_t sstab = staging + (uint32_t)(p.staging_warps * p.slabs_per_warp * SLAB_BYTES);   // [NUM_EPI_WARPS][SS_BYTES]
     const uint32_t ring = sstab + NUM_EPI_WARPS * SS_BYTES;          // (3 KB: the ring stays 1024-byte aligned)
     const uint32_t bars = ring + (uint32_t)p.stages * stage_bytes;
     auto full = [&](uint32_t s) { return bars + 8u * s; };                              // TMA landed
@@ -306,17 +331,19 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             // L2 prefetch cursor: runs L2_PREFETCH_DISTANCE k-blocks ahead of the shared-memory ring, so that HBM
             // latency is covered by requests that cost no shared memory (the ring only has to cover L2 latency).
             int pf_tile = blockIdx.x, pf_kb = 0;
+            TileIter pf_ti(blockIdx.x, gridDim.x, p.n_tiles);
             auto prefetch_next = [&]() {
                 if (pf_tile >= num_tiles) return;
-                const int m0 = (pf_tile / p.n_tiles) * BM;
+                const int m0 = pf_ti.mt * BM;
                 tma_prefetch_l2_2d(&map_a, pf_kb * BK, m0);
                 if (pf_kb * BK + 32 < p.K) tma_prefetch_l2_2d(&map_a, pf_kb * BK + 32, m0);
-                if (++pf_kb == num_k) { pf_kb = 0; pf_tile += gridDim.x; }
+                if (++pf_kb == num_k) { pf_kb = 0; pf_tile += gridDim.x; pf_ti.next(); }
             };
             for (int i = 0; i < L2_PREFETCH_DISTANCE; ++i) prefetch_next();
             uint32_t s = 0, ph = 0, step = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
+            TileIter ti(blockIdx.x, gridDim.x, p.n_tiles);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ti.next()) {
+                const int m0 = ti.mt * BM, n0 = ti.nt * p.BN;
                 for (int kb = 0; kb < num_k; ++kb, ++step) {
                     prefetch_next();
                     const bool two = kb * BK + 32 < p.K;          // the second 32-wide fp32 box holds real columns
@@ -410,13 +437,16 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t src_off = (uint32_t)(box * A_BOX_BYTES + row0 * 128 + (((2 * (q & 3) + box) ^ sw) * 16));   // second chunk: ^ 16
         const uint32_t dst_off = (uint32_t)(row0 * 128 + ((q ^ sw) * 16));
         uint32_t s = 0, ph = 0, xstep = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        TileIter xti(blockIdx.x, gridDim.x, p.n_tiles);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, xti.next()) {
             const float* grow[XR];
             if (gated) {
-                const int m0 = (tile / p.n_tiles) * BM;
+                const int m0 = xti.mt * BM;
 #pragma unroll
-                for (int i = 0; i < XR; ++i)
-                    grow[i] = p.gate + (int64_t)(min(m0 + row0 + (int)(rstride >> 7) * i, p.M - 1) / p.rows_per_frame) * p.K;
+                for (int i = 0; i < XR; ++i) {
+                    const uint32_t row = (uint32_t)min(m0 + row0 + (int)(rstride >> 7) * i, p.M - 1);
+                    grow[i] = p.gate + (int64_t)(p.rpf_mul ? (__umulhi(row, p.rpf_mul) >> p.rpf_shift) : row) * p.K;
+                }
             }
             for (int kb = 0; kb < num_k; ++kb) {
                 const int krem = p.K - kb * BK;                               // real columns left in this k-block
@@ -494,12 +524,16 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int n_slabs = ceil_div(p.BN, 32);     // BN <= 96 -> <= 3 slabs -> one per warp of a lane group
         const uint32_t t_lane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         uint32_t tcount = 0, res_phase = 0, slab_count = 0, it = 0, mb = 0, mph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        TileIter eti(blockIdx.x, gridDim.x, p.n_tiles);
+        uint32_t rot = 0;                            // tcount % EPI_SPLIT
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount, eti.next(), rot = (rot + 1 == EPI_SPLIT) ? 0u : rot + 1) {
             const uint32_t acc = tcount & 1;
-            const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.BN;
+            const int m0 = eti.mt * BM, n0 = eti.nt * p.BN;
             const int row0 = m0 + lane_grp * 32;
             // slab sl belongs to share (sl + tile counter) % EPI_SPLIT: uneven slab counts even out over tiles
-            const int sl = (share + EPI_SPLIT - (int)(tcount % EPI_SPLIT)) % EPI_SPLIT;
+            int sl = share - (int)rot;
+            if (sl < 0) sl += EPI_SPLIT;
+            if (p.fixed_slabs) sl = share;
             const int c0 = sl * 32;
             const bool have = sl < n_slabs;                                  // this warp holds a slab of the tile
             if (!have) {
@@ -517,7 +551,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             const bool live = row0 < p.M && n0 + c0 < p.N;                   // ... that has rows / columns to store
             const bool wide = p.BN - c0 > 16;                                // the slab's second 16 columns exist in TMEM
-            const uint32_t stage = my_staging + (slab_count % nbuf) * SLAB_BYTES;
+            const uint32_t stage = my_staging + ((nbuf == 2) ? (slab_count & 1u) : 0u) * SLAB_BYTES;
             auto wait_staging_free = [&]() { if (nbuf == 2) tma_store_wait_read1(); else tma_store_wait_read0(); };
             // per-column scale / shift of this slab: one coalesced load per lane now, parked in shared memory after the
             // accumulation (columns beyond N get 0/0: their outputs are exact zeros and the TMA store clips them)
@@ -537,6 +571,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) sum[j] = 0ull;
             for (int kb = 0; kb < num_k; ++kb, ++it) {
+                if (ew == 0 && lane == 0 && kb == 0) trace_stamp(p.trace, it, 15);
                 mbar_wait(main_full(mb), mph);
                 if (ew == 0 && lane == 0) trace_stamp(p.trace, it, 8);
                 tc_fence_after();
@@ -576,6 +611,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) mbar_arrive(main_empty(mb));
                 if (++mb == NM) { mb = 0; mph ^= 1; }
             }
+            if (ew == 0 && lane == 0) trace_stamp(p.trace, it - 1, 10);
             if (SPLIT) {   // tcgen05.commit covers ALL earlier MMAs: the last main_full also completed the correction terms
                 {
                     float u[32];
@@ -596,6 +632,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) mbar_arrive(tmem_empty(acc));
             }
             if (!live) continue;
+            if (ew == 0 && lane == 0) trace_stamp(p.trace, it - 1, 11);
 
             // ---- scale/shift, activation, residual, store ----
             sts32(my_ss + lane * 4, my_sc);
@@ -607,6 +644,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) wait_staging_free();
             }
             __syncwarp();
+            if (ew == 0 && lane == 0) trace_stamp(p.trace, it - 1, 12);
             f2_t sc[2], sh[2], rr[2] = {0ull, 0ull};       // software pipeline: the loads of step q+1 are issued before step q computes
             lds128_f2(my_ss, sc[0], sc[1]);
             lds128_f2(my_ss + 128, sh[0], sh[1]);
@@ -623,7 +661,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     o[h] = f2_fma(sum[2 * q + h], sc[h], sh[h]);
-                    if (act == 1) o[h] = f2_silu(o[h]);
+                    if (act == 1) o[h] = ((ORBIT_SILU_FMA_MASK >> (2 * q + h)) & 1) ? silu2_fma(o[h]) : f2_silu(o[h]);
                     else if (act == 2) o[h] = f2_relu(o[h]);
                     else if (act == 4) { float x0, x1; f2_unpack(o[h], x0, x1); o[h] = f2_pack(gelu_erf(x0), gelu_erf(x1)); }
                     if (has_res) o[h] = f2_add(o[h], rr[h]);
@@ -633,9 +671,11 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                 for (int h = 0; h < 2; ++h) { sc[h] = scn[h]; sh[h] = shn[h]; rr[h] = rn[h]; }
             }
+            if (ew == 0 && lane == 0) trace_stamp(p.trace, it - 1, 13);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) tma_store_2d(&map_out, stage, n0 + c0, row0);
+            if (ew == 0 && lane == 0) trace_stamp(p.trace, it - 1, 14);
             ++slab_count;
         }
         if (lane == 0) tma_store_wait_all();
@@ -686,6 +726,12 @@ static int make_map(CUtensorMap* map, const void* base, bool f16, int64_t rows, 
 static float g_debias_kappa = 1.0f;   // one ulp of every promoted k-block partial (4 truncating MMAs: 0.5*(1+.75+.5+.25) ulp expected loss)
 static unsigned* g_gemm_trace = nullptr;
 static int g_narrow = 1;
+static int g_fixed_slabs = 0;        // dev A/B switches (orbit_set_global_option): tc_fixed_slabs, tc_double_min_stages
+static int g_double_min_stages = 3;  // double-buffered epilogue staging only when that still leaves this many ring stages
+void set_tcgen05_tuning(int fixed_slabs, int double_min_stages) {
+    if (fixed_slabs >= 0) g_fixed_slabs = fixed_slabs;
+    if (double_min_stages >= 0) g_double_min_stages = double_min_stages;
+}
 void set_tcgen05_narrow(int on) { g_narrow = on; }
 int get_tcgen05_narrow() { return g_narrow; }
 void set_tcgen05_trace(unsigned* dev_buffer) { g_gemm_trace = dev_buffer; }
@@ -698,9 +744,21 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     using namespace tc;
     if (K % 4 || N % 4 || (passes != 1 && passes != 3)) return ORBIT_ERR_UNSUPPORTED;
     if (M <= 0) return ORBIT_OK;
+    if (passes == 3 && (act == 0 || act == 1)) {       // the row-streaming kernel covers the small-K / small-N layer shapes
+        const int rc = launch_pointwise_stream(A, w_split, scale, shift, gate, residual, out, M, N, K, rows_per_frame, act, st);
+        if (rc != ORBIT_ERR_UNSUPPORTED) return rc;
+    }
     Params p;
     p.scale = scale; p.shift = shift; p.gate = gate; p.has_residual = residual != nullptr;
     p.M = M; p.N = N; p.K = K; p.rows_per_frame = rows_per_frame; p.act = act;
+    {   // row / rows_per_frame for row < 2^31: shift = 31 + ceil(log2 d) - 32, mul = floor(2^(31 + ceil(log2 d)) / d) + 1 < 2^32
+        const uint32_t d = (uint32_t)std::max(rows_per_frame, 1);
+        uint32_t l = 0;
+        while ((1ull << l) < d) ++l;
+        p.rpf_mul = d == 1 ? 0u : (uint32_t)(((1ull << (31 + l)) / d) + 1);      // 0: the quotient is the row itself
+        p.rpf_shift = d == 1 ? 0u : (31 + l - 32);
+    }
+
     p.debias = passes == 3 ? g_debias_kappa : 0.f;
     p.trace = g_gemm_trace;
     // n-tiles of at most 96 columns (3 store slabs = one per epilogue warp of a lane group); with several n-tiles
@@ -713,9 +771,12 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     const int stage_bytes = A_STAGE_BYTES + p.b_tile_bytes * (passes == 3 ? 2 : 1);
     const int bar_bytes = (3 * MAX_STAGES + 8 + NUM_EPI_WARPS) * 8 + 16;
     const int budget = 227 * 1024 - 1024 /*alignment slack*/ - bar_bytes - NUM_EPI_WARPS * SS_BYTES;
-    // double-buffered epilogue staging when that still leaves a 3-deep operand ring
-    p.slabs_per_warp = (budget - 2 * NUM_EPI_WARPS * SLAB_BYTES) / stage_bytes >= 3 ? 2 : 1;
-    const int staging_bytes = NUM_EPI_WARPS * p.slabs_per_warp * SLAB_BYTES;
+    const int n_slabs = ceil_div(p.BN, 32);
+    p.fixed_slabs = (g_fixed_slabs && n_slabs < EPI_SPLIT) ? 1 : 0;
+    p.staging_warps = p.fixed_slabs ? 4 * n_slabs : NUM_EPI_WARPS;
+    // double-buffered epilogue staging when that still leaves a deep enough operand ring
+    p.slabs_per_warp = (budget - 2 * p.staging_warps * SLAB_BYTES) / stage_bytes >= g_double_min_stages ? 2 : 1;
+    const int staging_bytes = p.staging_warps * p.slabs_per_warp * SLAB_BYTES;
     p.stages = std::min(MAX_STAGES, (budget - staging_bytes) / stage_bytes);
     if (p.stages < 2) return ORBIT_ERR_UNSUPPORTED;
     const size_t smem = (size_t)staging_bytes + NUM_EPI_WARPS * SS_BYTES + (size_t)p.stages * stage_bytes + bar_bytes + 1024;

@@ -15,6 +15,13 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
                              const float* gate, const float* residual, float* out, int M, int N, int K,
                              int rows_per_frame, int act, int passes, cudaStream_t st);
 
+// Row-streaming variant for the small-K / small-N layers (csrc/gemm_stream.cu): same contract and numerics scheme (FP16x3);
+// returns ORBIT_ERR_UNSUPPORTED when it has no instance for the shape. launch_pointwise_tcgen05 tries it first (passes == 3).
+int launch_pointwise_stream(const float* A, const float* w_split, const float* scale, const float* shift, const float* gate,
+                            const float* residual, float* out, int M, int N, int K, int rows_per_frame, int act, cudaStream_t st);
+void set_stream_gemm(int on);
+int get_stream_gemm();
+
 // kappa of the truncation de-biasing applied to every promoted k-block partial in FP16x3 mode (process-wide)
 void set_tcgen05_debias(float kappa);
 // dev aid: device buffer of 256 x 16 uint32 that CTA 0 of every following GEMM launch fills with per-role clock stamps (null = off)
@@ -23,5 +30,8 @@ float get_tcgen05_debias();
 // dev A/B switch: 4-lanes-per-row transform mapping for K <= 32 (default on)
 void set_tcgen05_narrow(int on);
 int get_tcgen05_narrow();
+// dev A/B switches: fixed slab -> warp mapping for tiles of < 3 slabs (frees staging memory for ring stages); minimum ring
+// depth at which the epilogue staging is double buffered. -1 leaves a value unchanged.
+void set_tcgen05_tuning(int fixed_slabs, int double_min_stages);
 
 }  // namespace orbit

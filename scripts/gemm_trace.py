@@ -34,6 +34,20 @@ for i, n in enumerate(names):
     d = np.diff((t[sel, i] - t0) & 0xffffffff)
     print(f"{n:16s} mean period {d.mean():8.1f} clk")
 lat = lambda a, b: float((((t[sel, b] - t[sel, a]) & 0xffffffff).astype('int64')).mean())
+if os.environ.get('EPI'):
+    # epilogue tail of warp EPI_WARP0 (stamps exist only for the tiles whose slab it owns): slots 8 (main_full seen), 9 (arrived),
+    # 10 (k loop done), 11 (correction added), 12 (staging free + scale/shift parked), 13 (slab written), 14 (TMA store issued)
+    rows = [r for r in range(32, 200) if t[r, 14] != 0 and t[r, 8] != 0]
+    for a, b, nm in ((8, 9, 'main_full -> arrived'), (9, 10, 'arrived -> k loop done'), (10, 11, 'correction ld + fma'), (11, 12, 'staging wait + table'),
+                     (12, 13, 'scale/act/sts loop'), (13, 14, 'fence + TMA store issue')):
+        d = [((int(t[r, b]) - int(t[r, a])) & 0xffffffff) for r in rows]
+        print(f"E {nm:28s} {np.mean(d):8.1f} clk  (n={len(d)})")
+    d = [((int(t[r, 8]) - int(t[r, 15])) & 0xffffffff) for r in rows if t[r, 15] != 0]
+    print(f"E loop top -> main_full seen        {np.mean(d):8.1f} clk  (n={len(d)})")
+    d = [((int(t[r + 1, 15]) - int(t[r, 14])) & 0xffffffff) for r in rows if r + 1 in rows and t[r + 1, 15] != 0]
+    print(f"E store issued -> next loop top     {np.mean(d):8.1f} clk  (n={len(d)})")
+    d = np.diff([int(t[r, 14]) for r in rows]) & 0xffffffff
+    print(f"E slab-to-slab period of warp 0   {np.mean(d):8.1f} clk")
 print(f"TMA issue -> X full_ok   {lat(1, 2):8.1f}\nX full_ok -> X ready      {lat(2, 3):8.1f}\nX ready -> M ready_ok     {lat(3, 6):8.1f}\n"
       f"M main_empty_ok->ready_ok {lat(4, 6):8.1f}\nM ready_ok -> committed   {lat(6, 7):8.1f}\nM committed -> E full_ok  {lat(7, 8):8.1f}\n"
       f"E full_ok -> E arrived    {lat(8, 9):8.1f}\nP empty_ok -> tma_issued  {lat(0, 1):8.1f}")

@@ -8,6 +8,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 modes = [int(m) for m in (sys.argv[2] if len(sys.argv) > 2 else "0,1,2").split(',')]
 lib = L.load()
 if os.environ.get('NARROW'): assert lib.orbit_set_global_option(b'tc_narrow', int(os.environ['NARROW'])) == 0
+if os.environ.get('STREAM'): assert lib.orbit_set_global_option(b'tc_stream', int(os.environ['STREAM'])) == 0
+if os.environ.get('FIXED'): assert lib.orbit_set_global_option(b'tc_fixed_slabs', int(os.environ['FIXED'])) == 0
+if os.environ.get('DMIN'): assert lib.orbit_set_global_option(b'tc_double_min_stages', int(os.environ['DMIN'])) == 0
 dev = torch.device('cuda:0')
 # (HW, K, N, act, gated, residual, name)
 layers = [(112*112, 32, 16, 0, 1, 0, 'b0 proj'), (112*112, 16, 96, 1, 0, 0, 'b1.0 exp'), (56*56, 96, 24, 0, 1, 0, 'b1.0 proj'),
