@@ -328,21 +328,6 @@ __device__ __forceinline__ f2_t f2_silu_pair(f2_t x) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(f2_pack(r0, r1)));
     return r;
 }
-// Fraction of the fused kernel's expand-phase SiLUs that take the SFU-free path (common.cuh silu2_fma): ncu (r02) shows the
-// XU pipe (MUFU + conversions) as the busiest pipe of mbx_kernel. 0 = none, 1 = half (the row-g+8 pair), 2 = all.
-#ifndef ORBIT_MBX_SILU_FMA
-#define ORBIT_MBX_SILU_FMA 0
-#endif
-#if ORBIT_MBX_SILU_FMA == 0
-#define MBX_SILU_LO(x) f2_silu_pair(x)
-#define MBX_SILU_HI(x) f2_silu_pair(x)
-#elif ORBIT_MBX_SILU_FMA == 1
-#define MBX_SILU_LO(x) f2_silu_pair(x)
-#define MBX_SILU_HI(x) silu2_fma(x)
-#else
-#define MBX_SILU_LO(x) silu2_fma(x)
-#define MBX_SILU_HI(x) silu2_fma(x)
-#endif
 template <int NP> struct PairIO;
 template <> struct PairIO<1> {
     static __device__ __forceinline__ void load(const float* p, f2_t* v) { v[0] = __ldg(reinterpret_cast<const f2_t*>(p)); }
@@ -505,10 +490,159 @@ dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const floa
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 5x5 stride-1 depthwise at the SMALL spatial sizes (14x14, 7x7: EfficientNet-B0 blocks 4.x / 5.x / 6.x), staged through
+// shared memory. dw2_kernel reads its input rows straight into registers and relies on occupancy to cover HBM latency; at
+// K = 5 it needs ~112 registers, so an SM holds 16 warps with 2 KB of loads in flight each = 32 KB where ~35 KB are needed
+// (measured: 2.0-2.5 TB/s on these layers). Here the loads cost no registers: a block owns one 64-channel chunk, walks over
+// the frames FPB at a time, and cp.async copies the NEXT iteration's [FPB][HW*HW][64 channels] tile (50 KB) into the other
+// half of a double buffer while the current one is convolved out of shared memory (two blocks per SM: ~100 KB in flight).
+// The arithmetic is dw2_kernel's: rolling accumulators over the rows on packed fma.rn.f32x2, taps in shared memory,
+// bn2 / FiLM scale-shift + SiLU, deterministic SE squeeze sums per (frame, chunk) -> partial[b][0][C] (one group).
+// grid (channel chunks of 64, frame slices); block 256 = 32 channel pairs x strips (4-column strips of a row) x FPB frames.
+// ------------------------------------------------------------------------------------------------
+template <int HW>
+__global__ void __launch_bounds__(256, 2)
+dw5s_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale, const float* __restrict__ shift,
+            float* __restrict__ y, float* __restrict__ partial, int B, int C, int act) {
+    constexpr int K = 5, TW = kDwTW, SPAN = TW + K - 1, R = K, HALF = K - 1, PAD = 2;
+    constexpr int STRIPS = (HW + TW - 1) / TW;            // 4 (14x14) or 2 (7x7)
+    constexpr int FPB = 256 / (32 * STRIPS);              // frames per block iteration: 2 or 4
+    constexpr int PIX = HW * HW;
+    constexpr int TILE_F2 = FPB * PIX * 32;               // channel pairs per stage
+    extern __shared__ __align__(16) float s_dyn[];
+    f2_t* s_w = reinterpret_cast<f2_t*>(s_dyn);                          // [25][32]
+    f2_t* s_x = s_w + K * K * 32;                                        // [2][FPB][PIX][32]
+    float* s_red = reinterpret_cast<float*>(s_x + 2 * TILE_F2);          // [256][2]
+    const int chunk = blockIdx.x, c0 = chunk * 64;
+    const int cw = min(64, C - c0);                       // channels of this chunk (64, or 32 in a tail chunk); C % 4 == 0
+    const int lx = threadIdx.x & 31, strip = (threadIdx.x >> 5) % STRIPS, fl = (threadIdx.x >> 5) / STRIPS;
+    const bool lane_live = 2 * lx < cw;
+    for (int i = threadIdx.x; i < K * K * 32; i += 256) {
+        const int tp = i >> 5, l = i & 31;
+        s_w[i] = (2 * l < cw) ? __ldg(reinterpret_cast<const f2_t*>(wt + (int64_t)tp * C + c0 + 2 * l)) : 0ull;
+    }
+    f2_t sc = 0ull, sh = 0ull;
+    if (lane_live) { sc = __ldg(reinterpret_cast<const f2_t*>(scale + c0 + 2 * lx)); sh = __ldg(reinterpret_cast<const f2_t*>(shift + c0 + 2 * lx)); }
+    const int units_per_pix = cw >> 2;                    // 16-byte units per pixel of this chunk
+    auto issue_tile = [&](int f0, int stage) {
+        const int nf = min(FPB, B - f0);
+        const int total = nf * PIX * units_per_pix;
+        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(s_x + (size_t)stage * TILE_F2);
+        for (int u = threadIdx.x; u < total; u += 256) {
+            const int q = u % units_per_pix, p = u / units_per_pix;       // p = frame-local pixel index (fl * PIX + pixel)
+            const float* src = x + ((int64_t)f0 * PIX + p) * C + c0 + 4 * q;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(p * 256 + q * 16)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int ox0 = strip * TW, ixb = ox0 - PAD;
+    unsigned cmask = 0;
+#pragma unroll
+    for (int j = 0; j < SPAN; ++j) cmask |= (ixb + j >= 0 && ixb + j < HW) ? (1u << j) : 0u;
+    int f0 = blockIdx.y * FPB, stage = 0;
+    if (f0 < B) issue_tile(f0, 0);
+    for (; f0 < B; f0 += gridDim.y * FPB, stage ^= 1) {
+        const int fnext = f0 + gridDim.y * FPB;
+        if (fnext < B) issue_tile(fnext, stage ^ 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const int f = f0 + fl;
+        float sum0 = 0.f, sum1 = 0.f;
+        if (f < B && lane_live) {
+            const f2_t* xs = s_x + (size_t)stage * TILE_F2 + (size_t)fl * PIX * 32 + lx;
+            float* yb = y + ((int64_t)f * PIX + ox0) * C + c0 + 2 * lx;
+            f2_t acc[R][TW];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int t = 0; t < TW; ++t) acc[r][t] = 0ull;
+            // iteration m consumes virtual row m (input row m - PAD); the oldest pending output row is m - HALF
+            for (int m = 0; m < HW + HALF; ++m) {
+                const int iy = m - PAD;
+                if (iy >= 0 && iy < HW) {
+                    f2_t v[SPAN];
+#pragma unroll
+                    for (int j = 0; j < SPAN; ++j) v[j] = (cmask & (1u << j)) ? xs[(iy * HW + ixb + j) * 32] : 0ull;
+#pragma unroll
+                    for (int ky = 0; ky < K; ++ky) {
+                        const int slot = HALF - ky;
+#pragma unroll
+                        for (int kx = 0; kx < K; ++kx) {
+                            const f2_t w = s_w[(ky * K + kx) * 32 + lx];
+#pragma unroll
+                            for (int t = 0; t < TW; ++t) acc[slot][t] = f2_fma(v[kx + t], w, acc[slot][t]);
+                        }
+                    }
+                }
+                const int oy = m - HALF;
+                if (oy >= 0) {
+                    float* yrow = yb + (int64_t)oy * HW * C;
+#pragma unroll
+                    for (int t = 0; t < TW; ++t) {
+                        if (ox0 + t < HW) {
+                            float r0, r1;
+                            f2_unpack(f2_fma(acc[0][t], sc, sh), r0, r1);
+                            r0 = act_fast(r0, act); r1 = act_fast(r1, act);
+                            sum0 += r0; sum1 += r1;
+                            *reinterpret_cast<float2*>(yrow + t * C) = make_float2(r0, r1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r + 1 < R; ++r)
+#pragma unroll
+                    for (int t = 0; t < TW; ++t) acc[r][t] = acc[r + 1][t];
+#pragma unroll
+                for (int t = 0; t < TW; ++t) acc[R - 1][t] = 0ull;
+            }
+        }
+        if (partial) {
+            s_red[2 * threadIdx.x] = sum0; s_red[2 * threadIdx.x + 1] = sum1;
+            __syncthreads();
+            if (strip == 0 && f < B && lane_live) {
+                float a = 0.f, b2 = 0.f;
+#pragma unroll
+                for (int r = 0; r < STRIPS; ++r) { a += s_red[2 * (threadIdx.x + 32 * r)]; b2 += s_red[2 * (threadIdx.x + 32 * r) + 1]; }   // fixed order
+                *reinterpret_cast<float2*>(partial + (int64_t)f * C + c0 + 2 * lx) = make_float2(a, b2);
+            }
+        }
+        __syncthreads();            // everyone is done with this stage before the next iteration's copies overwrite it
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+static int g_dw5s = 1;      // dev A/B switch (orbit_set_global_option "dw5_staged")
+void set_dw5_staged(int on) { g_dw5s = on; }      // 0 off, 1 = 7x7 only (default), 2 = 7x7 and 14x14
+int get_dw5_staged() { return g_dw5s; }
+
+template <int HW>
+static int launch_dw5s(const float* x, const float* wt, const float* scale, const float* shift, float* y, float* partial, int B, int C,
+                       int act, cudaStream_t st) {
+    constexpr int STRIPS = (HW + kDwTW - 1) / kDwTW, FPB = 256 / (32 * STRIPS), PIX = HW * HW;
+    const size_t smem = sizeof(f2_t) * (25 * 32 + 2 * (size_t)FPB * PIX * 32) + sizeof(float) * 512;
+    auto fn = dw5s_kernel<HW>;
+    ORBIT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int chunks = ceil_div(C, 64);
+    // 2 blocks per SM; every block should get at least 3 iterations so that the double buffer amortises its prologue
+    const int iters = ceil_div(B, FPB);
+    const int slices = std::max(1, std::min(iters, std::max(1, (2 * 148) / chunks)));
+    fn<<<dim3(chunks, slices), 256, smem, st>>>(x, wt, scale, shift, y, partial, B, C, act);
+    ORBIT_RETURN_IF_LAUNCH_FAILED();
+    return ORBIT_OK;
+}
+
 int launch_depthwise(const float* x, const float* wt, const float* scale, const float* shift, float* y, float* partial,
                      int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, int act,
                      cudaStream_t st) {
     if (C % 4) return ORBIT_ERR_UNSUPPORTED;
+    if (g_dw5s && k == 5 && stride == 1 && H == W && pad_t == 2 && pad_l == 2 && (act == ACT_SILU || act == ACT_NONE) &&
+        dw_plan(C, Ho, Wo, k, stride).groups == 1) {
+        // measured on B200 (us per 512 frames, dw2_kernel -> staged): 7x7x1152 113.5 -> 91.1; 14x14x672 218 -> 234 and 14x14x480
+        // 163 -> 169 (there the kernel is bound by its instruction count, not by load latency): 14x14 stays with dw2_kernel
+        if (H == 7) return launch_dw5s<7>(x, wt, scale, shift, y, partial, B, C, act, st);
+        if (H == 14 && g_dw5s == 2) return launch_dw5s<14>(x, wt, scale, shift, y, partial, B, C, act, st);
+    }
     const DwPlan pl = dw_plan(C, Ho, Wo, k, stride);
     dim3 grid(pl.groups, pl.nchunks, B), block(pl.LX * pl.LY);
     const size_t smem = sizeof(float) * ((size_t)pl.LY * pl.LX * pl.VEC + (size_t)k * k * 32 * pl.VEC);
@@ -721,15 +855,15 @@ mbx_kernel(const float* __restrict__ xin, const float* __restrict__ we, const fl
             // bn1 + SiLU on channel pairs (packed fp32x2 around the four MUFU ops), zero outside the image
             f2_t lo2 = f2_fma(f2_pack(acc0[0] + cor0[0], acc0[1] + cor0[1]), s1p[0], h1p[0]);
             f2_t hi2 = f2_fma(f2_pack(acc0[2] + cor0[2], acc0[3] + cor0[3]), s1p[0], h1p[0]);
-            lo2 = (ok & 1u) ? MBX_SILU_LO(lo2) : 0ull;
-            hi2 = (ok & 2u) ? MBX_SILU_HI(hi2) : 0ull;
+            lo2 = (ok & 1u) ? f2_silu_pair(lo2) : 0ull;
+            hi2 = (ok & 2u) ? f2_silu_pair(hi2) : 0ull;
             asm volatile("st.shared.b64 [%0], %1;" ::"r"(d), "l"(lo2) : "memory");
             asm volatile("st.shared.b64 [%0], %1;" ::"r"(d + (uint32_t)(8 * ES * VEC * 4)), "l"(hi2) : "memory");
             if (second) {
                 lo2 = f2_fma(f2_pack(acc1[0] + cor1[0], acc1[1] + cor1[1]), s1p[1], h1p[1]);
                 hi2 = f2_fma(f2_pack(acc1[2] + cor1[2], acc1[3] + cor1[3]), s1p[1], h1p[1]);
-                lo2 = (ok & 1u) ? MBX_SILU_LO(lo2) : 0ull;
-                hi2 = (ok & 2u) ? MBX_SILU_HI(hi2) : 0ull;
+                lo2 = (ok & 1u) ? f2_silu_pair(lo2) : 0ull;
+                hi2 = (ok & 2u) ? f2_silu_pair(hi2) : 0ull;
                 asm volatile("st.shared.b64 [%0], %1;" ::"r"(d + (uint32_t)(4 * VEC * 4)), "l"(lo2) : "memory");
                 asm volatile("st.shared.b64 [%0], %1;" ::"r"(d + (uint32_t)((8 * ES + 4) * VEC * 4)), "l"(hi2) : "memory");
             }
@@ -900,7 +1034,7 @@ int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scal
 // the kernel is a chain of L2 latencies, so what matters is how many loads each SM keeps in flight.
 // Per-frame arithmetic order is unchanged.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSeFrames = 8;
+constexpr int kSeFrames = 16;
 
 __global__ void __launch_bounds__(1024)
 se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const float* __restrict__ w1,
@@ -959,12 +1093,17 @@ se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const
     }
 }
 
+static int g_se_frames = 8;      // frames per block (<= kSeFrames); dev A/B switch "se_frames"
+void set_se_frames(int f) { g_se_frames = std::max(1, std::min(kSeFrames, f)); }
+
 int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2t,
                    const float* b2, float* gate, int B, int C, int R, cudaStream_t st) {
     if (B <= 0) return ORBIT_OK;
-    int F = kSeFrames;
-    while (F > 1 && sizeof(float) * (size_t)F * (C + R) > 44 * 1024) F >>= 1;   // stay inside the default 48 KB
+    int F = g_se_frames;
+    while (F > 1 && sizeof(float) * (size_t)F * (C + R) > 96 * 1024) F >>= 1;
+    while (F > 1 && ceil_div(B, F) < 148 && F > 8) F >>= 1;                    // keep every SM busy
     const size_t smem = sizeof(float) * (size_t)F * (C + R);
+    if (smem > 48 * 1024) ORBIT_CUDA(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     se_gate_kernel<<<ceil_div(B, F), C >= 256 ? 1024 : 256, smem, st>>>(partial, tiles, 1.0f / (float)hw, w1, b1, w2t, b2, gate, B, C, R, F);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;

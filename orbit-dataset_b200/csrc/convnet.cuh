@@ -43,6 +43,11 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
                      cudaStream_t st);
 
 
+void set_se_frames(int frames_per_block);    // dev A/B: frames per se_gate block (default 8, max 16)
+// dev A/B switch: shared-memory-staged 5x5 stride-1 depthwise kernel for 14x14 / 7x7 inputs (default on)
+void set_dw5_staged(int on);
+int get_dw5_staged();
+
 // Fused expand 1x1 (+bn1+SiLU) -> depthwise kxk (+bn2/FiLM+SiLU, SE squeeze partials) for MBConv blocks with 16 / 24 input
 // channels: xin [B,H,W,Cin] -> y [B,Ho,Wo,C]; we = expand weights [C][Cin] (torch layout), scale1/shift1 = folded bn1,
 // wt = depthwise taps [k*k][C], scale/shift = folded bn2. partial as launch_depthwise with mbx_partial_groups(...).

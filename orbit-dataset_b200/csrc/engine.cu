@@ -67,11 +67,10 @@ struct orbit_engine {
     std::vector<Op> ops;
     int chunk_frames = 256;   // frames per pass through the layer plan (workspace ~10 MB per 224-px frame)
     int gemm_mode = 1;        // tcgen05 FP16x3
-    int fuse_mbconv = 1;      // expand 1x1 -> depthwise in one kernel where the block input has 16 / 24 channels: 0 = never,
-                              // 1 = the stride-2 block with 16 input channels (B0 block 1.0: measured faster than the
-                              // streaming expand GEMM + depthwise pair), 3 = every stride-2 block (also B0 block 2.0, which the
-                              // unfused pair now beats), 2 = every supported block;   [the two comment lines below are older]
-                              // 1 = stride-2 blocks (measured faster: B0 blocks 1.0 and 2.0), 2 = every supported block
+    int fuse_mbconv = 1;      // expand 1x1 -> depthwise in one kernel (mbx_kernel) where the block input has 16 / 24 channels:
+                              // 0 = never; 1 = the stride-2 block with 16 input channels (B0 block 1.0: faster than the streaming
+                              // expand GEMM + depthwise pair); 3 = every stride-2 block (also B0 block 2.0, which the unfused pair
+                              // now matches); 2 = every supported block (block 1.1 too: measured slower)
     mutable std::atomic<int64_t> last_launches{0};
     // optional per-launch CUDA-event timing (option "profile"): one event before every launch + one at the end
     int profile = 0;

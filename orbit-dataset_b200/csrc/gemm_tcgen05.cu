@@ -49,12 +49,6 @@ int launch_weight_split(const float* w, int N, int K, float* out, cudaStream_t s
     return ORBIT_OK;
 }
 
-// which of a slab's 16 column pairs (bit 2q + h) take the SFU-free SiLU (common.cuh silu2_fma) instead of ex2 + rcp:
-// balances the MUFU port against the issue slots of the epilogue warps
-#ifndef ORBIT_SILU_FMA_MASK
-#define ORBIT_SILU_FMA_MASK 0x0
-#endif
-
 namespace tc {
 
 constexpr int BM = 128;          // rows per tile (= UMMA M, one TMEM lane per row)
@@ -661,7 +655,7 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     o[h] = f2_fma(sum[2 * q + h], sc[h], sh[h]);
-                    if (act == 1) o[h] = ((ORBIT_SILU_FMA_MASK >> (2 * q + h)) & 1) ? silu2_fma(o[h]) : f2_silu(o[h]);
+                    if (act == 1) o[h] = f2_silu(o[h]);
                     else if (act == 2) o[h] = f2_relu(o[h]);
                     else if (act == 4) { float x0, x1; f2_unpack(o[h], x0, x1); o[h] = f2_pack(gelu_erf(x0), gelu_erf(x1)); }
                     if (has_res) o[h] = f2_add(o[h], rr[h]);

@@ -5,6 +5,7 @@ import torch
 from orbit_b200 import lib as L
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 lib = L.load(); dev = torch.device('cuda:0')
+if os.environ.get('DW5S'): assert lib.orbit_set_global_option(b'dw5_staged', int(os.environ['DW5S'])) == 0
 layers = [(112, 32, 3, 1), (112, 96, 3, 2), (56, 144, 3, 1), (56, 144, 5, 2), (28, 240, 5, 1), (28, 240, 3, 2), (14, 480, 3, 1),
           (14, 480, 5, 1), (14, 672, 5, 1), (14, 672, 5, 2), (7, 1152, 5, 1), (7, 1152, 3, 1)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
