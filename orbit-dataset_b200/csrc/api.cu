@@ -48,7 +48,6 @@ extern "C" int orbit_set_global_option(const char* key, int value) {
     if (!strcmp(key, "tc_narrow")) { orbit::set_tcgen05_narrow(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "tc_stream")) { orbit::set_stream_gemm(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "dw5_staged")) { orbit::set_dw5_staged(value); return ORBIT_OK; }
-    if (!strcmp(key, "se_frames")) { orbit::set_se_frames(value); return ORBIT_OK; }
     if (!strcmp(key, "tc_fixed_slabs")) { orbit::set_tcgen05_tuning(value != 0, -1); return ORBIT_OK; }
     if (!strcmp(key, "tc_double_min_stages")) { orbit::set_tcgen05_tuning(-1, value); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;

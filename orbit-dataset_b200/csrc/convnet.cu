@@ -9,6 +9,8 @@
 //   conv_pw/conv_pwl/conv_head-> pw_ffma_kernel (this file, fp32 FFMA tiles) or the tcgen05 kernel
 //                                in gemm_tcgen05.cu; BN/FiLM scale-shift, SiLU, SE gate and residual fused
 //   global_pool               -> spatial_mean_kernel
+#include <type_traits>
+
 #include "convnet.cuh"
 
 namespace orbit {
@@ -495,19 +497,21 @@ dw2_kernel(const float* __restrict__ x, const float* __restrict__ wt, const floa
 // shared memory. dw2_kernel reads its input rows straight into registers and relies on occupancy to cover HBM latency; at
 // K = 5 it needs ~112 registers, so an SM holds 16 warps with 2 KB of loads in flight each = 32 KB where ~35 KB are needed
 // (measured: 2.0-2.5 TB/s on these layers). Here the loads cost no registers: a block owns one 64-channel chunk, walks over
-// the frames FPB at a time, and cp.async copies the NEXT iteration's [FPB][HW*HW][64 channels] tile (50 KB) into the other
-// half of a double buffer while the current one is convolved out of shared memory (two blocks per SM: ~100 KB in flight).
-// The arithmetic is dw2_kernel's: rolling accumulators over the rows on packed fma.rn.f32x2, taps in shared memory,
-// bn2 / FiLM scale-shift + SiLU, deterministic SE squeeze sums per (frame, chunk) -> partial[b][0][C] (one group).
-// grid (channel chunks of 64, frame slices); block 256 = 32 channel pairs x strips (4-column strips of a row) x FPB frames.
+// the frames FPB at a time, and cp.async copies the NEXT iteration's [FPB][HW*HW][64 channels] tile (50 / 25 KB) into the other
+// half of a double buffer while the current one is convolved out of shared memory (two / three blocks per SM).
+// Arithmetic: packed fma.rn.f32x2 on channel pairs, the 25 taps in registers, output-stationary (see below), bn2 / FiLM
+// scale-shift + SiLU, deterministic SE squeeze sums per (frame, chunk) -> partial[b][0][C] (one group).
+// grid (channel chunks of 64, frame slices); block 256 = 32 channel pairs x [strips (4 columns) x 2 row halves] x FPB frames.
 // ------------------------------------------------------------------------------------------------
 template <int HW>
 __global__ void __launch_bounds__(256, 2)
 dw5s_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale, const float* __restrict__ shift,
             float* __restrict__ y, float* __restrict__ partial, int B, int C, int act) {
-    constexpr int K = 5, TW = kDwTW, SPAN = TW + K - 1, R = K, HALF = K - 1, PAD = 2;
+    constexpr int K = 5, TW = kDwTW, SPAN = TW + K - 1, PAD = 2;
     constexpr int STRIPS = (HW + TW - 1) / TW;            // 4 (14x14) or 2 (7x7)
-    constexpr int FPB = 256 / (32 * STRIPS);              // frames per block iteration: 2 or 4
+    constexpr int RS = 2, RH = (HW + RS - 1) / RS;        // a strip's rows are split between RS warps (RH rows each)
+    constexpr int WPF = STRIPS * RS;                      // warps per frame: 8 or 4
+    constexpr int FPB = 8 / WPF;                          // frames per block iteration: 1 or 2
     constexpr int PIX = HW * HW;
     constexpr int TILE_F2 = FPB * PIX * 32;               // channel pairs per stage
     extern __shared__ __align__(16) float s_dyn[];
@@ -516,7 +520,8 @@ dw5s_kernel(const float* __restrict__ x, const float* __restrict__ wt, const flo
     float* s_red = reinterpret_cast<float*>(s_x + 2 * TILE_F2);          // [256][2]
     const int chunk = blockIdx.x, c0 = chunk * 64;
     const int cw = min(64, C - c0);                       // channels of this chunk (64, or 32 in a tail chunk); C % 4 == 0
-    const int lx = threadIdx.x & 31, strip = (threadIdx.x >> 5) % STRIPS, fl = (threadIdx.x >> 5) / STRIPS;
+    const int lx = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int fl = wid / WPF, strip = (wid % WPF) / RS, half = wid % RS;
     const bool lane_live = 2 * lx < cw;
     for (int i = threadIdx.x; i < K * K * 32; i += 256) {
         const int tp = i >> 5, l = i & 31;
@@ -540,6 +545,10 @@ dw5s_kernel(const float* __restrict__ x, const float* __restrict__ wt, const flo
     unsigned cmask = 0;
 #pragma unroll
     for (int j = 0; j < SPAN; ++j) cmask |= (ixb + j >= 0 && ixb + j < HW) ? (1u << j) : 0u;
+    __syncthreads();
+    f2_t wreg[K * K];                                     // the 25 taps of this lane's channel pair stay in registers
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) wreg[i] = s_w[i * 32 + lx];
     int f0 = blockIdx.y * FPB, stage = 0;
     if (f0 < B) issue_tile(f0, 0);
     for (; f0 < B; f0 += gridDim.y * FPB, stage ^= 1) {
@@ -552,58 +561,59 @@ dw5s_kernel(const float* __restrict__ x, const float* __restrict__ wt, const flo
         if (f < B && lane_live) {
             const f2_t* xs = s_x + (size_t)stage * TILE_F2 + (size_t)fl * PIX * 32 + lx;
             float* yb = y + ((int64_t)f * PIX + ox0) * C + c0 + 2 * lx;
-            f2_t acc[R][TW];
+            // Output-stationary, two output rows at a time: they gather their (up to) six input rows from shared memory --
+            // re-reading a staged row costs an LDS, not HBM traffic -- so there is no accumulator ring to rotate and no row
+            // phase logic. A warp is one strip of half the rows of one frame: interior strips run without column tests.
+            auto out_rows = [&](int oy, bool second, auto interior) {
+                f2_t acc0[TW], acc1[TW];
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+                for (int t = 0; t < TW; ++t) { acc0[t] = 0ull; acc1[t] = 0ull; }
 #pragma unroll
-                for (int t = 0; t < TW; ++t) acc[r][t] = 0ull;
-            // iteration m consumes virtual row m (input row m - PAD); the oldest pending output row is m - HALF
-            for (int m = 0; m < HW + HALF; ++m) {
-                const int iy = m - PAD;
-                if (iy >= 0 && iy < HW) {
+                for (int r = 0; r < K + 1; ++r) {                 // input row oy - PAD + r feeds row oy (ky = r) and oy + 1 (ky = r - 1)
+                    const int iy = oy - PAD + r;
+                    if (iy < 0 || iy >= HW) continue;
                     f2_t v[SPAN];
 #pragma unroll
-                    for (int j = 0; j < SPAN; ++j) v[j] = (cmask & (1u << j)) ? xs[(iy * HW + ixb + j) * 32] : 0ull;
+                    for (int j = 0; j < SPAN; ++j)
+                        v[j] = (decltype(interior)::value || (cmask & (1u << j))) ? xs[(iy * HW + ixb + j) * 32] : 0ull;
 #pragma unroll
-                    for (int ky = 0; ky < K; ++ky) {
-                        const int slot = HALF - ky;
+                    for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-                        for (int kx = 0; kx < K; ++kx) {
-                            const f2_t w = s_w[(ky * K + kx) * 32 + lx];
-#pragma unroll
-                            for (int t = 0; t < TW; ++t) acc[slot][t] = f2_fma(v[kx + t], w, acc[slot][t]);
+                        for (int t = 0; t < TW; ++t) {
+                            if (r < K) acc0[t] = f2_fma(v[kx + t], wreg[(r < K ? r : 0) * K + kx], acc0[t]);
+                            if (r > 0) acc1[t] = f2_fma(v[kx + t], wreg[(r > 0 ? r - 1 : 0) * K + kx], acc1[t]);
                         }
-                    }
                 }
-                const int oy = m - HALF;
-                if (oy >= 0) {
-                    float* yrow = yb + (int64_t)oy * HW * C;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    if (rr == 1 && !second) break;
+                    float* yrow = yb + (int64_t)(oy + rr) * HW * C;
 #pragma unroll
                     for (int t = 0; t < TW; ++t) {
-                        if (ox0 + t < HW) {
+                        if (decltype(interior)::value || ox0 + t < HW) {
                             float r0, r1;
-                            f2_unpack(f2_fma(acc[0][t], sc, sh), r0, r1);
+                            f2_unpack(f2_fma(rr ? acc1[t] : acc0[t], sc, sh), r0, r1);
                             r0 = act_fast(r0, act); r1 = act_fast(r1, act);
                             sum0 += r0; sum1 += r1;
                             *reinterpret_cast<float2*>(yrow + t * C) = make_float2(r0, r1);
                         }
                     }
                 }
-#pragma unroll
-                for (int r = 0; r + 1 < R; ++r)
-#pragma unroll
-                    for (int t = 0; t < TW; ++t) acc[r][t] = acc[r + 1][t];
-#pragma unroll
-                for (int t = 0; t < TW; ++t) acc[R - 1][t] = 0ull;
+            };
+            const int row_lo = half * RH, row_hi = min(HW, row_lo + RH);
+            if (cmask == (1u << SPAN) - 1u && ox0 + TW <= HW) {
+                for (int oy = row_lo; oy < row_hi; oy += 2) out_rows(oy, oy + 1 < row_hi, std::true_type{});
+            } else {
+                for (int oy = row_lo; oy < row_hi; oy += 2) out_rows(oy, oy + 1 < row_hi, std::false_type{});
             }
         }
         if (partial) {
             s_red[2 * threadIdx.x] = sum0; s_red[2 * threadIdx.x + 1] = sum1;
             __syncthreads();
-            if (strip == 0 && f < B && lane_live) {
+            if (wid % WPF == 0 && f < B && lane_live) {
                 float a = 0.f, b2 = 0.f;
 #pragma unroll
-                for (int r = 0; r < STRIPS; ++r) { a += s_red[2 * (threadIdx.x + 32 * r)]; b2 += s_red[2 * (threadIdx.x + 32 * r) + 1]; }   // fixed order
+                for (int r = 0; r < WPF; ++r) { a += s_red[2 * (threadIdx.x + 32 * r)]; b2 += s_red[2 * (threadIdx.x + 32 * r) + 1]; }   // fixed order
                 *reinterpret_cast<float2*>(partial + (int64_t)f * C + c0 + 2 * lx) = make_float2(a, b2);
             }
         }
@@ -613,20 +623,20 @@ dw5s_kernel(const float* __restrict__ x, const float* __restrict__ wt, const flo
 }
 
 static int g_dw5s = 1;      // dev A/B switch (orbit_set_global_option "dw5_staged")
-void set_dw5_staged(int on) { g_dw5s = on; }      // 0 off, 1 = 7x7 only (default), 2 = 7x7 and 14x14
+void set_dw5_staged(int on) { g_dw5s = on; }
 int get_dw5_staged() { return g_dw5s; }
 
 template <int HW>
 static int launch_dw5s(const float* x, const float* wt, const float* scale, const float* shift, float* y, float* partial, int B, int C,
                        int act, cudaStream_t st) {
-    constexpr int STRIPS = (HW + kDwTW - 1) / kDwTW, FPB = 256 / (32 * STRIPS), PIX = HW * HW;
+    constexpr int STRIPS = (HW + kDwTW - 1) / kDwTW, FPB = 8 / (STRIPS * 2), PIX = HW * HW;
     const size_t smem = sizeof(f2_t) * (25 * 32 + 2 * (size_t)FPB * PIX * 32) + sizeof(float) * 512;
     auto fn = dw5s_kernel<HW>;
     ORBIT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int chunks = ceil_div(C, 64);
-    // 2 blocks per SM; every block should get at least 3 iterations so that the double buffer amortises its prologue
+    // 2 (14x14: 109 KB) or 3 (7x7: 59 KB) blocks per SM
     const int iters = ceil_div(B, FPB);
-    const int slices = std::max(1, std::min(iters, std::max(1, (2 * 148) / chunks)));
+    const int slices = std::max(1, std::min(iters, std::max(1, ((HW == 14 ? 2 : 3) * 148) / chunks)));
     fn<<<dim3(chunks, slices), 256, smem, st>>>(x, wt, scale, shift, y, partial, B, C, act);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
@@ -638,10 +648,9 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
     if (C % 4) return ORBIT_ERR_UNSUPPORTED;
     if (g_dw5s && k == 5 && stride == 1 && H == W && pad_t == 2 && pad_l == 2 && (act == ACT_SILU || act == ACT_NONE) &&
         dw_plan(C, Ho, Wo, k, stride).groups == 1) {
-        // measured on B200 (us per 512 frames, dw2_kernel -> staged): 7x7x1152 113.5 -> 91.1; 14x14x672 218 -> 234 and 14x14x480
-        // 163 -> 169 (there the kernel is bound by its instruction count, not by load latency): 14x14 stays with dw2_kernel
+        // measured on B200 (us per 1,024 frames, dw2_kernel -> staged): 7x7x1152 210 -> 155, 14x14x672 419 -> 368, 14x14x480 310 -> 266
         if (H == 7) return launch_dw5s<7>(x, wt, scale, shift, y, partial, B, C, act, st);
-        if (H == 14 && g_dw5s == 2) return launch_dw5s<14>(x, wt, scale, shift, y, partial, B, C, act, st);
+        if (H == 14) return launch_dw5s<14>(x, wt, scale, shift, y, partial, B, C, act, st);
     }
     const DwPlan pl = dw_plan(C, Ho, Wo, k, stride);
     dim3 grid(pl.groups, pl.nchunks, B), block(pl.LX * pl.LY);
@@ -1034,7 +1043,7 @@ int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scal
 // the kernel is a chain of L2 latencies, so what matters is how many loads each SM keeps in flight.
 // Per-frame arithmetic order is unchanged.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSeFrames = 16;
+constexpr int kSeFrames = 8;
 
 __global__ void __launch_bounds__(1024)
 se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const float* __restrict__ w1,
@@ -1093,17 +1102,12 @@ se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const
     }
 }
 
-static int g_se_frames = 8;      // frames per block (<= kSeFrames); dev A/B switch "se_frames"
-void set_se_frames(int f) { g_se_frames = std::max(1, std::min(kSeFrames, f)); }
-
 int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2t,
                    const float* b2, float* gate, int B, int C, int R, cudaStream_t st) {
     if (B <= 0) return ORBIT_OK;
-    int F = g_se_frames;
-    while (F > 1 && sizeof(float) * (size_t)F * (C + R) > 96 * 1024) F >>= 1;
-    while (F > 1 && ceil_div(B, F) < 148 && F > 8) F >>= 1;                    // keep every SM busy
+    int F = kSeFrames;      // (16 frames per block measured no faster: the kernel is a chain of L2 latencies, not L2 bandwidth)
+    while (F > 1 && sizeof(float) * (size_t)F * (C + R) > 44 * 1024) F >>= 1;   // stay inside the default 48 KB
     const size_t smem = sizeof(float) * (size_t)F * (C + R);
-    if (smem > 48 * 1024) ORBIT_CUDA(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     se_gate_kernel<<<ceil_div(B, F), C >= 256 ? 1024 : 256, smem, st>>>(partial, tiles, 1.0f / (float)hw, w1, b1, w2t, b2, gate, B, C, R, F);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;

@@ -43,7 +43,6 @@ int launch_depthwise(const float* x, const float* wt, const float* scale, const 
                      cudaStream_t st);
 
 
-void set_se_frames(int frames_per_block);    // dev A/B: frames per se_gate block (default 8, max 16)
 // dev A/B switch: shared-memory-staged 5x5 stride-1 depthwise kernel for 14x14 / 7x7 inputs (default on)
 void set_dw5_staged(int on);
 int get_dw5_staged();
