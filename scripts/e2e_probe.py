@@ -33,15 +33,20 @@ def step_dev():
     m.personalise(cd, cyd); lg = m.predict(td); m._reset(); return lg.cpu()
 
 fe = m.feature_extractor
-for chunk in (640, 1600):
+for chunk in (() if os.environ.get('RAMP_ONLY') else (640, 1600)):
     fe.set_option('chunk_frames', chunk)
     print(f"device-resident, chunk {chunk}: {run(step_dev):.1f} ms", flush=True)
 fe.set_option('chunk_frames', 1600)
-for cf, ramp in ((160, (96, 224, 480)), (160, (128, 448)), (160, (160, 480)), (160, (96, 288, 640)), (160, (64, 192, 512)), (160, (192, 608)),
-                 (320, (96, 224, 480)), (80, (96, 224, 480))):
+RAMPS = ((160, (96, 224, 480)), (160, (160, 320, 480)), (160, (64, 160, 288, 448)), (160, (128, 288, 544)), (160, (96, 192, 320, 416)),
+         (160, (160, 352, 512)), (160, (96, 224, 480)), (160, (160, 320, 480)))
+if os.environ.get('RAMP_ONLY'):
+    fe.set_option('chunk_frames', 1600)
+for cf, ramp in RAMPS:
     m.stage_copy_frames, m.stage_ramp = cf, ramp
     step_host()
     print(f"host clips, copy {cf} ramp {ramp}: {run(step_host, 6):.1f} ms", flush=True)
+if os.environ.get('RAMP_ONLY'):
+    sys.exit(0)
 # CPU-side cost of enqueueing one device-resident episode (no sync inside)
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(3):
