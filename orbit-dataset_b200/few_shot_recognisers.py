@@ -94,9 +94,13 @@ class _HostStager:
         behind = self.last_done is not None and not self.last_done.query()
         sizes = self._plan(total, behind)
         pinned_src = frames_cpu.is_pinned()
+        # Pinned source: every copy of the call is enqueued up front (the copy engine runs ahead of the backbone), then the
+        # passes are handed out. Pageable source (what the reference's loaders deliver, data/queues.py:52): the host-side
+        # staging memcpy of a pass runs while the device works on the previous pass, so a pass is handed out as soon as ITS
+        # copies are enqueued (staging everything first left the device idle for the whole 25 ms of host copying).
         events, pos, j = [], 0, 0
         for n in sizes:
-            end = pos + n
+            start, end = pos, pos + n
             while pos < end:
                 m = min(self.copy_frames, end - pos)
                 src = frames_cpu[pos:pos + m]
@@ -119,13 +123,19 @@ class _HostStager:
                 pos += m
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-            events.append(ev)
-        self.bytes_copied += need * 4
-        pos = 0
-        for n, ev in zip(sizes, events):
-            compute.wait_event(ev)
-            yield dst[pos:pos + n]
-            pos += n
+            if pinned_src:
+                events.append(ev)
+            else:
+                self.bytes_copied += n * per_frame * 4
+                compute.wait_event(ev)
+                yield dst[start:end]
+        if pinned_src:
+            self.bytes_copied += need * 4
+            pos = 0
+            for n, ev in zip(sizes, events):
+                compute.wait_event(ev)
+                yield dst[pos:pos + n]
+                pos += n
         self.release(i)
 
     def release(self, i):
