@@ -155,6 +155,18 @@ int orbit_pointwise_conv(const float* A, const float* W, const float* scale, con
                          const float* gate, const float* residual, float* out, int M, int N, int K,
                          int rows_per_frame, int act, int mode, float* w_split, void* stream);
 
+/* 3x3 convolution, stride 1, padding 1, on NHWC activations with the folded BatchNorm scale-shift, activation (0 none, 1 SiLU,
+ * 2 ReLU, 18 = ReLU after the residual add) and residual fused: the BasicBlock convolutions of the resnet18 extension
+ * (BASELINE.json configs 1 and 3), SimplePrePoolNet layers 2-5 of the set encoder (model/set_encoders.py:91-105) and the
+ * EdgeResidual expand of tf_efficientnetv2_s. weight [Cout,Cin,3,3] (torch layout).
+ *   implicit = 1: implicit GEMM on the tcgen05 kernel (Cin % 64 == 0): no im2col matrix, the nine taps are row-shifted TMA
+ *                 boxes of the activation; implicit = 0: explicit im2col + the same GEMM (any Cin % 4 == 0). Same arithmetic.
+ *   scratch: orbit_conv3x3_scratch_floats(...) floats.                                                                     */
+int64_t orbit_conv3x3_scratch_floats(int B, int H, int W, int Cin, int Cout, int implicit);
+int orbit_conv3x3(const float* x, const float* weight, const float* scale, const float* shift, const float* residual,
+                  float* out, int B, int H, int W, int Cin, int Cout, int act, int implicit, float* scratch,
+                  int64_t scratch_floats, void* stream);
+
 /* Depthwise k x k convolution (k in {3,5}, stride in {1,2}, TF "SAME" padding) on NHWC activations with the folded
  * BatchNorm/FiLM scale-shift and activation fused: timm conv_dw + BatchNormAct2d of every MBConv block.
  *   x [B,H,W,C] -> y [B,ceil(H/s),ceil(W/s),C]; weight [C,1,k,k] (torch layout); weight_scratch: k*k*C floats.

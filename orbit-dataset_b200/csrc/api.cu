@@ -40,6 +40,33 @@ extern "C" int orbit_pointwise_conv(const float* A, const float* W, const float*
                                     mode == 1 ? 3 : 1, st);
 }
 
+extern "C" int orbit_conv3x3(const float* x, const float* weight, const float* scale, const float* shift, const float* residual,
+                             float* out, int B, int H, int W, int Cin, int Cout, int act, int implicit, float* scratch,
+                             int64_t scratch_floats, void* stream) {
+    using namespace orbit;
+    if (!x || !weight || !scale || !shift || !out || !scratch || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return ORBIT_ERR_ARG;
+    if (Cin % 4 || Cout % 4 || !aligned16(x) || !aligned16(out) || !aligned16(scratch)) return ORBIT_ERR_UNSUPPORTED;
+    if (scratch_floats < orbit_conv3x3_scratch_floats(B, H, W, Cin, Cout, implicit)) return ORBIT_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = 9 * Cin;
+    float* w_gemm = scratch;                       // [Cout][K] in (tap, channel) order
+    float* w_split = w_gemm + (int64_t)Cout * K;   // fp16 hi | lo
+    int rc = launch_conv_weight_relayout(weight, w_gemm, Cout, Cin, 9, K, 0, st);
+    if (rc) return rc;
+    rc = launch_weight_split(w_gemm, Cout, K, w_split, st);
+    if (rc || B == 0) return rc;
+    if (implicit) return launch_conv3x3_tcgen05(x, w_split, scale, shift, residual, out, B, H, W, Cin, Cout, act, st);
+    float* col = w_split + 2 * (int64_t)Cout * K;
+    rc = launch_im2col(x, col, B, H, W, Cin, 3, 1, 1, 1, H, W, K, 0, st);
+    if (rc) return rc;
+    return launch_pointwise_tcgen05(col, w_split, scale, shift, nullptr, residual, out, B * H * W, Cout, K, H * W, act, 3, st);
+}
+
+extern "C" int64_t orbit_conv3x3_scratch_floats(int B, int H, int W, int Cin, int Cout, int implicit) {
+    const int64_t K = 9 * (int64_t)Cin;
+    return 3 * (int64_t)Cout * K + 16 + (implicit ? 0 : (int64_t)B * H * W * K);
+}
+
 extern "C" int orbit_debug_set_gemm_trace(void* dev_buffer) { orbit::set_tcgen05_trace(static_cast<unsigned*>(dev_buffer)); return ORBIT_OK; }
 
 extern "C" int orbit_set_global_option(const char* key, int value) {

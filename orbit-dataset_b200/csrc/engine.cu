@@ -67,6 +67,7 @@ struct orbit_engine {
     std::vector<Op> ops;
     int chunk_frames = 256;   // frames per pass through the layer plan (workspace ~10 MB per 224-px frame)
     int gemm_mode = 1;        // tcgen05 FP16x3
+    int implicit_conv = 1;    // 3x3 stride-1 convolutions (Cin % 64 == 0) as implicit GEMM instead of im2col + GEMM
     int fuse_mbconv = 1;      // expand 1x1 -> depthwise in one kernel (mbx_kernel) where the block input has 16 / 24 channels:
                               // 0 = never; 1 = the stride-2 block with 16 input channels (B0 block 1.0: faster than the streaming
                               // expand GEMM + depthwise pair); 3 = every stride-2 block (also B0 block 2.0, which the unfused pair
@@ -561,6 +562,7 @@ extern "C" int orbit_engine_set_option(orbit_engine* e, const char* key, int val
     if (!std::strcmp(key, "gemm")) { if (value < 0 || value > 2) return ORBIT_ERR_ARG; e->gemm_mode = value; return ORBIT_OK; }
     if (!std::strcmp(key, "profile")) { e->profile = value != 0; return ORBIT_OK; }
     if (!std::strcmp(key, "fuse_mbconv")) { if (value < 0 || value > 3) return ORBIT_ERR_ARG; e->fuse_mbconv = value; return ORBIT_OK; }
+    if (!std::strcmp(key, "implicit_conv")) { e->implicit_conv = value != 0; return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 extern "C" int orbit_engine_get_option(const orbit_engine* e, const char* key, int* value) {
@@ -569,6 +571,7 @@ extern "C" int orbit_engine_get_option(const orbit_engine* e, const char* key, i
     if (!std::strcmp(key, "gemm")) { *value = e->gemm_mode; return ORBIT_OK; }
     if (!std::strcmp(key, "profile")) { *value = e->profile; return ORBIT_OK; }
     if (!std::strcmp(key, "fuse_mbconv")) { *value = e->fuse_mbconv; return ORBIT_OK; }
+    if (!std::strcmp(key, "implicit_conv")) { *value = e->implicit_conv; return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 
@@ -831,6 +834,19 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                         int cho, cwo, cpt, cpl;
                         conv_geometry(op, h, w, &cho, &cwo, &cpt, &cpl);
                         const int M = B * cho * cwo;
+                        // 3x3 stride-1 convolutions over >= 64 channels: implicit GEMM (no im2col matrix in HBM)
+                        if (e->implicit_conv && e->gemm_mode == 1 && !raw && op.k == 3 && op.stride == 1 && cpt == 1 && cpl == 1 && !op.nchw_in &&
+                            op.cin % 64 == 0 && (act == ACT_RELU || act == 16 + ACT_RELU || act == ACT_NONE || act == ACT_SILU)) {
+                            const float* res_i = ptr(op.res);
+                            rc = launch_conv3x3_tcgen05(ptr(op.in), derived + op.w_split, scale, shift, res_i, ptr(op.out), B, h, w, op.cin,
+                                                        op.cout, act, st);
+                            if (rc != ORBIT_ERR_UNSUPPORTED) {
+                                p_bytes = 4.0 * ((double)M * op.cin + (double)M * op.cout * (res_i ? 2 : 1) + (double)op.kpad * op.cout);
+                                p_flops = 2.0 * M * (double)op.kpad * op.cout;
+                                if (op.out != BUF_D) { ho = cho; wo = cwo; }
+                                break;
+                            }
+                        }
                         rc = launch_im2col(ptr(op.in), buf[BUF_COL], B, h, w, op.cin, op.k, op.stride, cpt, cpl, cho, cwo, op.kpad,
                                            op.nchw_in, st);
                         if (rc) return rc;
@@ -1121,11 +1137,17 @@ extern "C" int orbit_engine_forward_train(const orbit_engine* e, const float* pa
                 // raw convolution (no bias: it is folded into shift) into the arena; im2col + the tcgen05 GEMM as in run_plan
                 const float* in = op.nchw_in ? ptr(op.in) : saved + t.a_off[i - 1] * B;
                 const int M = B * h * w;
-                rc = launch_im2col(in, buf[BUF_COL], B, h, w, op.cin, 3, 1, 1, 1, h, w, op.kpad, op.nchw_in, st);
-                if (rc) return rc;
-                rc = launch_pointwise_tcgen05(buf[BUF_COL], derived + op.w_split, ones, zeros, nullptr, nullptr, c, M, op.cout, op.kpad, h * w,
-                                              ACT_NONE, 3, st);
-                launches += 2;
+                rc = ORBIT_ERR_UNSUPPORTED;
+                if (e->implicit_conv && !op.nchw_in && op.cin % 64 == 0)      // layers 2-5: implicit GEMM, no im2col matrix
+                    rc = launch_conv3x3_tcgen05(in, derived + op.w_split, ones, zeros, nullptr, c, B, h, w, op.cin, op.cout, ACT_NONE, st);
+                if (rc == ORBIT_ERR_UNSUPPORTED) {
+                    rc = launch_im2col(in, buf[BUF_COL], B, h, w, op.cin, 3, 1, 1, 1, h, w, op.kpad, op.nchw_in, st);
+                    if (rc) return rc;
+                    rc = launch_pointwise_tcgen05(buf[BUF_COL], derived + op.w_split, ones, zeros, nullptr, nullptr, c, M, op.cout, op.kpad,
+                                                  h * w, ACT_NONE, 3, st);
+                    ++launches;
+                }
+                ++launches;
                 break;
             }
             case OP_MAXPOOL: {
@@ -1200,11 +1222,17 @@ static int set_encoder_backward(const orbit_engine* e, const TrainGeom& t, const
             if (rc) return rc;
             rc = launch_weight_split(wd, op.cin, 9 * op.cout, wd + (int64_t)op.cin * 9 * op.cout, st);
             if (rc) return rc;
-            rc = launch_im2col(dc, buf[BUF_COL], B, h, w, op.cout, 3, 1, 1, 1, h, w, 9 * op.cout, 0, st);
-            if (rc) return rc;
             float* dprev = buf[e->ops[i - 1].out];               // the previous maxpool's output buffer
-            rc = launch_pointwise_tcgen05(buf[BUF_COL], wd + (int64_t)op.cin * 9 * op.cout, ones, zeros, nullptr, nullptr, dprev, B * h * w,
-                                          op.cin, 9 * op.cout, h * w, ACT_NONE, 3, st);
+            rc = ORBIT_ERR_UNSUPPORTED;
+            if (e->implicit_conv && op.cout % 64 == 0)
+                rc = launch_conv3x3_tcgen05(dc, wd + (int64_t)op.cin * 9 * op.cout, ones, zeros, nullptr, dprev, B, h, w, op.cout, op.cin,
+                                            ACT_NONE, st);
+            if (rc == ORBIT_ERR_UNSUPPORTED) {
+                rc = launch_im2col(dc, buf[BUF_COL], B, h, w, op.cout, 3, 1, 1, 1, h, w, 9 * op.cout, 0, st);
+                if (rc) return rc;
+                rc = launch_pointwise_tcgen05(buf[BUF_COL], wd + (int64_t)op.cin * 9 * op.cout, ones, zeros, nullptr, nullptr, dprev, B * h * w,
+                                              op.cin, 9 * op.cout, h * w, ACT_NONE, 3, st);
+            }
             if (rc) return rc;
             launches += 6;
             dp = dprev;

@@ -223,6 +223,10 @@ struct Params {
     int has_residual;
     int M, N, K, rows_per_frame, act;
     uint32_t rpf_mul, rpf_shift;   // row / rows_per_frame = __umulhi(row, rpf_mul) >> rpf_shift for row < 2^31 (host: fast_div)
+    // implicit 3x3 stride-1 pad-1 convolution (CONV3 instances): A = the NHWC activation [B*H*W, Cin] itself; k-block kb covers
+    // tap kb / conv_kpt (ky = tap / 3, kx = tap % 3), channels (kb % conv_kpt) * 64 ..; its A tile = the rows m + (ky-1) W + (kx-1)
+    int conv_w, conv_h, conv_kpt;
+    uint32_t cw_mul, cw_shift, ch_mul, ch_shift;   // fast division by W and by H
     int BN, n_tiles, m_tiles, stages;
     int b_tile_bytes;        // BN * 128 (multiple of 2048)
     int slabs_per_warp;      // 1 or 2 staging slabs per epilogue warp
@@ -262,7 +266,9 @@ constexpr int SS_BYTES = 256;   // per epilogue warp: scale[32] | shift[32] of t
 //   SPLIT  FP16x3 (hi/lo, fp32-grade) or one plain fp16 product (the `fast` numerics mode, 2^-11 relative per product);
 //   GATED / RES  0, 1, or -1 = look at the arguments;  ACT  activation or -1;  XFW  transform warps (4 or 8).
 //   NARROW the transform's lane mapping for K <= 32 (one k-block, fp32 box 0 only), see the transform role.
-template <bool SPLIT, int GATED, int ACT, int RES, int XFW, bool NARROW>
+//   CONV3  implicit 3x3 convolution: the producer walks the nine taps with row-shifted TMA boxes, the transform zeroes the rows
+//          whose tap falls outside the image (no im2col matrix in HBM).
+template <bool SPLIT, int GATED, int ACT, int RES, int XFW, bool NARROW, bool CONV3 = false>
 __global__ void __launch_bounds__(num_threads(XFW), 1)
 pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
@@ -324,29 +330,41 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t b_bytes = (uint32_t)p.b_tile_bytes * (SPLIT ? 2 : 1);
             // L2 prefetch cursor: runs L2_PREFETCH_DISTANCE k-blocks ahead of the shared-memory ring, so that HBM
             // latency is covered by requests that cost no shared memory (the ring only has to cover L2 latency).
-            int pf_tile = blockIdx.x, pf_kb = 0;
+            int pf_tile = blockIdx.x, pf_kb = 0, pf_tap = 0, pf_kc = 0;
             TileIter pf_ti(blockIdx.x, gridDim.x, p.n_tiles);
             auto prefetch_next = [&]() {
                 if (pf_tile >= num_tiles) return;
-                const int m0 = pf_ti.mt * BM;
-                tma_prefetch_l2_2d(&map_a, pf_kb * BK, m0);
-                if (pf_kb * BK + 32 < p.K) tma_prefetch_l2_2d(&map_a, pf_kb * BK + 32, m0);
-                if (++pf_kb == num_k) { pf_kb = 0; pf_tile += gridDim.x; pf_ti.next(); }
+                int m0 = pf_ti.mt * BM, c0 = pf_kb * BK;
+                if (CONV3) {
+                    c0 = pf_kc * BK;
+                    m0 += (pf_tap / 3 - 1) * p.conv_w + (pf_tap % 3 - 1);
+                    if (++pf_kc == p.conv_kpt) { pf_kc = 0; ++pf_tap; }
+                }
+                tma_prefetch_l2_2d(&map_a, c0, m0);
+                if (CONV3 || pf_kb * BK + 32 < p.K) tma_prefetch_l2_2d(&map_a, c0 + 32, m0);
+                if (++pf_kb == num_k) { pf_kb = 0; pf_tap = 0; pf_kc = 0; pf_tile += gridDim.x; pf_ti.next(); }
             };
             for (int i = 0; i < L2_PREFETCH_DISTANCE; ++i) prefetch_next();
             uint32_t s = 0, ph = 0, step = 0;
             TileIter ti(blockIdx.x, gridDim.x, p.n_tiles);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ti.next()) {
                 const int m0 = ti.mt * BM, n0 = ti.nt * p.BN;
+                int tap = 0, kc = 0;
                 for (int kb = 0; kb < num_k; ++kb, ++step) {
                     prefetch_next();
-                    const bool two = kb * BK + 32 < p.K;          // the second 32-wide fp32 box holds real columns
+                    const bool two = CONV3 || kb * BK + 32 < p.K;  // the second 32-wide fp32 box holds real columns
+                    int a_col = kb * BK, a_row = m0;
+                    if (CONV3) {                                   // tap-shifted rows of the activation; rows outside [0, M) are zero-filled
+                        a_col = kc * BK;
+                        a_row = m0 + (tap / 3 - 1) * p.conv_w + (tap % 3 - 1);
+                        if (++kc == p.conv_kpt) { kc = 0; ++tap; }
+                    }
                     mbar_wait(empty(s), ph ^ 1);
                     trace_stamp(p.trace, step, 0);
                     mbar_expect_tx(full(s), (two ? 2u : 1u) * A_BOX_BYTES + b_bytes);
                     const uint32_t st = ring + s * stage_bytes;
-                    tma_load_2d(st, &map_a, full(s), kb * BK, m0);
-                    if (two) tma_load_2d(st + A_BOX_BYTES, &map_a, full(s), kb * BK + 32, m0);
+                    tma_load_2d(st, &map_a, full(s), a_col, a_row);
+                    if (two) tma_load_2d(st + A_BOX_BYTES, &map_a, full(s), a_col + 32, a_row);
                     tma_load_2d(st + A_STAGE_BYTES, &map_bhi, full(s), kb * BK, n0);
                     if (SPLIT) tma_load_2d(st + A_STAGE_BYTES + p.b_tile_bytes, &map_blo, full(s), kb * BK, n0);
                     trace_stamp(p.trace, step, 1);
@@ -442,7 +460,24 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     grow[i] = p.gate + (int64_t)(p.rpf_mul ? (__umulhi(row, p.rpf_mul) >> p.rpf_shift) : row) * p.K;
                 }
             }
+            uint32_t pix[XR];                    // CONV3: x | y << 16 of this thread's rows (0xffffffff: row beyond M)
+            if (CONV3) {
+                const int m0 = xti.mt * BM;
+#pragma unroll
+                for (int i = 0; i < XR; ++i) {
+                    const uint32_t row = (uint32_t)(m0 + row0 + (int)(rstride >> 7) * i);
+                    const uint32_t q = p.cw_mul ? (__umulhi(row, p.cw_mul) >> p.cw_shift) : row;            // row / W
+                    const uint32_t q2 = p.ch_mul ? (__umulhi(q, p.ch_mul) >> p.ch_shift) : q;               // ... / H
+                    pix[i] = row < (uint32_t)p.M ? ((row - q * (uint32_t)p.conv_w) | ((q - q2 * (uint32_t)p.conv_h) << 16)) : 0xffffffffu;
+                }
+            }
+            int xtap = 0, xkc = 0;
             for (int kb = 0; kb < num_k; ++kb) {
+                int dy = 0, dx = 0;
+                if (CONV3) {
+                    dy = xtap / 3 - 1; dx = xtap % 3 - 1;
+                    if (++xkc == p.conv_kpt) { xkc = 0; ++xtap; }
+                }
                 const int krem = p.K - kb * BK;                               // real columns left in this k-block
                 const bool active = q * 8 < ceil_div(min(krem, BK), UMMA_K) * UMMA_K;   // the MMAs read this 8-column group
                 const bool ga_on = gated && ka < krem, gb_on = gated && kb4 < krem;
@@ -466,6 +501,12 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             for (int i = 0; i < RB; ++i) {
                                 va[i] = lds128(a + src_off + (b + i) * rstride);
                                 vb[i] = lds128(a + (src_off ^ 16u) + (b + i) * rstride);
+                                if (CONV3) {     // the tap of this k-block lies outside the image for this row: zero padding
+                                    const uint32_t xy = pix[b + i];
+                                    const bool ok = xy != 0xffffffffu && (uint32_t)((int)(xy & 0xffffu) + dx) < (uint32_t)p.conv_w &&
+                                                    (uint32_t)((int)(xy >> 16) + dy) < (uint32_t)p.conv_h;
+                                    if (!ok) { va[i] = make_float4(0.f, 0.f, 0.f, 0.f); vb[i] = va[i]; }
+                                }
                             }
                             __syncwarp(__activemask());      // in-place: every lane of the row has read before any lane writes
 #pragma unroll
@@ -732,27 +773,38 @@ void set_tcgen05_trace(unsigned* dev_buffer) { g_gemm_trace = dev_buffer; }
 void set_tcgen05_debias(float kappa) { g_debias_kappa = kappa; }
 float get_tcgen05_debias() { return g_debias_kappa; }
 
-int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* scale, const float* shift,
-                             const float* gate, const float* residual, float* out, int M, int N, int K,
-                             int rows_per_frame, int act, int passes, cudaStream_t st) {
+namespace {
+struct Conv3Geom { int W, H, Cin; };      // implicit 3x3 stride-1 pad-1 convolution over an NHWC activation
+void fast_div(uint32_t d, uint32_t* mul, uint32_t* shift) {      // x / d = umulhi(x, mul) >> shift for x < 2^31 (mul == 0: d == 1)
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    *mul = d <= 1 ? 0u : (uint32_t)(((1ull << (31 + l)) / d) + 1);
+    *shift = d <= 1 ? 0u : (31 + l - 32);
+}
+}  // namespace
+
+static int launch_tcgen05_impl(const float* A, const float* w_split, const float* scale, const float* shift,
+                               const float* gate, const float* residual, float* out, int M, int N, int K,
+                               int rows_per_frame, int act, int passes, const Conv3Geom* conv, cudaStream_t st) {
     using namespace tc;
     if (K % 4 || N % 4 || (passes != 1 && passes != 3)) return ORBIT_ERR_UNSUPPORTED;
     if (M <= 0) return ORBIT_OK;
-    if (passes == 3 && (act == 0 || act == 1)) {       // the row-streaming kernel covers the small-K / small-N layer shapes
+    if (!conv && passes == 3 && (act == 0 || act == 1)) {       // the row-streaming kernel covers the small-K / small-N layer shapes
         const int rc = launch_pointwise_stream(A, w_split, scale, shift, gate, residual, out, M, N, K, rows_per_frame, act, st);
         if (rc != ORBIT_ERR_UNSUPPORTED) return rc;
     }
     Params p;
     p.scale = scale; p.shift = shift; p.gate = gate; p.has_residual = residual != nullptr;
     p.M = M; p.N = N; p.K = K; p.rows_per_frame = rows_per_frame; p.act = act;
-    {   // row / rows_per_frame for row < 2^31: shift = 31 + ceil(log2 d) - 32, mul = floor(2^(31 + ceil(log2 d)) / d) + 1 < 2^32
-        const uint32_t d = (uint32_t)std::max(rows_per_frame, 1);
-        uint32_t l = 0;
-        while ((1ull << l) < d) ++l;
-        p.rpf_mul = d == 1 ? 0u : (uint32_t)(((1ull << (31 + l)) / d) + 1);      // 0: the quotient is the row itself
-        p.rpf_shift = d == 1 ? 0u : (31 + l - 32);
+    fast_div((uint32_t)std::max(rows_per_frame, 1), &p.rpf_mul, &p.rpf_shift);
+    p.conv_w = p.conv_h = p.conv_kpt = 0;
+    p.cw_mul = p.cw_shift = p.ch_mul = p.ch_shift = 0;
+    if (conv) {
+        if (conv->Cin % BK || K != 9 * conv->Cin || gate || passes != 3) return ORBIT_ERR_UNSUPPORTED;
+        p.conv_w = conv->W; p.conv_h = conv->H; p.conv_kpt = conv->Cin / BK;
+        fast_div((uint32_t)conv->W, &p.cw_mul, &p.cw_shift);
+        fast_div((uint32_t)conv->H, &p.ch_mul, &p.ch_shift);
     }
-
     p.debias = passes == 3 ? g_debias_kappa : 0.f;
     p.trace = g_gemm_trace;
     // n-tiles of at most 96 columns (3 store slabs = one per epilogue warp of a lane group); with several n-tiles
@@ -778,7 +830,7 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     const int Kp = (K + 7) / 8 * 8;                    // row pitch of the split weights (launch_weight_split)
     const __half* w16 = reinterpret_cast<const __half*>(w_split);
     CUtensorMap map_a, map_bhi, map_blo, map_out, map_res;
-    int rc = make_map(&map_a, A, false, M, K, K, BM);
+    int rc = conv ? make_map(&map_a, A, false, M, conv->Cin, conv->Cin, BM) : make_map(&map_a, A, false, M, K, K, BM);
     if (rc) return rc;
     rc = make_map(&map_bhi, w16, true, N, K, Kp, p.BN);
     if (rc) return rc;
@@ -795,7 +847,13 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     int xfw = 4;
     const bool g = gate != nullptr, r = residual != nullptr;
     const bool narrow = K <= 32 && g_narrow;
-    if (passes == 3) {
+    if (conv) {
+        if (act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4, false, true>;          // conv3x3 + ReLU (ResNet conv1 of a block, set encoder)
+        else if (act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4, false, true>;    // BasicBlock: relu(bn(conv3x3) + identity)
+        else if (act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4, false, true>;     // plain conv3x3 (data gradient of the set encoder)
+        else if (act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, false, true>;     // conv3x3 + SiLU (EfficientNet-V2 EdgeResidual expand)
+        else return ORBIT_ERR_UNSUPPORTED;
+    } else if (passes == 3) {
         if (g && act == 0 && !r && narrow) fn = pw_tcgen05_kernel<true, 1, 0, 0, 4, true>;           // first MBConv project (K = 32)
         else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8, false>; xfw = 8; }   // MBConv project
         else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8, false>; xfw = 8; }    // ... + skip
@@ -822,6 +880,19 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
     fn<<<grid, num_threads(xfw), smem, st>>>(map_a, map_bhi, map_blo, map_out, map_res, p);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
+}
+
+int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* scale, const float* shift,
+                             const float* gate, const float* residual, float* out, int M, int N, int K,
+                             int rows_per_frame, int act, int passes, cudaStream_t st) {
+    return launch_tcgen05_impl(A, w_split, scale, shift, gate, residual, out, M, N, K, rows_per_frame, act, passes, nullptr, st);
+}
+
+int launch_conv3x3_tcgen05(const float* x, const float* w_split, const float* scale, const float* shift, const float* residual,
+                           float* out, int B, int H, int W, int Cin, int N, int act, cudaStream_t st) {
+    if ((int64_t)B * H * W >= (1ll << 31) || W > 65535 || H > 65535) return ORBIT_ERR_UNSUPPORTED;
+    const Conv3Geom g{W, H, Cin};
+    return launch_tcgen05_impl(x, w_split, scale, shift, nullptr, residual, out, B * H * W, N, 9 * Cin, H * W, act, 3, &g, st);
 }
 
 }  // namespace orbit

@@ -15,6 +15,13 @@ int launch_pointwise_tcgen05(const float* A, const float* w_split, const float* 
                              const float* gate, const float* residual, float* out, int M, int N, int K,
                              int rows_per_frame, int act, int passes, cudaStream_t st);
 
+// Implicit-GEMM 3x3 convolution (stride 1, padding 1) on the same kernel: x [B,H,W,Cin] NHWC (Cin % 64 == 0), w_split = split of the
+// weights re-laid-out to [N][9*Cin] in (tap, channel) order (launch_conv_weight_relayout, nchw = 0). No im2col matrix: the TMA
+// producer walks the nine taps with row-shifted boxes of the activation, the transform warps zero what falls outside the image.
+// ORBIT_ERR_UNSUPPORTED when the shape / epilogue has no instance (callers fall back to im2col + launch_pointwise_tcgen05).
+int launch_conv3x3_tcgen05(const float* x, const float* w_split, const float* scale, const float* shift, const float* residual,
+                           float* out, int B, int H, int W, int Cin, int N, int act, cudaStream_t st);
+
 // Row-streaming variant for the small-K / small-N layers (csrc/gemm_stream.cu): same contract and numerics scheme (FP16x3);
 // returns ORBIT_ERR_UNSUPPORTED when it has no instance for the shape. launch_pointwise_tcgen05 tries it first (passes == 3).
 int launch_pointwise_stream(const float* A, const float* w_split, const float* scale, const float* shift, const float* gate,
