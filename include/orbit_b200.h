@@ -184,7 +184,10 @@ int orbit_depthwise_conv(const float* x, const float* weight, const float* scale
  *   x [B,H,W,Cin] NHWC; w_expand [C,Cin]; scale1/shift1 [C] folded bn1; w_dw [C,1,k,k]; scale2/shift2 [C] folded bn2;
  *   y [B,ceil(H/s),ceil(W/s),C]; partial: orbit_mbconv_partial_floats(...) floats (SE squeeze sums per block; nullable);
  *   weight_scratch: k*k*C floats.                                                                                    */
-int64_t orbit_mbconv_partial_floats(int B, int H, int W, int C, int k, int stride);
+int64_t orbit_mbconv_partial_floats(int B, int H, int W, int C, int k, int stride);   /* upper bound over Cin in {16, 24} */
+/* the partial sums are laid out [B][groups][C] with groups = orbit_mbconv_partial_groups(...) (depends on the kernel variant
+ * the shape selects: the register-resident 3x3 stride-2 kernel for 16 input channels writes one group per band of rows)      */
+int orbit_mbconv_partial_groups(int H, int W, int Cin, int C, int k, int stride);
 int orbit_mbconv_expand_dw(const float* x, const float* w_expand, const float* scale1, const float* shift1,
                            const float* w_dw, const float* scale2, const float* shift2, float* y, float* partial,
                            float* weight_scratch, int B, int H, int W, int Cin, int C, int k, int stride, void* stream);

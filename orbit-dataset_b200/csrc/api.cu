@@ -1,4 +1,5 @@
 // Library-level entry points of the C ABI (include/orbit_b200.h).
+#include <algorithm>
 #include <cstring>
 #include "convnet.cuh"
 #include "gemm_tcgen05.cuh"
@@ -75,6 +76,7 @@ extern "C" int orbit_set_global_option(const char* key, int value) {
     if (!strcmp(key, "tc_narrow")) { orbit::set_tcgen05_narrow(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "tc_stream")) { orbit::set_stream_gemm(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "dw5_staged")) { orbit::set_dw5_staged(value); return ORBIT_OK; }
+    if (!strcmp(key, "mbconv_stream")) { orbit::set_mbconv_stream(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "tc_fixed_slabs")) { orbit::set_tcgen05_tuning(value != 0, -1); return ORBIT_OK; }
     if (!strcmp(key, "tc_double_min_stages")) { orbit::set_tcgen05_tuning(-1, value); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
@@ -85,6 +87,7 @@ extern "C" int orbit_get_global_option(const char* key, int* value) {
     if (!strcmp(key, "tc_narrow")) { *value = orbit::get_tcgen05_narrow(); return ORBIT_OK; }
     if (!strcmp(key, "tc_stream")) { *value = orbit::get_stream_gemm(); return ORBIT_OK; }
     if (!strcmp(key, "dw5_staged")) { *value = orbit::get_dw5_staged(); return ORBIT_OK; }
+    if (!strcmp(key, "mbconv_stream")) { *value = orbit::get_mbconv_stream(); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 
@@ -100,10 +103,16 @@ extern "C" int64_t orbit_depthwise_partial_floats(int B, int H, int W, int C, in
     return (int64_t)B * orbit::dw_partial_groups(C, ho, wo, k, stride) * C;
 }
 
+extern "C" int orbit_mbconv_partial_groups(int H, int W, int Cin, int C, int k, int stride) {
+    int ho, wo, p;
+    same_geom(H, k, stride, &ho, &p); same_geom(W, k, stride, &wo, &p);
+    return orbit::mbx_partial_groups(Cin, C, ho, wo, k, stride);
+}
+
 extern "C" int64_t orbit_mbconv_partial_floats(int B, int H, int W, int C, int k, int stride) {
     int ho, wo, p;
     same_geom(H, k, stride, &ho, &p); same_geom(W, k, stride, &wo, &p);
-    return (int64_t)B * orbit::mbx_partial_groups(C, ho, wo, k, stride) * C;
+    return (int64_t)B * std::max(orbit::mbx_partial_groups(16, C, ho, wo, k, stride), orbit::mbx_partial_groups(24, C, ho, wo, k, stride)) * C;
 }
 
 extern "C" int orbit_mbconv_expand_dw(const float* x, const float* w_expand, const float* scale1, const float* shift1,

@@ -1011,11 +1011,17 @@ bool mbx_fits(int Cin, int C, int Ho, int Wo, int k, int stride) {
     const MbxPlan pl = mbx_plan(Cin, C, Ho, Wo, k, stride);
     return pl.smem <= 100 * 1024 && (size_t)pl.P * Cin / 4 <= (size_t)3 * pl.threads && (pl.LX / 4 + 1) / 2 <= pl.threads / 32 && pl.threads <= 192;
 }
-int mbx_partial_groups(int C, int Ho, int Wo, int k, int stride) { return mbx_plan(16, C, Ho, Wo, k, stride).groups; }
+int mbx_partial_groups(int Cin, int C, int Ho, int Wo, int k, int stride) {
+    if (stride == 2 && mbs_supported(Cin, C, 2 * Ho, 2 * Wo, k, stride)) return mbs_partial_groups(Ho);   // register-resident variant
+    return mbx_plan(16, C, Ho, Wo, k, stride).groups;
+}
 
 int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scale1, const float* shift1, const float* wt,
                             const float* scale, const float* shift, float* y, float* partial, int B, int H, int W, int Cin,
                             int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, cudaStream_t st) {
+    // 3x3 stride-2 block with 16 input channels on an even size (TF-SAME: no padding above / left): register-resident variant
+    if (pad_t == 0 && pad_l == 0 && H == 2 * Ho && W == 2 * Wo && mbs_supported(Cin, C, H, W, k, stride))
+        return launch_mbconv_stream(xin, we, scale1, shift1, wt, scale, shift, y, partial, B, H, W, Cin, C, st);
     if (!mbx_fits(Cin, C, Ho, Wo, k, stride)) return ORBIT_ERR_UNSUPPORTED;
     const MbxPlan pl = mbx_plan(Cin, C, Ho, Wo, k, stride);
     dim3 grid(pl.groups, pl.nchunks, B), block(pl.threads);

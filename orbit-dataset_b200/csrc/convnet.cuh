@@ -52,7 +52,15 @@ int get_dw5_staged();
 // wt = depthwise taps [k*k][C], scale/shift = folded bn2. partial as launch_depthwise with mbx_partial_groups(...).
 bool mbx_supported(int cin, int k, int stride);
 bool mbx_fits(int Cin, int C, int Ho, int Wo, int k, int stride);
-int mbx_partial_groups(int C, int Ho, int Wo, int k, int stride);
+int mbx_partial_groups(int Cin, int C, int Ho, int Wo, int k, int stride);
+// register-resident variant for the 3x3 stride-2 block with 16 input channels (csrc/mbconv_stream.cu); dev A/B switch "mbconv_stream"
+bool mbs_supported(int Cin, int C, int H, int W, int k, int stride);
+int mbs_partial_groups(int Ho);
+int launch_mbconv_stream(const float* xin, const float* we, const float* scale1, const float* shift1, const float* wt,
+                         const float* scale, const float* shift, float* y, float* partial, int B, int H, int W, int Cin, int C,
+                         cudaStream_t st);
+void set_mbconv_stream(int on);
+int get_mbconv_stream();
 int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scale1, const float* shift1, const float* wt,
                             const float* scale, const float* shift, float* y, float* partial, int B, int H, int W, int Cin,
                             int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l, cudaStream_t st);

@@ -470,7 +470,7 @@ static int plan_buffers(const orbit_engine* e, int H, int W, BufSizes* bs) {
                 if (op.kind == OP_DW) {
                     need(BUF_PARTIAL, (int64_t)dw_partial_groups(op.cout, h, w, op.k, op.stride) * op.cout);
                     if (op.cout % 2 == 0 && (op.k == 3 || op.k == 5))     // the fused expand + depthwise kernel tiles differently
-                        need(BUF_PARTIAL, (int64_t)mbx_partial_groups(op.cout, h, w, op.k, op.stride) * op.cout);
+                        need(BUF_PARTIAL, (int64_t)std::max(mbx_partial_groups(16, op.cout, h, w, op.k, op.stride), mbx_partial_groups(24, op.cout, h, w, op.k, op.stride)) * op.cout);
                 }
                 break;
             }
@@ -745,7 +745,7 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                                              buf[BUF_PARTIAL], B, h, w, op.cin, op.cout, ho, wo, dw.k, dw.stride, pt, pl, st);
                 if (rc) return rc;
                 ++launches;
-                se_tiles = mbx_partial_groups(op.cout, ho, wo, dw.k, dw.stride); se_hw = ho * wo;
+                se_tiles = mbx_partial_groups(op.cin, op.cout, ho, wo, dw.k, dw.stride); se_hw = ho * wo;
                 if (e->profile)
                     e->prof_recs.push_back({(int)OP_DW, 4.0 * B * ((double)h * w * op.cin + (double)ho * wo * dw.cout + (double)se_tiles * dw.cout),
                                             2.0 * B * ((double)h * w * op.cin * op.cout + (double)dw.k * dw.k * dw.cout * ho * wo)});

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "orbit_depthwise_partial_floats": (_i64, [_i, _i, _i, _i, _i, _i]),
     "orbit_depthwise_conv": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "orbit_mbconv_partial_floats": (_i64, [_i, _i, _i, _i, _i, _i]),
+    "orbit_mbconv_partial_groups": (_i, [_i, _i, _i, _i, _i, _i]),
     "orbit_mbconv_expand_dw": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "orbit_engine_create": (_i, [C.POINTER(_p), _i]),
     "orbit_engine_destroy": (None, [_p]),
