@@ -16,7 +16,7 @@ for r in rows[1:]:
         v *= {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
     d[r[im]] = v
 def short(n):
-    m = re.match(r'(?:void )?(?:orbit::)?(?:tc::|st::)?([A-Za-z0-9_]+)', n)
+    m = re.match(r'(?:void )?(?:orbit::)?(?:tc::|st::|mbs::)?([A-Za-z0-9_]+)', n)
     base = m.group(1) if m else n
     t = re.search(r'<(.*)>', n)
     return base + ('<' + t.group(1).replace('(int)', '').replace('(bool)', '').replace(' ', '') + '>' if t else '')
@@ -30,7 +30,7 @@ with open(f'{ROOT}/profiles/{tag}_launches_summary.csv', 'w') as f:
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['us']):
         f.write(f"\"{k}\",{a['launches']},{a['us']:.1f},{100*a['us']/tot:.2f},{a['us']/a['launches']:.1f},{a['rd']/1e9:.3f},{a['wr']/1e9:.3f},"
                 f"{(a['rd']+a['wr'])/max(a['us'],1e-9)/1e3:.0f}\n")
-fam = {'pointwise_gemm': 'pw_tcgen05|pw_stream', 'depthwise_conv': 'dw2_kernel|dw5s_kernel|mbx_kernel', 'stem_conv': 'stem_kernel', 'se_gate': 'se_gate', 'spatial_mean': 'spatial_mean'}
+fam = {'pointwise_gemm': 'pw_tcgen05|pw_stream', 'depthwise_conv': 'dw2_kernel|dw5s_kernel|mbx_kernel|mbs_kernel', 'stem_conv': 'stem_kernel', 'se_gate': 'se_gate', 'spatial_mean': 'spatial_mean'}
 # the TIMED episode only: the bench command runs calibration, 3 warm-up episodes, then ONE timed episode = the launches
 # from the second-to-last stem_kernel (support pass; the last one is the query pass) to the end of the process
 order = list(launch.values())
