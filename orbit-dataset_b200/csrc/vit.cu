@@ -102,55 +102,103 @@ int launch_layernorm(const float* x, int64_t row_stride, const float* gamma, con
     return ORBIT_OK;
 }
 
-// One block per (frame, head): Q, K, V tiles [T, dh] in shared memory (K padded against bank conflicts),
-// scores [T, T], row softmax by warps, then O = P V. T = 50, dh = 64 for ViT-*/32 at 224 px.
+// One block per (frame, head): Q, K, V tiles [T, dh] in shared memory, scores [T, T], row softmax by warps, then O = P V.
+// T = 50, dh = 64 for ViT-*/32 at 224 px. Both products are register-tiled 4 x 4 per thread with 128-bit shared-memory loads
+// (the first version did two scalar LDS per FMA and was bound by shared-memory bandwidth: 0.3 ms per layer for 240 frames).
 __global__ void __launch_bounds__(256)
 attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int heads, int dh) {
-    extern __shared__ float s_att[];
-    const int D = heads * dh, ld = dh + 1;
-    float* s_q = s_att;                 // [T][ld]
-    float* s_k = s_q + T * ld;          // [T][ld]
-    float* s_v = s_k + T * ld;          // [T][ld]
-    float* s_p = s_v + T * ld;          // [T][T]
+    extern __shared__ __align__(16) float s_att[];
+    const int D = heads * dh, ld = dh + 4;          // rows stay 16-byte aligned; +4 floats: consecutive rows start 4 banks apart
+    const int Tp = (T + 3) & ~3;                    // rows / columns padded to whole 4 x 4 tiles (zero-filled)
+    float* s_q = s_att;                 // [Tp][ld]
+    float* s_k = s_q + Tp * ld;         // [Tp][ld]
+    float* s_v = s_k + Tp * ld;         // [Tp][ld]
+    float* s_p = s_v + Tp * ld;         // [Tp][Tp]
     const int b = blockIdx.x / heads, h = blockIdx.x % heads;
     const float* base = qkv + (int64_t)b * T * 3 * D + h * dh;
-    for (int i = threadIdx.x; i < T * dh; i += blockDim.x) {
-        const int t = i / dh, d = i % dh;
-        const float* p = base + (int64_t)t * 3 * D + d;
-        s_q[t * ld + d] = p[0];
-        s_k[t * ld + d] = p[D];
-        s_v[t * ld + d] = p[2 * D];
+    const int dh4 = dh >> 2;
+    for (int i = threadIdx.x; i < Tp * dh4; i += blockDim.x) {
+        const int t = i / dh4, d = (i % dh4) * 4;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q;
+        if (t < T) {
+            const float* p = base + (int64_t)t * 3 * D + d;
+            q = ldg4(p); k = ldg4(p + D); v = ldg4(p + 2 * D);
+        }
+        *reinterpret_cast<float4*>(s_q + t * ld + d) = q;
+        *reinterpret_cast<float4*>(s_k + t * ld + d) = k;
+        *reinterpret_cast<float4*>(s_v + t * ld + d) = v;
     }
     __syncthreads();
     const float scale = 1.0f / sqrtf((float)dh);
-    for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-        const int r = i / T, c = i % T;
-        float s = 0.f;
-        for (int d = 0; d < dh; ++d) s = fmaf(s_q[r * ld + d], s_k[c * ld + d], s);
-        s_p[i] = s * scale;
+    const int nt = Tp >> 2;
+    for (int tile = threadIdx.x; tile < nt * nt; tile += blockDim.x) {       // S = scale Q K^T, 4 x 4 tile per thread
+        const int r0 = (tile / nt) * 4, c0 = (tile % nt) * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int d = 0; d < dh; d += 4) {
+            float4 q[4], k[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                q[i] = *reinterpret_cast<const float4*>(s_q + (r0 + i) * ld + d);
+                k[i] = *reinterpret_cast<const float4*>(s_k + (c0 + i) * ld + d);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j] = fmaf(q[i].x, k[j].x, acc[i][j]); acc[i][j] = fmaf(q[i].y, k[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(q[i].z, k[j].z, acc[i][j]); acc[i][j] = fmaf(q[i].w, k[j].w, acc[i][j]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(s_p + (r0 + i) * Tp + c0) = make_float4(acc[i][0] * scale, acc[i][1] * scale, acc[i][2] * scale, acc[i][3] * scale);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (int r = warp; r < T; r += n_warps) {
         float m = -INFINITY;
-        for (int c = lane; c < T; c += 32) m = fmaxf(m, s_p[r * T + c]);
+        for (int c = lane; c < T; c += 32) m = fmaxf(m, s_p[r * Tp + c]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         float z = 0.f;
-        for (int c = lane; c < T; c += 32) { const float e = expf(s_p[r * T + c] - m); s_p[r * T + c] = e; z += e; }
+        for (int c = lane; c < T; c += 32) { const float e = expf(s_p[r * Tp + c] - m); s_p[r * Tp + c] = e; z += e; }
         z = warp_sum(z);
-        for (int c = lane; c < T; c += 32) s_p[r * T + c] /= z;
+        for (int c = lane; c < Tp; c += 32) s_p[r * Tp + c] = c < T ? s_p[r * Tp + c] / z : 0.f;     // padded columns: exact zeros
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < T * dh; i += blockDim.x) {
-        const int t = i / dh, d = i % dh;
-        float s = 0.f;
-        for (int c = 0; c < T; ++c) s = fmaf(s_p[t * T + c], s_v[c * ld + d], s);
-        out[((int64_t)b * T + t) * D + h * dh + d] = s;
+    for (int tile = threadIdx.x; tile < nt * dh4; tile += blockDim.x) {      // O = P V, 4 rows x 4 channels per thread
+        const int r0 = (tile / dh4) * 4, d0 = (tile % dh4) * 4;
+        float4 acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < Tp; c += 4) {
+            float4 p[4], v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                p[i] = *reinterpret_cast<const float4*>(s_p + (r0 + i) * Tp + c);
+                v[i] = *reinterpret_cast<const float4*>(s_v + (c + i) * ld + d0);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i].x = fmaf(p[i].x, v[0].x, acc[i].x); acc[i].y = fmaf(p[i].x, v[0].y, acc[i].y); acc[i].z = fmaf(p[i].x, v[0].z, acc[i].z); acc[i].w = fmaf(p[i].x, v[0].w, acc[i].w);
+                acc[i].x = fmaf(p[i].y, v[1].x, acc[i].x); acc[i].y = fmaf(p[i].y, v[1].y, acc[i].y); acc[i].z = fmaf(p[i].y, v[1].z, acc[i].z); acc[i].w = fmaf(p[i].y, v[1].w, acc[i].w);
+                acc[i].x = fmaf(p[i].z, v[2].x, acc[i].x); acc[i].y = fmaf(p[i].z, v[2].y, acc[i].y); acc[i].z = fmaf(p[i].z, v[2].z, acc[i].z); acc[i].w = fmaf(p[i].z, v[2].w, acc[i].w);
+                acc[i].x = fmaf(p[i].w, v[3].x, acc[i].x); acc[i].y = fmaf(p[i].w, v[3].y, acc[i].y); acc[i].z = fmaf(p[i].w, v[3].z, acc[i].z); acc[i].w = fmaf(p[i].w, v[3].w, acc[i].w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (r0 + i < T) *reinterpret_cast<float4*>(out + ((int64_t)b * T + r0 + i) * D + h * dh + d0) = acc[i];
     }
 }
 int launch_attention(const float* qkv, float* out, int B, int T, int heads, int dh, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)3 * T * (dh + 1) + (size_t)T * T);
+    if (dh % 4 || (heads * dh) % 4) return ORBIT_ERR_UNSUPPORTED;
+    const int Tp = (T + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)3 * Tp * (dh + 4) + (size_t)Tp * Tp);
     if (smem > 200 * 1024) return ORBIT_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) ORBIT_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (B <= 0) return ORBIT_OK;
