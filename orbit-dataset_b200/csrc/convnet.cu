@@ -1452,9 +1452,40 @@ spatial_mean_kernel(const float* __restrict__ x, float* __restrict__ y, int B, i
     *reinterpret_cast<float4*>(y + (int64_t)b * C + q * 4) = make_float4(s.x / d, s.y / d, s.z / d, s.w / d);
 }
 
+// The same mean with the rows of a frame split over the 8 warps of a block (fixed-order reduction: deterministic): for large
+// HW and few frames (training passes keep the squeeze means of every depthwise layer) the one-thread-per-column kernel above
+// is a serial chain of HW loads on a handful of warps. grid (B, ceil(C / 128)); lane = 4 channels, warp = a slice of the rows.
+__global__ void __launch_bounds__(256)
+spatial_mean_split_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C) {
+    __shared__ float4 s_part[8][32];
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5, b = blockIdx.x;
+    const int c0 = blockIdx.y * 128 + lane * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 < C) {
+        const float* p = x + (int64_t)b * HW * C + c0;
+        const int per = (HW + 7) >> 3, r0 = rg * per, r1 = min(HW, r0 + per);
+        for (int r = r0; r < r1; ++r) add4(s, ldg4_stream(p + (int64_t)r * C));
+    }
+    s_part[rg][lane] = s;
+    __syncthreads();
+    if (rg == 0 && c0 < C) {
+        float4 t = s_part[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) add4(t, s_part[k][lane]);
+        const float d = (float)HW;
+        *reinterpret_cast<float4*>(y + (int64_t)b * C + c0) = make_float4(t.x / d, t.y / d, t.z / d, t.w / d);
+    }
+}
+
 int launch_spatial_mean(const float* x, float* y, int B, int HW, int C, cudaStream_t st) {
     if (C % 4) return ORBIT_ERR_UNSUPPORTED;
-    spatial_mean_kernel<<<(unsigned)ceil_div64((int64_t)B * (C / 4), 256), 256, 0, st>>>(x, y, B, HW, C);
+    if (B <= 0) return ORBIT_OK;
+    // enough columns to fill the GPU with the simple kernel (the 7x7x1280 pool of an inference pass), else split the rows
+    if ((int64_t)B * (C / 4) >= 148 * 256 * 4 || HW < 64) {
+        spatial_mean_kernel<<<(unsigned)ceil_div64((int64_t)B * (C / 4), 256), 256, 0, st>>>(x, y, B, HW, C);
+    } else {
+        spatial_mean_split_kernel<<<dim3(B, ceil_div(C, 128)), 256, 0, st>>>(x, y, HW, C);
+    }
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }
