@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liborbit_b200.so")
 SOURCES = ["api.cu", "head.cu", "convnet.cu", "engine.cu", "gemm_tcgen05.cu", "gemm_stream.cu", "finetune.cu", "adapters.cu", "vit.cu", "mahalanobis.cu",
-           "evaluator.cu", "train.cu", "train_setenc.cu", "mbconv_stream.cu"]
+           "evaluator.cu", "train.cu", "train_setenc.cu", "mbconv_stream.cu", "conv_first.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -77,6 +77,7 @@ extern "C" int orbit_set_global_option(const char* key, int value) {
     if (!strcmp(key, "tc_stream")) { orbit::set_stream_gemm(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "dw5_staged")) { orbit::set_dw5_staged(value); return ORBIT_OK; }
     if (!strcmp(key, "mbconv_stream")) { orbit::set_mbconv_stream(value != 0); return ORBIT_OK; }
+    if (!strcmp(key, "conv_first")) { orbit::set_conv_first(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "tc_fixed_slabs")) { orbit::set_tcgen05_tuning(value != 0, -1); return ORBIT_OK; }
     if (!strcmp(key, "tc_double_min_stages")) { orbit::set_tcgen05_tuning(-1, value); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
@@ -88,6 +89,7 @@ extern "C" int orbit_get_global_option(const char* key, int* value) {
     if (!strcmp(key, "tc_stream")) { *value = orbit::get_stream_gemm(); return ORBIT_OK; }
     if (!strcmp(key, "dw5_staged")) { *value = orbit::get_dw5_staged(); return ORBIT_OK; }
     if (!strcmp(key, "mbconv_stream")) { *value = orbit::get_mbconv_stream(); return ORBIT_OK; }
+    if (!strcmp(key, "conv_first")) { *value = orbit::get_conv_first(); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }
 

@@ -86,6 +86,14 @@ int launch_conv_weight_relayout(const float* w, float* out, int Cout, int Cin, i
 int launch_maxpool(const float* x, float* y, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
                    cudaStream_t st);
 
+// first convolution on 3-channel NCHW frames (3x3 stride 1 pad 1, 7x7 stride 2 pad 3; 64 output channels) as a direct tensor-core
+// convolution (csrc/conv_first.cu): x [B,3,H,W] -> y [B,Ho,Wo,64] NHWC, w in torch layout [64,3,k,k]; act ACT_NONE / ACT_RELU.
+// ORBIT_ERR_UNSUPPORTED for other geometries (callers fall back to im2col + GEMM). dev A/B switch "conv_first".
+int launch_conv_first(const float* x, const float* w, const float* scale, const float* shift, float* y, int B, int H, int W, int Cin,
+                      int Cout, int k, int stride, int pad, int Ho, int Wo, int act, cudaStream_t st);
+void set_conv_first(int on);
+int get_conv_first();
+
 // spatial mean: x [B,HW,C] -> y [B,C]
 int launch_spatial_mean(const float* x, float* y, int B, int HW, int C, cudaStream_t st);
 

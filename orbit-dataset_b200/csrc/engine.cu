@@ -847,6 +847,17 @@ static int run_plan(const orbit_engine* e, const float* params, float* calib, fl
                                 break;
                             }
                         }
+                        // first convolution on the 3-channel NCHW frames (resnet conv1, set-encoder layer 1): direct tensor-core conv
+                        if (e->implicit_conv && e->gemm_mode == 1 && !raw && op.nchw_in && cpt == cpl && op.res == BUF_NONE) {
+                            rc = launch_conv_first(ptr(op.in), params + op.w, scale, shift, ptr(op.out), B, h, w, op.cin, op.cout, op.k,
+                                                   op.stride, cpt, cho, cwo, act, st);
+                            if (rc != ORBIT_ERR_UNSUPPORTED) {
+                                p_bytes = 4.0 * ((double)B * op.cin * h * w + (double)M * op.cout);
+                                p_flops = 2.0 * M * (double)op.k * op.k * op.cin * op.cout;
+                                if (op.out != BUF_D) { ho = cho; wo = cwo; }
+                                break;
+                            }
+                        }
                         rc = launch_im2col(ptr(op.in), buf[BUF_COL], B, h, w, op.cin, op.k, op.stride, cpt, cpl, cho, cwo, op.kpad,
                                            op.nchw_in, st);
                         if (rc) return rc;
@@ -1140,6 +1151,8 @@ extern "C" int orbit_engine_forward_train(const orbit_engine* e, const float* pa
                 rc = ORBIT_ERR_UNSUPPORTED;
                 if (e->implicit_conv && !op.nchw_in && op.cin % 64 == 0)      // layers 2-5: implicit GEMM, no im2col matrix
                     rc = launch_conv3x3_tcgen05(in, derived + op.w_split, ones, zeros, nullptr, c, B, h, w, op.cin, op.cout, ACT_NONE, st);
+                else if (e->implicit_conv && op.nchw_in)                      // layer 1: direct convolution on the frames
+                    rc = launch_conv_first(in, params + op.w, ones, zeros, c, B, h, w, op.cin, op.cout, 3, 1, 1, h, w, ACT_NONE, st);
                 if (rc == ORBIT_ERR_UNSUPPORTED) {
                     rc = launch_im2col(in, buf[BUF_COL], B, h, w, op.cin, 3, 1, 1, 1, h, w, op.kpad, op.nchw_in, st);
                     if (rc) return rc;

@@ -29,3 +29,7 @@ for k, e in engines.items():
     prof = e.profile_read(); e.set_option('profile', 0)
     tot = sum(p['ms'] for p in prof.values())
     print(k, f"total {tot:.2f} ms", {f: (round(p['ms'], 2), p['launches'], round(p['flops'] / max(p['ms'], 1e-9) / 1e9, 1)) for f, p in prof.items() if p['launches']})
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    step(); torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70))
