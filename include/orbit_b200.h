@@ -167,6 +167,13 @@ int orbit_conv3x3(const float* x, const float* weight, const float* scale, const
                   float* out, int B, int H, int W, int Cin, int Cout, int act, int implicit, float* scratch,
                   int64_t scratch_floats, void* stream);
 
+/* First convolution on the 3-channel NCHW frames, 64 output channels, folded BatchNorm scale-shift (+ ReLU: act 2) fused, NHWC
+ * output [B,Ho,Wo,64]: SimplePrePoolNet.layer1 of the set encoder (k 3, stride 1, pad 1; model/set_encoders.py:91-105) and conv1 of
+ * the resnet18 extension (k 7, stride 2, pad 3). Direct tensor-core convolution, no im2col matrix. weight [64,3,k,k] (torch).
+ * Other geometries: ORBIT_ERR_UNSUPPORTED.                                                                                  */
+int orbit_conv_first(const float* x, const float* weight, const float* scale, const float* shift, float* y, int B, int H,
+                     int W, int k, int stride, int pad, int act, void* stream);
+
 /* Depthwise k x k convolution (k in {3,5}, stride in {1,2}, TF "SAME" padding) on NHWC activations with the folded
  * BatchNorm/FiLM scale-shift and activation fused: timm conv_dw + BatchNormAct2d of every MBConv block.
  *   x [B,H,W,C] -> y [B,ceil(H/s),ceil(W/s),C]; weight [C,1,k,k] (torch layout); weight_scratch: k*k*C floats.

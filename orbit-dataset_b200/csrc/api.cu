@@ -63,6 +63,15 @@ extern "C" int orbit_conv3x3(const float* x, const float* weight, const float* s
     return launch_pointwise_tcgen05(col, w_split, scale, shift, nullptr, residual, out, B * H * W, Cout, K, H * W, act, 3, st);
 }
 
+extern "C" int orbit_conv_first(const float* x, const float* weight, const float* scale, const float* shift, float* y, int B, int H,
+                                int W, int k, int stride, int pad, int act, void* stream) {
+    using namespace orbit;
+    if (!x || !weight || !scale || !shift || !y || B < 0 || H <= 0 || W <= 0) return ORBIT_ERR_ARG;
+    const int ho = (H + 2 * pad - k) / stride + 1, wo = (W + 2 * pad - k) / stride + 1;
+    if (ho < 1 || wo < 1) return ORBIT_ERR_ARG;
+    return launch_conv_first(x, weight, scale, shift, y, B, H, W, 3, 64, k, stride, pad, ho, wo, act, (cudaStream_t)stream);
+}
+
 extern "C" int64_t orbit_conv3x3_scratch_floats(int B, int H, int W, int Cin, int Cout, int implicit) {
     const int64_t K = 9 * (int64_t)Cin;
     return 3 * (int64_t)Cout * K + 16 + (implicit ? 0 : (int64_t)B * H * W * K);

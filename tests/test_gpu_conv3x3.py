@@ -54,3 +54,26 @@ def test_conv3x3_implicit_matches_torch(cuda_device, B, H, W, Cin, Cout, act, re
     explicit = _run(xd, wd, sc, sh, rd, act, 0).permute(0, 3, 1, 2).cpu().double()
     assert (explicit - ref).abs().max().item() <= tol
     assert (got - explicit).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,W,k,stride,pad,act", [(3, 224, 224, 3, 1, 1, 2), (2, 224, 224, 7, 2, 3, 2), (5, 84, 84, 7, 2, 3, 2),
+                                                    (4, 64, 64, 3, 1, 1, 0), (3, 37, 53, 3, 1, 1, 2), (2, 45, 31, 7, 2, 3, 0)])
+def test_conv_first_matches_torch(cuda_device, B, H, W, k, stride, pad, act):
+    """the direct first convolution on 3-channel NCHW frames (C ABI orbit_conv_first) against torch conv2d in float64"""
+    from orbit_b200 import lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(H + W + k)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, k, k, generator=g) * (3 * k * k) ** -0.5
+    scale, shift = 1 + 0.1 * torch.randn(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    ref = F.conv2d(x.double(), w.double(), None, stride, pad) * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]
+    if act == 2:
+        ref = ref.relu()
+    Ho, Wo = ref.shape[-2:]
+    y = torch.full((B, Ho, Wo, 64), float('nan'), device=cuda_device)
+    keep = [t.to(cuda_device) for t in (x, w, scale, shift)]
+    L.check(lib.orbit_conv_first(*(L.ptr(t) for t in keep), L.ptr(y), B, H, W, k, stride, pad, act, L.stream_ptr(cuda_device)),
+            "orbit_conv_first")
+    torch.cuda.synchronize()
+    got = y.permute(0, 3, 1, 2).cpu().double()
+    assert (got - ref).abs().max().item() <= 3e-6 * max(1.0, ref.abs().max().item())
