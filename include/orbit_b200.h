@@ -174,6 +174,14 @@ int orbit_conv3x3(const float* x, const float* weight, const float* scale, const
 int orbit_conv_first(const float* x, const float* weight, const float* scale, const float* shift, float* y, int B, int H,
                      int W, int k, int stride, int pad, int act, void* stream);
 
+/* Squeeze-excite gate of one MBConv block: timm SqueezeExcite (conv_reduce + SiLU + conv_expand + sigmoid on the spatial mean),
+ * inside the extractor invoked at model/few_shot_recognisers.py:114-117,143-146.
+ *   partial [B][groups][C]: per-group channel sums of the depthwise output (orbit_depthwise_conv), hw = pixels per frame;
+ *   w1 [R,C] (conv_reduce.weight), b1 [R], w2t [R,C] (conv_expand.weight TRANSPOSED), b2 [C]  ->  gate [B,C] in (0,1).
+ * The weight matrices stream through shared memory (cp.async.bulk ring) when C % 4 == 0 and every tensor is 16-byte aligned.  */
+int orbit_se_gate(const float* partial, int groups, int hw, const float* w1, const float* b1, const float* w2t, const float* b2,
+                  float* gate, int B, int C, int R, void* stream);
+
 /* Depthwise k x k convolution (k in {3,5}, stride in {1,2}, TF "SAME" padding) on NHWC activations with the folded
  * BatchNorm/FiLM scale-shift and activation fused: timm conv_dw + BatchNormAct2d of every MBConv block.
  *   x [B,H,W,C] -> y [B,ceil(H/s),ceil(W/s),C]; weight [C,1,k,k] (torch layout); weight_scratch: k*k*C floats.

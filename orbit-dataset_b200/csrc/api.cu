@@ -63,6 +63,13 @@ extern "C" int orbit_conv3x3(const float* x, const float* weight, const float* s
     return launch_pointwise_tcgen05(col, w_split, scale, shift, nullptr, residual, out, B * H * W, Cout, K, H * W, act, 3, st);
 }
 
+extern "C" int orbit_se_gate(const float* partial, int groups, int hw, const float* w1, const float* b1, const float* w2t,
+                             const float* b2, float* gate, int B, int C, int R, void* stream) {
+    using namespace orbit;
+    if (!partial || !w1 || !b1 || !w2t || !b2 || !gate || B < 0 || C <= 0 || R <= 0 || groups <= 0 || hw <= 0) return ORBIT_ERR_ARG;
+    return launch_se_gate(partial, groups, hw, w1, b1, w2t, b2, gate, B, C, R, (cudaStream_t)stream);
+}
+
 extern "C" int orbit_conv_first(const float* x, const float* weight, const float* scale, const float* shift, float* y, int B, int H,
                                 int W, int k, int stride, int pad, int act, void* stream) {
     using namespace orbit;
@@ -86,6 +93,7 @@ extern "C" int orbit_set_global_option(const char* key, int value) {
     if (!strcmp(key, "tc_stream")) { orbit::set_stream_gemm(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "dw5_staged")) { orbit::set_dw5_staged(value); return ORBIT_OK; }
     if (!strcmp(key, "mbconv_stream")) { orbit::set_mbconv_stream(value != 0); return ORBIT_OK; }
+    if (!strcmp(key, "se_ring")) { orbit::set_se_ring(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "conv_first")) { orbit::set_conv_first(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "tc_fixed_slabs")) { orbit::set_tcgen05_tuning(value != 0, -1); return ORBIT_OK; }
     if (!strcmp(key, "tc_double_min_stages")) { orbit::set_tcgen05_tuning(-1, value); return ORBIT_OK; }
@@ -98,6 +106,7 @@ extern "C" int orbit_get_global_option(const char* key, int* value) {
     if (!strcmp(key, "tc_stream")) { *value = orbit::get_stream_gemm(); return ORBIT_OK; }
     if (!strcmp(key, "dw5_staged")) { *value = orbit::get_dw5_staged(); return ORBIT_OK; }
     if (!strcmp(key, "mbconv_stream")) { *value = orbit::get_mbconv_stream(); return ORBIT_OK; }
+    if (!strcmp(key, "se_ring")) { *value = orbit::get_se_ring(); return ORBIT_OK; }
     if (!strcmp(key, "conv_first")) { *value = orbit::get_conv_first(); return ORBIT_OK; }
     return ORBIT_ERR_UNSUPPORTED;
 }

@@ -1043,18 +1043,25 @@ int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scal
 }
 
 // ------------------------------------------------------------------------------------------------
-// Squeeze-excite gate. One block handles kSeFrames frames so that the two FC weight matrices (up to 2 x 221 KB in
-// EfficientNet-B0) are fetched once per 8 frames instead of once per frame (round 1: one block per frame, 39 us per
-// launch, all of it L2 traffic for the weights), with 1024 threads and deeply unrolled independent weight loads:
-// the kernel is a chain of L2 latencies, so what matters is how many loads each SM keeps in flight.
-// Per-frame arithmetic order is unchanged.
+// Squeeze-excite gate: mean over the depthwise kernel's per-group sums -> FC (C -> R) + SiLU -> FC (R -> C) + sigmoid.
+// Reference op site: timm SqueezeExcite inside the extractor invoked at model/few_shot_recognisers.py:114-117,143-146.
+//
+// The arithmetic is tiny (2 C R MACs per frame); what the launch costs is fetching the two weight matrices (up to
+// 2 x 221 KB) from L2. se_gate_kernel streams them through a shared-memory ring with cp.async.bulk (one elected thread
+// issues, mbarrier completion): kSeSlots chunks of whole rows are in flight from the first instruction, under the mean
+// phase and under the arithmetic of the previous chunk, and no register holds a load in flight. (r02c: per-thread
+// __ldg loads in unrolled batches were a chain of ~18 dependent L2 round trips per block, 42 us per wave at C = 1152.)
+// A block handles F = ceil(B / SMs) frames (<= 12) so that the whole launch is ONE wave and the weights are fetched once
+// per F frames; per-frame arithmetic order: means and the second FC as before (sequential over groups / over r), the
+// first FC sums 4-channel groups per lane before the warp tree.
+// se_gate_simple_kernel is the plain version for shapes the ring cannot take (C % 4 != 0, unaligned tensors).
 // ------------------------------------------------------------------------------------------------
 constexpr int kSeFrames = 8;
 
 __global__ void __launch_bounds__(1024)
-se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const float* __restrict__ w1,
-               const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
-               float* __restrict__ gate, int B, int C, int R, int F) {
+se_gate_simple_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const float* __restrict__ w1,
+                      const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
+                      float* __restrict__ gate, int B, int C, int R, int F) {
     extern __shared__ float s_se[];  // mean[F][C], hidden[F][R]
     float* s_mean = s_se;
     float* s_hid = s_se + F * C;
@@ -1108,13 +1115,190 @@ se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const
     }
 }
 
+namespace seg {
+constexpr int kMaxThreads = 1024, kSlots = 2, kChunkBytes = 72 * 1024, kMaxFrames = 12, kMaxSmem = 220 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {      // bounded: a protocol bug traps, never hangs
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        if (spin > 400000u) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float dot4(const float4& w, const float4& m, float s) {
+    return fmaf(w.w, m.w, fmaf(w.z, m.z, fmaf(w.y, m.y, fmaf(w.x, m.x, s))));
+}
+
+// shared memory: ring [kSlots][rows_per_chunk * C] | mean [FR][C] | hidden [FR][Rp] | mbarriers [kSlots]
+// chunk k < nch: rows k * rows_per_chunk .. of w1 [R][C];  chunk nch + k: the same rows of w2t [R][C].
+// FR = frames per block rounded up to a compile-time size: the rows of frames the block does not have are zeros, so that
+// the hot loops carry no per-frame branch (with one, every frame's shared-memory load waited for the previous frame's FMAs).
+// FR = 12 runs 640 threads (2 x 12 + 2 x 12 accumulators want ~100 registers), the smaller sizes up to 1024.
+constexpr int max_threads(int fr) { return fr > 8 ? 640 : kMaxThreads; }
+
+template <int FR>
+__global__ void __launch_bounds__(max_threads(FR), 1)
+se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw, const float* __restrict__ w1,
+               const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
+               float* __restrict__ gate, int B, int C, int R, int F, int rows_per_chunk) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    const int chunk_floats = rows_per_chunk * C, Rp = (R + 3) & ~3, C4 = C >> 2, C2 = C >> 1;
+    float* ring = reinterpret_cast<float*>(s_raw);
+    float* s_mean = ring + kSlots * chunk_floats;
+    float* s_hid = s_mean + FR * C;
+    const uint32_t bars = smem_u32(s_hid + FR * Rp);
+    const int nch = ceil_div(R, rows_per_chunk), NC = 2 * nch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const int f0 = blockIdx.x * F, nf = min(F, B - f0);
+    auto issue = [&](int k) {
+        const int second = k >= nch, r0 = (k - second * nch) * rows_per_chunk, rows = min(rows_per_chunk, R - r0);
+        const uint32_t bytes = (uint32_t)(rows * C) * 4u, bar = bars + 8u * (uint32_t)(k % kSlots);
+        mbar_expect_tx(bar, bytes);
+        bulk_load(smem_u32(ring + (k % kSlots) * chunk_floats), (second ? w2t : w1) + (int64_t)r0 * C, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kSlots; ++s) mbar_init(bars + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int k = 0; k < min(NC, kSlots); ++k) issue(k);
+    }
+    for (int i = tid; i < FR * Rp; i += nthreads) s_hid[i] = 0.f;      // the padding columns are read (times zero weights)
+    for (int i = tid; i < FR * C4; i += nthreads) {                     // spatial means; zeros for the frames beyond nf
+        const int f = i / C4, c4 = i - f * C4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < nf) {
+            const float4* pb = reinterpret_cast<const float4*>(partial + (int64_t)(f0 + f) * tiles * C) + c4;
+#pragma unroll 4
+            for (int t = 0; t < tiles; ++t) {
+                const float4 v = __ldg(pb + (int64_t)t * C4);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        }
+        reinterpret_cast<float4*>(s_mean)[i] = make_float4(s.x * inv_hw, s.y * inv_hw, s.z * inv_hw, s.w * inv_hw);
+    }
+    float acc[FR][2];                         // second FC: this thread's channel pair (tid < C / 2); live from chunk nch on
+    __syncthreads();
+    for (int k = 0; k < NC; ++k) {
+        const int slot = k % kSlots, second = k >= nch;
+        const int r0 = (k - second * nch) * rows_per_chunk, rows = min(rows_per_chunk, R - r0);
+        mbar_wait(bars + 8u * (uint32_t)slot, (uint32_t)(k / kSlots) & 1u);
+        const float* wch = ring + slot * chunk_floats;
+        if (k == nch) {
+            const float2 bias = tid < C2 ? __ldg(reinterpret_cast<const float2*>(b2) + tid) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int f = 0; f < FR; ++f) { acc[f][0] = bias.x; acc[f][1] = bias.y; }
+        }
+        if (!second) {
+            // hidden[f][r] = silu(b1[r] + w1[r] . mean[f]): a warp takes TWO rows, so that every mean quad it reads from shared
+            // memory (the traffic that bounds this phase: 4 wavefronts per 128-bit warp load) feeds 8 FMAs instead of 4
+            for (int rr = 2 * warp; rr < rows; rr += 2 * nwarps) {
+                const bool two = rr + 1 < rows;
+                float sa[FR], sb[FR];
+#pragma unroll
+                for (int f = 0; f < FR; ++f) { sa[f] = 0.f; sb[f] = 0.f; }
+                const float4* wa = reinterpret_cast<const float4*>(wch + rr * C);
+                const float4* wb = reinterpret_cast<const float4*>(wch + (two ? rr + 1 : rr) * C);
+                for (int c4 = lane; c4 < C4; c4 += 32) {
+                    const float4 va = wa[c4], vb = wb[c4];
+#pragma unroll
+                    for (int f = 0; f < FR; ++f) {
+                        const float4 m = reinterpret_cast<const float4*>(s_mean + f * C)[c4];
+                        sa[f] = dot4(va, m, sa[f]);
+                        sb[f] = dot4(vb, m, sb[f]);
+                    }
+                }
+                float mine_a = 0.f, mine_b = 0.f;      // lane f keeps frame f's totals: one SiLU per lane, not FR in sequence
+#pragma unroll
+                for (int f = 0; f < FR; ++f) {
+                    const float ta = warp_sum(sa[f]), tb = warp_sum(sb[f]);
+                    if (lane == f) { mine_a = ta; mine_b = tb; }
+                }
+                if (lane < FR) {
+                    s_hid[lane * Rp + r0 + rr] = siluf_(mine_a + __ldg(b1 + r0 + rr));
+                    if (two) s_hid[lane * Rp + r0 + rr + 1] = siluf_(mine_b + __ldg(b1 + r0 + rr + 1));
+                }
+            }
+        } else if (tid < C2) {                // gate[f][c] += w2t[r][c] hidden[f][r], sequential over r
+            const float2* wc = reinterpret_cast<const float2*>(wch) + tid;
+            for (int rr = 0; rr < rows; rr += 4) {          // r0 and rows_per_chunk are multiples of 4: aligned float4 of hidden
+                float2 w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w[j] = rr + j < rows ? wc[(rr + j) * C2] : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int f = 0; f < FR; ++f) {
+                    const float4 h = *reinterpret_cast<const float4*>(s_hid + f * Rp + r0 + rr);
+                    acc[f][0] = fmaf(w[3].x, h.w, fmaf(w[2].x, h.z, fmaf(w[1].x, h.y, fmaf(w[0].x, h.x, acc[f][0]))));
+                    acc[f][1] = fmaf(w[3].y, h.w, fmaf(w[2].y, h.z, fmaf(w[1].y, h.y, fmaf(w[0].y, h.x, acc[f][1]))));
+                }
+            }
+        }
+        __syncthreads();                      // the slot is drained (and, after the last w1 chunk, hidden is complete)
+        if (tid == 0 && k + kSlots < NC) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(k + kSlots);
+        }
+    }
+    if (tid < C2) {
+#pragma unroll
+        for (int f = 0; f < FR; ++f)
+            if (f < nf)
+                *reinterpret_cast<float2*>(gate + (int64_t)(f0 + f) * C + 2 * tid) = make_float2(sigmoidf_(acc[f][0]), sigmoidf_(acc[f][1]));
+    }
+}
+}  // namespace seg
+
+static int g_se_ring = 1;      // dev A/B switch (orbit_set_global_option "se_ring")
+void set_se_ring(int on) { g_se_ring = on; }
+int get_se_ring() { return g_se_ring; }
+
 int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2t,
                    const float* b2, float* gate, int B, int C, int R, cudaStream_t st) {
     if (B <= 0) return ORBIT_OK;
-    int F = kSeFrames;      // (16 frames per block measured no faster: the kernel is a chain of L2 latencies, not L2 bandwidth)
+    if (g_se_ring && C % 4 == 0 && C <= 2 * seg::kMaxThreads && R >= 1 && aligned16(partial) && aligned16(w1) && aligned16(w2t) &&
+        aligned16(b2) && aligned16(gate)) {
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            ORBIT_CUDA(cudaGetDevice(&dev));
+            ORBIT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const int Rp = (R + 3) / 4 * 4;
+        int rows_per_chunk = std::max(4, seg::kChunkBytes / (C * 4) / 4 * 4);
+        if (rows_per_chunk >= R) rows_per_chunk = Rp;                      // one chunk per matrix
+        int F = std::min(seg::kMaxFrames, std::max(1, ceil_div(B, sms)));            // one wave of blocks
+        if (F > 8 && C > 2 * seg::max_threads(12)) F = 8;                            // the 12-frame instance maps C / 2 <= 640 threads
+        const int FR = F <= 2 ? 2 : (F <= 4 ? 4 : (F <= 8 ? 8 : 12));
+        const size_t smem = sizeof(float) * ((size_t)seg::kSlots * rows_per_chunk * C + (size_t)FR * (C + Rp)) + 8 * seg::kSlots;
+        if (smem <= (size_t)seg::kMaxSmem) {
+            const float inv_hw = 1.0f / (float)hw;
+            const int threads = C <= 256 ? 256 : seg::max_threads(FR);
+#define ORBIT_SEG(N) { ORBIT_CUDA(cudaFuncSetAttribute(seg::se_gate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                       seg::se_gate_kernel<N><<<ceil_div(B, F), threads, smem, st>>>(partial, tiles, inv_hw, w1, b1, w2t, b2, gate, B, C, R, F, rows_per_chunk); }
+            if (FR == 2) ORBIT_SEG(2) else if (FR == 4) ORBIT_SEG(4) else if (FR == 8) ORBIT_SEG(8) else ORBIT_SEG(12)
+#undef ORBIT_SEG
+            ORBIT_RETURN_IF_LAUNCH_FAILED();
+            return ORBIT_OK;
+        }
+    }
+    int F = kSeFrames;
     while (F > 1 && sizeof(float) * (size_t)F * (C + R) > 44 * 1024) F >>= 1;   // stay inside the default 48 KB
     const size_t smem = sizeof(float) * (size_t)F * (C + R);
-    se_gate_kernel<<<ceil_div(B, F), C >= 256 ? 1024 : 256, smem, st>>>(partial, tiles, 1.0f / (float)hw, w1, b1, w2t, b2, gate, B, C, R, F);
+    se_gate_simple_kernel<<<ceil_div(B, F), C >= 256 ? 1024 : 256, smem, st>>>(partial, tiles, 1.0f / (float)hw, w1, b1, w2t, b2, gate, B, C, R, F);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }
