@@ -182,6 +182,14 @@ int orbit_conv_first(const float* x, const float* weight, const float* scale, co
 int orbit_se_gate(const float* partial, int groups, int hw, const float* w1, const float* b1, const float* w2t, const float* b2,
                   float* gate, int B, int C, int R, void* stream);
 
+/* EfficientNet stem: timm conv_stem (3x3, stride 2, TF "SAME" padding, 3 -> 32) + bn1 (folded scale / shift) + activation on the
+ * NCHW fp32 frames the recogniser is handed (model/few_shot_recognisers.py:114-117,143-146).
+ *   x [B,3,H,W] -> y [B,ceil(H/2),ceil(W/2),32] NHWC; weight [32,3,3,3] (torch); act: 0 none, 1 SiLU, 2 ReLU.
+ * fp32 FMA kernel (stem_kernel). A tensor-core variant (FP16x3, the conv_first scheme with 27 of 48 k slots used) measured
+ * 1,597 us per 1,600 frames against 1,322 us and was not kept.                                                                    */
+int orbit_stem_conv(const float* x, const float* weight, const float* scale, const float* shift, float* y, int B, int H, int W,
+                    int act, void* stream);
+
 /* Depthwise k x k convolution (k in {3,5}, stride in {1,2}, TF "SAME" padding) on NHWC activations with the folded
  * BatchNorm/FiLM scale-shift and activation fused: timm conv_dw + BatchNormAct2d of every MBConv block.
  *   x [B,H,W,C] -> y [B,ceil(H/s),ceil(W/s),C]; weight [C,1,k,k] (torch layout); weight_scratch: k*k*C floats.

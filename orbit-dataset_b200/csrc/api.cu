@@ -70,6 +70,15 @@ extern "C" int orbit_se_gate(const float* partial, int groups, int hw, const flo
     return launch_se_gate(partial, groups, hw, w1, b1, w2t, b2, gate, B, C, R, (cudaStream_t)stream);
 }
 
+extern "C" int orbit_stem_conv(const float* x, const float* weight, const float* scale, const float* shift, float* y, int B, int H,
+                               int W, int act, void* stream) {
+    using namespace orbit;
+    if (!x || !weight || !scale || !shift || !y || B < 0 || H <= 0 || W <= 0) return ORBIT_ERR_ARG;
+    const int ho = (H + 1) / 2, wo = (W + 1) / 2;
+    const int pad_t = std::max((ho - 1) * 2 + 3 - H, 0) / 2, pad_l = std::max((wo - 1) * 2 + 3 - W, 0) / 2;   // TF "SAME": the odd pixel goes below / right
+    return launch_stem(x, weight, scale, shift, y, B, H, W, ho, wo, pad_t, pad_l, 32, act, (cudaStream_t)stream);
+}
+
 extern "C" int orbit_conv_first(const float* x, const float* weight, const float* scale, const float* shift, float* y, int B, int H,
                                 int W, int k, int stride, int pad, int act, void* stream) {
     using namespace orbit;

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "orbit_engine_macs": (_i64, [_p, _i, _i]),
     "orbit_video_stats": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _p, _p]),
     "orbit_se_gate": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "orbit_stem_conv": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "orbit_conv_first": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "orbit_conv3x3_scratch_floats": (_i64, [_i, _i, _i, _i, _i, _i]),
     "orbit_conv3x3": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i64, _p]),

@@ -77,3 +77,30 @@ def test_conv_first_matches_torch(cuda_device, B, H, W, k, stride, pad, act):
     torch.cuda.synchronize()
     got = y.permute(0, 3, 1, 2).cpu().double()
     assert (got - ref).abs().max().item() <= 3e-6 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,W,act", [(3, 224, 224, 1), (5, 84, 84, 1), (2, 85, 63, 1), (4, 64, 64, 0), (2, 33, 47, 2), (1, 16, 16, 1)])
+def test_stem_matches_torch(cuda_device, B, H, W, act):
+    """the EfficientNet stem (C ABI orbit_stem_conv: 3x3 stride 2, TF-SAME, 3 -> 32) against torch conv2d in float64"""
+    from orbit_b200 import lib as L
+    from oracle.backbones import tf_same_pad
+    lib = L.load()
+    g = torch.Generator().manual_seed(H + W + act)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 27 ** -0.5
+    scale, shift = 1 + 0.1 * torch.randn(32, generator=g), 0.1 * torch.randn(32, generator=g)
+    (pt, pb), (pl, pr) = tf_same_pad(H, 3, 2), tf_same_pad(W, 3, 2)
+    ref = F.conv2d(F.pad(x.double(), (pl, pr, pt, pb)), w.double(), None, 2, 0)
+    ref = ref * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]
+    if act == 1:
+        ref = ref * torch.sigmoid(ref)
+    elif act == 2:
+        ref = ref.relu()
+    Ho, Wo = ref.shape[-2:]
+    assert (Ho, Wo) == ((H + 1) // 2, (W + 1) // 2)
+    y = torch.full((B, Ho, Wo, 32), float('nan'), device=cuda_device)
+    keep = [t.to(cuda_device) for t in (x, w, scale, shift)]
+    L.check(lib.orbit_stem_conv(*(L.ptr(t) for t in keep), L.ptr(y), B, H, W, act, L.stream_ptr(cuda_device)), "orbit_stem_conv")
+    torch.cuda.synchronize()
+    got = y.permute(0, 3, 1, 2).cpu().double()
+    assert (got - ref).abs().max().item() <= 3e-6 * max(1.0, ref.abs().max().item())
