@@ -151,7 +151,7 @@ __device__ __forceinline__ stem_f2_t stem_fma2(stem_f2_t a, stem_f2_t b, stem_f2
 }
 
 template <int COUT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
             const float* __restrict__ shift, float* __restrict__ y, int B, int H, int W, int Ho, int Wo, int pad_t,
             int pad_l, int act) {
@@ -242,6 +242,7 @@ int launch_stem(const float* x, const float* w, const float* scale, const float*
                 int Ho, int Wo, int pad_t, int pad_l, int cout, int act, cudaStream_t st) {
     if (cout != 32) return ORBIT_ERR_UNSUPPORTED;
     const int64_t total = (int64_t)B * Ho * ((Wo + 1) / 2);
+    ORBIT_CUDA(cudaFuncSetAttribute(stem_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // 4 blocks x 36 KB per SM
     stem_kernel<32><<<(unsigned)ceil_div64(total, 128), 128, 0, st>>>(x, w, scale, shift, y, B, H, W, Ho, Wo, pad_t, pad_l, act);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
