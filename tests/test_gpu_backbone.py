@@ -134,6 +134,39 @@ def test_finetune_kernel_matches_torch_optimisers(cuda_device):
         assert dw <= 2e-4 * max(1.0, oracle.head[0].abs().max().item()) and db <= 2e-4
 
 
+@pytest.mark.parametrize("n,d,c,steps", [(80, 768, 8, 50), (300, 1280, 10, 20), (13, 260, 4, 20)])
+def test_finetune_grid_and_single_cta_kernels(cuda_device, n, d, c, steps):
+    """the cooperative-grid kernel (default; (300, 1280, 10) takes its two-level logit reduction, (13, 260, 4) has D % 16 != 0
+    and falls back) and the single-CTA kernel against torch.optim.Adam driven through the oracle's batch loop"""
+    import orbit_b200
+    from orbit_b200 import lib as L
+    from orbit_b200.finetune import finetune_linear_head
+    from oracle.recogniser import OracleRecogniser
+    lib = L.load()
+    g = torch.Generator().manual_seed(n + d)
+    feats = torch.randn(n, d, generator=g) * 0.5 + 0.1
+    labels = (torch.arange(n) * 7 % (c + 1)).clamp(max=c - 1)       # unbalanced class counts (see the test above)
+    oracle = OracleRecogniser.__new__(OracleRecogniser)
+    oracle.batch_size, oracle.feat_dim, oracle.logit_scale, oracle.clip_length = 64, d, 1.0, 1
+    oracle._features = lambda clips, film=None: clips
+    oracle.personalise_finetune(feats, labels, num_grad_steps=steps, learning_rate=1e-3, optimizer='adam')
+    got = {}
+    for mode in (1, 0):
+        assert lib.orbit_set_global_option(b'finetune_grid', mode) == 0
+        try:
+            head = orbit_b200.LinearClassifier(d, 1.0)
+            head.init(c)
+            head.to(cuda_device)
+            finetune_linear_head(head, feats.to(cuda_device), labels, 64, steps, 1e-3, 'adam', {}, 1.0)
+            got[mode] = (head.weight.detach().cpu(), head.bias.detach().cpu())
+        finally:
+            assert lib.orbit_set_global_option(b'finetune_grid', 1) == 0
+        dw = (got[mode][0] - oracle.head[0]).abs().max().item()
+        db = (got[mode][1] - oracle.head[1]).abs().max().item()
+        assert dw <= 2e-4 * max(1.0, oracle.head[0].abs().max().item()) and db <= 2e-4, (mode, dw, db)
+    assert (got[0][0] - got[1][0]).abs().max().item() <= 2e-4
+
+
 def test_finetuner_matches_oracle(cuda_device):
     """MultiStepFewShotRecogniser.personalise (features from the native extractor, then the device-side Adam loop
     on the linear head) vs the oracle, with the reference's default FineTuner hyper-parameters (Adam, lr 1e-3,
