@@ -762,11 +762,14 @@ static float g_debias_kappa = 1.0f;   // one ulp of every promoted k-block parti
 static unsigned* g_gemm_trace = nullptr;
 static int g_narrow = 1;
 static int g_fixed_slabs = 0;        // dev A/B switches (orbit_set_global_option): tc_fixed_slabs, tc_double_min_stages
+static int g_wide_xf = 1;
 static int g_double_min_stages = 3;  // double-buffered epilogue staging only when that still leaves this many ring stages
 void set_tcgen05_tuning(int fixed_slabs, int double_min_stages) {
     if (fixed_slabs >= 0) g_fixed_slabs = fixed_slabs;
     if (double_min_stages >= 0) g_double_min_stages = double_min_stages;
 }
+void set_tcgen05_wide_xf(int v) { g_wide_xf = v; }
+int get_tcgen05_wide_xf() { return g_wide_xf; }
 void set_tcgen05_narrow(int on) { g_narrow = on; }
 int get_tcgen05_narrow() { return g_narrow; }
 void set_tcgen05_trace(unsigned* dev_buffer) { g_gemm_trace = dev_buffer; }
@@ -847,8 +850,13 @@ static int launch_tcgen05_impl(const float* A, const float* w_split, const float
     int xfw = 4;
     const bool g = gate != nullptr, r = residual != nullptr;
     const bool narrow = K <= 32 && g_narrow;
+    // every n-tile re-loads and re-splits its A k-blocks: with several n-tiles and a deep K the four transform warps (~1,700 clk
+    // per k-block) are slower than the twelve MMAs (1,116 clk): eight transform warps there (g_wide_xf: 0 off, 1 Linear layers, 2 + SiLU)
+    const int wide_xf = (g_wide_xf && p.n_tiles >= 2 && K >= 2 * BK) ? g_wide_xf : 0;
     if (conv) {
-        if (act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4, false, true>;          // conv3x3 + ReLU (ResNet conv1 of a block, set encoder)
+        if (act == 2 && !r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 2, 0, 8, false, true>; xfw = 8; }
+        else if (act == 18 && r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 18, 1, 8, false, true>; xfw = 8; }
+        else if (act == 2 && !r) fn = pw_tcgen05_kernel<true, 0, 2, 0, 4, false, true>;     // conv3x3 + ReLU (ResNet conv1 of a block, set encoder)
         else if (act == 18 && r) fn = pw_tcgen05_kernel<true, 0, 18, 1, 4, false, true>;    // BasicBlock: relu(bn(conv3x3) + identity)
         else if (act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4, false, true>;     // plain conv3x3 (data gradient of the set encoder)
         else if (act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, false, true>;     // conv3x3 + SiLU (EfficientNet-V2 EdgeResidual expand)
@@ -858,6 +866,10 @@ static int launch_tcgen05_impl(const float* A, const float* w_split, const float
         else if (g && act == 0 && !r) { fn = pw_tcgen05_kernel<true, 1, 0, 0, 8, false>; xfw = 8; }   // MBConv project
         else if (g && act == 0 && r) { fn = pw_tcgen05_kernel<true, 1, 0, 1, 8, false>; xfw = 8; }    // ... + skip
         else if (!g && act == 1 && !r && narrow) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, true>;    // MBConv expand at 112x112 / 56x56 (K = 16, 24)
+        else if (!g && act == 1 && !r && wide_xf == 2) { fn = pw_tcgen05_kernel<true, 0, 1, 0, 8, false>; xfw = 8; }
+        else if (!g && act == 0 && !r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 0, 0, 8, false>; xfw = 8; }
+        else if (!g && act == 0 && r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 0, 1, 8, false>; xfw = 8; }
+        else if (!g && act == 4 && !r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 4, 0, 8, false>; xfw = 8; }
         else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, false>;    // MBConv expand / conv_head (SiLU)
         else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4, false>;    // Linear / downsample
         else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4, false>;     // Linear + residual (ViT), EdgeResidual project

@@ -35,6 +35,8 @@ void set_tcgen05_debias(float kappa);
 void set_tcgen05_trace(unsigned* dev_buffer);
 float get_tcgen05_debias();
 // dev A/B switch: 4-lanes-per-row transform mapping for K <= 32 (default on)
+void set_tcgen05_wide_xf(int v);   // 8 transform warps for ungated multi-n-tile layers: 0 off, 1 Linear, 2 + SiLU expands
+int get_tcgen05_wide_xf();
 void set_tcgen05_narrow(int on);
 int get_tcgen05_narrow();
 // dev A/B switches: fixed slab -> warp mapping for tiles of < 3 slabs (frees staging memory for ring stages); minimum ring

@@ -5,6 +5,10 @@ import torch
 import bench
 from orbit_b200.synthetic import make_episode
 name = os.environ.get('CFG', 'S4')
+from orbit_b200 import lib as L
+for kv in filter(None, os.environ.get('OPTS', '').split(',')):
+    k, v = kv.split('=')
+    assert L.load().orbit_set_global_option(k.encode(), int(v)) == 0, kv
 dev = torch.device('cuda:0')
 model = bench.build_model(name, dev, 1, 1600)
 spec = bench.config_spec(name)
@@ -19,6 +23,7 @@ for _ in range(3): bench.run_episode(name, model, c, cy, t)
 e1.record(); torch.cuda.synchronize()
 print(f"{name}: {e0.elapsed_time(e1) / 3:.2f} ms per episode")
 from torch.profiler import profile, ProfilerActivity
+if os.environ.get('NOPROF'): sys.exit(0)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     bench.run_episode(name, model, c, cy, t); torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=24, max_name_column_width=90))
