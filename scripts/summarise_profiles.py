@@ -16,7 +16,7 @@ for r in rows[1:]:
         v *= {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
     d[r[im]] = v
 def short(n):
-    m = re.match(r'(?:void )?(?:orbit::)?(?:tc::|st::|mbs::)?([A-Za-z0-9_]+)', n)
+    m = re.match(r'(?:void )?(?:orbit::)?(?:tc::|st::|mbs::|seg::|cf::)?([A-Za-z0-9_]+)', n)
     base = m.group(1) if m else n
     t = re.search(r'<(.*)>', n)
     return base + ('<' + t.group(1).replace('(int)', '').replace('(bool)', '').replace(' ', '') + '>' if t else '')
@@ -59,10 +59,14 @@ keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum']
 with open(f'{ROOT}/profiles/{tag}_ncu_full.csv', 'w') as f:
     first = True
-    for rep in (f'{tag}_gemm_full', f'{tag}_stream_full', f'{tag}_dw_full', f'{tag}_dw5s_full', f'{tag}_mbx_full'):
-        path = f'{ROOT}/gpurun_out/{rep}.ncu-rep'
-        if not os.path.exists(path): continue
-        raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    for rep in (f'{tag}_gemm_full', f'{tag}_stream_full', f'{tag}_dw_full', f'{tag}_dw5s_full', f'{tag}_mbx_full', f'{tag}_se_full'):
+        path, exported = f'{ROOT}/gpurun_out/{rep}.ncu-rep', f'{ROOT}/gpurun_out/{rep}_raw.csv'   # (profile_round.sh exports on the box)
+        if os.path.exists(exported) and os.path.getsize(exported) > 0:
+            raw = open(exported).read()
+        elif os.path.exists(path):
+            raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        else:
+            continue
         rr = list(csv.reader(io.StringIO(raw)))
         h, u = rr[0], rr[1]
         idx = [h.index(k) for k in keys if k in h]
