@@ -28,7 +28,8 @@ class _HostStager:
     One call = one whole-call device buffer (two are kept and alternate between calls), so the copy engine never
     waits for the backbone inside a call and the NEXT call's copy (e.g. the query set while the support set is still
     being processed) starts as soon as it is issued. The backbone consumes the buffer in chunks that only wait for
-    their own bytes: a short ramp (160, 320, 480 frames) so that the first kernels start after ~2 ms of copy, then
+    their own bytes: a short ramp (96, 192, 320, 416 frames: the first kernels start after ~1.3 ms of copy and, at the
+    measured 91 frames/ms of copy against ~75 frames/ms of backbone, no later pass waits for its bytes), then
     chunks of ``chunk_frames``. Pageable sources are staged through two pinned slices."""
 
     def __init__(self, device, chunk_frames, copy_frames=160):
@@ -42,7 +43,7 @@ class _HostStager:
         self.pinned_free = [None, None]
         self.calls = 0
         self.bytes_copied = 0
-        self.ramp = (160, 320, 480)
+        self.ramp = (96, 192, 320, 416)
         self.last_done = None                   # completion event of the previous call's last backbone pass
         self.last_buffer = None                 # (index, device view) of the most recent call's whole-call buffer
 
@@ -188,7 +189,7 @@ class FewShotRecogniser(nn.Module):
         # sizes of the first backbone passes of a call (frames). Tuned on B200 with the measured pass times (scripts/e2e_probe.py,
         # scripts/pass_overhead.py): the copy of a 1,600-frame support set ends at 17.4 ms and the LAST pass can only start then, so
         # it should be short (640), while earlier passes must not be so small that their fixed cost dominates: 39.1 -> 37.7 ms
-        self.stage_ramp = (160, 320, 480)
+        self.stage_ramp = (96, 192, 320, 416)
 
     def _set_device(self, device):
         self.device = torch.device(device)
