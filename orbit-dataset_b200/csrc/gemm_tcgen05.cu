@@ -852,7 +852,8 @@ static int launch_tcgen05_impl(const float* A, const float* w_split, const float
     const bool narrow = K <= 32 && g_narrow;
     // every n-tile re-loads and re-splits its A k-blocks: with several n-tiles and a deep K the four transform warps (~1,700 clk
     // per k-block) are slower than the twelve MMAs (1,116 clk): eight transform warps there (g_wide_xf: 0 off, 1 Linear layers, 2 + SiLU)
-    const int wide_xf = (g_wide_xf && p.n_tiles >= 2 && K >= 2 * BK) ? g_wide_xf : 0;
+    // (the implicit 3x3 convolution has K >= 576 and a transform that also masks the out-of-image taps: always eight)
+    const int wide_xf = (g_wide_xf && (conv || p.n_tiles >= 2) && K >= 2 * BK) ? g_wide_xf : 0;
     if (conv) {
         if (act == 2 && !r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 2, 0, 8, false, true>; xfw = 8; }
         else if (act == 18 && r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 18, 1, 8, false, true>; xfw = 8; }
@@ -870,6 +871,8 @@ static int launch_tcgen05_impl(const float* A, const float* w_split, const float
         else if (!g && act == 0 && !r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 0, 0, 8, false>; xfw = 8; }
         else if (!g && act == 0 && r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 0, 1, 8, false>; xfw = 8; }
         else if (!g && act == 4 && !r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 4, 0, 8, false>; xfw = 8; }
+        else if (!g && act == 2 && !r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 2, 0, 8, false>; xfw = 8; }
+        else if (!g && act == 18 && r && wide_xf) { fn = pw_tcgen05_kernel<true, 0, 18, 1, 8, false>; xfw = 8; }
         else if (!g && act == 1 && !r) fn = pw_tcgen05_kernel<true, 0, 1, 0, 4, false>;    // MBConv expand / conv_head (SiLU)
         else if (!g && act == 0 && !r) fn = pw_tcgen05_kernel<true, 0, 0, 0, 4, false>;    // Linear / downsample
         else if (!g && act == 0 && r) fn = pw_tcgen05_kernel<true, 0, 0, 1, 4, false>;     // Linear + residual (ViT), EdgeResidual project
