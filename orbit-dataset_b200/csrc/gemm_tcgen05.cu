@@ -361,12 +361,27 @@ pw_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     mbar_wait(empty(s), ph ^ 1);
                     trace_stamp(p.trace, step, 0);
-                    mbar_expect_tx(full(s), (two ? 2u : 1u) * A_BOX_BYTES + b_bytes);
+#ifdef ORBIT_EXP_SKIP_B      // timing experiment only (wrong results): the weight tiles are fetched during the first trip round the ring only
+                    const bool load_b = step < (uint32_t)p.stages;
+#else
+                    const bool load_b = true;
+#endif
+#ifdef ORBIT_EXP_SKIP_A
+                    const bool load_a = step < (uint32_t)p.stages;
+#else
+                    const bool load_a = true;
+#endif
+                    if (!load_a && !load_b) { mbar_arrive(full(s)); }
+                    else mbar_expect_tx(full(s), (load_a ? (two ? 2u : 1u) * A_BOX_BYTES : 0u) + (load_b ? b_bytes : 0u));
                     const uint32_t st = ring + s * stage_bytes;
-                    tma_load_2d(st, &map_a, full(s), a_col, a_row);
-                    if (two) tma_load_2d(st + A_BOX_BYTES, &map_a, full(s), a_col + 32, a_row);
-                    tma_load_2d(st + A_STAGE_BYTES, &map_bhi, full(s), kb * BK, n0);
-                    if (SPLIT) tma_load_2d(st + A_STAGE_BYTES + p.b_tile_bytes, &map_blo, full(s), kb * BK, n0);
+                    if (load_a) {
+                        tma_load_2d(st, &map_a, full(s), a_col, a_row);
+                        if (two) tma_load_2d(st + A_BOX_BYTES, &map_a, full(s), a_col + 32, a_row);
+                    }
+                    if (load_b) {
+                        tma_load_2d(st + A_STAGE_BYTES, &map_bhi, full(s), kb * BK, n0);
+                        if (SPLIT) tma_load_2d(st + A_STAGE_BYTES + p.b_tile_bytes, &map_blo, full(s), kb * BK, n0);
+                    }
                     trace_stamp(p.trace, step, 1);
                     if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
