@@ -12,8 +12,15 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 
+STAMP = LIB + ".flags"      # the nvcc flags the library on disk was built with (an experiment build must not pass for the shipped one)
+
+
+def _flags():
+    return " ".join(NVCC_FLAGS + os.environ.get("ORBIT_NVCC_EXTRA", "").split() + (["-lcuda"] if os.environ.get("ORBIT_LINK_LIBCUDA") else []))
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP) or open(STAMP).read() != _flags():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "orbit_b200.h")]
@@ -33,6 +40,8 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc failed building liborbit_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(_flags())
     return LIB
 
 
