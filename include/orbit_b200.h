@@ -44,6 +44,9 @@ extern "C" {
 #define ORBIT_MAX_CLASSES 64
 
 int         orbit_abi_version(void);
+/* 1 when the library was compiled with a timing-experiment flag (-DORBIT_EXP_SKIP_A / -DORBIT_EXP_SKIP_B: wrong results by design);
+ * the Python host side refuses to load such a build unless ORBIT_ALLOW_EXPERIMENT_BUILD is set.                                   */
+int         orbit_experiment_build(void);
 const char* orbit_error_string(int code);
 /* 0 if the current CUDA device is sm_100 and the library's kernels can run, else ORBIT_ERR_NO_DEVICE */
 int         orbit_device_check(void);

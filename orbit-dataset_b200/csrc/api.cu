@@ -10,6 +10,13 @@ int get_finetune_grid();
 }
 
 extern "C" int orbit_abi_version(void) { return ORBIT_ABI_VERSION; }
+extern "C" int orbit_experiment_build(void) {
+#if defined(ORBIT_EXP_SKIP_A) || defined(ORBIT_EXP_SKIP_B)
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 extern "C" const char* orbit_error_string(int code) {
     switch (code) {

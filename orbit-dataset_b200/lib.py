@@ -55,6 +55,7 @@ _SIGNATURES = {
     "orbit_engine_macs": (_i64, [_p, _i, _i]),
     "orbit_video_stats": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _p, _p]),
     "orbit_se_gate": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "orbit_experiment_build": (_i, []),
     "orbit_stem_conv": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "orbit_conv_first": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "orbit_conv3x3_scratch_floats": (_i64, [_i, _i, _i, _i, _i, _i]),
@@ -122,6 +123,9 @@ def load():
             fn.restype, fn.argtypes = res, args
         if lib.orbit_abi_version() != 1:
             raise OrbitError("liborbit_b200.so ABI version mismatch; rebuild")
+        if lib.orbit_experiment_build() and not os.environ.get("ORBIT_ALLOW_EXPERIMENT_BUILD"):
+            raise OrbitError("liborbit_b200.so was compiled with a timing-experiment flag (ORBIT_EXP_*: wrong results by design); "
+                             "rebuild with `python __graft_entry__.py build`, or set ORBIT_ALLOW_EXPERIMENT_BUILD=1 to time it")
         _lib = _Lib(lib, list(_SIGNATURES))
     return _lib
 

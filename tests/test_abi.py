@@ -74,3 +74,9 @@ def test_engine_plan_metadata_matches_timm_efficientnet_b0():
     assert torch.equal(fe._blob[off:off + numel], ref.state_dict()[name].flatten())
     with pytest.raises(ValueError):
         FeatureExtractor('resnet9000')
+
+
+def test_shipped_library_is_not_an_experiment_build():
+    """a library compiled with a timing-experiment flag (ORBIT_EXP_*: wrong results by design) must never pass for the product"""
+    from orbit_b200 import lib as L
+    assert L.load().orbit_experiment_build() == 0
