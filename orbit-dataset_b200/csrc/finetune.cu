@@ -37,6 +37,21 @@ struct FinetuneParams {
     float lr, beta1, beta2, eps, weight_decay, momentum, logit_scale;
 };
 
+// one optimiser update (shared by both kernels): returns the new parameter value
+__device__ __forceinline__ float finetune_update(const FinetuneParams& p, float w, float grad, float& m, float& v, int step, float bc1,
+                                                 float bc2_sqrt) {
+    if (p.weight_decay != 0.f) grad = fmaf(p.weight_decay, w, grad);
+    if (p.optimizer == 0) {   // torch.optim.Adam (no amsgrad)
+        const float mm = p.beta1 * m + (1.f - p.beta1) * grad;
+        const float vv = p.beta2 * v + (1.f - p.beta2) * grad * grad;
+        m = mm; v = vv;
+        return w - (p.lr / bc1) * (mm / (sqrtf(vv) / bc2_sqrt + p.eps));
+    }
+    float buf = grad;         // torch.optim.SGD with momentum (dampening 0, no nesterov)
+    if (p.momentum != 0.f) { buf = step == 1 ? grad : p.momentum * m + grad; m = buf; }
+    return w - p.lr * buf;
+}
+
 __global__ void __launch_bounds__(1024, 1) linear_finetune_kernel(const FinetuneParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
     const int CD = p.C * p.D;
@@ -82,42 +97,13 @@ __global__ void __launch_bounds__(1024, 1) linear_finetune_kernel(const Finetune
             if (is_bias) for (int i = 0; i < p.N; ++i) grad += p.g[(int64_t)i * p.C + c];
             else for (int i = 0; i < p.N; ++i) grad = fmaf(p.g[(int64_t)i * p.C + c], p.x[(int64_t)i * p.D + d], grad);
             float* param = is_bias ? p.b + c : p.w + e;
-            float* m = is_bias ? p.mb + c : p.mw + e;
-            float* v = is_bias ? p.vb + c : p.vw + e;
-            float w = *param;
-            if (p.weight_decay != 0.f) grad = fmaf(p.weight_decay, w, grad);
-            if (p.optimizer == 0) {   // torch.optim.Adam (no amsgrad)
-                const float mm = p.beta1 * *m + (1.f - p.beta1) * grad;
-                const float vv = p.beta2 * *v + (1.f - p.beta2) * grad * grad;
-                *m = mm; *v = vv;
-                w -= (p.lr / bc1) * (mm / (sqrtf(vv) / bc2_sqrt + p.eps));
-            } else {                  // torch.optim.SGD with momentum (dampening 0, no nesterov)
-                float buf = grad;
-                if (p.momentum != 0.f) { buf = step == 1 ? grad : p.momentum * *m + grad; *m = buf; }
-                w -= p.lr * buf;
-            }
-            *param = w;
+            *param = finetune_update(p, *param, grad, is_bias ? p.mb[c] : p.mw[e], is_bias ? p.vb[c] : p.vw[e], step, bc1, bc2_sqrt);
         }
         __syncthreads();
     }
 }
 
 constexpr int kFtCols = 16, kFtThreads = 256;
-
-// one optimiser update (shared by both kernels): returns the new parameter value
-__device__ __forceinline__ float finetune_update(const FinetuneParams& p, float w, float grad, float& m, float& v, int step, float bc1,
-                                                 float bc2_sqrt) {
-    if (p.weight_decay != 0.f) grad = fmaf(p.weight_decay, w, grad);
-    if (p.optimizer == 0) {   // torch.optim.Adam (no amsgrad)
-        const float mm = p.beta1 * m + (1.f - p.beta1) * grad;
-        const float vv = p.beta2 * v + (1.f - p.beta2) * grad * grad;
-        m = mm; v = vv;
-        return w - (p.lr / bc1) * (mm / (sqrtf(vv) / bc2_sqrt + p.eps));
-    }
-    float buf = grad;         // torch.optim.SGD with momentum (dampening 0, no nesterov)
-    if (p.momentum != 0.f) { buf = step == 1 ? grad : p.momentum * m + grad; m = buf; }
-    return w - p.lr * buf;
-}
 
 // grid = D / 16 CTAs (cooperative launch). part: [2][grid][N * C] partial logits (double-buffered across steps), then
 // [2][N * C] totals (two_level).
