@@ -115,6 +115,7 @@ extern "C" int orbit_set_global_option(const char* key, int value) {
     if (!strcmp(key, "dw5_staged")) { orbit::set_dw5_staged(value); return ORBIT_OK; }
     if (!strcmp(key, "mbconv_stream")) { orbit::set_mbconv_stream(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "se_ring")) { orbit::set_se_ring(value != 0); return ORBIT_OK; }
+    if (!strcmp(key, "stem_groups")) { orbit::set_stem_groups(value); return ORBIT_OK; }
     if (!strcmp(key, "tc_wide_xf")) { orbit::set_tcgen05_wide_xf(value); return ORBIT_OK; }
     if (!strcmp(key, "finetune_grid")) { orbit::set_finetune_grid(value != 0); return ORBIT_OK; }
     if (!strcmp(key, "conv_first")) { orbit::set_conv_first(value != 0); return ORBIT_OK; }
@@ -130,6 +131,7 @@ extern "C" int orbit_get_global_option(const char* key, int* value) {
     if (!strcmp(key, "dw5_staged")) { *value = orbit::get_dw5_staged(); return ORBIT_OK; }
     if (!strcmp(key, "mbconv_stream")) { *value = orbit::get_mbconv_stream(); return ORBIT_OK; }
     if (!strcmp(key, "se_ring")) { *value = orbit::get_se_ring(); return ORBIT_OK; }
+    if (!strcmp(key, "stem_groups")) { *value = orbit::get_stem_groups(); return ORBIT_OK; }
     if (!strcmp(key, "tc_wide_xf")) { *value = orbit::get_tcgen05_wide_xf(); return ORBIT_OK; }
     if (!strcmp(key, "finetune_grid")) { *value = orbit::get_finetune_grid(); return ORBIT_OK; }
     if (!strcmp(key, "conv_first")) { *value = orbit::get_conv_first(); return ORBIT_OK; }

@@ -162,8 +162,11 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) { s_sc[i] = scale[i]; s_sh[i] = shift[i]; }
     __syncthreads();
     const int Wp = (Wo + 1) / 2;                      // pixel pairs per output row
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)B * Ho * Wp) return;
+    const int64_t total_pairs = (int64_t)B * Ho * Wp;
+    // a block walks over several 128-pair groups (grid-stride): the weight staging above is paid once per block, not once per 256 pixels
+    for (int64_t grp = blockIdx.x; grp * blockDim.x < total_pairs; grp += gridDim.x) {
+    const int64_t idx = grp * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= total_pairs) break;                    // (whole warps leave together except in the last group: no block barrier below)
     const int ox = 2 * (int)(idx % Wp), oy = (int)((idx / Wp) % Ho), b = (int)(idx / ((int64_t)Wp * Ho));
     const bool second = ox + 1 < Wo;
     stem_f2_t acc[2][NP];
@@ -207,7 +210,7 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
     __shared__ __align__(16) float4 s_out[4][64 * 8];
     const int64_t pix = ((int64_t)b * Ho + oy) * Wo + ox;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool staged = (Wo & 1) == 0 && (blockIdx.x + 1) * (int64_t)blockDim.x <= (int64_t)B * Ho * Wp;   // full block, no odd tail
+    const bool staged = (Wo & 1) == 0 && (grp + 1) * (int64_t)blockDim.x <= total_pairs;   // full group, no odd tail
 #pragma unroll
     for (int px = 0; px < 2; ++px) {
         if (px == 1 && !second) break;
@@ -235,15 +238,23 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
             const int i = it * 32 + lane, p = i >> 3, q = i & 7;
             yw[i] = s_out[warp][p * 8 + (q ^ ((p >> 1) & 7))];
         }
+        __syncwarp();                                 // the warp's staging tile is free for the next group
+    }
     }
 }
+
+static int g_stem_groups = 8;      // dev A/B switch (orbit_set_global_option "stem_groups"): 128-pair groups per stem block
+void set_stem_groups(int n) { g_stem_groups = n < 1 ? 1 : n; }
+int get_stem_groups() { return g_stem_groups; }
 
 int launch_stem(const float* x, const float* w, const float* scale, const float* shift, float* y, int B, int H, int W,
                 int Ho, int Wo, int pad_t, int pad_l, int cout, int act, cudaStream_t st) {
     if (cout != 32) return ORBIT_ERR_UNSUPPORTED;
     const int64_t total = (int64_t)B * Ho * ((Wo + 1) / 2);
     ORBIT_CUDA(cudaFuncSetAttribute(stem_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // 4 blocks x 36 KB per SM
-    stem_kernel<32><<<(unsigned)ceil_div64(total, 128), 128, 0, st>>>(x, w, scale, shift, y, B, H, W, Ho, Wo, pad_t, pad_l, act);
+    const int64_t groups = ceil_div64(total, 128);
+    const unsigned grid = (unsigned)std::min<int64_t>(groups, std::max<int64_t>(148 * 4, ceil_div64(groups, g_stem_groups)));   // ~g_stem_groups groups per block
+    stem_kernel<32><<<grid, 128, 0, st>>>(x, w, scale, shift, y, B, H, W, Ho, Wo, pad_t, pad_l, act);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }

@@ -67,6 +67,8 @@ int launch_mbconv_expand_dw(const float* xin, const float* we, const float* scal
 
 // squeeze-excite gate: partial [B][tiles][C] -> gate [B][C] = sigmoid(W2 silu(W1 mean + b1) + b2);
 // w2t = the expand weight [C][R] transposed to [R][C] (launch_dw_relayout(w2, C, R, w2t))
+void set_stem_groups(int n);   // dev A/B switch: 128-pixel-pair groups a stem block walks over (default 8)
+int get_stem_groups();
 void set_se_ring(int on);   // dev A/B switch: ring-streamed SE gate kernel (default) or the plain one
 int get_se_ring();
 int launch_se_gate(const float* partial, int tiles, int hw, const float* w1, const float* b1, const float* w2t,
