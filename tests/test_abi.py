@@ -80,3 +80,21 @@ def test_shipped_library_is_not_an_experiment_build():
     """a library compiled with a timing-experiment flag (ORBIT_EXP_*: wrong results by design) must never pass for the product"""
     from orbit_b200 import lib as L
     assert L.load().orbit_experiment_build() == 0
+
+
+def test_build_is_stale_when_the_nvcc_flags_differ(monkeypatch):
+    """build.py must not mistake a library built with other flags (ORBIT_NVCC_EXTRA: trace / experiment builds) for the shipped
+    one: the flags are stamped next to the .so and compared, not only the file times"""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("orbit_build", os.path.join(root, "orbit-dataset_b200", "build.py"))
+    build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build)
+    monkeypatch.delenv("ORBIT_NVCC_EXTRA", raising=False)
+    monkeypatch.delenv("ORBIT_LINK_LIBCUDA", raising=False)
+    build.build_library()                       # up to date after this (no-op when the tree was just built)
+    assert not build._stale()
+    monkeypatch.setenv("ORBIT_NVCC_EXTRA", "-DORBIT_GEMM_TRACE")
+    assert build._stale()
+    monkeypatch.delenv("ORBIT_NVCC_EXTRA")
+    assert not build._stale()
