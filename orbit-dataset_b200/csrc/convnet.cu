@@ -1599,35 +1599,37 @@ int launch_conv_weight_relayout(const float* w, float* out, int Cout, int Cin, i
     return ORBIT_OK;
 }
 
+// grid (B * Ho output rows, column chunks); a thread = one output pixel x 4 channels. The row index comes from blockIdx (one
+// 32-bit division per thread); the first version derived (b, oy, ox, q) from a flat 64-bit index with three 64-bit divisions
+// per output (the eight pools of an S3 episode, 4.0 GB of traffic: 1.16 -> 1.11 ms; what remains is the 9-fold re-read of the 3x3 pool).
 __global__ void __launch_bounds__(256)
-maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C, int k, int stride, int pad,
-               int Ho, int Wo) {
+maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo) {
     const int C4 = C >> 2;
-    const int64_t total = (int64_t)B * Ho * Wo * C4;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int q = (int)(i % C4);
-        const int64_t pix = i / C4;
-        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
-        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        for (int ky = 0; ky < k; ++ky) {
-            const int iy = oy * stride - pad + ky;
-            if (iy < 0 || iy >= H) continue;
-            for (int kx = 0; kx < k; ++kx) {
-                const int ix = ox * stride - pad + kx;
-                if (ix < 0 || ix >= W) continue;
-                const float4 v = ldg4(x + (((int64_t)b * H + iy) * W + ix) * C + q * 4);
-                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-            }
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= Wo * C4) return;
+    const int ox = i / C4, q = i - ox * C4;
+    const int b = blockIdx.x / Ho, oy = blockIdx.x - b * Ho;
+    const float* xb = x + (int64_t)b * H * W * C + q * 4;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int ky = 0; ky < k; ++ky) {
+        const int iy = oy * stride - pad + ky;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < k; ++kx) {
+            const int ix = ox * stride - pad + kx;
+            if (ix < 0 || ix >= W) continue;
+            const float4 v = ldg4(xb + ((int64_t)iy * W + ix) * C);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
         }
-        *reinterpret_cast<float4*>(y + pix * C + q * 4) = m;
     }
+    *reinterpret_cast<float4*>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + q * 4) = m;
 }
 int launch_maxpool(const float* x, float* y, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
                    cudaStream_t st) {
     if (C % 4) return ORBIT_ERR_UNSUPPORTED;
-    const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
-    if (total == 0) return ORBIT_OK;
-    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(x, y, B, H, W, C, k, stride, pad, Ho, Wo);
+    const int64_t rows = (int64_t)B * Ho, cols = (int64_t)Wo * (C / 4);
+    if (rows == 0 || cols == 0) return ORBIT_OK;
+    if (rows > 0x7fffffffLL || ceil_div64(cols, 256) > 65535) return ORBIT_ERR_UNSUPPORTED;
+    maxpool_kernel<<<dim3((unsigned)rows, (unsigned)ceil_div64(cols, 256)), 256, 0, st>>>(x, y, H, W, C, k, stride, pad, Ho, Wo);
     ORBIT_RETURN_IF_LAUNCH_FAILED();
     return ORBIT_OK;
 }
