@@ -1,5 +1,6 @@
+"""Dev helper: FineTuner inner loop (orbit_linear_finetune), cooperative-grid kernel against the single-CTA one."""
 import sys, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, orbit_b200
 from orbit_b200.finetune import finetune_linear_head
 from orbit_b200 import lib as L

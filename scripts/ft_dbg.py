@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, '/root/repo/tests')
 import numpy as np, torch
 import orbit_b200
 from orbit_b200 import lib as L

@@ -1,5 +1,6 @@
+"""Dev helper: e2e S2 episode time for several host-clip ramps, pinned and pageable sources, on one box."""
 import sys, os, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, orbit_b200
 from orbit_b200.synthetic import S2, load_synthetic_checkpoint, make_episode
 dev = torch.device('cuda:0')
