@@ -139,7 +139,8 @@ int orbit_mahalanobis_predict(const float* clip_feats, int num_clips, int feat_d
  *   clip_feats [num_clips, feat_dim] pooled support features; class_index as in orbit_proto_configure
  *   optimizer 0 = Adam(lr, betas, eps, weight_decay), 1 = SGD(lr, momentum, weight_decay)
  *   weight [num_classes, feat_dim], bias [num_classes]: in = initial head (zeros, classifier_heads.py:59-60),
- *   out = personalised head.  scratch >= orbit_linear_finetune_scratch_bytes().                        */
+ *   out = personalised head.  scratch >= orbit_linear_finetune_scratch_bytes() (optimiser moments, the gradient of the
+ *   logits and, for the cooperative-grid kernel that runs when feat_dim % 16 == 0, the per-CTA partial logits).           */
 int64_t orbit_linear_finetune_scratch_bytes(int num_clips, int feat_dim, int num_classes);
 int orbit_linear_finetune(const float* clip_feats, const int32_t* class_index, int num_clips, int feat_dim,
                           int num_classes, int num_grad_steps, int optimizer, float lr, float beta1, float beta2,
